@@ -1,0 +1,256 @@
+"""CPU oracle — numpy front-end over oracle/oracle.c (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import
+this package, and only as the checker / CPU baseline.  polars_b200/ never imports it.
+
+Each wrapper cites the reference file:line in oracle.c.  Conventions:
+  * validity arrays are numpy bool (one byte per row) or None (= no nulls);
+  * IdxSize = uint32, null index = 0xFFFFFFFF;
+  * group_by keys are passed through key_bits() (unsigned bit repr / canonical float bits,
+    polars-core/src/frame/group_by/into_groups.rs:142-191, polars-utils/src/total_ord.rs:37-47).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+IDX_NULL = np.uint32(0xFFFFFFFF)
+
+OPS = {"add": 0, "sub": 1, "mul": 2, "floordiv": 3, "mod": 4, "truediv": 5}
+CMPS = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5}
+_SUFFIX = {np.dtype("int64"): "i64", np.dtype("int32"): "i32", np.dtype("uint64"): "u64",
+           np.dtype("uint32"): "u32", np.dtype("float64"): "f64", np.dtype("float32"): "f32"}
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle.c with the committed Makefile (gcc; seconds)."""
+    src = os.path.join(_HERE, "oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.or_group_by.restype = C.c_int64
+        _lib.or_filter.restype = C.c_int64
+        _lib.or_hash_join.restype = C.c_int64
+        _lib.or_max_threads.restype = C.c_int
+    return _lib
+
+
+def max_threads() -> int:
+    return int(lib().or_max_threads())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _valid(v, n):
+    if v is None:
+        return None
+    v = np.ascontiguousarray(v, dtype=np.bool_)
+    assert v.shape == (n,)
+    return v
+
+
+# ------------------------------------------------------------------ hashing
+def dirty_hash(keys_u64: np.ndarray) -> np.ndarray:
+    k = np.ascontiguousarray(keys_u64, dtype=np.uint64)
+    out = np.empty_like(k)
+    lib().or_dirty_hash_u64(_p(k), C.c_int64(k.size), _p(out))
+    return out
+
+
+def hash_to_partition(h: np.ndarray, n_partitions: int) -> np.ndarray:
+    h = np.ascontiguousarray(h, dtype=np.uint64)
+    out = np.empty_like(h)
+    lib().or_hash_to_partition(_p(h), C.c_int64(h.size), C.c_uint64(n_partitions), _p(out))
+    return out
+
+
+def key_bits(keys: np.ndarray) -> np.ndarray:
+    """Unsigned bit representation used for hashing/equality of group/join keys."""
+    keys = np.ascontiguousarray(keys)
+    if keys.dtype == np.float64:
+        out = np.empty(keys.size, np.uint64)
+        lib().or_canonical_f64_bits(_p(keys), C.c_int64(keys.size), _p(out))
+        return out
+    if keys.dtype == np.float32:
+        out = np.empty(keys.size, np.uint64)
+        lib().or_canonical_f32_bits(_p(keys), C.c_int64(keys.size), _p(out))
+        return out
+    if keys.dtype.kind == "i":
+        return keys.view(np.dtype(f"u{keys.dtype.itemsize}")).astype(np.uint64)
+    if keys.dtype.kind in "ub":
+        return keys.astype(np.uint64)
+    raise TypeError(keys.dtype)
+
+
+# ------------------------------------------------------------------ elementwise
+def arith(op: str, lhs, rhs, lhs_valid=None, rhs_valid=None):
+    """Returns (values, valid|None).  One side may be a Python/numpy scalar."""
+    l_scalar, r_scalar = np.isscalar(lhs), np.isscalar(rhs)
+    arr = rhs if l_scalar else lhs
+    arr = np.ascontiguousarray(arr)
+    dt, n = arr.dtype, arr.size
+    sfx = _SUFFIX[dt]
+    mode = 2 if l_scalar else (1 if r_scalar else 0)
+    L = np.array([lhs], dtype=dt) if l_scalar else arr
+    R = np.array([rhs], dtype=dt) if r_scalar else np.ascontiguousarray(rhs, dtype=dt)
+    lv, rv = _valid(lhs_valid, n), _valid(rhs_valid, n)
+    ov = np.ones(n, np.bool_)
+    out = np.empty(n, dt)
+    fn = getattr(lib(), f"or_arith_{sfx}")
+    if dt.kind in "iu":
+        out_f = np.empty(n, np.float64)
+        fn(C.c_int(OPS[op]), C.c_int(mode), _p(L), _p(lv), _p(R), _p(rv), C.c_int64(n), _p(out), _p(out_f), _p(ov))
+        if op == "truediv":
+            out = out_f
+    else:
+        fn(C.c_int(OPS[op]), C.c_int(mode), _p(L), _p(lv), _p(R), _p(rv), C.c_int64(n), _p(out), _p(ov))
+    return out, (None if ov.all() else ov)
+
+
+def compare(op: str, lhs, rhs, lhs_valid=None, rhs_valid=None, missing: bool = False):
+    """Returns (bool values, valid|None).  rhs may be a scalar."""
+    lhs = np.ascontiguousarray(lhs)
+    dt, n = lhs.dtype, lhs.size
+    r_scalar = np.isscalar(rhs)
+    R = np.array([rhs], dtype=dt) if r_scalar else np.ascontiguousarray(rhs, dtype=dt)
+    lv, rv = _valid(lhs_valid, n), _valid(rhs_valid, n)
+    out = np.empty(n, np.bool_)
+    ov = np.ones(n, np.bool_)
+    getattr(lib(), f"or_cmp_{_SUFFIX[dt]}")(C.c_int(CMPS[op]), C.c_int(1 if r_scalar else 0), C.c_int(int(missing)),
+                                           _p(lhs), _p(lv), _p(R), _p(rv), C.c_int64(n), _p(out), _p(ov))
+    return out, (None if ov.all() else ov)
+
+
+def filter(values, valid, mask, mask_valid=None):
+    values = np.ascontiguousarray(values)
+    n = values.size
+    mask = np.ascontiguousarray(mask, dtype=np.bool_)
+    out = np.empty(n, values.dtype)
+    ov = np.ones(n, np.bool_)
+    k = lib().or_filter(_p(values), _p(_valid(valid, n)), C.c_int64(n), C.c_int(values.dtype.itemsize),
+                        _p(mask), _p(_valid(mask_valid, n)), _p(out), _p(ov))
+    return out[:k].copy(), (None if valid is None else ov[:k].copy())
+
+
+def gather(values, valid, idx, idx_valid=None):
+    values = np.ascontiguousarray(values)
+    idx = np.ascontiguousarray(idx, dtype=np.uint32)
+    m = idx.size
+    out = np.empty(m, values.dtype)
+    ov = np.ones(m, np.bool_)
+    lib().or_gather(_p(values), _p(_valid(valid, values.size)), C.c_int(values.dtype.itemsize), _p(idx),
+                    _p(_valid(idx_valid, m)), C.c_int64(m), _p(out), _p(ov))
+    return out, (None if (valid is None and idx_valid is None) else ov)
+
+
+# ------------------------------------------------------------------ group_by
+class Groups:
+    """GroupsIdx {first, all} in CSR form (polars-core/src/frame/group_by/position.rs:16-22)."""
+
+    def __init__(self, first, offsets, idx):
+        self.first, self.offsets, self.idx = first, offsets, idx
+
+    def __len__(self):
+        return self.first.size
+
+
+def group_by(keys, key_valid=None, n_partitions: int | None = None, maintain_order: bool = True) -> Groups:
+    bits = key_bits(keys)
+    n = bits.size
+    P = n_partitions if n_partitions is not None else max_threads()
+    first = np.empty(max(n, 1), np.uint32)
+    offsets = np.empty(n + 1, np.uint64)
+    idx = np.empty(max(n, 1), np.uint32)
+    G = lib().or_group_by(_p(bits), _p(_valid(key_valid, n)), C.c_int64(n), C.c_int(P), C.c_int(int(maintain_order)),
+                          _p(first), _p(offsets), _p(idx))
+    return Groups(first[:G].copy(), offsets[:G + 1].copy(), idx[:n])
+
+
+def agg(kind: str, values, valid, groups: Groups):
+    """kind in sum/mean/min/max/count/len.  Returns (values, valid|None) per group."""
+    G = len(groups)
+    off, idx = groups.offsets, groups.idx
+    L = lib()
+    if kind == "len":
+        out = np.empty(G, np.uint32)
+        L.or_agg_len(_p(off), C.c_int64(G), _p(out))
+        return out, None
+    values = np.ascontiguousarray(values)
+    v = _valid(valid, values.size)
+    if kind == "count":
+        out = np.empty(G, np.uint32)
+        L.or_agg_count(_p(v), _p(off), _p(idx), C.c_int64(G), _p(out))
+        return out, None
+    sfx = _SUFFIX[values.dtype]
+    if kind == "sum":
+        out = np.empty(G, values.dtype)
+        getattr(L, f"or_agg_sum_{sfx}")(_p(values), _p(v), _p(off), _p(idx), C.c_int64(G), _p(out))
+        return out, None
+    ov = np.empty(G, np.bool_)
+    if kind == "mean":
+        out = np.empty(G, np.float64)
+        getattr(L, f"or_agg_mean_{sfx}")(_p(values), _p(v), _p(off), _p(idx), C.c_int64(G), _p(out), _p(ov))
+        if values.dtype == np.float32:
+            out = out.astype(np.float32)
+        return out, (None if ov.all() else ov)
+    if kind in ("min", "max"):
+        out = np.empty(G, values.dtype)
+        getattr(L, f"or_agg_{kind}_{sfx}")(_p(values), _p(v), _p(off), _p(idx), C.c_int64(G), _p(out), _p(ov))
+        return out, (None if ov.all() else ov)
+    raise ValueError(kind)
+
+
+def group_by_agg(keys, key_valid, aggs, n_partitions=None, maintain_order=True):
+    """aggs: list of (kind, values, valid).  Returns (key values, key valid, [(vals, valid)...], Groups).
+    Key output = take(first) (polars-core/src/frame/group_by/mod.rs:258-266)."""
+    g = group_by(keys, key_valid, n_partitions, maintain_order)
+    keys = np.ascontiguousarray(keys)
+    kout = keys[g.first] if len(g) else keys[:0]
+    kv = None if key_valid is None else np.asarray(key_valid, np.bool_)[g.first]
+    outs = [agg(kind, vals, valid, g) for (kind, vals, valid) in aggs]
+    return kout, kv, outs, g
+
+
+# ------------------------------------------------------------------ join
+def hash_join(left_keys, right_keys, left_valid=None, right_valid=None, how: str = "inner", nulls_equal: bool = False,
+              maintain_order: str = "none", n_threads: int | None = None):
+    """Returns (left_idx u32, right_idx u32); unmatched right idx (left join) = IDX_NULL."""
+    lk, rk = key_bits(left_keys), key_bits(right_keys)
+    T = n_threads if n_threads is not None else max_threads()
+    pl, pr = C.c_void_p(), C.c_void_p()
+    m = lib().or_hash_join(_p(lk), _p(_valid(left_valid, lk.size)), C.c_int64(lk.size), _p(rk),
+                           _p(_valid(right_valid, rk.size)), C.c_int64(rk.size), C.c_int({"inner": 0, "left": 1}[how]),
+                           C.c_int(int(nulls_equal)), C.c_int(T), C.byref(pl), C.byref(pr))
+    li = np.ctypeslib.as_array(C.cast(pl, C.POINTER(C.c_uint32)), shape=(max(m, 1),))[:m].copy()
+    ri = np.ctypeslib.as_array(C.cast(pr, C.POINTER(C.c_uint32)), shape=(max(m, 1),))[:m].copy()
+    lib().or_free(pl)
+    lib().or_free(pr)
+    if how == "inner" and maintain_order != "none":
+        # polars-ops/src/frame/join/mod.rs:577-642: left probes (sorted) iff len(left) > len(right)
+        left_sorted = lk.size > rk.size
+        if maintain_order in ("left", "left_right"):
+            if not left_sorted:
+                lib().or_stable_sort_pairs(_p(li), _p(ri), C.c_int64(m), C.c_int(0))
+        elif maintain_order in ("right", "right_left"):
+            lib().or_stable_sort_pairs(_p(li), _p(ri), C.c_int64(m), C.c_int(1))
+        else:
+            raise ValueError(maintain_order)
+    return li, ri

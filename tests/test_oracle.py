@@ -1,0 +1,253 @@
+"""CPU tests (-m "not gpu"): pin the oracle against the reference's golden vectors and
+cross-check it against independent engines (pyarrow Acero, numpy) on random inputs."""
+import numpy as np
+import pyarrow as pa
+import pytest
+
+import oracle
+from helpers import IDX_NULL, OracleImpl, assert_close, pairs_sorted, run_group_by_kat, run_join_kat, sort_groups
+
+
+# ---------------------------------------------------------------- golden vectors
+def test_hash_partition_kat(kats):
+    vecs = kats["hash"][0]["vectors"]
+    keys = np.array([int(v["key_u64"]) for v in vecs], dtype=np.uint64)
+    h = oracle.dirty_hash(keys)
+    assert [int(x) for x in h] == [int(v["dirty_hash"]) for v in vecs]
+    for P in (1, 2, 3, 7, 8, 16, 148):
+        p = oracle.hash_to_partition(h, P)
+        assert [int(x) for x in p] == [v["part"][str(P)] for v in vecs]
+
+
+@pytest.mark.parametrize("threads", [1, 2, 4, 7])
+def test_group_by_kats(kats, threads):
+    for case in kats["group_by"]:
+        run_group_by_kat(OracleImpl(threads), case)
+
+
+def test_join_kats(kats):
+    for case in kats["join"]:
+        impl = OracleImpl()
+        run_join_kat(impl, case, set_threads=lambda t: setattr(impl, "n_threads", t))
+
+
+# ---------------------------------------------------------------- cross-checks
+def _arrow(values, valid):
+    return pa.array(values, mask=None if valid is None else ~valid)
+
+
+@pytest.mark.parametrize("n,k,nulls", [(0, 5, False), (1, 1, False), (1000, 7, True), (1001, 50, True), (50_000, 1000, True), (200_000, 100_000, False)])
+def test_group_by_vs_acero(n, k, nulls):
+    rng = np.random.default_rng(n + k)
+    key = rng.integers(-k // 2, k // 2 + 1, n).astype(np.int64)
+    vi = rng.integers(-1000, 1000, n).astype(np.int64)
+    vf = rng.uniform(0, 100, n).round(6)
+    kvalid = (rng.random(n) > 0.05) if nulls else None
+    ivalid = (rng.random(n) > 0.05) if nulls else None
+    fvalid = (rng.random(n) > 0.3) if nulls else None
+    aggs = [("sum", vi, ivalid), ("mean", vf, fvalid), ("len", None, None), ("min", vi, ivalid), ("max", vf, fvalid),
+            ("count", vf, fvalid), ("sum", vf, fvalid), ("mean", vi, ivalid)]
+    for threads, order in [(1, True), (4, True), (8, False)]:
+        keys, kv, outs, g = oracle.group_by_agg(key, kvalid, aggs, threads, order)
+        if order and n:
+            assert np.all(np.diff(g.first.astype(np.int64)) > 0)           # first-occurrence order
+            # first really is the first row of that key
+            for gi in range(min(len(g), 50)):
+                rows = g.idx[g.offsets[gi]:g.offsets[gi + 1]]
+                assert rows[0] == g.first[gi] and np.all(np.diff(rows.astype(np.int64)) > 0)
+        tbl = pa.table({"k": _arrow(key, kvalid), "vi": _arrow(vi, ivalid), "vf": _arrow(vf, fvalid)})
+        ref = tbl.group_by("k", use_threads=False).aggregate(
+            [("vi", "sum"), ("vf", "mean"), ([], "count_all"), ("vi", "min"), ("vf", "max"), ("vf", "count"), ("vf", "sum"), ("vi", "mean")])
+        rk = ref["k"].to_numpy(zero_copy_only=False)
+        rkv = ~np.array(ref["k"].is_null().to_pylist(), dtype=bool) if n else np.zeros(0, bool)
+        rk = np.where(rkv, rk, 0).astype(np.int64) if n else np.zeros(0, np.int64)
+        names = ["vi_sum", "vf_mean", "count_all", "vi_min", "vf_max", "vf_count", "vf_sum", "vi_mean"]
+        routs = []
+        for nm, (kind, _, _) in zip(names, aggs):
+            c = ref[nm]
+            m = ~np.array(c.is_null().to_pylist(), dtype=bool)
+            v = np.array([0 if x is None else x for x in c.to_pylist()])
+            routs.append((v, None if m.all() else m))
+        keys, kv, outs = sort_groups(keys, kv, outs)
+        rk, rkv2, routs = sort_groups(rk, None if rkv.all() else rkv, routs)
+        assert_close(keys, rk, kv, rkv2, "keys")
+        for (kind, _, _), (v, m), (rv, rm) in zip(aggs, outs, routs):
+            if kind == "sum":
+                # Acero: all-null group sum is null; reference: 0 (aggregations/mod.rs:862-865)
+                rv = np.where(np.ones(rv.shape, bool) if rm is None else rm, rv, 0)
+                rm = None
+            assert_close(v.astype(np.float64) if kind in ("len", "count") else v,
+                         rv.astype(np.float64) if kind in ("len", "count") else rv.astype(v.dtype), m, rm, kind)
+
+
+def test_sum_semantics_edge():
+    # wrapping int sum, all-null group sums to 0 / means to null, NaN handling of min/max
+    key = np.array([0, 0, 1, 1, 2, 2, 3], np.int64)
+    vi = np.array([2**62, 2**62, 1, 2, 5, 6, 7], np.int64)
+    valid = np.array([1, 1, 0, 0, 1, 0, 1], bool)
+    _, _, outs, _ = oracle.group_by_agg(key, None, [("sum", vi, valid), ("mean", vi, valid), ("min", vi, valid), ("count", vi, valid), ("len", None, None)], 1, True)
+    assert outs[0][0].tolist() == [-2**63, 0, 5, 7] and outs[0][1] is None
+    assert outs[1][1].tolist() == [True, False, True, True]
+    assert outs[2][1].tolist() == [True, False, True, True] and outs[2][0][2] == 5
+    assert outs[3][0].tolist() == [2, 0, 1, 1] and outs[4][0].tolist() == [2, 2, 2, 1]
+    vf = np.array([np.nan, 1.0, np.nan, np.nan, -0.0, 3.0, np.inf])
+    _, _, outs, _ = oracle.group_by_agg(key, None, [("min", vf, None), ("max", vf, None)], 1, True)
+    assert outs[0][0][0] == 1.0 and np.isnan(outs[0][0][1]) and outs[1][0][2] == 3.0 and outs[0][0][3] == np.inf
+
+
+def test_float_keys_canonical():
+    key = np.array([0.0, -0.0, np.nan, -np.nan, 1.5, np.float64.fromhex("0x1.8p0")])
+    keys, _, outs, g = oracle.group_by_agg(key, None, [("len", None, None)], 1, True)
+    assert outs[0][0].tolist() == [2, 2, 2]
+    assert np.signbit(keys[0]) == False and g.first.tolist() == [0, 2, 4]  # noqa: E712
+
+
+@pytest.mark.parametrize("nl,nr,krange,dups", [(0, 0, 10, 1), (5, 0, 10, 1), (300, 100, 150, 1), (2000, 3000, 500, 3), (40_000, 10_000, 20_000, 2)])
+def test_join_vs_bruteforce(nl, nr, krange, dups):
+    rng = np.random.default_rng(nl * 7 + nr)
+    lk = rng.integers(0, krange, nl).astype(np.int64)
+    rk = np.repeat(rng.permutation(max(krange, nr))[: max(nr // dups, 0)], dups)[:nr].astype(np.int64)
+    rk = np.concatenate([rk, rng.integers(0, krange, nr - rk.size).astype(np.int64)])
+    rng.shuffle(rk)
+    lv = rng.random(nl) > 0.1
+    rv = rng.random(nr) > 0.1
+    for nulls_equal in (False, True):
+        for threads in (1, 3, 8):
+            li, ri = oracle.hash_join(lk, rk, lv, rv, "inner", nulls_equal, "none", threads)
+            # brute force with pandas-free numpy: sort-merge on (valid, key)
+            exp = []
+            from collections import defaultdict
+            d = defaultdict(list)
+            for j in range(nr):
+                if rv[j] or nulls_equal:
+                    d[(bool(rv[j]), int(rk[j]) if rv[j] else 0)].append(j)
+            for i in range(nl):
+                if lv[i] or nulls_equal:
+                    for j in d.get((bool(lv[i]), int(lk[i]) if lv[i] else 0), []):
+                        exp.append((i, j))
+            got = sorted(zip(li.tolist(), ri.tolist()))
+            assert got == sorted(exp)
+            # ordering rule (hash_join/mod.rs:41-50): probe side ascending, build idx ascending per probe row
+            if nl > nr:
+                assert np.all(np.diff(li.astype(np.int64)) >= 0)
+                same = np.diff(li.astype(np.int64)) == 0
+                assert np.all(np.diff(ri.astype(np.int64))[same] > 0)
+            elif li.size:
+                assert np.all(np.diff(ri.astype(np.int64)) >= 0)
+                same = np.diff(ri.astype(np.int64)) == 0
+                assert np.all(np.diff(li.astype(np.int64))[same] > 0)
+            # left join: every left row appears; misses have null right
+            l2, r2 = oracle.hash_join(lk, rk, lv, rv, "left", nulls_equal, "none", threads)
+            assert np.all(np.diff(l2.astype(np.int64)) >= 0) and set(l2.tolist()) == set(range(nl))
+            hit = r2 != IDX_NULL
+            assert np.array_equal(pairs_sorted(l2[hit], r2[hit]), pairs_sorted(li, ri))
+
+
+def test_join_vs_acero():
+    rng = np.random.default_rng(5)
+    lk = rng.integers(0, 5000, 30_000).astype(np.int64)
+    rk = rng.integers(0, 5000, 8_000).astype(np.int64)
+    li, ri = oracle.hash_join(lk, rk, None, None, "inner", False, "none", 4)
+    lt = pa.table({"k": lk, "li": np.arange(lk.size, dtype=np.uint32)})
+    rt = pa.table({"k": rk, "ri": np.arange(rk.size, dtype=np.uint32)})
+    j = lt.join(rt, "k", join_type="inner")
+    assert np.array_equal(pairs_sorted(li, ri), pairs_sorted(j["li"].to_numpy(), j["ri"].to_numpy()))
+
+
+# ---------------------------------------------------------------- elementwise / filter / gather
+@pytest.mark.parametrize("dtype", ["int64", "int32", "uint64", "uint32", "float64", "float32"])
+def test_arith_vs_numpy(dtype):
+    rng = np.random.default_rng(11)
+    dt = np.dtype(dtype)
+    n = 1000
+    if dt.kind == "f":
+        a = rng.normal(0, 100, n).astype(dt)
+        b = rng.normal(0, 100, n).astype(dt)
+        b[::17] = 0
+        a[::31] = np.nan
+    else:
+        lo = 0 if dt.kind == "u" else -1000
+        a = rng.integers(lo, 1000, n).astype(dt)
+        b = rng.integers(lo, 1000, n).astype(dt)
+        b[::17] = 0
+        if dt.kind == "i":
+            a[0], b[0] = np.iinfo(dt).min, -1          # wrapping_div overflow case
+    av = rng.random(n) > 0.1
+    with np.errstate(all="ignore"):
+        for op, f in [("add", np.add), ("sub", np.subtract), ("mul", np.multiply)]:
+            out, v = oracle.arith(op, a, b, av, None)
+            assert np.array_equal(out, f(a, b), equal_nan=True) and np.array_equal(v, av)
+        out, v = oracle.arith("floordiv", a, b, av, None)
+        if dt.kind == "f":
+            assert np.array_equal(out, np.floor(a / b), equal_nan=True) and np.array_equal(v, av)
+            out, _ = oracle.arith("mod", a, b)
+            assert np.array_equal(out, a - b * np.floor(a / b), equal_nan=True)
+        else:
+            nz = b != 0
+            assert np.array_equal(v, av & nz)
+            ok = nz.copy()
+            ok[0] = False
+            assert np.array_equal(out[ok], np.floor_divide(a[ok], b[ok]))
+            if dt.kind == "i":
+                assert out[0] == np.iinfo(dt).min          # MIN // -1 wraps
+            out, v = oracle.arith("mod", a, b, av, None)
+            assert np.array_equal(out[ok], np.mod(a[ok], b[ok])) and np.all(out[~nz] == 0)
+            out, v = oracle.arith("truediv", a, b)
+            assert out.dtype == np.float64 and np.array_equal(out[nz], a[nz].astype(np.float64) / b[nz].astype(np.float64))
+        # scalar forms
+        out, _ = oracle.arith("add", a, dt.type(3))
+        assert np.array_equal(out, a + dt.type(3), equal_nan=True)
+        out, _ = oracle.arith("sub", dt.type(3), a)
+        assert np.array_equal(out, dt.type(3) - a, equal_nan=True)
+        if dt.kind == "f":
+            out, _ = oracle.arith("truediv", a, dt.type(3))
+            assert np.array_equal(out, a * (dt.type(1) / dt.type(3)), equal_nan=True)   # float.rs:113-115
+        else:
+            out, v = oracle.arith("floordiv", a, dt.type(0))
+            assert v is not None and not v.any()                                      # signed.rs:103-105
+
+
+@pytest.mark.parametrize("dtype", ["int64", "float64", "float32", "uint32"])
+def test_compare_total_order(dtype):
+    dt = np.dtype(dtype)
+    if dt.kind == "f":
+        a = np.array([1.0, np.nan, np.nan, -np.inf, 0.0, -0.0, 5.0], dt)
+        b = np.array([2.0, np.nan, 1.0, np.nan, -0.0, 0.0, 5.0], dt)
+        exp = {"eq": [0, 1, 0, 0, 1, 1, 1], "ne": [1, 0, 1, 1, 0, 0, 0], "lt": [1, 0, 0, 1, 0, 0, 0], "le": [1, 1, 0, 1, 1, 1, 1],
+               "gt": [0, 0, 1, 0, 0, 0, 0], "ge": [0, 1, 1, 0, 1, 1, 1]}
+    else:
+        a = np.array([1, 5, 3, 0, 7, 7, 2], dt)
+        b = np.array([2, 5, 1, 9, 7, 6, 2], dt)
+        exp = {op: f(a, b).astype(int).tolist() for op, f in [("eq", np.equal), ("ne", np.not_equal), ("lt", np.less), ("le", np.less_equal), ("gt", np.greater), ("ge", np.greater_equal)]}
+    av = np.array([1, 1, 1, 0, 1, 1, 0], bool)
+    bv = np.array([1, 1, 1, 1, 1, 1, 0], bool)
+    for op, e in exp.items():
+        out, v = oracle.compare(op, a, b, av, bv)
+        assert out.astype(int).tolist() == e, op
+        assert np.array_equal(v, av & bv)
+        out, v = oracle.compare(op, a, a[4])
+        assert v is None
+    out, v = oracle.compare("eq", a, b, av, bv, missing=True)
+    assert v is None and out[3] == False and out[6] == True   # noqa: E712
+    out, v = oracle.compare("ne", a, b, av, bv, missing=True)
+    assert out[3] == True and out[6] == False                 # noqa: E712
+
+
+def test_filter_gather_kat():
+    # filter KAT generator of the reference: py-polars/tests/unit/operations/test_filter.py:271-286
+    for size in list(range(0, 64)) + [100, 1000, 10_000]:
+        for sel in (0.0, 0.01, 0.1, 0.5, 0.9, 0.99, 1.0):
+            rng = np.random.Generator(np.random.PCG64(size * 100 + int(sel * 100)))
+            mask = rng.random(size) < sel
+            vals = rng.integers(-2**62, 2**62, size).astype(np.int64)
+            valid = rng.random(size) > 0.2
+            mvalid = rng.random(size) > 0.1
+            out, ov = oracle.filter(vals, valid, mask, mvalid)
+            keep = mask & mvalid
+            assert np.array_equal(out, vals[keep]) and np.array_equal(ov, valid[keep])
+    vals = np.arange(10, dtype=np.float64) * 1.5
+    valid = np.arange(10) % 3 != 0
+    idx = np.array([9, 0, 3, 3, 7], np.uint32)
+    iv = np.array([1, 1, 0, 1, 1], bool)
+    out, ov = oracle.gather(vals, valid, idx, iv)
+    assert out.tolist() == [13.5, 0.0, 0.0, 4.5, 10.5] and ov.tolist() == [False, False, False, False, True]
