@@ -1,0 +1,207 @@
+/*
+ * polars_b200.h — C ABI of the B200-native hot-path library (libpolars_b200.so).
+ *
+ * This is the drop-in boundary B3 of SURVEY.md §8(b): the operator-level entry points a thin
+ * Rust `extern "C"` crate inside polars-mem-engine binds in place of the Rayon dispatch of
+ *   FilterExec::execute        crates/polars-mem-engine/src/executors/filter.rs:60-144
+ *   group_by_helper            crates/polars-mem-engine/src/executors/group_by.rs:60-98
+ *   DataFrameJoinOps::_join_impl  crates/polars-ops/src/frame/join/mod.rs:125-459
+ *   DataFrame::take_unchecked  crates/polars-core/src/frame/mod.rs:1238-1294
+ *   apply_operator             crates/polars-expr/src/expressions/binary.rs:61-131
+ * (binding stubs: INTEGRATION.md).  Plain C: pointers, sizes, PODs.  No torch / C++ types.
+ *
+ * Memory model.  A `bl_column` describes one contiguous Arrow-layout primitive array
+ * (crates/polars-arrow/src/array/primitive/mod.rs:56-60): a values buffer, an optional
+ * LSB-first bit-packed validity bitmap (crates/polars-arrow/src/bitmap/immutable.rs:56-68) and
+ * a logical element `offset` that applies to both (so arbitrary bitmap bit offsets are legal).
+ * `location` says where the buffers live: BL_HOST (pageable or pinned host memory; pinned
+ * buffers — bl_alloc_pinned or cudaHostRegister'ed — are DMA'd directly, pageable ones are staged
+ * through an internal pinned ring) or BL_DEVICE (device pointers on the library's device).
+ * A ChunkedArray (crates/polars-core/src/chunked_array/mod.rs:139-148) is an array of
+ * bl_column chunks; the library concatenates chunks while uploading (the "rechunk" the
+ * reference does first: executors/group_by.rs:70, join/mod.rs:194-218).
+ *
+ * Ownership.  Inputs are caller-owned and only read.  Outputs are written into caller-provided
+ * `bl_column` structs; their buffers are library-owned (`owner != NULL`) in the requested
+ * `out_location` and released with bl_column_free().  Nothing is retained across calls.
+ *
+ * Errors.  Every entry point returns a bl_status; BL_OK == 0.  On failure outputs are untouched
+ * and bl_last_error() returns a thread-local NUL-terminated message (the channel the plugin ABI
+ * forwards through _polars_plugin_get_last_error_message).  No exceptions cross the boundary,
+ * the process is never aborted.  If the CUDA runtime or a device is missing every call fails
+ * with BL_ERR_CUDA — there is no CPU fallback.
+ *
+ * Threading.  Entry points are thread-safe (calls are serialised per library context).
+ */
+#ifndef POLARS_B200_H
+#define POLARS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BL_ABI_VERSION 1
+
+typedef int32_t bl_status;
+enum {
+    BL_OK = 0,
+    BL_ERR_INVALID = 1,     /* bad argument (null pointer, length mismatch, ...) */
+    BL_ERR_CUDA = 2,        /* CUDA runtime / driver error, or no device */
+    BL_ERR_OOM = 3,         /* device or pinned-host allocation failed */
+    BL_ERR_UNSUPPORTED = 4, /* dtype / mode outside the hot path (caller falls back to its CPU path) */
+    BL_ERR_DTYPE = 5,       /* key dtypes differ etc. (reference: ComputeError, join/mod.rs:231-241) */
+    BL_ERR_BOUNDS = 6       /* gather index out of bounds (reference: check_bounds_ca, gather.rs:14-39) */
+};
+
+/* physical dtypes (Arrow primitive types) */
+enum {
+    BL_INT8 = 0, BL_INT16 = 1, BL_INT32 = 2, BL_INT64 = 3,
+    BL_UINT8 = 4, BL_UINT16 = 5, BL_UINT32 = 6, BL_UINT64 = 7,
+    BL_FLOAT32 = 8, BL_FLOAT64 = 9,
+    BL_BOOL = 10            /* bit-packed values buffer (BooleanArray) */
+};
+
+enum { BL_HOST = 0, BL_DEVICE = 1 };
+
+typedef struct bl_column {
+    int32_t dtype;            /* BL_INT64 ... */
+    int32_t location;         /* BL_HOST | BL_DEVICE */
+    int64_t length;           /* logical number of rows */
+    int64_t offset;           /* logical element offset into values and validity */
+    int64_t null_count;       /* -1 = unknown */
+    const void* values;       /* length+offset elements (BL_BOOL: bits) */
+    const uint8_t* validity;  /* NULL = no nulls */
+    void* owner;              /* NULL = caller-owned; else release with bl_column_free */
+} bl_column;
+
+/* IdxSize = u32 (crates/polars-utils/src/index.rs:9); null index (left join, gather) */
+#define BL_IDX_NULL 0xFFFFFFFFu
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int32_t bl_abi_version(void);
+/* Binds the library to a CUDA device (-1 = current device / LOCAL_RANK env).  Idempotent. */
+bl_status bl_init(int32_t device);
+void bl_shutdown(void);
+const char* bl_last_error(void);
+/* device facts for the host side: writes sm count, L2 bytes, total/free HBM bytes */
+bl_status bl_device_info(int32_t* sm_count, int64_t* l2_bytes, int64_t* hbm_total, int64_t* hbm_free);
+
+/* ---- memory ---------------------------------------------------------------------------- */
+/* Pinned host buffers (the SharedStorage::ForeignOwner seam, crates/polars-buffer/src/storage.rs:37-53). */
+bl_status bl_alloc_pinned(size_t bytes, void** out);
+void bl_free_pinned(void* p);
+bl_status bl_dev_alloc(size_t bytes, void** out);
+void bl_dev_free(void* p);
+bl_status bl_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes);
+bl_status bl_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes);
+/* Copies a (possibly chunked) column to the other location; result is library-owned. */
+bl_status bl_column_to(const bl_column* chunks, int32_t n_chunks, int32_t location, bl_column* out);
+void bl_column_free(bl_column* col);
+/* Blocks until all work queued by this thread's calls has finished (outputs are already
+ * complete when an entry point returns; this is for bl_dev_* / profiling users). */
+bl_status bl_sync(void);
+/* The CUDA stream (cudaStream_t) every kernel of this library is launched on. */
+void* bl_stream(void);
+
+/* ---- K1: elementwise arithmetic  (ArithmeticKernel, polars-compute/src/arithmetic/mod.rs:8-76) */
+enum { BL_OP_ADD = 0, BL_OP_SUB = 1, BL_OP_MUL = 2, BL_OP_FLOOR_DIV = 3, BL_OP_MOD = 4, BL_OP_TRUE_DIV = 5 };
+/* lhs (op) rhs.  A length-1 side broadcasts as a scalar (apply_operator, binary.rs:61-131) and
+ * takes the reference's scalar code path (e.g. float x / c == x * (1/c), float.rs:113-115).
+ * Integer FLOOR_DIV / MOD by zero yield null (signed.rs:35-70); integer TRUE_DIV yields FLOAT64.
+ * Output validity = AND of input validities (arity.rs:90). */
+bl_status bl_elementwise(int32_t op, const bl_column* lhs, const bl_column* rhs, int32_t out_location, bl_column* out);
+
+/* ---- K2: comparisons -> BooleanArray  (TotalOrdKernel/TotalEqKernel, comparisons/mod.rs:4-76) */
+enum { BL_CMP_EQ = 0, BL_CMP_NE = 1, BL_CMP_LT = 2, BL_CMP_LE = 3, BL_CMP_GT = 4, BL_CMP_GE = 5 };
+/* Total order on floats: NaN == NaN, NaN greatest (polars-utils/src/total_ord.rs:317-364).
+ * missing != 0 selects eq_missing / ne_missing (null == null, never-null result). */
+bl_status bl_compare(int32_t op, const bl_column* lhs, const bl_column* rhs, int32_t missing, int32_t out_location, bl_column* out);
+
+/* ---- K3: filter  (polars-compute/src/filter/mod.rs:18-110; DataFrame::filter frame/mod.rs:1148-1180) */
+/* mask: BL_BOOL column; a null mask slot counts as false.  All n_cols columns are compacted with
+ * one mask pass.  outs[i] keeps cols[i].dtype. */
+bl_status bl_filter(const bl_column* cols, int32_t n_cols, const bl_column* mask, int32_t out_location, bl_column* outs);
+/* Fused predicate + compaction: keep rows where cols[pred_col] (cmp_op) scalar
+ * (FilterExec over BinaryExpr(col, op, lit), executors/filter.rs:117-144).  scalar: length-1 column. */
+bl_status bl_filter_cmp(const bl_column* cols, int32_t n_cols, int32_t pred_col, int32_t cmp_op, const bl_column* scalar,
+                        int32_t out_location, bl_column* outs);
+
+/* ---- K4: gather  (take_primitive_unchecked, polars-compute/src/gather/primitive.rs:9-78) */
+/* idx: BL_UINT32 column (IdxSize).  A null idx slot or idx == BL_IDX_NULL gives a null row with
+ * value 0.  check_bounds != 0 validates idx < col.length first (BL_ERR_BOUNDS). */
+bl_status bl_gather(const bl_column* cols, int32_t n_cols, const bl_column* idx, int32_t check_bounds, int32_t out_location, bl_column* outs);
+
+/* ---- K5: hash group_by + aggregation --------------------------------------------------- */
+/* (group_by_threaded_slice hashing.rs:116-167 + agg_sum/mean/min/max aggregations/mod.rs:486-1018,
+ *  fused: index lists are never materialised) */
+enum { BL_AGG_SUM = 0, BL_AGG_MEAN = 1, BL_AGG_MIN = 2, BL_AGG_MAX = 3, BL_AGG_COUNT = 4, BL_AGG_LEN = 5 };
+typedef struct bl_agg {
+    int32_t kind;           /* BL_AGG_* */
+    int32_t n_chunks;       /* chunks of the value column (ignored for BL_AGG_LEN) */
+    const bl_column* values;
+} bl_agg;
+/* Single numeric key (ints are grouped on their bit pattern, floats canonicalised: -0 == +0,
+ * all NaNs equal; a null key is its own group — into_groups.rs:25-58,142-191).
+ * maintain_order != 0: groups ordered by first occurrence (hashing.rs:41-63); else unspecified.
+ * out_key = key taken at each group's first row (group_by/mod.rs:258-266).
+ * Output dtypes: SUM keeps the dtype (Int8/16,UInt8/16 -> Int64), ints wrap; MEAN -> FLOAT64
+ * (FLOAT32 stays); MIN/MAX keep dtype; COUNT/LEN -> UINT32.  All-null group: SUM 0, MEAN/MIN/MAX null. */
+bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, const bl_agg* aggs, int32_t n_aggs,
+                         int32_t maintain_order, int32_t out_location, bl_column* out_key, bl_column* out_aggs);
+
+/* ---- K7/K8: hash join on one numeric key ----------------------------------------------- */
+/* (build_tables single_keys.rs:16-167, probe_inner single_keys_inner.rs:11-149,
+ *  hash_join_tuples_left single_keys_left.rs:106-195) */
+enum { BL_JOIN_INNER = 0, BL_JOIN_LEFT = 1 };
+enum { BL_ORDER_NONE = 0, BL_ORDER_LEFT = 1, BL_ORDER_LEFT_RIGHT = 2, BL_ORDER_RIGHT = 3, BL_ORDER_RIGHT_LEFT = 4 };
+/* Returns the join tuples as two UINT32 columns.  BL_ORDER_NONE reproduces the in-memory engine's
+ * order (probe = longer relation, tie -> right probes; probe-row order; matches ascending build
+ * idx — hash_join/mod.rs:41-50).  Null keys match only if nulls_equal.  Left join: unmatched
+ * right idx = BL_IDX_NULL (and a null slot). */
+bl_status bl_hash_join(const bl_column* left_key, int32_t n_left_chunks, const bl_column* right_key, int32_t n_right_chunks,
+                       int32_t how, int32_t nulls_equal, int32_t maintain_order, int32_t out_location,
+                       bl_column* out_left_idx, bl_column* out_right_idx);
+
+/* ---- K6: radix hash partition (multi-GPU exchange step) --------------------------------- */
+/* partition id = hash_to_partition(dirty_hash(key), n_partitions)
+ *              = ((key * 0x55fbfd6bfc5458e9 mod 2^64) * n_partitions) >> 64   (hashing.rs:62-69,132-142),
+ * null keys -> partition 0 (hashing.rs:113-115,183-187).  Rows are scattered so that partition p
+ * occupies [offsets[p], offsets[p+1]) of every output column, in stable row order.
+ * offsets: caller array of n_partitions+1 int64 (host). */
+bl_status bl_hash_partition(const bl_column* key, const bl_column* payload, int32_t n_payload, int32_t n_partitions,
+                            int32_t out_location, bl_column* out_key, bl_column* out_payload, int64_t* offsets);
+
+/* ---- streaming group_by state (device-resident; used for chunked H2D overlap and multi-GPU) */
+typedef struct bl_groupby bl_groupby;
+/* key_dtype / value dtypes fix the plan; expected_groups <= 0 lets the library estimate. */
+bl_status bl_groupby_create(int32_t key_dtype, const int32_t* agg_kinds, const int32_t* value_dtypes, int32_t n_aggs,
+                            int64_t expected_groups, bl_groupby** out);
+/* Accumulate one batch: key + one value column per agg (values[i] ignored for LEN).  Columns may
+ * be BL_HOST or BL_DEVICE.  row_base = global index of the batch's first row. */
+bl_status bl_groupby_consume(bl_groupby* g, const bl_column* key, const bl_column* values, int64_t row_base);
+/* Partial-aggregate exchange for the partitioned multi-GPU plan:
+ * export the table as dense rows of `*row_words` 64-bit words, scattered by key partition
+ * (device memory, library-owned: free with bl_dev_free); offsets: n_partitions+1 int64 (host). */
+bl_status bl_groupby_export_partials(bl_groupby* g, int32_t n_partitions, void** out_rows_dev, int32_t* row_words, int64_t* offsets);
+/* Merge partial rows (from any rank) into this state. */
+bl_status bl_groupby_merge_partials(bl_groupby* g, const void* rows_dev, int64_t n_rows);
+bl_status bl_groupby_finish(bl_groupby* g, int32_t maintain_order, int32_t out_location, bl_column* out_key, bl_column* out_aggs);
+void bl_groupby_reset(bl_groupby* g);
+void bl_groupby_destroy(bl_groupby* g);
+
+/* ---- profiling (CUDA events on the library stream) -------------------------------------- */
+/* enable != 0: every kernel launch is bracketed by events; totals accumulate per kernel name. */
+void bl_profile_enable(int32_t enable);
+void bl_profile_reset(void);
+/* Writes a JSON object {"kernel": {"launches": n, "ms": t}, ...} into buf; returns bytes needed. */
+int64_t bl_profile_json(char* buf, int64_t cap);
+/* Kernel launches issued by this library since bl_profile_reset (counted even when timing is off). */
+int64_t bl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLARS_B200_H */

@@ -1,0 +1,458 @@
+"""polars_b200 — host-side Python binding of libpolars_b200.so (the C ABI in include/polars_b200.h).
+
+This module is plumbing: ctypes structs, numpy <-> bl_column marshalling and error translation.
+All compute happens in the CUDA library; if the library (or a GPU) is missing every call raises —
+there is no CPU fallback and this package never imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from typing import Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_lib", "libpolars_b200.so")
+
+HOST, DEVICE = 0, 1
+IDX_NULL = 0xFFFFFFFF
+
+DTYPES = {np.dtype("int8"): 0, np.dtype("int16"): 1, np.dtype("int32"): 2, np.dtype("int64"): 3,
+          np.dtype("uint8"): 4, np.dtype("uint16"): 5, np.dtype("uint32"): 6, np.dtype("uint64"): 7,
+          np.dtype("float32"): 8, np.dtype("float64"): 9, np.dtype("bool"): 10}
+NP_OF = {v: k for k, v in DTYPES.items()}
+BOOL = 10
+OPS = {"add": 0, "sub": 1, "mul": 2, "floordiv": 3, "mod": 4, "truediv": 5}
+CMPS = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5}
+AGGS = {"sum": 0, "mean": 1, "min": 2, "max": 3, "count": 4, "len": 5}
+JOINS = {"inner": 0, "left": 1}
+ORDERS = {"none": 0, "left": 1, "left_right": 2, "right": 3, "right_left": 4}
+STATUS = {1: "INVALID", 2: "CUDA", 3: "OOM", 4: "UNSUPPORTED", 5: "DTYPE", 6: "BOUNDS"}
+
+
+class BlColumn(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("location", C.c_int32), ("length", C.c_int64), ("offset", C.c_int64),
+                ("null_count", C.c_int64), ("values", C.c_void_p), ("validity", C.c_void_p), ("owner", C.c_void_p)]
+
+
+class BlAgg(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_chunks", C.c_int32), ("values", C.POINTER(BlColumn))]
+
+
+class B200Error(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"[{STATUS.get(status, status)}] {msg}")
+        self.status = status
+
+
+class ComputeError(B200Error):
+    """dtype mismatches etc. — the reference raises ComputeError (join/mod.rs:231-241)."""
+
+
+class OutOfBoundsError(B200Error):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads libpolars_b200.so.  Fails loudly when it has not been built (python -m polars_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise ImportError(f"{_SO} is missing: build it with `python -m polars_b200.build` (nvcc, sm_100a). "
+                              "polars_b200 has no CPU fallback.")
+        L = C.CDLL(_SO)
+        L.bl_last_error.restype = C.c_char_p
+        L.bl_profile_json.restype = C.c_int64
+        L.bl_launch_count.restype = C.c_int64
+        L.bl_stream.restype = C.c_void_p
+        for name in ("bl_column_free", "bl_free_pinned", "bl_dev_free", "bl_profile_enable", "bl_profile_reset", "bl_shutdown",
+                     "bl_groupby_reset", "bl_groupby_destroy"):
+            getattr(L, name).restype = None
+        _lib = L
+    return _lib
+
+
+def _check(st: int):
+    if st != 0:
+        msg = lib().bl_last_error().decode("utf-8", "replace")
+        if st == 5:
+            raise ComputeError(st, msg)
+        if st == 6:
+            raise OutOfBoundsError(st, msg)
+        raise B200Error(st, msg)
+
+
+def init(device: int = -1):
+    _check(lib().bl_init(C.c_int32(device)))
+
+
+def device_info() -> dict:
+    sm, l2, tot, free = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int64()
+    _check(lib().bl_device_info(C.byref(sm), C.byref(l2), C.byref(tot), C.byref(free)))
+    return {"sm_count": sm.value, "l2_bytes": l2.value, "hbm_total": tot.value, "hbm_free": free.value}
+
+
+def sync():
+    _check(lib().bl_sync())
+
+
+def stream() -> int:
+    return int(lib().bl_stream() or 0)
+
+
+def profile_enable(on: bool):
+    lib().bl_profile_enable(C.c_int32(int(on)))
+
+
+def profile_reset():
+    lib().bl_profile_reset()
+
+
+def profile() -> dict:
+    n = lib().bl_profile_json(None, C.c_int64(0))
+    buf = C.create_string_buffer(int(n) + 16)
+    lib().bl_profile_json(buf, C.c_int64(len(buf)))
+    return json.loads(buf.value.decode() or "{}")
+
+
+def launch_count() -> int:
+    return int(lib().bl_launch_count())
+
+
+# ---------------------------------------------------------------------------------- pinned memory
+def pinned_empty(n: int, dtype) -> np.ndarray:
+    """numpy array backed by library pinned host memory (DMA-able without staging).
+    The buffer is returned to the library's pinned cache when the array is garbage collected."""
+    dt = np.dtype(dtype)
+    nbytes = max(int(n) * dt.itemsize, 1)
+    p = C.c_void_p()
+    _check(lib().bl_alloc_pinned(C.c_size_t(nbytes), C.byref(p)))
+    buf = (C.c_char * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(n))
+    import weakref
+    weakref.finalize(buf, lib().bl_free_pinned, C.c_void_p(p.value))
+    return arr
+
+
+def to_pinned(a: np.ndarray) -> np.ndarray:
+    out = pinned_empty(a.size, a.dtype)
+    out[:] = a
+    return out
+
+
+# ---------------------------------------------------------------------------------- columns
+def pack_bits(valid: np.ndarray) -> np.ndarray:
+    return np.packbits(np.asarray(valid, dtype=np.bool_), bitorder="little")
+
+
+def unpack_bits(buf: np.ndarray, n: int) -> np.ndarray:
+    return np.unpackbits(buf, count=n, bitorder="little").astype(np.bool_)
+
+
+class Column:
+    """A caller-owned host (numpy) or device column view passed INTO the library.
+
+    values: numpy array (host) or an int device pointer; valid: bool array / packed bitmap (host) or
+    device pointer to a bitmap.  `offset` exercises Arrow slicing semantics."""
+
+    def __init__(self, values, valid=None, *, dtype=None, length=None, offset: int = 0, location: int = HOST, null_count: int = -1):
+        self.location = location
+        self.offset = int(offset)
+        self._keep = []
+        if location == HOST:
+            values = np.asarray(values)
+            if values.dtype == np.bool_:
+                self.length = int(values.size - offset) if length is None else int(length)
+                bits = pack_bits(values)
+                self._keep.append(bits)
+                self.dtype = BOOL
+                self._vptr = bits.ctypes.data
+            else:
+                values = np.ascontiguousarray(values)
+                self._keep.append(values)
+                self.dtype = DTYPES[values.dtype]
+                self.length = int(values.size - offset) if length is None else int(length)
+                self._vptr = values.ctypes.data
+            if valid is None:
+                self._mptr, self.null_count = None, 0
+            else:
+                valid = np.asarray(valid)
+                bits = pack_bits(valid) if valid.dtype == np.bool_ else np.ascontiguousarray(valid, dtype=np.uint8)
+                self._keep.append(bits)
+                self._mptr, self.null_count = bits.ctypes.data, null_count
+        else:
+            self.dtype = DTYPES[np.dtype(dtype)] if not isinstance(dtype, int) else dtype
+            self.length = int(length)
+            self._vptr = int(values)
+            self._mptr = None if valid is None else int(valid)
+            self.null_count = 0 if valid is None else null_count
+
+    def struct(self) -> BlColumn:
+        return BlColumn(self.dtype, self.location, self.length, self.offset, self.null_count, self._vptr, self._mptr, None)
+
+
+class OutColumn:
+    """A library-owned output column.  `.to_numpy()` copies host outputs out; device outputs expose
+    raw pointers (`.values_ptr`, `.validity_ptr`).  Freed on `.free()` / garbage collection."""
+
+    def __init__(self, st: BlColumn):
+        self.st = st
+
+    @property
+    def length(self):
+        return int(self.st.length)
+
+    @property
+    def location(self):
+        return int(self.st.location)
+
+    @property
+    def values_ptr(self):
+        return int(self.st.values or 0)
+
+    @property
+    def validity_ptr(self):
+        return int(self.st.validity or 0)
+
+    def view(self) -> Column:
+        """Re-use a device output as an input column (no copy)."""
+        assert self.location == DEVICE
+        return Column(self.values_ptr, self.validity_ptr or None, dtype=int(self.st.dtype), length=self.length, location=DEVICE, null_count=int(self.st.null_count))
+
+    def to_numpy(self):
+        """-> (values, valid|None).  BOOL columns come back as numpy bool arrays."""
+        st, n = self.st, int(self.st.length)
+        if st.location == DEVICE:
+            host = BlColumn()
+            _check(lib().bl_column_to(C.byref(st), C.c_int32(1), C.c_int32(HOST), C.byref(host)))
+            try:
+                return OutColumn(host).to_numpy()
+            finally:
+                lib().bl_column_free(C.byref(host))
+        if st.dtype == BOOL:
+            raw = np.ctypeslib.as_array(C.cast(st.values, C.POINTER(C.c_uint8)), shape=((n + 7) // 8 or 1,)) if n else np.zeros(0, np.uint8)
+            vals = unpack_bits(raw, n)
+        else:
+            dt = NP_OF[int(st.dtype)]
+            vals = np.ctypeslib.as_array(C.cast(st.values, C.POINTER(C.c_uint8)), shape=(max(n * dt.itemsize, 1),))[: n * dt.itemsize].view(dt).copy() if n else np.zeros(0, dt)
+        valid = None
+        if st.validity:
+            raw = np.ctypeslib.as_array(C.cast(st.validity, C.POINTER(C.c_uint8)), shape=((n + 7) // 8 or 1,)) if n else np.zeros(0, np.uint8)
+            valid = unpack_bits(raw, n)
+            if valid.all():
+                valid = None
+        return vals, valid
+
+    def free(self):
+        if self.st.owner:
+            lib().bl_column_free(C.byref(self.st))
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _as_col(x) -> Column:
+    if isinstance(x, Column):
+        return x
+    if isinstance(x, OutColumn):
+        return x.view()
+    if isinstance(x, tuple):
+        return Column(x[0], x[1])
+    if np.isscalar(x):
+        raise TypeError("scalars must be passed as length-1 arrays with the column's dtype")
+    return Column(x)
+
+
+def _scalar_col(x, like: Column) -> Column:
+    if isinstance(x, (Column, OutColumn, tuple, np.ndarray)):
+        return _as_col(x)
+    return Column(np.array([x], dtype=NP_OF[like.dtype]))
+
+
+def _finish(outs, location):
+    res = [OutColumn(o) for o in outs]
+    if location == HOST:
+        np_res = [r.to_numpy() for r in res]
+        for r in res:
+            r.free()
+        return np_res
+    return res
+
+
+# ---------------------------------------------------------------------------------- operators
+def elementwise(op: str, lhs, rhs, location: int = HOST):
+    l = _as_col(lhs) if not np.isscalar(lhs) else None
+    r = _as_col(rhs) if not np.isscalar(rhs) else None
+    if l is None:
+        l = _scalar_col(lhs, r)
+    if r is None:
+        r = _scalar_col(rhs, l)
+    out = BlColumn()
+    ls, rs = l.struct(), r.struct()
+    _check(lib().bl_elementwise(C.c_int32(OPS[op]), C.byref(ls), C.byref(rs), C.c_int32(location), C.byref(out)))
+    return _finish([out], location)[0]
+
+
+def compare(op: str, lhs, rhs, missing: bool = False, location: int = HOST):
+    l = _as_col(lhs)
+    r = _scalar_col(rhs, l)
+    out = BlColumn()
+    ls, rs = l.struct(), r.struct()
+    _check(lib().bl_compare(C.c_int32(CMPS[op]), C.byref(ls), C.byref(rs), C.c_int32(int(missing)), C.c_int32(location), C.byref(out)))
+    return _finish([out], location)[0]
+
+
+def _col_array(cols: Sequence[Column]):
+    arr = (BlColumn * len(cols))(*[c.struct() for c in cols])
+    return arr
+
+
+def filter(cols: Sequence, mask, location: int = HOST):
+    cs = [_as_col(c) for c in cols]
+    m = _as_col(mask)
+    arr, outs = _col_array(cs), (BlColumn * len(cs))()
+    ms = m.struct()
+    _check(lib().bl_filter(arr, C.c_int32(len(cs)), C.byref(ms), C.c_int32(location), outs))
+    return _finish(list(outs), location)
+
+
+def filter_cmp(cols: Sequence, pred_col: int, op: str, scalar, location: int = HOST):
+    cs = [_as_col(c) for c in cols]
+    s = _scalar_col(scalar, cs[pred_col])
+    arr, outs = _col_array(cs), (BlColumn * len(cs))()
+    ss = s.struct()
+    _check(lib().bl_filter_cmp(arr, C.c_int32(len(cs)), C.c_int32(pred_col), C.c_int32(CMPS[op]), C.byref(ss), C.c_int32(location), outs))
+    return _finish(list(outs), location)
+
+
+def gather(cols: Sequence, idx, check_bounds: bool = True, location: int = HOST):
+    cs = [_as_col(c) for c in cols]
+    ix = _as_col(idx)
+    arr, outs = _col_array(cs), (BlColumn * len(cs))()
+    ixs = ix.struct()
+    _check(lib().bl_gather(arr, C.c_int32(len(cs)), C.byref(ixs), C.c_int32(int(check_bounds)), C.c_int32(location), outs))
+    return _finish(list(outs), location)
+
+
+def group_by_agg(key, aggs: Sequence, maintain_order: bool = False, location: int = HOST):
+    """key: column or list of chunks; aggs: [(kind, column | [chunks] | None)].
+    Returns (key_out, [agg_outs])."""
+    kchunks = [_as_col(c) for c in (key if isinstance(key, list) else [key])]
+    karr = _col_array(kchunks)
+    keep, agg_structs = [], []
+    cache = {}
+    for kind, vals in aggs:
+        if kind == "len" or vals is None:
+            agg_structs.append(BlAgg(AGGS[kind], 0, None))
+            continue
+        ident = id(vals)
+        if ident not in cache:
+            chunks = [_as_col(c) for c in (vals if isinstance(vals, list) else [vals])]
+            cache[ident] = (chunks, _col_array(chunks))
+        chunks, arr = cache[ident]
+        keep.append((chunks, arr))
+        agg_structs.append(BlAgg(AGGS[kind], len(chunks), C.cast(arr, C.POINTER(BlColumn))))
+    aarr = (BlAgg * max(len(agg_structs), 1))(*agg_structs)
+    out_key, out_aggs = BlColumn(), (BlColumn * max(len(agg_structs), 1))()
+    _check(lib().bl_groupby_agg(karr, C.c_int32(len(kchunks)), aarr, C.c_int32(len(agg_structs)), C.c_int32(int(maintain_order)), C.c_int32(location),
+                                C.byref(out_key), out_aggs))
+    res = _finish([out_key] + list(out_aggs)[: len(agg_structs)], location)
+    return res[0], res[1:]
+
+
+def hash_join(left_key, right_key, how: str = "inner", nulls_equal: bool = False, maintain_order: str = "none", location: int = HOST):
+    lch = [_as_col(c) for c in (left_key if isinstance(left_key, list) else [left_key])]
+    rch = [_as_col(c) for c in (right_key if isinstance(right_key, list) else [right_key])]
+    la, ra = _col_array(lch), _col_array(rch)
+    ol, orr = BlColumn(), BlColumn()
+    _check(lib().bl_hash_join(la, C.c_int32(len(lch)), ra, C.c_int32(len(rch)), C.c_int32(JOINS[how]), C.c_int32(int(nulls_equal)),
+                              C.c_int32(ORDERS[maintain_order]), C.c_int32(location), C.byref(ol), C.byref(orr)))
+    res = _finish([ol, orr], location)
+    return res[0], res[1]
+
+
+def hash_partition(key, payload: Sequence, n_partitions: int, location: int = HOST):
+    k = _as_col(key)
+    ps = [_as_col(p) for p in payload]
+    parr = _col_array(ps) if ps else None
+    ok, op = BlColumn(), (BlColumn * max(len(ps), 1))()
+    offs = (C.c_int64 * (n_partitions + 1))()
+    ks = k.struct()
+    _check(lib().bl_hash_partition(C.byref(ks), parr, C.c_int32(len(ps)), C.c_int32(n_partitions), C.c_int32(location), C.byref(ok), op, offs))
+    res = _finish([ok] + list(op)[: len(ps)], location)
+    return res[0], res[1:], np.array(list(offs), dtype=np.int64)
+
+
+class GroupBy:
+    """Streaming group_by state (bl_groupby_*): consume batches, exchange partial aggregates, finish."""
+
+    def __init__(self, key_dtype, aggs: Sequence, expected_groups: int = 0):
+        """aggs: [(kind, value_dtype | None)]"""
+        self.kinds = [AGGS[k] for k, _ in aggs]
+        dts = [DTYPES[np.dtype(d)] if d is not None else 3 for _, d in aggs]
+        n = len(aggs)
+        self.n = n
+        self.h = C.c_void_p()
+        _check(lib().bl_groupby_create(C.c_int32(DTYPES[np.dtype(key_dtype)]), (C.c_int32 * max(n, 1))(*self.kinds), (C.c_int32 * max(n, 1))(*dts),
+                                       C.c_int32(n), C.c_int64(expected_groups), C.byref(self.h)))
+
+    def consume(self, key, values: Sequence, row_base: int = 0):
+        k = _as_col(key)
+        cols = [(_as_col(v) if v is not None else Column(np.zeros(0, np.int64))) for v in values]
+        arr = _col_array(cols) if cols else None
+        ks = k.struct()
+        _check(lib().bl_groupby_consume(self.h, C.byref(ks), arr, C.c_int64(row_base)))
+
+    def export_partials(self, n_partitions: int):
+        """-> (device pointer, row_words, offsets[n_partitions+1]); free the pointer with dev_free()."""
+        p, rw = C.c_void_p(), C.c_int32()
+        offs = (C.c_int64 * (n_partitions + 1))()
+        _check(lib().bl_groupby_export_partials(self.h, C.c_int32(n_partitions), C.byref(p), C.byref(rw), offs))
+        return int(p.value or 0), int(rw.value), np.array(list(offs), dtype=np.int64)
+
+    def merge_partials(self, rows_dev_ptr: int, n_rows: int):
+        _check(lib().bl_groupby_merge_partials(self.h, C.c_void_p(rows_dev_ptr), C.c_int64(n_rows)))
+
+    def finish(self, maintain_order: bool = False, location: int = HOST):
+        ok, oa = BlColumn(), (BlColumn * max(self.n, 1))()
+        _check(lib().bl_groupby_finish(self.h, C.c_int32(int(maintain_order)), C.c_int32(location), C.byref(ok), oa))
+        res = _finish([ok] + list(oa)[: self.n], location)
+        return res[0], res[1:]
+
+    def reset(self):
+        lib().bl_groupby_reset(self.h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().bl_groupby_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def dev_free(ptr: int):
+    lib().bl_dev_free(C.c_void_p(ptr))
+
+
+def dev_alloc(nbytes: int) -> int:
+    p = C.c_void_p()
+    _check(lib().bl_dev_alloc(C.c_size_t(nbytes), C.byref(p)))
+    return int(p.value)
+
+
+def to_device(values: np.ndarray, valid=None) -> OutColumn:
+    """Uploads a numpy column; returns a library-owned device column."""
+    c = Column(values, valid)
+    out = BlColumn()
+    cs = c.struct()
+    _check(lib().bl_column_to(C.byref(cs), C.c_int32(1), C.c_int32(DEVICE), C.byref(out)))
+    return OutColumn(out)

@@ -1,0 +1,218 @@
+// cabi.cu — extern "C" operator entry points of include/polars_b200.h.
+// Each entry point: import the bl_column arguments (pinned DMA / zero-copy device views), run the
+// device operator, export the outputs into the requested location.  No CPU compute path exists.
+#include "common.cuh"
+#include "groupby.h"
+
+using namespace plb;
+
+static void require_out(const void* p, const char* what) { PLB_REQUIRE(p != nullptr, BL_ERR_INVALID, std::string("null output: ") + what); }
+
+extern "C" {
+
+bl_status bl_elementwise(int32_t op, const bl_column* lhs, const bl_column* rhs, int32_t out_location, bl_column* out) {
+    BL_TRY
+    require_out(out, "out");
+    PLB_REQUIRE(lhs && rhs, BL_ERR_INVALID, "elementwise: null input");
+    DevCol l = import_column(lhs, 1), r = import_column(rhs, 1);
+    DevCol o = op_elementwise(op, l, r);
+    export_column(o, out_location, out);
+    BL_CATCH
+}
+
+bl_status bl_compare(int32_t op, const bl_column* lhs, const bl_column* rhs, int32_t missing, int32_t out_location, bl_column* out) {
+    BL_TRY
+    require_out(out, "out");
+    PLB_REQUIRE(lhs && rhs, BL_ERR_INVALID, "compare: null input");
+    DevCol l = import_column(lhs, 1), r = import_column(rhs, 1);
+    DevCol o = op_compare(op, l, r, missing != 0);
+    export_column(o, out_location, out);
+    BL_CATCH
+}
+
+static void filter_impl(const bl_column* cols, int32_t n_cols, const DevCol& mask, int32_t out_location, bl_column* outs, const std::vector<DevCol>* pre = nullptr) {
+    std::vector<DevCol> in, o;
+    for (int i = 0; i < n_cols; i++) in.push_back(pre ? (*pre)[i] : import_column(&cols[i], 1));
+    op_filter(in, mask, o);
+    std::vector<bl_column> tmp(n_cols);
+    int done = 0;
+    try { for (; done < n_cols; done++) export_column(o[done], out_location, &tmp[done]); }
+    catch (...) { for (int i = 0; i < done; i++) bl_column_free(&tmp[i]); throw; }
+    for (int i = 0; i < n_cols; i++) outs[i] = tmp[i];
+}
+
+bl_status bl_filter(const bl_column* cols, int32_t n_cols, const bl_column* mask, int32_t out_location, bl_column* outs) {
+    BL_TRY
+    PLB_REQUIRE(cols && mask && outs && n_cols >= 1, BL_ERR_INVALID, "filter: null argument");
+    DevCol m = import_column(mask, 1);
+    filter_impl(cols, n_cols, m, out_location, outs);
+    BL_CATCH
+}
+
+bl_status bl_filter_cmp(const bl_column* cols, int32_t n_cols, int32_t pred_col, int32_t cmp_op, const bl_column* scalar, int32_t out_location, bl_column* outs) {
+    BL_TRY
+    PLB_REQUIRE(cols && scalar && outs && n_cols >= 1, BL_ERR_INVALID, "filter_cmp: null argument");
+    PLB_REQUIRE(pred_col >= 0 && pred_col < n_cols, BL_ERR_INVALID, "filter_cmp: pred_col out of range");
+    PLB_REQUIRE(scalar->length == 1, BL_ERR_INVALID, "filter_cmp: scalar must be a length-1 column");
+    std::vector<DevCol> in;
+    for (int i = 0; i < n_cols; i++) in.push_back(import_column(&cols[i], 1));
+    DevCol s = import_column(scalar, 1);
+    DevCol m = op_cmp_scalar_mask(in[pred_col], cmp_op, s);
+    filter_impl(cols, n_cols, m, out_location, outs, &in);
+    BL_CATCH
+}
+
+bl_status bl_gather(const bl_column* cols, int32_t n_cols, const bl_column* idx, int32_t check_bounds, int32_t out_location, bl_column* outs) {
+    BL_TRY
+    PLB_REQUIRE(cols && idx && outs && n_cols >= 1, BL_ERR_INVALID, "gather: null argument");
+    std::vector<DevCol> in, o;
+    for (int i = 0; i < n_cols; i++) in.push_back(import_column(&cols[i], 1));
+    DevCol ix = import_column(idx, 1);
+    op_gather(in, ix, check_bounds != 0, o);
+    std::vector<bl_column> tmp(n_cols);
+    int done = 0;
+    try { for (; done < n_cols; done++) export_column(o[done], out_location, &tmp[done]); }
+    catch (...) { for (int i = 0; i < done; i++) bl_column_free(&tmp[i]); throw; }
+    for (int i = 0; i < n_cols; i++) outs[i] = tmp[i];
+    BL_CATCH
+}
+
+bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, const bl_agg* aggs, int32_t n_aggs, int32_t maintain_order, int32_t out_location,
+                         bl_column* out_key, bl_column* out_aggs) {
+    BL_TRY
+    PLB_REQUIRE(key_chunks && n_key_chunks >= 1 && out_key, BL_ERR_INVALID, "groupby_agg: null key / output");
+    PLB_REQUIRE(n_aggs == 0 || (aggs && out_aggs), BL_ERR_INVALID, "groupby_agg: null aggs / outputs");
+    DevCol key = import_column(key_chunks, n_key_chunks);
+    std::vector<int> kinds, dts;
+    std::vector<DevCol> vals(n_aggs);
+    std::vector<const DevCol*> vptr(n_aggs, nullptr);
+    // aggregations over the same chunk list share one device copy
+    std::vector<std::pair<const bl_column*, int>> seen;
+    for (int i = 0; i < n_aggs; i++) {
+        kinds.push_back(aggs[i].kind);
+        if (aggs[i].kind == BL_AGG_LEN) { dts.push_back(BL_INT64); continue; }
+        PLB_REQUIRE(aggs[i].values && aggs[i].n_chunks >= 1, BL_ERR_INVALID, "groupby_agg: aggregation without a value column");
+        int dup = -1;
+        for (int j = 0; j < i; j++)
+            if (aggs[j].kind != BL_AGG_LEN && aggs[j].n_chunks == aggs[i].n_chunks &&
+                (aggs[j].values == aggs[i].values || (aggs[i].n_chunks == 1 && aggs[j].values[0].values == aggs[i].values[0].values && aggs[j].values[0].validity == aggs[i].values[0].validity &&
+                                                      aggs[j].values[0].offset == aggs[i].values[0].offset && aggs[j].values[0].length == aggs[i].values[0].length && aggs[j].values[0].dtype == aggs[i].values[0].dtype)))
+                { dup = j; break; }
+        if (dup >= 0) vals[i] = vals[dup]; else vals[i] = import_column(aggs[i].values, aggs[i].n_chunks);
+        vptr[i] = &vals[i];
+        dts.push_back(vals[i].dtype);
+    }
+    GroupByState st(key.dtype, kinds, dts, 0);
+    st.consume_all(key, vptr);
+    DevCol ok; std::vector<DevCol> oa;
+    st.finish(maintain_order != 0, &key, ok, oa);
+    bl_column tk; std::vector<bl_column> ta(n_aggs);
+    export_column(ok, out_location, &tk);
+    int done = 0;
+    try { for (; done < n_aggs; done++) export_column(oa[done], out_location, &ta[done]); }
+    catch (...) { bl_column_free(&tk); for (int i = 0; i < done; i++) bl_column_free(&ta[i]); throw; }
+    *out_key = tk;
+    for (int i = 0; i < n_aggs; i++) out_aggs[i] = ta[i];
+    BL_CATCH
+}
+
+bl_status bl_hash_join(const bl_column* left_key, int32_t n_left_chunks, const bl_column* right_key, int32_t n_right_chunks, int32_t how, int32_t nulls_equal,
+                       int32_t maintain_order, int32_t out_location, bl_column* out_left_idx, bl_column* out_right_idx) {
+    BL_TRY
+    PLB_REQUIRE(left_key && right_key && out_left_idx && out_right_idx, BL_ERR_INVALID, "hash_join: null argument");
+    PLB_REQUIRE(maintain_order >= BL_ORDER_NONE && maintain_order <= BL_ORDER_RIGHT_LEFT, BL_ERR_INVALID, "hash_join: unknown maintain_order");
+    DevCol l = import_column(left_key, n_left_chunks), r = import_column(right_key, n_right_chunks);
+    JoinResult jr = op_hash_join(l, r, how, nulls_equal != 0, maintain_order);
+    bl_column tl, tr;
+    export_column(jr.left, out_location, &tl);
+    try { export_column(jr.right, out_location, &tr); } catch (...) { bl_column_free(&tl); throw; }
+    *out_left_idx = tl; *out_right_idx = tr;
+    BL_CATCH
+}
+
+bl_status bl_hash_partition(const bl_column* key, const bl_column* payload, int32_t n_payload, int32_t n_partitions, int32_t out_location, bl_column* out_key,
+                            bl_column* out_payload, int64_t* offsets) {
+    BL_TRY
+    PLB_REQUIRE(key && out_key && offsets && (n_payload == 0 || (payload && out_payload)), BL_ERR_INVALID, "hash_partition: null argument");
+    DevCol k = import_column(key, 1);
+    std::vector<DevCol> pl, po;
+    for (int i = 0; i < n_payload; i++) pl.push_back(import_column(&payload[i], 1));
+    DevCol ok;
+    op_hash_partition(k, pl, n_partitions, ok, po, offsets);
+    bl_column tk; std::vector<bl_column> tp(n_payload);
+    export_column(ok, out_location, &tk);
+    int done = 0;
+    try { for (; done < n_payload; done++) export_column(po[done], out_location, &tp[done]); }
+    catch (...) { bl_column_free(&tk); for (int i = 0; i < done; i++) bl_column_free(&tp[i]); throw; }
+    *out_key = tk;
+    for (int i = 0; i < n_payload; i++) out_payload[i] = tp[i];
+    BL_CATCH
+}
+
+// ---- streaming group_by state ---------------------------------------------------------------
+struct bl_groupby { GroupByState* st; };
+
+bl_status bl_groupby_create(int32_t key_dtype, const int32_t* agg_kinds, const int32_t* value_dtypes, int32_t n_aggs, int64_t expected_groups, bl_groupby** out) {
+    BL_TRY
+    PLB_REQUIRE(out && (n_aggs == 0 || (agg_kinds && value_dtypes)), BL_ERR_INVALID, "groupby_create: null argument");
+    std::vector<int> k(agg_kinds, agg_kinds + n_aggs), d(value_dtypes, value_dtypes + n_aggs);
+    auto* g = new bl_groupby{new GroupByState(key_dtype, k, d, expected_groups)};
+    *out = g;
+    BL_CATCH
+}
+bl_status bl_groupby_consume(bl_groupby* g, const bl_column* key, const bl_column* values, int64_t row_base) {
+    BL_TRY
+    PLB_REQUIRE(g && key, BL_ERR_INVALID, "groupby_consume: null argument");
+    DevCol k = import_column(key, 1);
+    const size_t na = g->st->plans.size();
+    std::vector<DevCol> vals(na); std::vector<const DevCol*> vp(na, nullptr);
+    for (size_t i = 0; i < na; i++) {
+        if (g->st->plans[i].kind == BL_AGG_LEN) continue;
+        PLB_REQUIRE(values != nullptr, BL_ERR_INVALID, "groupby_consume: null values");
+        int dup = -1;
+        for (size_t j = 0; j < i; j++)
+            if (vp[j] && values[j].values == values[i].values && values[j].validity == values[i].validity && values[j].offset == values[i].offset && values[j].dtype == values[i].dtype) { dup = (int)j; break; }
+        vals[i] = dup >= 0 ? vals[dup] : import_column(&values[i], 1);
+        vp[i] = &vals[i];
+    }
+    g->st->consume(k, vp, row_base);
+    // inputs may be caller-owned host buffers: finish the batch before returning
+    PLB_CUDA(cudaStreamSynchronize(ctx().stream));
+    BL_CATCH
+}
+bl_status bl_groupby_export_partials(bl_groupby* g, int32_t n_partitions, void** out_rows_dev, int32_t* row_words, int64_t* offsets) {
+    BL_TRY
+    PLB_REQUIRE(g && out_rows_dev && row_words && offsets, BL_ERR_INVALID, "groupby_export_partials: null argument");
+    int rw = 0;
+    DevPtr rows = g->st->export_partials(n_partitions, &rw, offsets);
+    // hand the raw allocation to the caller (released with bl_dev_free)
+    rows->owned = false;
+    *out_rows_dev = rows->p; *row_words = rw;
+    BL_CATCH
+}
+bl_status bl_groupby_merge_partials(bl_groupby* g, const void* rows_dev, int64_t n_rows) {
+    BL_TRY
+    PLB_REQUIRE(g && (rows_dev || n_rows == 0), BL_ERR_INVALID, "groupby_merge_partials: null argument");
+    g->st->merge_partials(reinterpret_cast<const uint64_t*>(rows_dev), n_rows);
+    PLB_CUDA(cudaStreamSynchronize(ctx().stream));
+    BL_CATCH
+}
+bl_status bl_groupby_finish(bl_groupby* g, int32_t maintain_order, int32_t out_location, bl_column* out_key, bl_column* out_aggs) {
+    BL_TRY
+    PLB_REQUIRE(g && out_key, BL_ERR_INVALID, "groupby_finish: null argument");
+    DevCol ok; std::vector<DevCol> oa;
+    g->st->finish(maintain_order != 0, nullptr, ok, oa);
+    const int n_aggs = (int)oa.size();
+    bl_column tk; std::vector<bl_column> ta(n_aggs);
+    export_column(ok, out_location, &tk);
+    int done = 0;
+    try { for (; done < n_aggs; done++) export_column(oa[done], out_location, &ta[done]); }
+    catch (...) { bl_column_free(&tk); for (int i = 0; i < done; i++) bl_column_free(&ta[i]); throw; }
+    *out_key = tk;
+    for (int i = 0; i < n_aggs; i++) out_aggs[i] = ta[i];
+    BL_CATCH
+}
+void bl_groupby_reset(bl_groupby* g) { try { if (g) { std::lock_guard<std::recursive_mutex> lk(ctx().mu); g->st->reset(); } } catch (...) {} }
+void bl_groupby_destroy(bl_groupby* g) { try { if (g) { std::lock_guard<std::recursive_mutex> lk(ctx().mu); delete g->st; delete g; } } catch (...) {} }
+
+}  // extern "C"

@@ -1,0 +1,200 @@
+// filter.cu — K3: stream compaction of c columns by one bit mask, plus the tile-scan helper.
+//
+// Reference: polars-compute/src/filter/mod.rs:18-110 (null mask slot = false; values and validity
+// of the kept rows are compacted in row order), scalar.rs:9-138 / avx512.rs:45-115 (64-wide
+// compaction), DataFrame::filter polars-core/src/frame/mod.rs:1148-1180 (all columns, one mask).
+//
+// B200 design: the mask is a bitmap (1/64 of a column), so the prefix offsets are computed from
+// it once — per-tile popcounts (TILE rows) + one exclusive scan — and every column is compacted in
+// a single pass with no inter-CTA dependency: row -> rank = tile_offset + popcount of mask bits
+// before it.  Kept rows of a warp are contiguous in the output, so stores coalesce; unselected
+// rows are never loaded (predicated loads skip whole sectors at low selectivity).
+// Algorithmic bytes: 8*c + 8*c*s per row (+1/8 for the mask); bound: HBM.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+#include "dev_utils.cuh"
+
+namespace plb {
+
+constexpr int F_TILE = 4096;            // rows per tile
+constexpr int F_TILE_WORDS = F_TILE / 32;
+constexpr int F_THREADS = 256;
+
+// per-tile popcount of the mask
+__global__ void __launch_bounds__(128) k_mask_tile_counts(const uint32_t* __restrict__ mask, int64_t n, uint32_t* __restrict__ counts, int64_t ntiles) {
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int64_t w = t * F_TILE_WORDS + threadIdx.x;
+        int64_t row0 = w * 32;
+        uint32_t c = 0;
+        if (row0 < n) {
+            uint32_t m = mask[w];
+            if (row0 + 32 > n) m &= (1u << (n - row0)) - 1u;
+            c = __popc(m);
+        }
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        __shared__ uint32_t s[4];
+        if (lane_id() == 0) s[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) counts[t] = s[0] + s[1] + s[2] + s[3];
+        __syncthreads();
+    }
+}
+
+// single-CTA exclusive scan u32 -> u64 (n up to a few hundred thousand tiles; negligible time)
+__global__ void __launch_bounds__(1024) k_scan_u32_u64(const uint32_t* __restrict__ in, uint64_t* __restrict__ out, int64_t n, uint64_t* total) {
+    __shared__ uint64_t warp_sums[32];
+    __shared__ uint64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    for (int64_t base = 0; base < n; base += 1024) {
+        int64_t i = base + threadIdx.x;
+        uint64_t v = i < n ? in[i] : 0, x = v;
+        for (int o = 1; o < 32; o <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t s = warp_sums[lane], t = s;
+            for (int o = 1; o < 32; o <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= (unsigned)o) t += y; }
+            warp_sums[lane] = t - s;    // exclusive warp offsets
+        }
+        __syncthreads();
+        uint64_t carry = carry_s;
+        uint64_t incl = carry + warp_sums[warp] + x;
+        if (i < n) out[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry_s;
+}
+void exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out, int64_t n, uint64_t* total_dev) {
+    PLB_LAUNCH("scan_u32_u64", k_scan_u32_u64, 1, 1024, 0, in, out, n, total_dev);
+}
+
+struct FilterCol { const void* in; void* out; const uint32_t* vin; uint32_t* vout; int elem; int pad; };
+constexpr int F_MAX_COLS = 16;
+struct FilterArgs { FilterCol c[F_MAX_COLS]; };
+
+// grid.x = tiles (grid-stride), grid.y = column
+__global__ void __launch_bounds__(F_THREADS) k_compact(FilterArgs args, const uint32_t* __restrict__ mask, const uint64_t* __restrict__ tile_off, int64_t n, int64_t ntiles) {
+    const FilterCol col = args.c[blockIdx.y];
+    __shared__ uint32_t wmask[F_TILE_WORDS];
+    __shared__ uint32_t wpre[F_TILE_WORDS];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t row_base = t * F_TILE;
+        // load the tile's 128 mask words, exclusive-scan their popcounts (first 4 warps: 32 words each)
+        if (threadIdx.x < F_TILE_WORDS) {
+            int64_t w = t * F_TILE_WORDS + threadIdx.x;
+            int64_t row0 = w * 32;
+            uint32_t m = 0;
+            if (row0 < n) { m = mask[w]; if (row0 + 32 > n) m &= (1u << (n - row0)) - 1u; }
+            wmask[threadIdx.x] = m;
+            uint32_t c = __popc(m), x = c;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
+            wpre[threadIdx.x] = x - c;      // exclusive within this warp's 32 words
+        }
+        __syncthreads();
+        // add the totals of the preceding 32-word groups (4 groups)
+        __shared__ uint32_t gsum[5];
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (int g = 0; g < 4; g++) { gsum[g] = acc; acc += wpre[g * 32 + 31] + __popc(wmask[g * 32 + 31]); }
+            gsum[4] = acc;
+        }
+        __syncthreads();
+        const uint64_t out_base = tile_off[t];
+        // rows: iteration j covers rows row_base + j*256 + tid; word index = j*8 + warp
+#pragma unroll 4
+        for (int j = 0; j < F_TILE / F_THREADS; j++) {
+            const int widx = j * (F_THREADS / 32) + warp;
+            const uint32_t m = wmask[widx];
+            if (m == 0) continue;                                  // warp-uniform
+            const bool keep = (m >> lane) & 1u;
+            const uint32_t rank = gsum[widx >> 5] + wpre[widx] + __popc(m & lanemask_lt());
+            const int64_t row = row_base + (int64_t)widx * 32 + lane;
+            const uint64_t dst = out_base + rank;
+            if (keep) {
+                if (col.elem == 8) reinterpret_cast<uint64_t*>(col.out)[dst] = __ldcs(reinterpret_cast<const uint64_t*>(col.in) + row);
+                else reinterpret_cast<uint32_t*>(col.out)[dst] = __ldcs(reinterpret_cast<const uint32_t*>(col.in) + row);
+            }
+            if (col.vin != nullptr) {
+                // compact the validity bits of this 32-row word: kept rows occupy output bits
+                // [first, first + cnt) — build them with a warp OR-reduce, then <= 2 atomicOr
+                const uint32_t vw = col.vin[row_base / 32 + widx];
+                const uint32_t bit = (keep && ((vw >> lane) & 1u)) ? 1u : 0u;
+                const uint32_t rw = __popc(m & lanemask_lt());       // rank inside the warp
+                const uint64_t first = out_base + gsum[widx >> 5] + wpre[widx];
+                const unsigned sh = (unsigned)(first & 31);
+                uint64_t contrib = (uint64_t)bit << (rw + sh);       // rw + sh <= 62
+                uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)contrib);
+                uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(contrib >> 32));
+                if (lane == 0) {
+                    if (lo) atomicOr(&col.vout[first >> 5], lo);
+                    if (hi) atomicOr(&col.vout[(first >> 5) + 1], hi);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+void op_filter(const std::vector<DevCol>& cols, const DevCol& mask, std::vector<DevCol>& outs) {
+    PLB_REQUIRE(mask.dtype == BL_BOOL, BL_ERR_DTYPE, "filter: mask must be BL_BOOL");
+    const int64_t n = mask.len;
+    for (auto& c : cols) {
+        PLB_REQUIRE(c.len == n, BL_ERR_INVALID, "filter: column length " + std::to_string(c.len) + " != mask length " + std::to_string(n));
+        PLB_REQUIRE(dtype_size(c.dtype) == 8 || dtype_size(c.dtype) == 4, BL_ERR_UNSUPPORTED, std::string("filter: dtype ") + dtype_name(c.dtype) + " is outside the hot path");
+    }
+    outs.clear();
+    // null mask slots count as false (filter/mod.rs:21-27)
+    DevPtr eff = mask.values;
+    if (mask.validity) eff = bitmap_and(as<uint32_t>(mask.values), mask.vm(), nullptr, n);
+    const uint32_t* m = as<uint32_t>(eff);
+    const int64_t ntiles = (n + F_TILE - 1) / F_TILE;
+    uint64_t total = 0;
+    DevPtr counts, offs, tot;
+    if (n > 0) {
+        counts = dev_alloc((size_t)ntiles * 4); offs = dev_alloc((size_t)ntiles * 8); tot = dev_alloc(8);
+        PLB_LAUNCH("k3_tile_counts", k_mask_tile_counts, grid_for(ntiles * 128, 128, 16), 128, 0, m, n, as<uint32_t>(counts), ntiles);
+        exclusive_scan_u32_to_u64(as<uint32_t>(counts), as<uint64_t>(offs), ntiles, as<uint64_t>(tot));
+        total = read_scalar(as<uint64_t>(tot));
+    }
+    for (auto& c : cols) {
+        DevCol o = make_col(c.dtype, (int64_t)total, c.validity != nullptr);
+        if (o.validity) dev_memset(o.validity->p, 0, o.validity->bytes);
+        outs.push_back(o);
+    }
+    if (total == 0 || cols.empty()) return;
+    for (size_t base = 0; base < cols.size(); base += F_MAX_COLS) {
+        FilterArgs a; memset(&a, 0, sizeof a);
+        int nc = (int)std::min<size_t>(F_MAX_COLS, cols.size() - base);
+        for (int i = 0; i < nc; i++) {
+            a.c[i].in = cols[base + i].v(); a.c[i].out = outs[base + i].values->p;
+            a.c[i].vin = cols[base + i].vm(); a.c[i].vout = as<uint32_t>(outs[base + i].validity);
+            a.c[i].elem = dtype_size(cols[base + i].dtype);
+        }
+        dim3 grid((unsigned)std::min<int64_t>(ntiles, (int64_t)ctx().sm_count * 8), (unsigned)nc);
+        PLB_LAUNCH("k3_compact", k_compact, grid, F_THREADS, 0, a, m, as<uint64_t>(offs), n, ntiles);
+    }
+}
+
+// ---------------------------------------------------------------------------- sort helper
+// Stable ascending sort of (key u32, value u32) pairs — used only for the ordering modes
+// (maintain_order, duplicate build keys), never on the headline path.  CUB radix sort (library).
+void sort_pairs_u32(uint32_t* keys, uint32_t* vals, int64_t n) {
+    if (n <= 1) return;
+    Context& c = ctx();
+    DevPtr k2 = dev_alloc((size_t)n * 4), v2 = dev_alloc((size_t)n * 4);
+    size_t tmp_bytes = 0;
+    PLB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, as<uint32_t>(k2), vals, as<uint32_t>(v2), (int)n, 0, 32, c.stream));
+    DevPtr tmp = dev_alloc(tmp_bytes);
+    c.launch_count++;
+    PLB_CUDA(cub::DeviceRadixSort::SortPairs(tmp->p, tmp_bytes, keys, as<uint32_t>(k2), vals, as<uint32_t>(v2), (int)n, 0, 32, c.stream));
+    PLB_CUDA(cudaMemcpyAsync(keys, k2->p, (size_t)n * 4, cudaMemcpyDeviceToDevice, c.stream));
+    PLB_CUDA(cudaMemcpyAsync(vals, v2->p, (size_t)n * 4, cudaMemcpyDeviceToDevice, c.stream));
+}
+
+}  // namespace plb

@@ -1,0 +1,686 @@
+// groupby.cu — K5: fused hash group_by build + per-group aggregation, and K6 for partial
+// aggregates (hash-partitioned export / merge for the multi-GPU plan).
+//
+// Reference path being replaced (paths relative to /root/reference/crates):
+//   group_by_threaded_slice / finish_group_order   polars-core/src/frame/group_by/hashing.rs:26-167
+//   key representation, null group                 polars-core/src/frame/group_by/into_groups.rs:25-58,142-191
+//   agg_sum / agg_mean / agg_min / agg_max         polars-core/src/frame/group_by/aggregations/mod.rs:486-1018,1227-1296
+//   take_agg null handling                         polars-arrow/src/legacy/kernels/take_agg/mod.rs:16-84
+//   count / len                                    aggregations/dispatch.rs:25-55, position.rs:555-569
+// The reference first materialises per-group row-index lists (GroupsIdx) and then gather-reduces
+// every aggregate per group.  Here the index lists are never built: one pass over the rows
+// finds/claims the key's entry in an open-addressing table in HBM (L2-resident for <= ~2M groups)
+// and applies the row to the entry's accumulators with native 64-bit L2 atomics (RED.ADD.64,
+// RED.ADD.F64, RED.MIN/MAX.S64/U64).  All of these are order-independent except the f64 sum
+// (tolerance 1e-6 relative; the reference itself differs between its engines there).
+//
+// Entry layout (AoS, `stride` 64-bit words, 32-byte multiples so one entry = whole sectors):
+//   word0 key bits (GB_EMPTY = free) | word1 lo32 = len, hi32 = first row idx | words 2.. accumulators
+// Slots [0, cap) are hashed; slot cap = the null-key group, slot cap+1 = the group whose key bits
+// equal GB_EMPTY (their word0 is only a "used" marker).
+//
+// Algorithmic bytes: 8*(1 + value columns) per row in, G*(8 + 8*n_aggs) out.
+// Roofline: HBM for the scan; the binding unit in practice is L2 atomic throughput
+// (1 key load + 1 RED per accumulator per row).
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "dev_utils.cuh"
+#include "groupby.h"
+
+namespace plb {
+
+__host__ __device__ inline uint64_t word_identity(int op) {
+    switch (op) {
+        case W_MIN_S64: return 0x7FFFFFFFFFFFFFFFULL;
+        case W_MAX_S64: return 0x8000000000000000ULL;
+        case W_MIN_U64: case W_MIN_F64: return 0xFFFFFFFFFFFFFFFFULL;
+        default: return 0;   // adds, MAX_U64, MAX_F64
+    }
+}
+
+// ---------------------------------------------------------------------------- device pieces
+template <int KEY_CANON> __device__ __forceinline__ uint64_t canon_key(uint64_t raw) {
+    if (KEY_CANON == 1) return canonical_f64_bits(__longlong_as_double((long long)raw));
+    if (KEY_CANON == 2) return canonical_f32_bits(__uint_as_float((uint32_t)raw));
+    return raw;
+}
+__device__ __forceinline__ uint64_t load_key_rt(const void* keys, int dtype, int64_t row) {
+    switch (dtype) {
+        case BL_INT64: case BL_UINT64: return reinterpret_cast<const uint64_t*>(keys)[row];
+        case BL_FLOAT64: return canonical_f64_bits(reinterpret_cast<const double*>(keys)[row]);
+        case BL_FLOAT32: return canonical_f32_bits(reinterpret_cast<const float*>(keys)[row]);
+        default: return (uint64_t)reinterpret_cast<const uint32_t*>(keys)[row];   // i32/u32 bit pattern, zero-extended
+    }
+}
+
+// claim / find the entry of `key`.  nullptr => probe limit hit (table too small): status set.
+__device__ __forceinline__ uint64_t* gb_find_or_insert(const GbTableDev& T, uint64_t key) {
+    uint64_t slot = dirty_hash(key) >> T.shift;
+    const uint64_t mask = T.cap - 1;
+    for (int probes = 0; probes < GB_MAX_PROBE; ++probes) {
+        uint64_t* e = T.entries + slot * T.stride;
+        uint64_t k = __ldcg(reinterpret_cast<const unsigned long long*>(e));
+        if (k == key) return e;
+        if (k == GB_EMPTY) {
+            unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(e), (unsigned long long)GB_EMPTY, (unsigned long long)key);
+            if (old == GB_EMPTY || old == key) return e;
+        }
+        slot = (slot + 1) & mask;
+    }
+    *T.status = 1;
+    return nullptr;
+}
+__device__ __forceinline__ uint64_t* gb_special(const GbTableDev& T, int which) {
+    uint64_t* e = T.entries + (T.cap + which) * T.stride;
+    if (__ldcg(reinterpret_cast<const unsigned long long*>(e)) == GB_EMPTY)
+        atomicCAS(reinterpret_cast<unsigned long long*>(e), (unsigned long long)GB_EMPTY, (unsigned long long)which);
+    return e;
+}
+
+__device__ __forceinline__ double raw_to_f64(int dtype, uint64_t raw) {
+    switch (dtype) {
+        case BL_INT64: return (double)(long long)raw;
+        case BL_UINT64: return (double)(unsigned long long)raw;
+        case BL_INT32: return (double)(int)(uint32_t)raw;
+        case BL_UINT32: return (double)(uint32_t)raw;
+        case BL_FLOAT64: return __longlong_as_double((long long)raw);
+        default: return (double)__uint_as_float((uint32_t)raw);
+    }
+}
+__device__ __forceinline__ uint64_t raw_to_int(int dtype, uint64_t raw) {
+    return dtype == BL_INT32 ? (uint64_t)(long long)(int)(uint32_t)raw : raw;   // sign-extend i32; u32 already zero-extended
+}
+
+__device__ __forceinline__ void gb_apply(int op, uint64_t* addr, int dtype, uint64_t raw, bool valid) {
+    switch (op) {
+        case W_ADD_INT: { uint64_t v = raw_to_int(dtype, raw); if (valid && v) atomicAdd(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)v); break; }
+        case W_ADD_F64: { double f = raw_to_f64(dtype, raw); if (valid && f != 0.0) atomicAdd(reinterpret_cast<double*>(addr), f); break; }
+        case W_MIN_S64: if (valid) atomicMin(reinterpret_cast<long long*>(addr), (long long)raw_to_int(dtype, raw)); break;
+        case W_MAX_S64: if (valid) atomicMax(reinterpret_cast<long long*>(addr), (long long)raw_to_int(dtype, raw)); break;
+        case W_MIN_U64: if (valid) atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)raw); break;
+        case W_MAX_U64: if (valid) atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)raw); break;
+        case W_MIN_F64: { double f = raw_to_f64(dtype, raw); if (valid && f == f) atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)f64_to_ordered(f)); break; }
+        case W_MAX_F64: { double f = raw_to_f64(dtype, raw); if (valid && f == f) atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)f64_to_ordered(f)); break; }
+        default: if (!valid) atomicAdd(reinterpret_cast<unsigned long long*>(addr), 1ull); break;   // W_NULLCNT
+    }
+}
+
+// ---------------------------------------------------------------------------- K5 main kernel
+// Each thread owns PAIRS x 2 consecutive-pair rows per iteration: 128-bit loads of the key pair and
+// of every value-column pair (64-bit loads for 4-byte types), then probe + RED per row.
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC>
+__global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const __grid_constant__ GbBatch B) {
+    const int64_t npairs = B.n >> 1;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    int iter = 0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += gstride) {
+        if (((iter++) & 15) == 0 && *reinterpret_cast<volatile int*>(T.status)) return;
+        uint64_t kraw[2];
+        if (KEY_ELEM == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(B.keys) + 2 * p); kraw[0] = t.x; kraw[1] = t.y; }
+        else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(B.keys) + 2 * p); kraw[0] = t.x; kraw[1] = t.y; }
+        uint64_t raw[MAXC][2];
+#pragma unroll
+        for (int c = 0; c < MAXC; c++) {
+            if (c < L.n_cols) {
+                if (B.cols[c].elem == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(B.cols[c].values) + 2 * p); raw[c][0] = t.x; raw[c][1] = t.y; }
+                else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(B.cols[c].values) + 2 * p); raw[c][0] = t.x; raw[c][1] = t.y; }
+            }
+        }
+        // issue both table probes before touching the accumulators
+        uint64_t* ent[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int64_t row = 2 * p + j;
+            bool kvalid = true;
+            if (KEY_NULLS) kvalid = bit_get(B.key_validity, row);
+            const uint64_t key = canon_key<KEY_CANON>(kraw[j]);
+            if (!kvalid) ent[j] = gb_special(T, 0);
+            else if (key == GB_EMPTY) ent[j] = gb_special(T, 1);
+            else ent[j] = gb_find_or_insert(T, key);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            uint64_t* e = ent[j];
+            if (e == nullptr) continue;
+            const int64_t row = 2 * p + j;
+            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + 1), 1u);
+            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + 1) + 1, B.row_base + (uint32_t)row);
+#pragma unroll
+            for (int c = 0; c < MAXC; c++) {
+                if (c < L.n_cols) {
+                    const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
+                    const int dt = B.cols[c].dtype;
+                    for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + 2 + L.wslot[k], dt, raw[c][j], valid);
+                }
+            }
+        }
+    }
+    // odd tail row
+    if ((B.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t row = B.n - 1;
+        bool kvalid = B.key_validity == nullptr || bit_get(B.key_validity, row);
+        uint64_t key = load_key_rt(B.keys, B.key_dtype, row);
+        uint64_t* e = !kvalid ? gb_special(T, 0) : (key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key));
+        if (e) {
+            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + 1), 1u);
+            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + 1) + 1, B.row_base + (uint32_t)row);
+            for (int c = 0; c < L.n_cols; c++) {
+                const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
+                uint64_t raw = B.cols[c].elem == 8 ? reinterpret_cast<const uint64_t*>(B.cols[c].values)[row] : (uint64_t)reinterpret_cast<const uint32_t*>(B.cols[c].values)[row];
+                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + 2 + L.wslot[k], B.cols[c].dtype, raw, valid);
+            }
+        }
+    }
+}
+
+__global__ void k_gb_init(uint64_t* entries, int64_t n_entries, int stride, const __grid_constant__ GbLayout L) {
+    const int64_t total = n_entries * stride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int w = (int)(i % stride);
+        uint64_t v = 0;
+        if (w == 0) v = GB_EMPTY; else if (w == 1) v = GB_W1_INIT; else if (w - 2 < L.n_words) v = L.init[w - 2];
+        entries[i] = v;
+    }
+}
+
+// cardinality sample: insert m strided keys into a scratch key table, count distinct
+__global__ void k_gb_estimate(const void* keys, const uint32_t* key_validity, int key_dtype, int64_t n, int64_t m, uint64_t* scratch, uint64_t cap, int shift, unsigned* distinct) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = (int64_t)(((unsigned __int128)i * (unsigned __int128)n) / (unsigned __int128)m);
+        bool ins = false;
+        if (key_validity == nullptr || bit_get(key_validity, row)) {
+            uint64_t key = load_key_rt(keys, key_dtype, row);
+            if (key != GB_EMPTY) {
+                uint64_t slot = dirty_hash(key) >> shift;
+                for (int pr = 0; pr < (int)cap; pr++) {
+                    uint64_t k = __ldcg(reinterpret_cast<const unsigned long long*>(scratch + slot));
+                    if (k == key) break;
+                    if (k == GB_EMPTY) {
+                        unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(scratch + slot), (unsigned long long)GB_EMPTY, (unsigned long long)key);
+                        if (old == GB_EMPTY) { ins = true; break; }
+                        if (old == key) break;
+                    }
+                    slot = (slot + 1) & (cap - 1);
+                }
+            }
+        }
+        unsigned act = __activemask();
+        unsigned b = __ballot_sync(act, ins);
+        if (b && lane_id() == (unsigned)(__ffs(act) - 1)) atomicAdd(distinct, (unsigned)__popc(b));
+    }
+}
+__global__ void k_fill_u64(uint64_t* p, uint64_t v, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------- merge (partials / rehash)
+// rows: n_rows x row_words.  table_mode: rows are the slots of another table (stride = row_words,
+// special slots at src_cap, src_cap+1); else exported partial rows whose last word is meta
+// (0 normal, 1 null-key group, 2 GB_EMPTY-key group).
+__global__ void __launch_bounds__(256) k_gb_merge(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const uint64_t* __restrict__ rows, int64_t n_rows, int row_words, int table_mode, int64_t src_cap) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t* src = rows + r * row_words;
+        const uint64_t key = src[0];
+        int meta;
+        if (table_mode) { if (key == GB_EMPTY) continue; meta = r == src_cap ? 1 : (r == src_cap + 1 ? 2 : 0); }
+        else meta = (int)src[row_words - 1];
+        uint64_t* e = meta == 1 ? gb_special(T, 0) : (meta == 2 ? gb_special(T, 1) : gb_find_or_insert(T, key));
+        if (!e) continue;
+        const uint64_t lf = src[1];
+        if ((uint32_t)lf) atomicAdd(reinterpret_cast<unsigned*>(e + 1), (uint32_t)lf);
+        if ((uint32_t)(lf >> 32) != 0xFFFFFFFFu) atomicMin(reinterpret_cast<unsigned*>(e + 1) + 1, (uint32_t)(lf >> 32));
+        for (int w = 0; w < L.n_words; w++) {
+            const uint64_t v = src[2 + w];
+            if (v == L.init[w]) continue;
+            uint64_t* a = e + 2 + w;
+            switch (L.slot_op[w]) {
+                case W_ADD_F64: atomicAdd(reinterpret_cast<double*>(a), __longlong_as_double((long long)v)); break;
+                case W_MIN_S64: atomicMin(reinterpret_cast<long long*>(a), (long long)v); break;
+                case W_MAX_S64: atomicMax(reinterpret_cast<long long*>(a), (long long)v); break;
+                case W_MIN_U64: case W_MIN_F64: atomicMin(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v); break;
+                case W_MAX_U64: case W_MAX_F64: atomicMax(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v); break;
+                default: atomicAdd(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v); break;   // ADD_INT, NULLCNT
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- extraction
+__global__ void k_gb_count_used(const uint64_t* entries, int64_t n_entries, int stride, unsigned long long* count) {
+    unsigned long long c = 0;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_entries; s += (int64_t)gridDim.x * blockDim.x)
+        c += entries[s * stride] != GB_EMPTY;
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane_id() == 0 && c) atomicAdd(count, c);
+}
+
+// Dense SoA extraction.  Group order = slot order within 256-slot tiles, tiles in atomic-arrival
+// order (unspecified, like the reference's hashbrown iteration order).
+// out_words: n_words arrays of G u64.  null_pos: position of the null-key group or -1.
+__global__ void __launch_bounds__(256) k_gb_extract(const uint64_t* __restrict__ entries, int64_t cap, int stride, int n_words, unsigned long long* cursor,
+                                                    uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_first, uint32_t* __restrict__ out_len,
+                                                    uint64_t* __restrict__ out_words, int64_t G, long long* null_pos) {
+    const int64_t n_entries = cap + 2;
+    __shared__ unsigned warp_cnt[8];
+    __shared__ unsigned long long tile_base;
+    const int64_t ntiles = (n_entries + 255) / 256;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t s = t * 256 + threadIdx.x;
+        uint64_t key = GB_EMPTY;
+        if (s < n_entries) key = entries[s * stride];
+        const bool used = key != GB_EMPTY;
+        const unsigned b = __ballot_sync(0xffffffffu, used);
+        if (lane_id() == 0) warp_cnt[threadIdx.x >> 5] = __popc(b);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tot = 0;
+            for (int w = 0; w < 8; w++) { unsigned c = warp_cnt[w]; warp_cnt[w] = tot; tot += c; }
+            tile_base = tot ? atomicAdd(cursor, (unsigned long long)tot) : 0ull;
+        }
+        __syncthreads();
+        if (used) {
+            const int64_t pos = (int64_t)tile_base + warp_cnt[threadIdx.x >> 5] + __popc(b & lanemask_lt());
+            const uint64_t* e = entries + s * stride;
+            uint64_t kout = key;
+            if (s == cap) { kout = 0; *null_pos = pos; }
+            else if (s == cap + 1) kout = GB_EMPTY;
+            out_keys[pos] = kout;
+            const uint64_t lf = e[1];
+            out_len[pos] = (uint32_t)lf;
+            out_first[pos] = (uint32_t)(lf >> 32);
+            for (int w = 0; w < n_words; w++) out_words[(int64_t)w * G + pos] = e[2 + w];
+        }
+        __syncthreads();
+    }
+}
+
+// per-aggregate finalisation over the dense arrays
+struct FinalizeArgs {
+    int kind, in_dtype, out_dtype;
+    const uint64_t* main_word;     // sum / min / max accumulator (G)
+    const uint64_t* nullcnt_word;  // per-group null count or nullptr
+    const uint32_t* len;           // per-group len
+    void* out; uint32_t* out_valid; int64_t G;
+};
+__global__ void __launch_bounds__(256) k_gb_finalize(const __grid_constant__ FinalizeArgs a) {
+    const int64_t rounded = (a.G + 31) / 32 * 32;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < rounded; g += (int64_t)gridDim.x * blockDim.x) {
+        bool valid = false;
+        if (g < a.G) {
+            const uint64_t len = a.len ? a.len[g] : 0;
+            const uint64_t cnt = len - (a.nullcnt_word ? a.nullcnt_word[g] : 0);
+            const uint64_t w = a.main_word ? a.main_word[g] : 0;
+            valid = true;
+            switch (a.kind) {
+                case BL_AGG_SUM:
+                    if (a.out_dtype == BL_FLOAT64) reinterpret_cast<double*>(a.out)[g] = __longlong_as_double((long long)w);
+                    else if (a.out_dtype == BL_FLOAT32) reinterpret_cast<float*>(a.out)[g] = (float)__longlong_as_double((long long)w);
+                    else if (dtype_size_dev(a.out_dtype) == 8) reinterpret_cast<uint64_t*>(a.out)[g] = w;
+                    else reinterpret_cast<uint32_t*>(a.out)[g] = (uint32_t)w;
+                    break;
+                case BL_AGG_MEAN: {
+                    valid = cnt > 0;
+                    double m = valid ? __longlong_as_double((long long)w) / (double)cnt : 0.0;
+                    if (a.out_dtype == BL_FLOAT32) reinterpret_cast<float*>(a.out)[g] = (float)m; else reinterpret_cast<double*>(a.out)[g] = m;
+                    break;
+                }
+                case BL_AGG_MIN: case BL_AGG_MAX: {
+                    valid = cnt > 0;
+                    if (a.out_dtype == BL_FLOAT64 || a.out_dtype == BL_FLOAT32) {
+                        const uint64_t sentinel = a.kind == BL_AGG_MIN ? 0xFFFFFFFFFFFFFFFFULL : 0ULL;
+                        double v = !valid ? 0.0 : (w == sentinel ? __longlong_as_double(0x7ff8000000000000LL) : ordered_to_f64(w));   // all-NaN group -> NaN
+                        if (a.out_dtype == BL_FLOAT32) reinterpret_cast<float*>(a.out)[g] = (float)v; else reinterpret_cast<double*>(a.out)[g] = v;
+                    } else {
+                        const uint64_t v = valid ? w : 0;
+                        if (dtype_size_dev(a.out_dtype) == 8) reinterpret_cast<uint64_t*>(a.out)[g] = v; else reinterpret_cast<uint32_t*>(a.out)[g] = (uint32_t)v;
+                    }
+                    break;
+                }
+                case BL_AGG_COUNT: reinterpret_cast<uint32_t*>(a.out)[g] = (uint32_t)cnt; break;
+                default: reinterpret_cast<uint32_t*>(a.out)[g] = (uint32_t)len; break;
+            }
+        }
+        if (a.out_valid) { unsigned b = __ballot_sync(0xffffffffu, valid); if (lane_id() == 0) a.out_valid[g >> 5] = b; }
+    }
+}
+
+// typed key column from u64 key bits (+ validity with the null group cleared)
+__global__ void k_gb_keys_out(const uint64_t* bits, int64_t G, int elem, void* out, uint32_t* out_valid, long long null_pos) {
+    const int64_t rounded = (G + 31) / 32 * 32;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < rounded; g += (int64_t)gridDim.x * blockDim.x) {
+        if (g < G) { if (elem == 8) reinterpret_cast<uint64_t*>(out)[g] = bits[g]; else reinterpret_cast<uint32_t*>(out)[g] = (uint32_t)bits[g]; }
+        if (out_valid) { unsigned b = __ballot_sync(0xffffffffu, g < G && g != null_pos); if (lane_id() == 0) out_valid[g >> 5] = b; }
+    }
+}
+
+// ---------------------------------------------------------------------------- K6: partitioned export of partial rows
+// row = [key, len|first, words..., meta]; partition = hash_to_partition(dirty_hash(key), P), null-key group -> 0.
+// Block-local reservation: smem histogram -> one global atomicAdd per (block, partition) -> smem cursors.
+constexpr int EXP_MAX_PARTS = 64;
+__device__ __forceinline__ int gb_row_partition(uint64_t key, int64_t s, int64_t cap, int P) {
+    if (s == cap) return 0;                                            // null key -> partition 0 (hashing.rs:113-115)
+    return (int)hash_to_partition(dirty_hash(s == cap + 1 ? GB_EMPTY : key), (uint32_t)P);
+}
+__global__ void __launch_bounds__(256) k_gb_export_count(const uint64_t* __restrict__ entries, int64_t cap, int stride, int P, unsigned long long* part_counts) {
+    __shared__ unsigned hist[EXP_MAX_PARTS];
+    if (threadIdx.x < EXP_MAX_PARTS) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap + 2; s += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t key = entries[s * stride];
+        if (key != GB_EMPTY) atomicAdd(&hist[gb_row_partition(key, s, cap, P)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < P && hist[threadIdx.x]) atomicAdd(&part_counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_gb_export_scatter(const uint64_t* __restrict__ entries, int64_t cap, int stride, int n_words, int P,
+                                                           const unsigned long long* __restrict__ part_off, unsigned long long* part_cursor, uint64_t* __restrict__ rows) {
+    __shared__ unsigned hist[EXP_MAX_PARTS];
+    __shared__ unsigned long long base[EXP_MAX_PARTS];
+    const int row_words = n_words + 3;
+    const int64_t n_entries = cap + 2;
+    const int64_t ntiles = (n_entries + 255) / 256;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        if (threadIdx.x < EXP_MAX_PARTS) hist[threadIdx.x] = 0;
+        __syncthreads();
+        const int64_t s = t * 256 + threadIdx.x;
+        uint64_t key = GB_EMPTY; int p = 0; unsigned local = 0;
+        if (s < n_entries) key = entries[s * stride];
+        if (key != GB_EMPTY) { p = gb_row_partition(key, s, cap, P); local = atomicAdd(&hist[p], 1u); }
+        __syncthreads();
+        if (threadIdx.x < P && hist[threadIdx.x]) base[threadIdx.x] = part_off[threadIdx.x] + atomicAdd(&part_cursor[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+        __syncthreads();
+        if (key != GB_EMPTY) {
+            const uint64_t* e = entries + s * stride;
+            uint64_t* dst = rows + (base[p] + local) * row_words;
+            dst[0] = s == cap ? 0 : (s == cap + 1 ? GB_EMPTY : key);
+            dst[1] = e[1];
+            for (int w = 0; w < n_words; w++) dst[2 + w] = e[2 + w];
+            dst[2 + n_words] = s == cap ? 1 : (s == cap + 1 ? 2 : 0);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace plb
+
+// =============================================================================================
+// Host side: plan, table sizing (sampled cardinality estimate, overflow -> grow), finish.
+// Mirrors group_by_helper + evaluate_aggs (crates/polars-mem-engine/src/executors/group_by.rs:5-98).
+// =============================================================================================
+namespace plb {
+
+static int sum_out_dtype(int dt) {
+    // series/implementations/mod.rs:145-154: Int8/16, UInt8/16 sums are computed as Int64
+    if (dt == BL_INT8 || dt == BL_INT16 || dt == BL_UINT8 || dt == BL_UINT16) return BL_INT64;
+    return dt;
+}
+
+GroupByState::GroupByState(int key_dt, const std::vector<int>& kinds, const std::vector<int>& dtypes, int64_t expected)
+    : key_dtype(key_dt), agg_kinds(kinds), agg_dtypes(dtypes), expected_groups(expected) {
+    PLB_REQUIRE(key_dt == BL_INT64 || key_dt == BL_UINT64 || key_dt == BL_INT32 || key_dt == BL_UINT32 || key_dt == BL_FLOAT64 || key_dt == BL_FLOAT32,
+                BL_ERR_UNSUPPORTED, std::string("group_by: key dtype ") + dtype_name(key_dt) + " is outside the hot path");
+    memset(&L, 0, sizeof L);
+    int nw = 0;
+    auto add_word = [&](int op) { PLB_REQUIRE(nw < GB_MAX_WORDS, BL_ERR_UNSUPPORTED, "group_by: too many aggregations for one pass"); L.slot_op[nw] = op; L.init[nw] = word_identity(op); return nw++; };
+    for (size_t i = 0; i < kinds.size(); i++) {
+        AggPlan ap; ap.kind = kinds[i]; ap.in_dtype = dtypes[i]; ap.main = -1; ap.nullcnt = -1;
+        if (ap.kind != BL_AGG_LEN)
+            PLB_REQUIRE(ap.in_dtype == BL_INT64 || ap.in_dtype == BL_UINT64 || ap.in_dtype == BL_INT32 || ap.in_dtype == BL_UINT32 || ap.in_dtype == BL_FLOAT64 || ap.in_dtype == BL_FLOAT32,
+                        BL_ERR_UNSUPPORTED, std::string("group_by: value dtype ") + dtype_name(ap.in_dtype) + " is outside the hot path");
+        const bool flt = dtype_is_float(ap.in_dtype), sgn = dtype_is_signed(ap.in_dtype);
+        switch (ap.kind) {
+            case BL_AGG_SUM: ap.main = add_word(flt ? W_ADD_F64 : W_ADD_INT); ap.out_dtype = sum_out_dtype(ap.in_dtype); break;
+            case BL_AGG_MEAN: ap.main = add_word(W_ADD_F64); ap.nullcnt = add_word(W_NULLCNT); ap.out_dtype = ap.in_dtype == BL_FLOAT32 ? BL_FLOAT32 : BL_FLOAT64; L.need_len = 1; break;
+            case BL_AGG_MIN: ap.main = add_word(flt ? W_MIN_F64 : (sgn ? W_MIN_S64 : W_MIN_U64)); ap.nullcnt = add_word(W_NULLCNT); ap.out_dtype = ap.in_dtype; L.need_len = 1; break;
+            case BL_AGG_MAX: ap.main = add_word(flt ? W_MAX_F64 : (sgn ? W_MAX_S64 : W_MAX_U64)); ap.nullcnt = add_word(W_NULLCNT); ap.out_dtype = ap.in_dtype; L.need_len = 1; break;
+            case BL_AGG_COUNT: ap.nullcnt = add_word(W_NULLCNT); ap.out_dtype = BL_UINT32; L.need_len = 1; break;
+            case BL_AGG_LEN: ap.out_dtype = BL_UINT32; L.need_len = 1; break;
+            default: fail(BL_ERR_INVALID, "group_by: unknown aggregation kind");
+        }
+        plans.push_back(ap);
+    }
+    L.n_words = nw;
+    L.stride = ((2 + nw + 3) / 4) * 4;      // whole 32-byte sectors per entry
+    L.need_first = 1;                        // needed for maintain_order and for float key output; one 32-bit RED
+    status = dev_alloc(4);
+}
+
+void GroupByState::alloc_table(uint64_t new_cap) {
+    cap = new_cap;
+    entries = dev_alloc((size_t)(cap + 2) * L.stride * 8);
+    int shift = 64; for (uint64_t c = cap; c > 1; c >>= 1) shift--;
+    T.entries = as<uint64_t>(entries); T.cap = cap; T.shift = shift; T.stride = L.stride; T.status = as<int>(status);
+    PLB_LAUNCH("k5_table_init", k_gb_init, grid_for((int64_t)(cap + 2) * L.stride, 256), 256, 0, T.entries, (int64_t)(cap + 2), L.stride, L);
+    dev_memset(status->p, 0, 4);
+}
+
+static uint64_t pow2_at_least(double x) { uint64_t c = 1024; while ((double)c < x && c < (1ull << 40)) c <<= 1; return c; }
+
+// Birthday-style inversion: d distinct keys in a sample of m rows out of n  ->  estimate of the
+// number of groups.  (The reference samples too: executors/group_by_streaming.rs:117-139.)
+static double estimate_groups(double d, double m, double n) {
+    if (d >= m * 0.995) return n;               // (almost) all distinct: could be anything up to n
+    double lo = d, hi = n > d ? n : d;
+    for (int it = 0; it < 60; it++) { double G = 0.5 * (lo + hi); double ex = G * (1.0 - exp(-m / G)); if (ex < d) lo = G; else hi = G; }
+    return hi;
+}
+
+uint64_t GroupByState::choose_cap(const DevCol& key) {
+    double G;
+    if (expected_groups > 0) G = (double)expected_groups;
+    else {
+        const int64_t n = key.len, m = std::min<int64_t>(n, 65536);
+        const uint64_t scap = 1 << 18;
+        DevPtr scratch = dev_alloc(scap * 8), cnt = dev_alloc(4);
+        PLB_LAUNCH("k5_fill", k_fill_u64, grid_for(scap, 256), 256, 0, as<uint64_t>(scratch), GB_EMPTY, (int64_t)scap);
+        dev_memset(cnt->p, 0, 4);
+        PLB_LAUNCH("k5_estimate", k_gb_estimate, grid_for(m, 256), 256, 0, key.v(), key.vm(), key.dtype, n, m, as<uint64_t>(scratch), scap, 64 - 18, as<unsigned>(cnt));
+        unsigned d = read_scalar(as<unsigned>(cnt));
+        G = estimate_groups((double)d, (double)m, (double)n) * 1.25 + 64;
+        if (G > (double)n) G = (double)n;
+    }
+    return pow2_at_least(G / 0.6);      // load factor <= 0.6
+}
+
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS>
+static void launch_consume(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int grid) {
+    if (L.n_cols <= 1) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 1>), grid, 256, 0, L, T, B);
+    else if (L.n_cols <= 2) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 2>), grid, 256, 0, L, T, B);
+    else if (L.n_cols <= 4) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 4>), grid, 256, 0, L, T, B);
+    else PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 8>), grid, 256, 0, L, T, B);
+}
+
+void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCol*>& values, int64_t row_base) {
+    // per-batch column binding: aggregations over the same buffer share one column slot
+    GbBatch B; memset(&B, 0, sizeof B);
+    B.keys = key.v(); B.key_validity = key.vm(); B.n = key.len; B.row_base = (uint32_t)row_base; B.key_dtype = key.dtype;
+    std::vector<const void*> col_ptr; std::vector<int> col_of_agg(plans.size(), -1);
+    for (size_t i = 0; i < plans.size(); i++) {
+        if (plans[i].kind == BL_AGG_LEN) continue;
+        const DevCol* v = values[i];
+        PLB_REQUIRE(v != nullptr && v->len == key.len, BL_ERR_INVALID, "group_by: value column length differs from key length");
+        PLB_REQUIRE(v->dtype == plans[i].in_dtype, BL_ERR_DTYPE, "group_by: value dtype differs from the plan");
+        int c = -1;
+        for (size_t j = 0; j < col_ptr.size(); j++) if (col_ptr[j] == v->v() && B.cols[j].validity == v->vm()) c = (int)j;
+        if (c < 0) {
+            PLB_REQUIRE(col_ptr.size() < GB_MAX_COLS, BL_ERR_UNSUPPORTED, "group_by: more than 8 distinct value columns in one pass");
+            c = (int)col_ptr.size(); col_ptr.push_back(v->v());
+            B.cols[c].values = v->v(); B.cols[c].validity = v->vm(); B.cols[c].dtype = v->dtype; B.cols[c].elem = dtype_size(v->dtype);
+        }
+        col_of_agg[i] = c;
+    }
+    GbLayout Lb = L;
+    Lb.n_cols = (int)col_ptr.size();
+    int k = 0;
+    for (int c = 0; c < Lb.n_cols; c++) {
+        Lb.col_kbegin[c] = k;
+        for (size_t i = 0; i < plans.size(); i++) {
+            if (col_of_agg[i] != c) continue;
+            if (plans[i].main >= 0) { Lb.wslot[k] = plans[i].main; Lb.wop[k] = L.slot_op[plans[i].main]; k++; }
+            // null counters only matter when the column can hold nulls
+            if (plans[i].nullcnt >= 0 && B.cols[c].validity != nullptr) { Lb.wslot[k] = plans[i].nullcnt; Lb.wop[k] = W_NULLCNT; k++; }
+        }
+    }
+    for (int c = Lb.n_cols; c <= GB_MAX_COLS; c++) Lb.col_kbegin[c] = k;
+    const int64_t n = key.len;
+    if (n == 0) return;
+    const int grid = grid_for((n / 2 + 1), 256, 8);
+    const bool kn = key.validity != nullptr;
+    const int elem = dtype_size(key.dtype);
+    const int canon = key.dtype == BL_FLOAT64 ? 1 : (key.dtype == BL_FLOAT32 ? 2 : 0);
+    // keys must be 16-byte aligned for the 128-bit path (device columns always are)
+#define GB_DISPATCH(E, C)                                                            \
+    do { if (kn) launch_consume<E, C, true>(Lb, T, B, grid); else launch_consume<E, C, false>(Lb, T, B, grid); } while (0)
+    if (elem == 8) { if (canon == 1) GB_DISPATCH(8, 1); else GB_DISPATCH(8, 0); }
+    else { if (canon == 2) GB_DISPATCH(4, 2); else GB_DISPATCH(4, 0); }
+#undef GB_DISPATCH
+}
+
+void GroupByState::grow(uint64_t new_cap) {
+    // rehash: merge the old table's entries into a bigger one
+    DevPtr old = entries; const uint64_t old_cap = cap;
+    alloc_table(new_cap);
+    if (old) PLB_LAUNCH("k5_rehash", k_gb_merge, grid_for((int64_t)old_cap + 2, 256), 256, 0, L, T, as<uint64_t>(old), (int64_t)old_cap + 2, L.stride, 1, (int64_t)old_cap);
+}
+
+int64_t GroupByState::count_groups() {
+    DevPtr c = dev_alloc(8); dev_memset(c->p, 0, 8);
+    PLB_LAUNCH("k5_count_used", k_gb_count_used, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap + 2, L.stride, as<unsigned long long>(c));
+    return (int64_t)read_scalar(as<unsigned long long>(c));
+}
+
+// One-shot consume with restart: if the optimistic table overflows the whole pass is redone into a
+// table 8x larger (the batch stays resident on the device, so this costs compute only).
+void GroupByState::consume_all(const DevCol& key, const std::vector<const DevCol*>& values) {
+    PLB_REQUIRE(key.dtype == key_dtype, BL_ERR_DTYPE, "group_by: key dtype differs from the plan");
+    PLB_REQUIRE(key.len <= 0xFFFFFFFEll, BL_ERR_UNSUPPORTED, "group_by: more than 2^32-2 rows (IdxSize = u32)");
+    uint64_t c = choose_cap(key);
+    for (int attempt = 0; attempt < 8; attempt++) {
+        alloc_table(c);
+        launch_batch(key, values, 0);
+        if (read_scalar(as<int>(status)) == 0) { rows_seen = key.len; return; }
+        c *= 8;
+    }
+    fail(BL_ERR_OOM, "group_by: hash table kept overflowing");
+}
+
+// Streaming consume (chunked H2D overlap, multi-GPU): the table is grown between batches so that it
+// can absorb a batch of entirely new keys up to 4x the groups seen so far; an overflow inside a
+// batch is reported (pass expected_groups to bl_groupby_create).
+void GroupByState::consume(const DevCol& key, const std::vector<const DevCol*>& values, int64_t row_base) {
+    PLB_REQUIRE(key.dtype == key_dtype, BL_ERR_DTYPE, "group_by: key dtype differs from the plan");
+    PLB_REQUIRE(row_base + key.len <= 0xFFFFFFFEll, BL_ERR_UNSUPPORTED, "group_by: more than 2^32-2 rows (IdxSize = u32)");
+    if (!entries) alloc_table(choose_cap(key));
+    else if (expected_groups <= 0) {
+        int64_t g = count_groups();
+        if ((double)g > 0.25 * (double)cap) grow(cap * 4);
+    }
+    launch_batch(key, values, row_base);
+    if (read_scalar(as<int>(status)) != 0)
+        fail(BL_ERR_UNSUPPORTED, "group_by: table overflow inside a streamed batch — create the state with expected_groups set");
+    rows_seen += key.len;
+}
+
+void GroupByState::reset() {
+    if (entries) {
+        PLB_LAUNCH("k5_table_init", k_gb_init, grid_for((int64_t)(cap + 2) * L.stride, 256), 256, 0, T.entries, (int64_t)(cap + 2), L.stride, L);
+        dev_memset(status->p, 0, 4);
+    }
+    rows_seen = 0;
+}
+
+void GroupByState::merge_partials(const uint64_t* rows, int64_t n_rows) {
+    const int row_words = L.n_words + 3;
+    if (!entries) alloc_table(pow2_at_least((double)std::max<int64_t>(n_rows, 1) / 0.6));
+    else {
+        int64_t g = count_groups();
+        if ((double)(g + n_rows) > 0.6 * (double)cap) grow(pow2_at_least((double)(g + n_rows) / 0.5));
+    }
+    if (n_rows == 0) return;
+    PLB_LAUNCH("k5_merge_partials", k_gb_merge, grid_for(n_rows, 256), 256, 0, L, T, rows, n_rows, row_words, 0, (int64_t)0);
+    if (read_scalar(as<int>(status)) != 0) fail(BL_ERR_OOM, "group_by: table overflow while merging partial aggregates");
+}
+
+DevPtr GroupByState::export_partials(int n_partitions, int* row_words_out, int64_t* offsets_host) {
+    PLB_REQUIRE(n_partitions >= 1 && n_partitions <= EXP_MAX_PARTS, BL_ERR_INVALID, "export_partials: 1..64 partitions");
+    const int row_words = L.n_words + 3;
+    *row_words_out = row_words;
+    if (!entries) { for (int p = 0; p <= n_partitions; p++) offsets_host[p] = 0; return dev_alloc(16); }
+    DevPtr counts = dev_alloc(8 * EXP_MAX_PARTS), cursor = dev_alloc(8 * EXP_MAX_PARTS), off = dev_alloc(8 * EXP_MAX_PARTS);
+    dev_memset(counts->p, 0, 8 * EXP_MAX_PARTS); dev_memset(cursor->p, 0, 8 * EXP_MAX_PARTS);
+    PLB_LAUNCH("k6_export_count", k_gb_export_count, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, L.stride, n_partitions, as<unsigned long long>(counts));
+    unsigned long long h[EXP_MAX_PARTS];
+    PLB_CUDA(cudaMemcpyAsync(h, counts->p, 8 * n_partitions, cudaMemcpyDeviceToHost, ctx().stream));
+    PLB_CUDA(cudaStreamSynchronize(ctx().stream));
+    unsigned long long ho[EXP_MAX_PARTS + 1]; ho[0] = 0;
+    for (int p = 0; p < n_partitions; p++) ho[p + 1] = ho[p] + h[p];
+    for (int p = 0; p <= n_partitions; p++) offsets_host[p] = (int64_t)ho[p];
+    PLB_CUDA(cudaMemcpyAsync(off->p, ho, 8 * n_partitions, cudaMemcpyHostToDevice, ctx().stream));
+    const int64_t G = (int64_t)ho[n_partitions];
+    DevPtr rows = dev_alloc((size_t)std::max<int64_t>(G, 1) * row_words * 8);
+    if (G > 0)
+        PLB_LAUNCH("k6_export_scatter", k_gb_export_scatter, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, L.stride, L.n_words, n_partitions,
+                   as<unsigned long long>(off), as<unsigned long long>(cursor), as<uint64_t>(rows));
+    PLB_CUDA(cudaStreamSynchronize(ctx().stream));   // ho[] is on this stack frame
+    return rows;
+}
+
+void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather, DevCol& out_key, std::vector<DevCol>& out_aggs) {
+    out_aggs.clear();
+    int64_t G = entries ? count_groups() : 0;
+    const int kelem = dtype_size(key_dtype);
+    DevPtr keys = dev_alloc((size_t)std::max<int64_t>(G, 1) * 8), first = dev_alloc((size_t)std::max<int64_t>(G, 1) * 4), len = dev_alloc((size_t)std::max<int64_t>(G, 1) * 4);
+    DevPtr words = dev_alloc((size_t)std::max<int64_t>(G, 1) * 8 * std::max(L.n_words, 1));
+    DevPtr cursor = dev_alloc(8), nullpos = dev_alloc(8);
+    dev_memset(cursor->p, 0, 8); dev_memset(nullpos->p, 0xFF, 8);
+    if (G > 0)
+        PLB_LAUNCH("k5_extract", k_gb_extract, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, L.stride, L.n_words, as<unsigned long long>(cursor),
+                   as<uint64_t>(keys), as<uint32_t>(first), as<uint32_t>(len), as<uint64_t>(words), G, as<long long>(nullpos));
+    long long null_pos = G > 0 ? read_scalar(as<long long>(nullpos)) : -1;
+    // key column
+    out_key = make_col(key_dtype, G, null_pos >= 0);
+    if (G > 0)
+        PLB_LAUNCH("k5_keys_out", k_gb_keys_out, grid_for(G, 256), 256, 0, as<uint64_t>(keys), G, kelem, out_key.values->p, as<uint32_t>(out_key.validity), null_pos);
+    out_key.null_count = null_pos >= 0 ? 1 : 0;
+    // aggregates
+    for (auto& ap : plans) {
+        const bool nullable = ap.kind == BL_AGG_MEAN || ap.kind == BL_AGG_MIN || ap.kind == BL_AGG_MAX;
+        DevCol o = make_col(ap.out_dtype, G, nullable);
+        if (G > 0) {
+            FinalizeArgs fa; memset(&fa, 0, sizeof fa);
+            fa.kind = ap.kind; fa.in_dtype = ap.in_dtype; fa.out_dtype = ap.out_dtype; fa.G = G;
+            fa.main_word = ap.main >= 0 ? as<uint64_t>(words) + (int64_t)ap.main * G : nullptr;
+            fa.nullcnt_word = ap.nullcnt >= 0 ? as<uint64_t>(words) + (int64_t)ap.nullcnt * G : nullptr;
+            fa.len = as<uint32_t>(len); fa.out = o.values->p; fa.out_valid = as<uint32_t>(o.validity);
+            PLB_LAUNCH("k5_finalize", k_gb_finalize, grid_for(G, 256), 256, 0, fa);
+        }
+        out_aggs.push_back(o);
+    }
+    // float keys (and any key when the column is at hand): output = key at the group's first row
+    // (group_by/mod.rs:258-266) so that -0.0 / NaN payloads of the first occurrence survive
+    const bool gather_keys = key_col_for_gather != nullptr && dtype_is_float(key_dtype) && G > 0;
+    DevCol first_col; first_col.dtype = BL_UINT32; first_col.len = G; first_col.values = first; first_col.null_count = 0;
+    if (gather_keys) {
+        std::vector<DevCol> in{*key_col_for_gather}, outv;
+        op_gather(in, first_col, false, outv);
+        out_key = outv[0];
+        if (!out_key.validity && null_pos >= 0) { /* unreachable: nullable key col gathers validity */ }
+    }
+    if (maintain_order && G > 1) {
+        // sort groups by first row idx (hashing.rs:41-63) and permute every output column
+        DevPtr perm = dev_alloc((size_t)G * 4), fkeys = dev_alloc((size_t)G * 4);
+        PLB_CUDA(cudaMemcpyAsync(fkeys->p, first->p, (size_t)G * 4, cudaMemcpyDeviceToDevice, ctx().stream));
+        iota_u32(as<uint32_t>(perm), G, 0);
+        sort_pairs_u32(as<uint32_t>(fkeys), as<uint32_t>(perm), G);
+        DevCol pidx; pidx.dtype = BL_UINT32; pidx.len = G; pidx.values = perm; pidx.null_count = 0;
+        std::vector<DevCol> in{out_key}, outv;
+        for (auto& a : out_aggs) in.push_back(a);
+        op_gather(in, pidx, false, outv);
+        out_key = outv[0];
+        for (size_t i = 0; i < out_aggs.size(); i++) out_aggs[i] = outv[i + 1];
+    }
+}
+
+}  // namespace plb

@@ -1,0 +1,62 @@
+// groupby.h — shared definitions + host-side state of the fused hash group_by (K5); see groupby.cu.
+#pragma once
+#include "common.cuh"
+
+namespace plb {
+
+constexpr uint64_t GB_EMPTY = 0x8000000000000000ULL;   // i64::MIN / -0.0 bits (never a canonical float key)
+constexpr uint64_t GB_W1_INIT = 0xFFFFFFFF00000000ULL;  // first = u32::MAX, len = 0
+constexpr int GB_MAX_COLS = 8;
+constexpr int GB_MAX_WORDS = 14;
+constexpr int GB_MAX_PROBE = 1024;
+
+enum WordOp { W_ADD_INT = 0, W_ADD_F64 = 1, W_MIN_S64 = 2, W_MAX_S64 = 3, W_MIN_U64 = 4, W_MAX_U64 = 5, W_MIN_F64 = 6, W_MAX_F64 = 7, W_NULLCNT = 8 };
+
+struct GbColDev { const void* values; const uint32_t* validity; int32_t dtype; int32_t elem; };
+struct GbLayout {
+    int32_t stride, n_words, n_cols, need_len, need_first;
+    int32_t wslot[GB_MAX_WORDS];      // iteration order k -> accumulator word index (table word = 2 + slot)
+    int32_t wop[GB_MAX_WORDS];        // iteration order k -> WordOp
+    int32_t col_kbegin[GB_MAX_COLS + 1];
+    int32_t slot_op[GB_MAX_WORDS];    // word index -> WordOp (merge / init)
+    uint64_t init[GB_MAX_WORDS];      // word index -> identity
+};
+struct GbTableDev { uint64_t* entries; uint64_t cap; int32_t shift; int32_t stride; int32_t* status; };
+struct GbBatch {
+    const void* keys; const uint32_t* key_validity; int64_t n; uint32_t row_base; int32_t key_dtype;
+    GbColDev cols[GB_MAX_COLS];
+};
+
+
+struct AggPlan { int kind, in_dtype, out_dtype; int main, nullcnt; };
+
+// Host mirror of group_by_helper (crates/polars-mem-engine/src/executors/group_by.rs:60-98): owns
+// the device hash table and the aggregation plan.
+struct GroupByState {
+    int key_dtype;
+    std::vector<int> agg_kinds, agg_dtypes;
+    int64_t expected_groups;
+    std::vector<AggPlan> plans;
+    GbLayout L;
+    GbTableDev T{};
+    DevPtr entries, status;
+    uint64_t cap = 0;
+    int64_t rows_seen = 0;
+
+    GroupByState(int key_dt, const std::vector<int>& kinds, const std::vector<int>& dtypes, int64_t expected);
+    void consume_all(const DevCol& key, const std::vector<const DevCol*>& values);
+    void consume(const DevCol& key, const std::vector<const DevCol*>& values, int64_t row_base);
+    void merge_partials(const uint64_t* rows, int64_t n_rows);
+    DevPtr export_partials(int n_partitions, int* row_words_out, int64_t* offsets_host);
+    void finish(bool maintain_order, const DevCol* key_col_for_gather, DevCol& out_key, std::vector<DevCol>& out_aggs);
+    void reset();
+    int64_t count_groups();
+
+   private:
+    void alloc_table(uint64_t new_cap);
+    uint64_t choose_cap(const DevCol& key);
+    void launch_batch(const DevCol& key, const std::vector<const DevCol*>& values, int64_t row_base);
+    void grow(uint64_t new_cap);
+};
+
+}  // namespace plb

@@ -1,0 +1,315 @@
+// join.cu — K7 (hash-join build) and K8 (probe + deterministic tuple emission).
+//
+// Reference path being replaced (paths relative to /root/reference/crates):
+//   build_tables            polars-ops/src/frame/join/hash_join/single_keys.rs:16-167
+//   probe_inner / hash_join_tuples_inner   .../single_keys_inner.rs:11-149
+//   hash_join_tuples_left   .../single_keys_left.rs:106-195
+//   which side builds       .../hash_join/mod.rs:41-50 (probe = longer relation, tie -> right probes)
+//   maintain_order sort     polars-ops/src/frame/join/mod.rs:577-642
+// The reference radix-partitions the build side over threads and keeps a hashbrown map
+// key -> ascending row-index vector per partition; probing walks the probe side in row order and
+// emits (probe idx, build idx) for every build idx in ascending order.
+//
+// B200 design.  One open-addressing table in HBM of 16-byte entries {key, val, cnt} (one 128-bit
+// load per probe step; slot = mulhi(key * RANDOM_ODD, cap) — the reference's own
+// hash_to_partition — so the capacity is exactly 2x the build rows, no power-of-two padding).
+//   build:  claim the key's entry (CAS), cnt += 1, val = min(val, row).  Unique build keys (the
+//           primary-key case) need nothing else: val is the build row.  With duplicates the rows
+//           are stably sorted by entry and an exclusive scan of cnt turns val into a CSR offset,
+//           so every entry owns an ascending row list — the reference's IdxVec.
+//   probe:  pass 1 looks every probe row up once and stores its match handle (4 B/row) plus
+//           per-tile match counts; an exclusive scan of the tile counts gives every tile its
+//           output offset; pass 2 expands the handles into (probe idx, build idx) tuples.  The
+//           output is therefore in exact reference order with no atomics or spin-waits.
+// Algorithmic bytes: build 8 B read + 16 B table write per build row; probe
+// 8 B key read + 8 B tuple write per match.  Bound: random 32-byte sector reads of the table
+// (HBM when the table exceeds L2, L2 otherwise).
+#include "common.cuh"
+#include "dev_utils.cuh"
+
+namespace plb {
+
+constexpr uint64_t J_EMPTY = 0x8000000000000000ULL;
+constexpr uint32_t J_NONE = 0xFFFFFFFFu;
+constexpr int J_TILE = 2048;
+
+struct JoinTableDev { uint4* entries; uint64_t cap; };   // entries[cap] = null-key entry, [cap+1] = J_EMPTY-key entry
+
+__device__ __forceinline__ uint64_t j_load_key(const void* keys, int dtype, int64_t row) {
+    switch (dtype) {
+        case BL_INT64: case BL_UINT64: return reinterpret_cast<const uint64_t*>(keys)[row];
+        case BL_FLOAT64: return canonical_f64_bits(reinterpret_cast<const double*>(keys)[row]);   // NaN joins NaN (single_keys_dispatch.rs:316-322)
+        case BL_FLOAT32: return canonical_f32_bits(reinterpret_cast<const float*>(keys)[row]);
+        default: return (uint64_t)reinterpret_cast<const uint32_t*>(keys)[row];
+    }
+}
+
+__global__ void k_join_init(uint4* entries, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        entries[i] = make_uint4((uint32_t)J_EMPTY, (uint32_t)(J_EMPTY >> 32), J_NONE, 0u);
+}
+
+// ---------------------------------------------------------------------------- K7 build
+__global__ void __launch_bounds__(256) k_join_build(JoinTableDev T, const void* __restrict__ keys, const uint32_t* __restrict__ valid, int key_dtype, int64_t n,
+                                                    int nulls_equal, uint32_t* __restrict__ slot_of_row, int* __restrict__ has_dups) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const bool v = valid == nullptr || bit_get(valid, r);
+        uint64_t slot;
+        if (!v) {
+            if (!nulls_equal) { slot_of_row[r] = J_NONE; continue; }     // null keys are not inserted (single_keys.rs:41,148)
+            slot = T.cap;
+            atomicCAS(reinterpret_cast<unsigned long long*>(&T.entries[slot]), (unsigned long long)J_EMPTY, 0ull);
+        } else {
+            const uint64_t key = j_load_key(keys, key_dtype, r);
+            if (key == J_EMPTY) { slot = T.cap + 1; atomicCAS(reinterpret_cast<unsigned long long*>(&T.entries[slot]), (unsigned long long)J_EMPTY, 1ull); }
+            else {
+                slot = __umul64hi(dirty_hash(key), T.cap);
+                while (true) {
+                    unsigned long long* kp = reinterpret_cast<unsigned long long*>(&T.entries[slot]);
+                    unsigned long long k = __ldcg(kp);
+                    if (k == key) break;
+                    if (k == J_EMPTY) { unsigned long long old = atomicCAS(kp, (unsigned long long)J_EMPTY, (unsigned long long)key); if (old == J_EMPTY || old == key) break; }
+                    if (++slot == T.cap) slot = 0;
+                }
+            }
+        }
+        uint32_t* w = reinterpret_cast<uint32_t*>(&T.entries[slot]);
+        const uint32_t old = atomicAdd(w + 3, 1u);
+        atomicMin(w + 2, (uint32_t)r);
+        if (old != 0) *has_dups = 1;
+        slot_of_row[r] = (uint32_t)slot;
+    }
+}
+
+// duplicates: val <- CSR offset (exclusive scan of cnt over the entries, in entry order)
+__global__ void __launch_bounds__(256) k_join_tile_sums(const uint4* __restrict__ entries, int64_t n, uint32_t* __restrict__ sums) {
+    __shared__ uint32_t ws[8];
+    const int64_t ntiles = (n + J_TILE - 1) / J_TILE;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        uint32_t c = 0;
+        for (int k = 0; k < J_TILE / 256; k++) { int64_t i = t * J_TILE + k * 256 + threadIdx.x; if (i < n) c += entries[i].w; }
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane_id() == 0) ws[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) { uint32_t s = 0; for (int w = 0; w < 8; w++) s += ws[w]; sums[t] = s; }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) k_join_csr_offsets(uint4* __restrict__ entries, int64_t n, const uint64_t* __restrict__ tile_off) {
+    __shared__ uint32_t ws[8];
+    __shared__ uint32_t carry;
+    const int64_t ntiles = (n + J_TILE - 1) / J_TILE;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        if (threadIdx.x == 0) carry = (uint32_t)tile_off[t];
+        __syncthreads();
+        for (int k = 0; k < J_TILE / 256; k++) {
+            const int64_t i = t * J_TILE + k * 256 + threadIdx.x;
+            const uint32_t c = i < n ? entries[i].w : 0;
+            uint32_t x = c;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane_id() >= (unsigned)o) x += y; }
+            if (lane_id() == 31) ws[threadIdx.x >> 5] = x;
+            __syncthreads();
+            uint32_t wbase = 0;
+            for (unsigned w = 0; w < (threadIdx.x >> 5); w++) wbase += ws[w];
+            if (i < n) entries[i].z = carry + wbase + x - c;
+            __syncthreads();
+            if (threadIdx.x == 255) carry += wbase + x;
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- K8 probe, pass 1
+// handle[i] = unique mode: build row (J_NONE on miss); CSR mode: entry index (J_NONE on miss).
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS>
+__global__ void __launch_bounds__(256) k_join_probe(JoinTableDev T, const void* __restrict__ keys, const uint32_t* __restrict__ valid, int64_t n, int nulls_equal, int csr_mode,
+                                                    int left_join, uint32_t* __restrict__ handle, uint32_t* __restrict__ tile_counts, unsigned long long* __restrict__ total) {
+    const int64_t npairs = (n + 1) >> 1;
+    const int64_t rounded = (npairs + 31) / 32 * 32;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < rounded; p += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t kraw[2] = {0, 0};
+        const int64_t r0 = 2 * p;
+        if (r0 + 1 < n) {
+            if (KEY_ELEM == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(keys) + r0); kraw[0] = t.x; kraw[1] = t.y; }
+            else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(keys) + r0); kraw[0] = t.x; kraw[1] = t.y; }
+        } else if (r0 < n) {
+            kraw[0] = KEY_ELEM == 8 ? reinterpret_cast<const uint64_t*>(keys)[r0] : (uint64_t)reinterpret_cast<const uint32_t*>(keys)[r0];
+        }
+        uint32_t h[2] = {J_NONE, J_NONE};
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int64_t row = r0 + j;
+            if (row >= n) continue;
+            bool v = true;
+            if (KEY_NULLS) v = bit_get(valid, row);
+            uint64_t key = kraw[j];
+            if (KEY_CANON == 1) key = canonical_f64_bits(__longlong_as_double((long long)key));
+            if (KEY_CANON == 2) key = canonical_f32_bits(__uint_as_float((uint32_t)key));
+            uint64_t slot; bool hit = false; uint4 e;
+            if (!v) { slot = T.cap; if (nulls_equal) { e = __ldg(&T.entries[slot]); hit = e.w != 0; } }
+            else if (key == J_EMPTY) { slot = T.cap + 1; e = __ldg(&T.entries[slot]); hit = e.w != 0; }
+            else {
+                slot = __umul64hi(dirty_hash(key), T.cap);
+                while (true) {
+                    e = __ldg(&T.entries[slot]);
+                    const uint64_t k = ((uint64_t)e.y << 32) | e.x;
+                    if (k == key) { hit = true; break; }
+                    if (k == J_EMPTY) break;
+                    if (++slot == T.cap) slot = 0;
+                }
+            }
+            if (hit) { h[j] = csr_mode ? (uint32_t)slot : e.z; cnt += csr_mode ? e.w : 1u; }
+            else if (left_join) cnt += 1u;
+        }
+        if (r0 + 1 < n) *reinterpret_cast<uint2*>(handle + r0) = make_uint2(h[0], h[1]);
+        else if (r0 < n) handle[r0] = h[0];
+        // 32 lanes x 2 rows = 64 consecutive rows: always inside one J_TILE
+        uint32_t c = cnt;
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane_id() == 0 && c) { atomicAdd(&tile_counts[(r0) / J_TILE], c); atomicAdd(total, (unsigned long long)c); }
+    }
+}
+
+// ---------------------------------------------------------------------------- K8 probe, pass 2 (emit)
+// thread t of the CTA owns rows [tile*2048 + 8t, +8): thread-local exclusive counts, CTA scan, then
+// contiguous writes.
+__global__ void __launch_bounds__(256) k_join_emit(JoinTableDev T, const uint32_t* __restrict__ handle, int64_t n, int csr_mode, int left_join,
+                                                   const uint32_t* __restrict__ sorted_rows, const uint64_t* __restrict__ tile_off,
+                                                   uint32_t* __restrict__ out_probe, uint32_t* __restrict__ out_build) {
+    __shared__ uint32_t ws[8];
+    const int64_t ntiles = (n + J_TILE - 1) / J_TILE;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t r0 = t * J_TILE + (int64_t)threadIdx.x * 8;
+        uint32_t h[8], c[8], off[8];
+        if (r0 + 7 < n) {
+            uint4 a = *reinterpret_cast<const uint4*>(handle + r0), b = *reinterpret_cast<const uint4*>(handle + r0 + 4);
+            h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) h[k] = r0 + k < n ? handle[r0 + k] : J_NONE;
+        }
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t ck = 0;
+            if (r0 + k < n) {
+                if (h[k] != J_NONE) {
+                    if (csr_mode) { uint4 e = __ldg(&T.entries[h[k]]); ck = e.w; off[k] = e.z; } else ck = 1;
+                } else if (left_join) ck = 1;
+            }
+            c[k] = ck; mine += ck;
+        }
+        uint32_t x = mine;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane_id() >= (unsigned)o) x += y; }
+        if (lane_id() == 31) ws[threadIdx.x >> 5] = x;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (unsigned w = 0; w < (threadIdx.x >> 5); w++) wbase += ws[w];
+        uint64_t pos = tile_off[t] + wbase + x - mine;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (c[k] == 0) continue;
+            const uint32_t pi = (uint32_t)(r0 + k);
+            if (h[k] == J_NONE) { out_probe[pos] = pi; out_build[pos] = J_NONE; pos++; }
+            else if (!csr_mode) { out_probe[pos] = pi; out_build[pos] = h[k]; pos++; }
+            else for (uint32_t j = 0; j < c[k]; j++) { out_probe[pos] = pi; out_build[pos] = sorted_rows[off[k] + j]; pos++; }
+        }
+        __syncthreads();
+    }
+}
+
+template <int KEY_ELEM, int KEY_CANON>
+static void launch_probe(bool kn, int grid, JoinTableDev T, const DevCol& probe, int nulls_equal, int csr, int left, uint32_t* handle, uint32_t* tc, unsigned long long* total) {
+    if (kn) PLB_LAUNCH("k8_join_probe", (k_join_probe<KEY_ELEM, KEY_CANON, true>), grid, 256, 0, T, probe.v(), probe.vm(), probe.len, nulls_equal, csr, left, handle, tc, total);
+    else PLB_LAUNCH("k8_join_probe", (k_join_probe<KEY_ELEM, KEY_CANON, false>), grid, 256, 0, T, probe.v(), probe.vm(), probe.len, nulls_equal, csr, left, handle, tc, total);
+}
+
+static DevCol idx_col(DevPtr p, int64_t n, int64_t null_count) { DevCol c; c.dtype = BL_UINT32; c.len = n; c.values = p; c.null_count = null_count; return c; }
+
+JoinResult op_hash_join(const DevCol& left, const DevCol& right, int how, bool nulls_equal, int maintain_order) {
+    PLB_REQUIRE(how == BL_JOIN_INNER || how == BL_JOIN_LEFT, BL_ERR_UNSUPPORTED, "join: only inner and left joins are on the hot path");
+    PLB_REQUIRE(left.dtype == right.dtype, BL_ERR_DTYPE, std::string("join: key dtypes differ (") + dtype_name(left.dtype) + " vs " + dtype_name(right.dtype) + ")");   // join/mod.rs:231-241
+    const int dt = left.dtype;
+    PLB_REQUIRE(dt == BL_INT64 || dt == BL_UINT64 || dt == BL_INT32 || dt == BL_UINT32 || dt == BL_FLOAT64 || dt == BL_FLOAT32, BL_ERR_UNSUPPORTED,
+                std::string("join: key dtype ") + dtype_name(dt) + " is outside the hot path");
+    PLB_REQUIRE(left.len < 0xFFFFFFFFll && right.len < 0xFFFFFFFFll, BL_ERR_UNSUPPORTED, "join: more than 2^32-2 rows (IdxSize = u32)");
+    // hash_join/mod.rs:41-50: probe the longer relation; on a tie the right side probes (swapped)
+    const bool swapped = how == BL_JOIN_INNER && !(left.len > right.len);
+    const DevCol& probe = swapped ? right : left;
+    const DevCol& build = swapped ? left : right;
+    const int64_t nb = build.len, np = probe.len;
+    Context& c = ctx();
+
+    // ---- build
+    JoinTableDev T; T.cap = (uint64_t)std::max<int64_t>(2 * nb, 16);
+    DevPtr entries = dev_alloc((size_t)(T.cap + 2) * 16);
+    T.entries = as<uint4>(entries);
+    PLB_LAUNCH("k7_join_init", k_join_init, grid_for((int64_t)T.cap + 2, 256), 256, 0, T.entries, (int64_t)T.cap + 2);
+    DevPtr slot_of_row = dev_alloc((size_t)std::max<int64_t>(nb, 1) * 4), has_dups = dev_alloc(4);
+    dev_memset(has_dups->p, 0, 4);
+    if (nb > 0)
+        PLB_LAUNCH("k7_join_build", k_join_build, grid_for(nb, 256), 256, 0, T, build.v(), build.vm(), dt, nb, nulls_equal ? 1 : 0, as<uint32_t>(slot_of_row), as<int>(has_dups));
+    const bool csr = nb > 0 && read_scalar(as<int>(has_dups)) != 0;
+    DevPtr sorted_rows;
+    if (csr) {
+        const int64_t ne = (int64_t)T.cap + 2, ntiles = (ne + J_TILE - 1) / J_TILE;
+        DevPtr sums = dev_alloc((size_t)ntiles * 4), offs = dev_alloc((size_t)ntiles * 8);
+        PLB_LAUNCH("k7_tile_sums", k_join_tile_sums, grid_for(ntiles * 256, 256), 256, 0, T.entries, ne, as<uint32_t>(sums));
+        exclusive_scan_u32_to_u64(as<uint32_t>(sums), as<uint64_t>(offs), ntiles, nullptr);
+        PLB_LAUNCH("k7_csr_offsets", k_join_csr_offsets, grid_for(ntiles * 256, 256), 256, 0, T.entries, ne, as<uint64_t>(offs));
+        // ascending row lists: stable sort of the build rows by entry index (skipped null rows sort last)
+        sorted_rows = dev_alloc((size_t)nb * 4);
+        iota_u32(as<uint32_t>(sorted_rows), nb, 0);
+        sort_pairs_u32(as<uint32_t>(slot_of_row), as<uint32_t>(sorted_rows), nb);
+    }
+
+    // ---- probe pass 1
+    const int64_t ntiles = (np + J_TILE - 1) / J_TILE;
+    DevPtr handle = dev_alloc((size_t)std::max<int64_t>(np, 1) * 4 + 16), tc = dev_alloc((size_t)std::max<int64_t>(ntiles, 1) * 4), toff = dev_alloc((size_t)std::max<int64_t>(ntiles, 1) * 8), total = dev_alloc(8);
+    dev_memset(tc->p, 0, (size_t)std::max<int64_t>(ntiles, 1) * 4); dev_memset(total->p, 0, 8);
+    uint64_t M = 0;
+    if (np > 0) {
+        const int grid = grid_for((np + 1) / 2, 256);
+        const bool kn = probe.validity != nullptr;
+        const int left_join = how == BL_JOIN_LEFT ? 1 : 0;
+        uint32_t* hp = as<uint32_t>(handle); uint32_t* tcp = as<uint32_t>(tc); unsigned long long* tp = as<unsigned long long>(total);
+        if (dt == BL_FLOAT64) launch_probe<8, 1>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp, tp);
+        else if (dt == BL_FLOAT32) launch_probe<4, 2>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp, tp);
+        else if (dtype_size(dt) == 8) launch_probe<8, 0>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp, tp);
+        else launch_probe<4, 0>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp, tp);
+        exclusive_scan_u32_to_u64(as<uint32_t>(tc), as<uint64_t>(toff), ntiles, nullptr);
+        M = read_scalar(as<unsigned long long>(total));
+    }
+    PLB_REQUIRE(M < 0xFFFFFFFFull, BL_ERR_UNSUPPORTED, "join: result has more than 2^32-2 rows (IdxSize = u32)");
+
+    // ---- probe pass 2
+    DevPtr out_probe = dev_alloc((size_t)std::max<uint64_t>(M, 1) * 4 + 16), out_build = dev_alloc((size_t)std::max<uint64_t>(M, 1) * 4 + 16);
+    if (M > 0)
+        PLB_LAUNCH("k8_join_emit", k_join_emit, (int)std::min<int64_t>(ntiles, (int64_t)c.sm_count * 8), 256, 0, T, as<uint32_t>(handle), np, csr ? 1 : 0, how == BL_JOIN_LEFT ? 1 : 0,
+                   as<uint32_t>(sorted_rows), as<uint64_t>(toff), as<uint32_t>(out_probe), as<uint32_t>(out_build));
+
+    JoinResult r;
+    r.left = idx_col(swapped ? out_build : out_probe, (int64_t)M, 0);
+    r.right = idx_col(swapped ? out_probe : out_build, (int64_t)M, how == BL_JOIN_LEFT ? -1 : 0);
+    // maintain_order (join/mod.rs:577-642): stable sort on the requested side unless already in that order
+    if (how == BL_JOIN_INNER && maintain_order != BL_ORDER_NONE && M > 1) {
+        const bool by_left = maintain_order == BL_ORDER_LEFT || maintain_order == BL_ORDER_LEFT_RIGHT;
+        const bool left_sorted = !swapped;
+        if (by_left && !left_sorted) sort_pairs_u32(as<uint32_t>(r.left.values), as<uint32_t>(r.right.values), (int64_t)M);
+        else if (!by_left && !swapped) sort_pairs_u32(as<uint32_t>(r.right.values), as<uint32_t>(r.left.values), (int64_t)M);
+    }
+    if (how == BL_JOIN_LEFT && M > 0) {
+        // Arrow-proper validity for the nullable right index: bit = (idx != BL_IDX_NULL)
+        DevCol none = make_col(BL_UINT32, 1, false);
+        const uint32_t nv = J_NONE;
+        PLB_CUDA(cudaMemcpyAsync(none.values->p, &nv, 4, cudaMemcpyHostToDevice, c.stream));
+        PLB_CUDA(cudaStreamSynchronize(c.stream));
+        DevCol m = op_compare(BL_CMP_NE, r.right, none, false);
+        r.right.validity = m.values;
+        r.right.null_count = -1;
+    }
+    return r;
+}
+
+}  // namespace plb
