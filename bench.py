@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — the hot path on synthetic data, one JSON line (contract: task brief).
+
+Default workload = BASELINE.json configs[1] (C2): hash group_by over 1e8 rows, 1e6 uniform Int64 keys,
+aggregations sum(v_i64), mean(v_f64), len, on ONE B200; inputs (2.4 GB) are larger than L2 (126 MB), so
+no explicit L2 flush is needed between timed iterations.
+
+  value     rows/s, whole job, inputs resident in HBM when the timed region starts, through the C ABI
+            with BL_DEVICE columns (estimate + table init + fused build/aggregate + extraction).
+  e2e       same call with BL_HOST columns in pinned memory: H2D of the three columns and D2H of the
+            result inside the timed region.
+  roofline  dominant kernel (k5_groupby_agg): algorithmic bytes (24 B/row) / its CUDA-event duration
+            on the library stream, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the CPU oracle (restatement of the reference's Rayon algorithm, "port") on the host
+            cores over a bounded sample.
+
+--workload join: configs[2] (C3) inner hash join 1e8 x 1e7 on Int64 (single GPU here).
+--gpus N (torchrun): weak scaling, every rank owns --rows rows; local pre-aggregation, hash partition of
+the partial aggregates, ONE all-to-all (NCCL), final merge.
+--impl reference: the oracle on the host cores (the reference itself cannot be installed: Rust, no
+toolchain/wheel — see DESIGN.md), same metric/config, bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="groupby", choices=["groupby", "join"])
+    ap.add_argument("--rows", type=int, default=100_000_000)
+    ap.add_argument("--keys", type=int, default=1_000_000)
+    ap.add_argument("--build-rows", type=int, default=10_000_000)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=20_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def gen_groupby(rows: int, keys: int, seed: int):
+    """uniform keys, v_i64 in [-1000,1000), v_f64 = U(0,100).round(6) (h2oai v3)."""
+    rng = np.random.default_rng(seed)
+    key = rng.integers(0, keys, rows, dtype=np.int64)
+    vi = rng.integers(-1000, 1000, rows, dtype=np.int64)
+    vf = rng.uniform(0, 100, rows).round(6)
+    return key, vi, vf
+
+
+def gen_join(rows: int, build_rows: int, seed: int):
+    """C3: build = permutation(build_rows) (unique keys), probe keys uniform in [0, build_rows): 100 % hit."""
+    rng = np.random.default_rng(seed)
+    build = rng.permutation(build_rows).astype(np.int64)
+    probe = rng.integers(0, build_rows, rows, dtype=np.int64)
+    return probe, build
+
+
+# ------------------------------------------------------------------------------------- reference arm
+def run_reference(a):
+    import oracle
+    oracle.build()
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = oracle.max_threads()
+    sample = min(a.rows, a.cpu_sample)
+    if a.workload == "groupby":
+        key, vi, vf = gen_groupby(sample, a.keys, 1)
+        aggs = [("sum", vi, None), ("mean", vf, None), ("len", None, None)]
+        fn = lambda: oracle.group_by_agg(key, None, aggs, cores, False)   # noqa: E731
+        unit_rows = sample
+        metric, wl = "group_by_agg_rows_per_sec", f"C2 hash group_by {a.rows} rows, {a.keys} Int64 keys, sum(i64)/mean(f64)/len"
+    else:
+        build_rows = max(1, int(a.build_rows * sample / a.rows))
+        probe, build = gen_join(sample, build_rows, 2)
+        fn = lambda: oracle.hash_join(probe, build, None, None, "inner", False, "none", cores)   # noqa: E731
+        unit_rows = sample
+        metric, wl = "hash_join_probe_rows_per_sec", f"C3 inner hash join {a.rows} x {a.build_rows} Int64"
+    for _ in range(min(a.warmup, 1)):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        fn()
+    dt = (time.perf_counter() - t0) / a.steps
+    v = unit_rows / dt
+    line = {"impl": "reference", "metric": metric, "value": v, "unit": "rows/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1),
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/float64", "data": "synthetic",
+            "config": {"workload": wl, "sample_rows_per_step": sample},
+            "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} rows/step of the same workload; oracle = C restatement of the reference's partitioned Rayon algorithm (not Polars itself: no Rust toolchain / wheel)"},
+            "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------- B200 arm
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    import torch
+    import torch.distributed as dist
+    import polars_b200 as plb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    plb.init(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ext = torch.cuda.ExternalStream(plb.stream(), device=torch.device("cuda", local))
+    peak_gbs, peak_src = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        plb.sync()
+
+    if a.workload == "groupby":
+        key, vi, vf = gen_groupby(a.rows, a.keys, 1 + rank)
+        hkey, hvi, hvf = plb.to_pinned(key), plb.to_pinned(vi), plb.to_pinned(vf)
+        dkey, dvi, dvf = plb.to_device(key), plb.to_device(vi), plb.to_device(vf)
+        del key, vi, vf
+        spec = [("sum", np.int64), ("mean", np.float64), ("len", None)]
+        out_bytes = 0
+
+        def step_device():
+            nonlocal out_bytes
+            if world == 1:
+                ok, outs = plb.group_by_agg(dkey.view(), [("sum", dvi.view()), ("mean", dvf.view()), ("len", None)], False, location=plb.DEVICE)
+                out_bytes = ok.length * (8 + 8 + 8 + 4)
+                return ok.length
+            # partitioned plan: local pre-aggregation -> hash partition of partials -> one all-to-all -> merge
+            g = plb.GroupBy(np.int64, spec)
+            g.consume(dkey.view(), [dvi.view(), dvf.view(), None], row_base=0)
+            ptr, rw, offs = g.export_partials(world)
+            counts = torch.tensor(np.diff(offs), dtype=torch.int64, device="cuda")
+            rcounts = torch.empty_like(counts)
+            dist.all_to_all_single(rcounts, counts)
+            rc = rcounts.cpu().numpy()
+            send = torch.as_tensor(_CudaArray(ptr, int(offs[-1]) * rw), device="cuda") if offs[-1] else torch.empty(0, dtype=torch.int64, device="cuda")
+            recv = torch.empty(int(rc.sum()) * rw, dtype=torch.int64, device="cuda")
+            dist.all_to_all_single(recv, send, output_split_sizes=(rc * rw).tolist(), input_split_sizes=(np.diff(offs) * rw).tolist())
+            torch.cuda.synchronize()
+            f = plb.GroupBy(np.int64, spec, expected_groups=max(int(rc.sum()), 1))
+            f.merge_partials(recv.data_ptr(), int(rc.sum()))
+            ok, outs = f.finish(False, location=plb.DEVICE)
+            plb.dev_free(ptr)
+            out_bytes = ok.length * 28
+            return ok.length
+
+        def step_e2e():
+            (k, _), outs = plb.group_by_agg(plb.Column(hkey), [("sum", plb.Column(hvi)), ("mean", plb.Column(hvf)), ("len", None)], False, location=plb.HOST)
+            return k.size, k.nbytes + sum(o[0].nbytes for o in outs)
+
+        unit_rows = a.rows
+        alg_bytes_per_row = 24.0
+        dominant = "k5_groupby_agg"
+        metric = "group_by_agg_rows_per_sec"
+        wl = f"C2 hash group_by {a.rows} rows/GPU, {a.keys} uniform Int64 keys, sum(v_i64)/mean(v_f64)/len; inputs 2.4 GB > L2 (no flush needed)"
+        h2d = a.rows * 24
+    else:
+        probe, build = gen_join(a.rows, a.build_rows, 2 + rank)
+        hp, hb = plb.to_pinned(probe), plb.to_pinned(build)
+        dp, db = plb.to_device(probe), plb.to_device(build)
+        del probe, build
+
+        def step_device():
+            li, ri = plb.hash_join(dp.view(), db.view(), "inner", False, "none", location=plb.DEVICE)
+            return li.length
+
+        def step_e2e():
+            (li, _), (ri, _) = plb.hash_join(plb.Column(hp), plb.Column(hb), "inner", False, "none", location=plb.HOST)
+            return li.size, li.nbytes + ri.nbytes
+
+        unit_rows = a.rows
+        alg_bytes_per_row = 16.0
+        dominant = "k8_join_probe"
+        metric = "hash_join_probe_rows_per_sec"
+        wl = f"C3 inner hash join: probe {a.rows} x build {a.build_rows} unique Int64 keys, 100% hit; outputs (left_idx,right_idx) u32"
+        h2d = (a.rows + a.build_rows) * 8
+
+    # ---- warm-up, then the timed region (device-resident inputs)
+    for _ in range(max(a.warmup, 3)):
+        n_out = step_device()
+    barrier()
+    plb.profile_reset()
+    plb.profile_enable(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    with torch.cuda.stream(ext):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            n_out = step_device()
+        e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = plb.profile()
+    launches = plb.launch_count()
+    plb.profile_enable(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / a.steps
+    value = unit_rows * world / (ms_per_step / 1e3)
+
+    # ---- end to end through the C ABI with pinned host buffers (H2D + compute + D2H per step)
+    e2e_vals, d2h = [], 0
+    for i in range(a.e2e_steps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        _, d2h = step_e2e()
+        dt = time.perf_counter() - t0
+        if i > 0:
+            e2e_vals.append(dt)
+    te = torch.tensor([float(np.mean(e2e_vals)) if e2e_vals else 0.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    dom = prof.get(dominant, {"launches": 0, "ms": 0.0})
+    dom_ms = dom["ms"] / max(dom["launches"], 1)
+    achieved = (alg_bytes_per_row * unit_rows / 1e9) / (dom_ms / 1e3) if dom_ms > 0 else 0.0
+    total_kernel_ms = sum(v["ms"] for v in prof.values()) / a.steps
+    line = {
+        "metric": metric, "value": value, "unit": "rows/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/float64", "data": "synthetic",
+        "config": {"workload": wl, "rows_per_gpu": a.rows, "groups_out": int(n_out), "l2_policy": "inputs larger than L2",
+                   "parallelism": "single GPU" if world == 1 else f"hash-partitioned x{world}: local pre-agg + one NCCL all-to-all of partial aggregates + merge"},
+        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs if peak_gbs else None,
+                     "traffic": None, "peak_source": peak_src, "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes_per_row * unit_rows,
+                     "kernel_share_of_step": (dom_ms / total_kernel_ms) if total_kernel_ms else None},
+        "kernels_ms_per_step": {k: v["ms"] / a.steps for k, v in prof.items()},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "e2e": {"value": unit_rows * world / e2e_s if e2e_s else None, "unit": "rows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
+                "path": "bl_groupby_agg / bl_hash_join with BL_HOST columns in pinned memory -> BL_HOST outputs"},
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(a)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class _CudaArray:
+    """Zero-copy view of a raw device pointer for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr: int, n_words: int):
+        self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+def cpu_baseline(a):
+    import oracle
+    oracle.build()
+    cores = oracle.max_threads()
+    sample = min(a.rows, a.cpu_sample)
+    if a.workload == "groupby":
+        key, vi, vf = gen_groupby(sample, a.keys, 1)
+        aggs = [("sum", vi, None), ("mean", vf, None), ("len", None, None)]
+        t0 = time.perf_counter()
+        oracle.group_by_agg(key, None, aggs, cores, False)
+        dt = time.perf_counter() - t0
+    else:
+        probe, build = gen_join(sample, max(1, int(a.build_rows * sample / a.rows)), 2)
+        t0 = time.perf_counter()
+        oracle.hash_join(probe, build, None, None, "inner", False, "none", cores)
+        dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "rows/s", "cores": cores, "kind": "port",
+            "sample": f"{sample} rows of the same workload, one pass; oracle = C/OpenMP restatement of the reference's partitioned algorithm (the Rust reference cannot be built here)"}
+
+
+if __name__ == "__main__":
+    main()

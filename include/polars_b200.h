@@ -176,9 +176,11 @@ bl_status bl_hash_partition(const bl_column* key, const bl_column* payload, int3
 
 /* ---- streaming group_by state (device-resident; used for chunked H2D overlap and multi-GPU) */
 typedef struct bl_groupby bl_groupby;
-/* key_dtype / value dtypes fix the plan; expected_groups <= 0 lets the library estimate. */
+/* key_dtype / value dtypes fix the plan; expected_groups <= 0 lets the library estimate.
+ * track_first != 0 records each group's first row index (one extra 32-bit atomic per row); it is
+ * required for bl_groupby_finish(maintain_order != 0). */
 bl_status bl_groupby_create(int32_t key_dtype, const int32_t* agg_kinds, const int32_t* value_dtypes, int32_t n_aggs,
-                            int64_t expected_groups, bl_groupby** out);
+                            int64_t expected_groups, int32_t track_first, bl_groupby** out);
 /* Accumulate one batch: key + one value column per agg (values[i] ignored for LEN).  Columns may
  * be BL_HOST or BL_DEVICE.  row_base = global index of the batch's first row. */
 bl_status bl_groupby_consume(bl_groupby* g, const bl_column* key, const bl_column* values, int64_t row_base);

@@ -444,6 +444,10 @@ void or_agg_sum_i32(const int32_t* v, const uint8_t* valid, const uint64_t* offs
         out[g] = (int32_t)s;
     }
 }
+void or_agg_sum_u64(const uint64_t* v, const uint8_t* valid, const uint64_t* offsets, const idx_t* idx,
+                    int64_t G, uint64_t* out) { or_agg_sum_i64((const int64_t*)v, valid, offsets, idx, G, (int64_t*)out); }
+void or_agg_sum_u32(const uint32_t* v, const uint8_t* valid, const uint64_t* offsets, const idx_t* idx,
+                    int64_t G, uint32_t* out) { or_agg_sum_i32((const int32_t*)v, valid, offsets, idx, G, (int32_t*)out); }
 void or_agg_sum_f64(const double* v, const uint8_t* valid, const uint64_t* offsets, const idx_t* idx,
                     int64_t G, double* out) {
 #pragma omp parallel for schedule(static)
@@ -491,6 +495,8 @@ void or_agg_sum_f32(const float* v, const uint8_t* valid, const uint64_t* offset
     }
 DEF_AGG_MEAN(or_agg_mean_i64, int64_t)
 DEF_AGG_MEAN(or_agg_mean_i32, int32_t)
+DEF_AGG_MEAN(or_agg_mean_u64, uint64_t)
+DEF_AGG_MEAN(or_agg_mean_u32, uint32_t)
 DEF_AGG_MEAN(or_agg_mean_f64, double)
 DEF_AGG_MEAN(or_agg_mean_f32, float)   /* caller casts the f64 result back to f32 (:976) */
 
@@ -514,6 +520,10 @@ DEF_AGG_MINMAX(or_agg_min_i64, int64_t, MIN_INT)
 DEF_AGG_MINMAX(or_agg_max_i64, int64_t, MAX_INT)
 DEF_AGG_MINMAX(or_agg_min_i32, int32_t, MIN_INT)
 DEF_AGG_MINMAX(or_agg_max_i32, int32_t, MAX_INT)
+DEF_AGG_MINMAX(or_agg_min_u64, uint64_t, MIN_INT)
+DEF_AGG_MINMAX(or_agg_max_u64, uint64_t, MAX_INT)
+DEF_AGG_MINMAX(or_agg_min_u32, uint32_t, MIN_INT)
+DEF_AGG_MINMAX(or_agg_max_u32, uint32_t, MAX_INT)
 DEF_AGG_MINMAX(or_agg_min_f64, double, fmin)     /* f64::min == IEEE minNum == C fmin */
 DEF_AGG_MINMAX(or_agg_max_f64, double, fmax)
 DEF_AGG_MINMAX(or_agg_min_f32, float, fminf)

@@ -394,7 +394,7 @@ def hash_partition(key, payload: Sequence, n_partitions: int, location: int = HO
 class GroupBy:
     """Streaming group_by state (bl_groupby_*): consume batches, exchange partial aggregates, finish."""
 
-    def __init__(self, key_dtype, aggs: Sequence, expected_groups: int = 0):
+    def __init__(self, key_dtype, aggs: Sequence, expected_groups: int = 0, track_first: bool = False):
         """aggs: [(kind, value_dtype | None)]"""
         self.kinds = [AGGS[k] for k, _ in aggs]
         dts = [DTYPES[np.dtype(d)] if d is not None else 3 for _, d in aggs]
@@ -402,7 +402,7 @@ class GroupBy:
         self.n = n
         self.h = C.c_void_p()
         _check(lib().bl_groupby_create(C.c_int32(DTYPES[np.dtype(key_dtype)]), (C.c_int32 * max(n, 1))(*self.kinds), (C.c_int32 * max(n, 1))(*dts),
-                                       C.c_int32(n), C.c_int64(expected_groups), C.byref(self.h)))
+                                       C.c_int32(n), C.c_int64(expected_groups), C.c_int32(int(track_first)), C.byref(self.h)))
 
     def consume(self, key, values: Sequence, row_base: int = 0):
         k = _as_col(key)

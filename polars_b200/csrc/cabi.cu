@@ -102,7 +102,7 @@ bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, cons
         vptr[i] = &vals[i];
         dts.push_back(vals[i].dtype);
     }
-    GroupByState st(key.dtype, kinds, dts, 0);
+    GroupByState st(key.dtype, kinds, dts, 0, maintain_order != 0 || dtype_is_float(key.dtype));
     st.consume_all(key, vptr);
     DevCol ok; std::vector<DevCol> oa;
     st.finish(maintain_order != 0, &key, ok, oa);
@@ -152,11 +152,11 @@ bl_status bl_hash_partition(const bl_column* key, const bl_column* payload, int3
 // ---- streaming group_by state ---------------------------------------------------------------
 struct bl_groupby { GroupByState* st; };
 
-bl_status bl_groupby_create(int32_t key_dtype, const int32_t* agg_kinds, const int32_t* value_dtypes, int32_t n_aggs, int64_t expected_groups, bl_groupby** out) {
+bl_status bl_groupby_create(int32_t key_dtype, const int32_t* agg_kinds, const int32_t* value_dtypes, int32_t n_aggs, int64_t expected_groups, int32_t track_first, bl_groupby** out) {
     BL_TRY
     PLB_REQUIRE(out && (n_aggs == 0 || (agg_kinds && value_dtypes)), BL_ERR_INVALID, "groupby_create: null argument");
     std::vector<int> k(agg_kinds, agg_kinds + n_aggs), d(value_dtypes, value_dtypes + n_aggs);
-    auto* g = new bl_groupby{new GroupByState(key_dtype, k, d, expected_groups)};
+    auto* g = new bl_groupby{new GroupByState(key_dtype, k, d, expected_groups, track_first != 0)};
     *out = g;
     BL_CATCH
 }

@@ -417,7 +417,7 @@ static int sum_out_dtype(int dt) {
     return dt;
 }
 
-GroupByState::GroupByState(int key_dt, const std::vector<int>& kinds, const std::vector<int>& dtypes, int64_t expected)
+GroupByState::GroupByState(int key_dt, const std::vector<int>& kinds, const std::vector<int>& dtypes, int64_t expected, bool track_first)
     : key_dtype(key_dt), agg_kinds(kinds), agg_dtypes(dtypes), expected_groups(expected) {
     PLB_REQUIRE(key_dt == BL_INT64 || key_dt == BL_UINT64 || key_dt == BL_INT32 || key_dt == BL_UINT32 || key_dt == BL_FLOAT64 || key_dt == BL_FLOAT32,
                 BL_ERR_UNSUPPORTED, std::string("group_by: key dtype ") + dtype_name(key_dt) + " is outside the hot path");
@@ -443,7 +443,7 @@ GroupByState::GroupByState(int key_dt, const std::vector<int>& kinds, const std:
     }
     L.n_words = nw;
     L.stride = ((2 + nw + 3) / 4) * 4;      // whole 32-byte sectors per entry
-    L.need_first = 1;                        // needed for maintain_order and for float key output; one 32-bit RED
+    L.need_first = track_first ? 1 : 0;      // maintain_order / first-occurrence key output; costs one 32-bit RED per row
     status = dev_alloc(4);
 }
 
@@ -629,6 +629,7 @@ DevPtr GroupByState::export_partials(int n_partitions, int* row_words_out, int64
 
 void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather, DevCol& out_key, std::vector<DevCol>& out_aggs) {
     out_aggs.clear();
+    PLB_REQUIRE(!maintain_order || L.need_first, BL_ERR_INVALID, "group_by: maintain_order needs a state created with track_first");
     int64_t G = entries ? count_groups() : 0;
     const int kelem = dtype_size(key_dtype);
     DevPtr keys = dev_alloc((size_t)std::max<int64_t>(G, 1) * 8), first = dev_alloc((size_t)std::max<int64_t>(G, 1) * 4), len = dev_alloc((size_t)std::max<int64_t>(G, 1) * 4);
@@ -660,7 +661,7 @@ void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather,
     }
     // float keys (and any key when the column is at hand): output = key at the group's first row
     // (group_by/mod.rs:258-266) so that -0.0 / NaN payloads of the first occurrence survive
-    const bool gather_keys = key_col_for_gather != nullptr && dtype_is_float(key_dtype) && G > 0;
+    const bool gather_keys = key_col_for_gather != nullptr && dtype_is_float(key_dtype) && G > 0 && L.need_first;
     DevCol first_col; first_col.dtype = BL_UINT32; first_col.len = G; first_col.values = first; first_col.null_count = 0;
     if (gather_keys) {
         std::vector<DevCol> in{*key_col_for_gather}, outv;

@@ -43,7 +43,7 @@ struct GroupByState {
     uint64_t cap = 0;
     int64_t rows_seen = 0;
 
-    GroupByState(int key_dt, const std::vector<int>& kinds, const std::vector<int>& dtypes, int64_t expected);
+    GroupByState(int key_dt, const std::vector<int>& kinds, const std::vector<int>& dtypes, int64_t expected, bool track_first);
     void consume_all(const DevCol& key, const std::vector<const DevCol*>& values);
     void consume(const DevCol& key, const std::vector<const DevCol*>& values, int64_t row_base);
     void merge_partials(const uint64_t* rows, int64_t n_rows);

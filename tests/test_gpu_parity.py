@@ -1,0 +1,470 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs, the reference's golden vectors, and size-independent properties.
+Integer / index results must be bit-exact; float aggregates within 1e-6 relative."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import IDX_NULL, assert_close, pairs_sorted, run_group_by_kat, run_join_kat, sort_groups
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def plb():
+    import polars_b200 as m
+    m.init()
+    return m
+
+
+class GpuImpl:
+    def __init__(self, plb):
+        self.plb = plb
+
+    def group_by_agg(self, key, key_valid, aggs, maintain_order):
+        cols = {}
+        specs = []
+        for kind, vals, valid in aggs:
+            if kind == "len":
+                specs.append(("len", None))
+                continue
+            k = (id(vals), id(valid))
+            if k not in cols:
+                cols[k] = self.plb.Column(vals, valid)
+            specs.append((kind, cols[k]))
+        (k, kv), outs = self.plb.group_by_agg(self.plb.Column(key, key_valid), specs, maintain_order)
+        return k, kv, outs
+
+    def hash_join(self, lk, rk, lvalid=None, rvalid=None, how="inner", nulls_equal=False, maintain_order="none"):
+        (li, _), (ri, _) = self.plb.hash_join(self.plb.Column(lk, lvalid), self.plb.Column(rk, rvalid), how, nulls_equal, maintain_order)
+        return li, ri
+
+
+# ------------------------------------------------------------------ golden vectors
+def test_group_by_kats(plb, kats):
+    for case in kats["group_by"]:
+        run_group_by_kat(GpuImpl(plb), case)
+
+
+def test_join_kats(plb, kats):
+    for case in kats["join"]:
+        c = dict(case)
+        c["threads"] = [None]
+        run_join_kat(GpuImpl(plb), c)
+
+
+def test_hash_partition_kat(plb, kats):
+    vecs = kats["hash"][0]["vectors"]
+    keys = np.array([int(v["key_u64"]) for v in vecs], dtype=np.uint64)
+    payload = np.arange(keys.size, dtype=np.int64)
+    for P in (1, 2, 3, 7, 8, 16):
+        (k, _), [(pl, _)], offs = plb.hash_partition(keys, [payload], P)
+        exp_part = np.array([v["part"][str(P)] for v in vecs])
+        assert offs[-1] == keys.size
+        for p in range(P):
+            got = sorted(pl[offs[p]:offs[p + 1]].tolist())
+            assert got == sorted(np.nonzero(exp_part == p)[0].tolist()), (P, p)
+            assert np.array_equal(keys[pl[offs[p]:offs[p + 1]]], k[offs[p]:offs[p + 1]])
+
+
+# ------------------------------------------------------------------ elementwise / compare
+@pytest.mark.parametrize("dtype", ["int64", "int32", "uint64", "uint32", "float64", "float32"])
+@pytest.mark.parametrize("n", [0, 1, 7, 255, 1000, 100_003])
+def test_elementwise_vs_oracle(plb, dtype, n):
+    rng = np.random.default_rng(n + 17)
+    dt = np.dtype(dtype)
+    if dt.kind == "f":
+        a = rng.normal(0, 100, n).astype(dt)
+        b = rng.normal(0, 100, n).astype(dt)
+        if n > 40:
+            b[::17] = 0
+            a[::31] = np.nan
+            a[5], b[5] = np.inf, -np.inf
+    else:
+        lo = 0 if dt.kind == "u" else -1000
+        a = rng.integers(lo, 1000, n).astype(dt)
+        b = rng.integers(lo, 1000, n).astype(dt)
+        if n > 40:
+            b[::17] = 0
+            if dt.kind == "i":
+                a[0], b[0] = np.iinfo(dt).min, -1
+    av = (rng.random(n) > 0.1) if n else None
+    bv = (rng.random(n) > 0.2) if n else None
+    for op in ("add", "sub", "mul", "floordiv", "mod", "truediv"):
+        for (l, lv, r, rv) in [(a, av, b, bv), (a, None, b, None)]:
+            exp, expv = oracle.arith(op, l, r, lv, rv)
+            got, gotv = plb.elementwise(op, (l, lv), (r, rv))
+            assert got.dtype == exp.dtype, (op, got.dtype, exp.dtype)
+            if dt.kind == "f" or op == "truediv":
+                assert np.array_equal(got.view(np.uint8), exp.view(np.uint8)) or np.array_equal(got, exp, equal_nan=True), op
+            else:
+                assert np.array_equal(got, exp), op
+            ev = np.ones(n, bool) if expv is None else expv
+            gv = np.ones(n, bool) if gotv is None else gotv
+            assert np.array_equal(gv, ev), op
+        if n == 0:
+            continue
+        for s in ([3, 0, -1] if dt.kind == "i" else [3, 0]):
+            sc = dt.type(s)
+            exp, expv = oracle.arith(op, a, sc, av, None)
+            got, gotv = plb.elementwise(op, (a, av), np.array([sc], dt))
+            assert np.array_equal(got, exp, equal_nan=True), (op, s)
+            assert np.array_equal(np.ones(n, bool) if gotv is None else gotv, np.ones(n, bool) if expv is None else expv), (op, s)
+            exp, expv = oracle.arith(op, sc, b, None, bv)
+            got, gotv = plb.elementwise(op, np.array([sc], dt), (b, bv))
+            assert np.array_equal(got, exp, equal_nan=True), (op, s, "lhs")
+            assert np.array_equal(np.ones(n, bool) if gotv is None else gotv, np.ones(n, bool) if expv is None else expv), (op, s, "lhs")
+
+
+@pytest.mark.parametrize("dtype", ["int64", "int32", "uint64", "uint32", "float64", "float32"])
+@pytest.mark.parametrize("n", [0, 1, 31, 64, 129, 4097, 100_003])
+def test_compare_vs_oracle(plb, dtype, n):
+    rng = np.random.default_rng(n + 3)
+    dt = np.dtype(dtype)
+    a = rng.integers(0, 50, n).astype(dt)
+    b = rng.integers(0, 50, n).astype(dt)
+    if dt.kind == "f" and n > 10:
+        a[::7] = np.nan
+        b[::11] = np.nan
+        a[3], b[3] = -0.0, 0.0
+    av = (rng.random(n) > 0.1) if n else None
+    bv = (rng.random(n) > 0.2) if n else None
+    for op in ("eq", "ne", "lt", "le", "gt", "ge"):
+        exp, expv = oracle.compare(op, a, b, av, bv)
+        got, gotv = plb.compare(op, (a, av), (b, bv))
+        assert np.array_equal(got, exp), op
+        assert np.array_equal(np.ones(n, bool) if gotv is None else gotv, np.ones(n, bool) if expv is None else expv), op
+        if n:
+            exp, expv = oracle.compare(op, a, dt.type(25), av, None)
+            got, gotv = plb.compare(op, (a, av), np.array([25], dt))
+            assert np.array_equal(got, exp), (op, "scalar")
+    for op in ("eq", "ne"):
+        exp, _ = oracle.compare(op, a, b, av, bv, missing=True)
+        got, gotv = plb.compare(op, (a, av), (b, bv), missing=True)
+        assert gotv is None and np.array_equal(got, exp), (op, "missing")
+
+
+def test_sliced_inputs_bit_offsets(plb):
+    # Arrow slices: element offset applies to values AND to the validity bitmap (arbitrary bit offset;
+    # regression in the reference: crates/polars/tests/it/core/joins.rs:651-684 test_4_threads_bit_offset)
+    rng = np.random.default_rng(0)
+    n = 5000
+    a = rng.integers(-100, 100, n).astype(np.int64)
+    av = rng.random(n) > 0.3
+    for off in (1, 3, 8, 13, 64, 77):
+        ln = n - off - 5
+        ca = plb.Column(a, av, offset=off, length=ln)
+        got, gotv = plb.elementwise("add", ca, np.array([1], np.int64))
+        assert np.array_equal(got, a[off:off + ln] + 1) and np.array_equal(gotv, av[off:off + ln])
+        (k, kv), outs = plb.group_by_agg(ca, [("len", None), ("sum", ca)], True)
+        ek, ekv, eo, _ = oracle.group_by_agg(a[off:off + ln], av[off:off + ln], [("len", None, None), ("sum", a[off:off + ln], av[off:off + ln])], 1, True)
+        assert_close(k, ek, kv, ekv, "sliced keys")
+        assert_close(outs[0][0], eo[0][0], what="len")
+        assert_close(outs[1][0], eo[1][0], what="sum")
+
+
+def test_chunked_inputs(plb):
+    # py-polars/tests/unit/operations/test_group_by.py:1248-1257 (chunked == rechunked)
+    rng = np.random.default_rng(1)
+    n = 30_000
+    key = rng.integers(0, 100, n).astype(np.int64)
+    v = rng.normal(size=n)
+    cuts = [0, 7, 5000, 5001, 20_000, n]
+    kch = [plb.Column(key[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    vch = [plb.Column(v[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    (k1, _), o1 = plb.group_by_agg(kch, [("sum", vch), ("len", None)], True)
+    (k2, _), o2 = plb.group_by_agg(key, [("sum", v), ("len", None)], True)
+    assert np.array_equal(k1, k2) and np.array_equal(o1[1][0], o2[1][0])
+    assert_close(o1[0][0], o2[0][0], what="chunked sum")
+
+
+# ------------------------------------------------------------------ filter / gather
+def test_filter_kat_generator(plb):
+    # reference KAT generator py-polars/tests/unit/operations/test_filter.py:271-286
+    for size in list(range(0, 64)) + [100, 1000, 10_000, 100_000]:
+        for sel in (0.0, 0.01, 0.1, 0.5, 0.9, 0.99, 1.0):
+            rng = np.random.Generator(np.random.PCG64(size * 100 + int(sel * 100)))
+            mask = rng.random(size) < sel
+            v64 = rng.integers(-2**62, 2**62, size).astype(np.int64)
+            v32 = rng.normal(size=size).astype(np.float32)
+            valid = rng.random(size) > 0.2
+            mvalid = rng.random(size) > 0.1
+            outs = plb.filter([(v64, valid), (v32, None)], (mask, mvalid))
+            keep = mask & mvalid
+            assert np.array_equal(outs[0][0], v64[keep]), (size, sel)
+            gv = np.ones(keep.sum(), bool) if outs[0][1] is None else outs[0][1]
+            assert np.array_equal(gv, valid[keep]), (size, sel)
+            assert np.array_equal(outs[1][0], v32[keep]) and outs[1][1] is None
+
+
+def test_filter_cmp_fused(plb):
+    rng = np.random.default_rng(9)
+    n = 1_000_003
+    x = rng.integers(-10**6, 10**6, n).astype(np.int64)
+    key = rng.integers(0, 1000, n).astype(np.int64)
+    xv = rng.random(n) > 0.05
+    outs = plb.filter_cmp([(x, xv), (key, None)], 0, "gt", 0)
+    keep = (x > 0) & xv
+    assert np.array_equal(outs[0][0], x[keep]) and np.array_equal(outs[1][0], key[keep])
+    assert outs[0][1] is None    # kept rows of the predicate column are all valid
+
+
+def test_gather(plb):
+    rng = np.random.default_rng(4)
+    for n, m in [(10, 0), (10, 5), (1000, 4099), (50_000, 200_001)]:
+        v64 = rng.normal(size=n)
+        v32 = rng.integers(-5, 5, n).astype(np.int32)
+        valid = rng.random(n) > 0.3
+        idx = rng.integers(0, n, m).astype(np.uint32)
+        ivalid = rng.random(m) > 0.2
+        outs = plb.gather([(v64, valid), (v32, None)], (idx, ivalid))
+        e0, e0v = oracle.gather(v64, valid, idx, ivalid)
+        e1, e1v = oracle.gather(v32, None, idx, ivalid)
+        assert_close(outs[0][0], e0, outs[0][1], e0v, "gather f64")
+        assert_close(outs[1][0], e1, outs[1][1], e1v, "gather i32")
+        outs = plb.gather([(v64, None)], idx)
+        assert np.array_equal(outs[0][0], v64[idx]) and outs[0][1] is None
+    with pytest.raises(plb.OutOfBoundsError):
+        plb.gather([np.arange(4.0)], np.array([1, 4], np.uint32))
+
+
+# ------------------------------------------------------------------ group_by
+def _gb_case(rng, n, k, nulls, key_dtype="int64"):
+    key = rng.integers(-k // 2, k // 2 + 1, n).astype(key_dtype)
+    vi = rng.integers(-1000, 1000, n).astype(np.int64)
+    vf = rng.uniform(0, 100, n).round(6)
+    kvalid = (rng.random(n) > 0.05) if nulls else None
+    ivalid = (rng.random(n) > 0.05) if nulls else None
+    fvalid = (rng.random(n) > 0.3) if nulls else None
+    return key, kvalid, vi, ivalid, vf, fvalid
+
+
+@pytest.mark.parametrize("n,k,nulls", [(0, 5, False), (1, 1, False), (2, 1, True), (1001, 7, True), (50_001, 1000, True), (300_000, 100_000, False), (1_000_000, 3, True)])
+def test_group_by_vs_oracle(plb, n, k, nulls):
+    rng = np.random.default_rng(n + k)
+    key, kvalid, vi, ivalid, vf, fvalid = _gb_case(rng, n, k, nulls)
+    kinds = [("sum", vi, ivalid), ("mean", vf, fvalid), ("len", None, None), ("min", vi, ivalid), ("max", vf, fvalid),
+             ("count", vf, fvalid), ("sum", vf, fvalid), ("mean", vi, ivalid), ("max", vi, ivalid), ("min", vf, fvalid)]
+    for order in (True, False):
+        for sub in (kinds[:3], kinds[3:7], kinds[7:]):
+            keys, kv, outs = GpuImpl(plb).group_by_agg(key, kvalid, sub, order)
+            ek, ekv, eouts, _ = oracle.group_by_agg(key, kvalid, sub, 4, order)
+            if not order:
+                keys, kv, outs = sort_groups(keys, kv, outs)
+                ek, ekv, eouts = sort_groups(ek, ekv, eouts)
+            assert_close(keys, ek, kv, ekv, "keys")
+            for (kind, _, _), (v, m), (ev, em) in zip(sub, outs, eouts):
+                assert v.dtype == ev.dtype, (kind, v.dtype, ev.dtype)
+                assert_close(v, ev, m, em, kind)
+
+
+@pytest.mark.parametrize("key_dtype,val_dtype", [("int32", "int32"), ("uint32", "float32"), ("uint64", "uint64"), ("float64", "int64"), ("float32", "float64")])
+def test_group_by_dtypes(plb, key_dtype, val_dtype):
+    rng = np.random.default_rng(5)
+    n = 20_000
+    key = rng.integers(0, 50, n).astype(key_dtype)
+    if np.dtype(key_dtype).kind == "f":
+        key[::9] = np.nan
+        key[1::9] = -0.0
+        key[2::9] = 0.0
+    val = (rng.uniform(0, 100, n) if np.dtype(val_dtype).kind == "f" else rng.integers(0, 1000, n)).astype(val_dtype)
+    vvalid = rng.random(n) > 0.1
+    aggs = [("sum", val, vvalid), ("mean", val, vvalid), ("min", val, vvalid), ("max", val, vvalid), ("count", val, vvalid)]
+    keys, kv, outs = GpuImpl(plb).group_by_agg(key, None, aggs, True)
+    ek, ekv, eouts, _ = oracle.group_by_agg(key, None, aggs, 1, True)
+    assert keys.dtype == ek.dtype
+    assert np.array_equal(keys.view(np.uint8), ek.view(np.uint8)), "key bits (first occurrence) differ"
+    for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
+        assert v.dtype == ev.dtype, (kind, v.dtype, ev.dtype)
+        assert_close(v, ev, m, em, kind)
+
+
+def test_group_by_edge_semantics(plb):
+    key = np.array([0, 0, 1, 1, 2, 2, 3, -2**63, -2**63], np.int64)
+    vi = np.array([2**62, 2**62, 1, 2, 5, 6, 7, 1, 1], np.int64)
+    valid = np.array([1, 1, 0, 0, 1, 0, 1, 1, 1], bool)
+    aggs = [("sum", vi, valid), ("mean", vi, valid), ("min", vi, valid), ("count", vi, valid), ("len", None, None)]
+    keys, kv, outs = GpuImpl(plb).group_by_agg(key, None, aggs, True)
+    assert keys.tolist() == [0, 1, 2, 3, -2**63]
+    assert outs[0][0].tolist() == [-2**63, 0, 5, 7, 2] and outs[0][1] is None          # wrapping; all-null sum = 0
+    assert outs[1][1].tolist() == [True, False, True, True, True]
+    assert outs[2][0][2] == 5 and outs[3][0].tolist() == [2, 0, 1, 1, 2] and outs[4][0].tolist() == [2, 2, 2, 1, 2]
+    vf = np.array([np.nan, 1.0, np.nan, np.nan, -0.0, 3.0, np.inf, 1.0, 2.0])
+    keys, kv, outs = GpuImpl(plb).group_by_agg(key, None, [("min", vf, None), ("max", vf, None), ("sum", vf, None)], True)
+    assert outs[0][0][0] == 1.0 and np.isnan(outs[0][0][1]) and outs[1][0][2] == 3.0 and outs[0][0][3] == np.inf
+    assert np.isnan(outs[2][0][0]) and np.isnan(outs[2][0][1])
+
+
+def test_group_by_high_cardinality_restart(plb):
+    # every key distinct: the sampled estimate must size (or regrow) the table correctly
+    n = 400_000
+    rng = np.random.default_rng(8)
+    key = rng.permutation(n).astype(np.int64) * 7919
+    v = np.ones(n, np.int64)
+    (k, _), [(s, _), (c, _)] = plb.group_by_agg(key, [("sum", v), ("len", None)], False)
+    assert k.size == n and np.array_equal(np.sort(k), np.sort(key)) and s.sum() == n and (c == 1).all()
+    # heavy skew: a 64K sample sees few keys, the tail forces the regrow path
+    key2 = np.where(rng.random(n) < 0.9, 5, key)
+    (k, _), [(s, _), (c, _)] = plb.group_by_agg(key2, [("sum", v), ("len", None)], False)
+    assert c.sum() == n and k.size == np.unique(key2).size
+
+
+def test_group_by_streaming_and_partials(plb):
+    # streaming consume == one shot; export -> merge of partial aggregates == single table
+    rng = np.random.default_rng(12)
+    n = 200_000
+    key, kvalid, vi, ivalid, vf, fvalid = _gb_case(rng, n, 5000, True)
+    spec = [("sum", np.int64), ("mean", np.float64), ("len", None), ("min", np.float64), ("max", np.int64), ("count", np.int64)]
+    aggs = [("sum", vi, ivalid), ("mean", vf, fvalid), ("len", None, None), ("min", vf, fvalid), ("max", vi, ivalid), ("count", vi, ivalid)]
+    ek, ekv, eouts, _ = oracle.group_by_agg(key, kvalid, aggs, 4, True)
+
+    def batch_cols(a, b):
+        return [plb.Column(vi[a:b], ivalid[a:b]), plb.Column(vf[a:b], fvalid[a:b]), None, plb.Column(vf[a:b], fvalid[a:b]), plb.Column(vi[a:b], ivalid[a:b]), plb.Column(vi[a:b], ivalid[a:b])]
+
+    g = plb.GroupBy(np.int64, spec, expected_groups=6000, track_first=True)
+    cuts = [0, 50_001, 120_000, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        g.consume(plb.Column(key[a:b], kvalid[a:b]), batch_cols(a, b), row_base=a)
+    (k, kv), outs = g.finish(maintain_order=True)
+    assert_close(k, ek, kv, ekv, "stream keys")
+    for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
+        assert_close(v, ev, m, em, "stream " + kind)
+    # two "ranks": each pre-aggregates half, exports P=2 partitions, rank p merges partition p of both
+    halves = [(0, n // 2), (n // 2, n)]
+    states = []
+    for a, b in halves:
+        s = plb.GroupBy(np.int64, spec, expected_groups=6000, track_first=True)
+        s.consume(plb.Column(key[a:b], kvalid[a:b]), batch_cols(a, b), row_base=a)
+        states.append(s)
+    exports = [s.export_partials(2) for s in states]
+    # partition ids must equal the oracle's hash_to_partition on the key bits (null -> 0)
+    finals = []
+    for p in range(2):
+        f = plb.GroupBy(np.int64, spec, expected_groups=6000, track_first=True)
+        for ptr, rw, offs in exports:
+            f.merge_partials(ptr + int(offs[p]) * rw * 8, int(offs[p + 1] - offs[p]))
+        finals.append(f.finish(maintain_order=True))
+    for ptr, _, _ in exports:
+        plb.dev_free(ptr)
+    part = oracle.hash_to_partition(oracle.dirty_hash(oracle.key_bits(ek)), 2)
+    if ekv is not None:
+        part = np.where(ekv, part, 0)
+    for p in range(2):
+        (k, kv), outs = finals[p]
+        sel = part == p
+        assert_close(k, ek[sel], kv, None if ekv is None or ekv[sel].all() else ekv[sel], f"partition {p} keys")
+        for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
+            assert_close(v, ev[sel], m, None if em is None or em[sel].all() else em[sel], f"partition {p} {kind}")
+
+
+# ------------------------------------------------------------------ join
+@pytest.mark.parametrize("nl,nr,krange,dups", [(0, 0, 10, 1), (5, 0, 10, 1), (0, 5, 10, 1), (300, 100, 150, 1), (3000, 2000, 500, 3), (40_000, 100_000, 20_000, 2), (300_000, 50_000, 50_000, 1)])
+@pytest.mark.parametrize("key_dtype", ["int64", "int32", "float64"])
+def test_join_vs_oracle(plb, nl, nr, krange, dups, key_dtype):
+    rng = np.random.default_rng(nl * 7 + nr)
+    lk = rng.integers(0, krange, nl).astype(key_dtype)
+    rk = np.repeat(rng.permutation(max(krange, nr))[: max(nr // dups, 0)], dups)[:nr]
+    rk = np.concatenate([rk, rng.integers(0, krange, nr - rk.size)]).astype(key_dtype)
+    rng.shuffle(rk)
+    if np.dtype(key_dtype).kind == "f" and nl > 10 and nr > 10:
+        lk[::13] = np.nan
+        rk[::17] = np.nan
+        lk[1::13] = -0.0
+        rk[1::17] = 0.0
+    lv = rng.random(nl) > 0.1
+    rv = rng.random(nr) > 0.1
+    impl = GpuImpl(plb)
+    for nulls_equal in (False, True):
+        for how in ("inner", "left"):
+            orders = ["none", "left", "right", "left_right"] if how == "inner" else ["none"]
+            for order in orders:
+                li, ri = impl.plb.hash_join(plb.Column(lk, lv), plb.Column(rk, rv), how, nulls_equal, order)
+                li, ri = li[0], ri[0]
+                eli, eri = oracle.hash_join(lk, rk, lv, rv, how, nulls_equal, order, 4)
+                # exact sequence: the oracle's emission order is the reference's (hash_join/mod.rs:41-50)
+                assert np.array_equal(li, eli), (how, nulls_equal, order, "left idx")
+                assert np.array_equal(ri, eri), (how, nulls_equal, order, "right idx")
+
+
+def test_join_dtype_mismatch_is_compute_error(plb):
+    with pytest.raises(plb.ComputeError):
+        plb.hash_join(np.arange(4, dtype=np.int64), np.arange(4, dtype=np.int32))
+
+
+def test_join_then_gather_materialises(plb, kats):
+    case = kats["join"][0]
+    lk = np.array(case["left_key"], np.int32)
+    rk = np.array(case["right_key"], np.int32)
+    (li, _), (ri, _) = plb.hash_join(lk, rk)
+    temp = np.array(case["payload_left"]["temp"])
+    rain = np.array(case["payload_right"]["rain"])
+    [(t, _)] = plb.gather([temp], li)
+    [(r, _)] = plb.gather([rain], ri)
+    assert t.tolist() == case["expect_payload"]["temp"] and r.tolist() == case["expect_payload"]["rain_right"]
+
+
+# ------------------------------------------------------------------ device-resident path + properties at size
+def test_device_resident_roundtrip(plb):
+    rng = np.random.default_rng(2)
+    n = 2_000_000
+    key = rng.integers(0, 10_000, n).astype(np.int64)
+    v = rng.integers(-1000, 1000, n).astype(np.int64)
+    dk, dv = plb.to_device(key), plb.to_device(v)
+    ok, [osum, olen] = plb.group_by_agg(dk.view(), [("sum", dv.view()), ("len", None)], False, location=plb.DEVICE)
+    k, _ = ok.to_numpy()
+    s, _ = osum.to_numpy()
+    c, _ = olen.to_numpy()
+    order = np.argsort(k)
+    exp = np.bincount(key, weights=None, minlength=10_000)
+    assert np.array_equal(k[order], np.arange(10_000)) and np.array_equal(c[order], exp)
+    esum = np.zeros(10_000, np.int64)
+    np.add.at(esum, key, v)
+    assert np.array_equal(s[order], esum)
+
+
+def test_config_c1_filter_groupby_sum(plb):
+    # BASELINE.json configs[0]: filter(x > 0).group_by(key).agg(x.sum()) on 10M Int64 rows, seed 0
+    rng = np.random.default_rng(0)
+    n = 10_000_000
+    key = rng.integers(0, 10**3, n).astype(np.int64)
+    x = rng.integers(-10**6, 10**6, n).astype(np.int64)
+    fx, fk = plb.filter_cmp([x, key], 0, "gt", 0, location=plb.DEVICE)
+    ok, [osum] = plb.group_by_agg(fk.view(), [("sum", fx.view())], False, location=plb.DEVICE)
+    k, _ = ok.to_numpy()
+    s, _ = osum.to_numpy()
+    keep = x > 0
+    esum = np.zeros(1000, np.int64)
+    np.add.at(esum, key[keep], x[keep])
+    order = np.argsort(k)
+    assert np.array_equal(k[order], np.arange(1000)) and np.array_equal(s[order], esum)
+    # size-independent checksum property: sum of group sums == sum of the filtered column
+    assert int(s.sum()) == int(x[keep].sum()) and fx.length == int(keep.sum())
+
+
+def test_large_properties_groupby_join(plb):
+    # 5e7-row property checks (full-size configs run in bench.py): conservation of counts and sums,
+    # and join round trip: gather(build_key, right_idx) == gather(probe_key, left_idx)
+    rng = np.random.default_rng(3)
+    n, K = 50_000_000, 1_000_000
+    key = rng.integers(0, K, n).astype(np.int64)
+    v = rng.integers(-1000, 1000, n).astype(np.int64)
+    dk, dv = plb.to_device(key), plb.to_device(v)
+    ok, [osum, olen] = plb.group_by_agg(dk.view(), [("sum", dv.view()), ("len", None)], False, location=plb.DEVICE)
+    k, _ = ok.to_numpy()
+    s, _ = osum.to_numpy()
+    c, _ = olen.to_numpy()
+    assert int(c.astype(np.int64).sum()) == n and int(s.sum()) == int(v.sum()) and np.unique(k).size == k.size
+    assert np.array_equal(np.sort(c), np.sort(np.bincount(key, minlength=K)[np.unique(key)]))
+    nb = 5_000_000
+    bkey = rng.permutation(nb).astype(np.int64)
+    db = plb.to_device(bkey)
+    pkey = rng.integers(0, 2 * nb, n).astype(np.int64)     # ~50 % hit
+    dp = plb.to_device(pkey)
+    li, ri = plb.hash_join(dp.view(), db.view(), "inner", False, "none", location=plb.DEVICE)
+    [gl] = plb.gather([dp.view()], li.view(), location=plb.DEVICE)
+    [gr] = plb.gather([db.view()], ri.view(), location=plb.DEVICE)
+    a, _ = gl.to_numpy()
+    b, _ = gr.to_numpy()
+    l_idx, _ = li.to_numpy()
+    assert np.array_equal(a, b) and a.size == int((pkey < nb).sum())
+    assert np.all(np.diff(l_idx.astype(np.int64)) > 0)       # probe order, unique build keys
