@@ -1,0 +1,86 @@
+"""Multi-GPU plumbing for the partitioned plan: one process per GPU,
+`torch.distributed` for the exchange.  The data path has exactly one exchange step — an all-to-all-v of
+hash-partitioned rows (partial aggregates for group_by, (key,row) pairs for join).
+
+The reference has no distributed path; the partition function is its in-memory one
+(hash_to_partition(dirty_hash(key), P), crates/polars-utils/src/hashing.rs:62-69,132-142), which
+the device kernels restate bit-exactly, so per-destination counts are checkable integers.
+
+This module is host logic only (split sizes, buffers, collective calls) and is backend-agnostic:
+NCCL on GPUs (`all_to_all_single`), gloo on CPU for the world_size-2 tests (isend/irecv pairs,
+because gloo has no all_to_all).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def exchange_counts(send_counts: np.ndarray, device) -> np.ndarray:
+    """send_counts[p] = rows this rank sends to rank p  ->  recv_counts[p] = rows rank p sends here."""
+    world = dist.get_world_size()
+    assert send_counts.shape == (world,)
+    sc = torch.tensor(send_counts, dtype=torch.int64, device=device)
+    if dist.get_backend() == "nccl":
+        rc = torch.empty_like(sc)
+        dist.all_to_all_single(rc, sc)
+    else:
+        gathered = [torch.empty_like(sc) for _ in range(world)]
+        dist.all_gather(gathered, sc)
+        rc = torch.stack([g[dist.get_rank()] for g in gathered])
+    return rc.cpu().numpy()
+
+
+def all_to_all_rows(send: torch.Tensor, send_counts: np.ndarray, row_words: int):
+    """send: int64 tensor of sum(send_counts)*row_words words, destination-major (partition p's rows
+    are contiguous).  Returns (recv tensor, recv_counts)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    recv_counts = exchange_counts(np.asarray(send_counts, dtype=np.int64), send.device)
+    recv = torch.empty(int(recv_counts.sum()) * row_words, dtype=torch.int64, device=send.device)
+    in_split = (np.asarray(send_counts, dtype=np.int64) * row_words).tolist()
+    out_split = (recv_counts * row_words).tolist()
+    if dist.get_backend() == "nccl":
+        dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split)
+    else:
+        so = np.concatenate([[0], np.cumsum(in_split)])
+        ro = np.concatenate([[0], np.cumsum(out_split)])
+        recv[ro[rank]:ro[rank + 1]] = send[so[rank]:so[rank + 1]]
+        reqs = []
+        for p in range(world):
+            if p == rank:
+                continue
+            if out_split[p]:
+                reqs.append(dist.irecv(recv[ro[p]:ro[p + 1]], src=p))
+            if in_split[p]:
+                reqs.append(dist.isend(send[so[p]:so[p + 1]].contiguous(), dst=p))
+        for r in reqs:
+            r.wait()
+    return recv, recv_counts
+
+
+class CudaWords:
+    """Zero-copy view of a raw device pointer as int64 words (CUDA array interface v2) for torch.as_tensor."""
+
+    def __init__(self, ptr: int, n_words: int):
+        self.__cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+
+def partitioned_group_by(plb, key_col, value_cols, spec, location=None):
+    """One rank's share of the partitioned group_by: local pre-aggregation (K5) -> hash-partitioned
+    export of the partial aggregates (K6) -> one all-to-all -> merge (K5 merge) -> finish.
+    Output stays partitioned: this rank owns the groups with hash_to_partition(key) == rank."""
+    world = dist.get_world_size()
+    g = plb.GroupBy(np.int64 if key_col is None else plb.NP_OF[key_col.dtype], spec)
+    g.consume(key_col, value_cols, row_base=0)
+    ptr, rw, offs = g.export_partials(world)
+    try:
+        n_send = int(offs[-1])
+        send = torch.as_tensor(CudaWords(ptr, n_send * rw), device="cuda") if n_send else torch.empty(0, dtype=torch.int64, device="cuda")
+        recv, rc = all_to_all_rows(send, np.diff(offs), rw)
+        torch.cuda.synchronize()
+        f = plb.GroupBy(plb.NP_OF[key_col.dtype], spec, expected_groups=max(int(rc.sum()), 1))
+        f.merge_partials(recv.data_ptr(), int(rc.sum()))
+        return f.finish(False, location=plb.DEVICE if location is None else location)
+    finally:
+        plb.dev_free(ptr)

@@ -102,7 +102,7 @@ def test_elementwise_vs_oracle(plb, dtype, n):
             ev = np.ones(n, bool) if expv is None else expv
             gv = np.ones(n, bool) if gotv is None else gotv
             assert np.array_equal(gv, ev), op
-        if n == 0:
+        if n <= 1:      # (1, 1) is the array/array kernel in the reference too (ops/arity.rs:910-911)
             continue
         for s in ([3, 0, -1] if dt.kind == "i" else [3, 0]):
             sc = dt.type(s)
