@@ -265,7 +265,7 @@ def main():
 
     # ---- end to end through the C ABI with pinned host buffers (H2D + compute + D2H per step)
     e2e_vals, d2h = [], 0
-    for i in range(a.e2e_steps + 1):
+    for i in range(a.e2e_steps + 1 if a.e2e_steps > 0 else 0):
         barrier()
         t0 = time.perf_counter()
         _, d2h = step_e2e()
@@ -281,6 +281,8 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    if a.workload == "join":      # hashed or dense probe, whichever ran
+        dominant = max((k for k in prof if k.startswith("k8_") and "probe" in k), key=lambda k: prof[k]["ms"], default=dominant)
     dom = prof.get(dominant, {"launches": 0, "ms": 0.0})
     dom_ms = dom["ms"] / max(dom["launches"], 1)
     achieved = (alg_bytes_per_row * unit_rows / 1e9) / (dom_ms / 1e3) if dom_ms > 0 else 0.0
@@ -296,6 +298,7 @@ def main():
         "kernels_ms_per_step": {k: v["ms"] / a.steps for k, v in prof.items()},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "knobs": {k: v for k, v in os.environ.items() if k.startswith("BL_")},
         "e2e": {"value": unit_rows * world / e2e_s if e2e_s else None, "unit": "rows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                 "path": "bl_groupby_agg / bl_hash_join with BL_HOST columns in pinned memory -> BL_HOST outputs"},
     }

@@ -122,11 +122,13 @@ bl_status bl_hash_join(const bl_column* left_key, int32_t n_left_chunks, const b
     PLB_REQUIRE(left_key && right_key && out_left_idx && out_right_idx, BL_ERR_INVALID, "hash_join: null argument");
     PLB_REQUIRE(maintain_order >= BL_ORDER_NONE && maintain_order <= BL_ORDER_RIGHT_LEFT, BL_ERR_INVALID, "hash_join: unknown maintain_order");
     DevCol l = import_column(left_key, n_left_chunks), r = import_column(right_key, n_right_chunks);
+    trace_point("cabi:join imported");
     JoinResult jr = op_hash_join(l, r, how, nulls_equal != 0, maintain_order);
     bl_column tl, tr;
     export_column(jr.left, out_location, &tl);
     try { export_column(jr.right, out_location, &tr); } catch (...) { bl_column_free(&tl); throw; }
     *out_left_idx = tl; *out_right_idx = tr;
+    trace_point("cabi:join exported");
     BL_CATCH
 }
 

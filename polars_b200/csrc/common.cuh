@@ -164,6 +164,9 @@ void op_hash_partition(const DevCol& key, const std::vector<DevCol>& payload, in
 
 void set_last_error(const std::string& m);
 
+// host-side phase tracing (BL_TRACE=1): wall-clock since the previous trace point, after a stream sync
+void trace_point(const char* label);
+
 }  // namespace plb
 
 // C-ABI boundary guards: serialise on the context, translate exceptions into bl_status

@@ -24,6 +24,7 @@
 // (1 key load + 1 RED per accumulator per row).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "dev_utils.cuh"
@@ -481,7 +482,8 @@ uint64_t GroupByState::choose_cap(const DevCol& key) {
         G = estimate_groups((double)d, (double)m, (double)n) * 1.25 + 64;
         if (G > (double)n) G = (double)n;
     }
-    return pow2_at_least(G / 0.6);      // load factor <= 0.6
+    static const double lf = [] { const char* e = getenv("BL_K5_LF"); double v = e ? atof(e) / 100.0 : 0.6; return (v > 0.05 && v < 0.95) ? v : 0.6; }();
+    return pow2_at_least(G / lf);       // load factor <= 0.6 by default
 }
 
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS>
@@ -526,7 +528,8 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
     for (int c = Lb.n_cols; c <= GB_MAX_COLS; c++) Lb.col_kbegin[c] = k;
     const int64_t n = key.len;
     if (n == 0) return;
-    const int grid = grid_for((n / 2 + 1), 256, 8);
+    static const int bps = [] { const char* e = getenv("BL_K5_BPS"); int v = e ? atoi(e) : 8; return v > 0 ? v : 8; }();
+    const int grid = grid_for((n / 2 + 1), 256, bps);
     const bool kn = key.validity != nullptr;
     const int elem = dtype_size(key.dtype);
     const int canon = key.dtype == BL_FLOAT64 ? 1 : (key.dtype == BL_FLOAT32 ? 2 : 0);

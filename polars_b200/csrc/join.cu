@@ -24,6 +24,8 @@
 // Algorithmic bytes: build 8 B read + 16 B table write per build row; probe
 // 8 B key read + 8 B tuple write per match.  Bound: random 32-byte sector reads of the table
 // (HBM when the table exceeds L2, L2 otherwise).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "dev_utils.cuh"
 
@@ -172,50 +174,123 @@ __global__ void __launch_bounds__(256) k_join_probe(JoinTableDev T, const void* 
 }
 
 // ---------------------------------------------------------------------------- K8 probe, pass 2 (emit)
-// thread t of the CTA owns rows [tile*2048 + 8t, +8): thread-local exclusive counts, CTA scan, then
-// contiguous writes.
+// Rows are mapped lane-strided (row = tile + j*256 + tid) so that loads of the handles and — when
+// every probe row has <= 1 match, the primary-key case — the tuple stores are fully coalesced.
+// Per (iteration j, warp) segment: shuffle scan of the per-row match counts; the 64 segment totals
+// of the tile are scanned by one warp; the tile base comes from the tile-count scan.
 __global__ void __launch_bounds__(256) k_join_emit(JoinTableDev T, const uint32_t* __restrict__ handle, int64_t n, int csr_mode, int left_join,
                                                    const uint32_t* __restrict__ sorted_rows, const uint64_t* __restrict__ tile_off,
                                                    uint32_t* __restrict__ out_probe, uint32_t* __restrict__ out_build) {
-    __shared__ uint32_t ws[8];
+    constexpr int ITERS = J_TILE / 256;           // 8
+    __shared__ uint32_t seg[ITERS * 8];           // segment = j * 8 + warp, in row order
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     const int64_t ntiles = (n + J_TILE - 1) / J_TILE;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t r0 = t * J_TILE + (int64_t)threadIdx.x * 8;
-        uint32_t h[8], c[8], off[8];
-        if (r0 + 7 < n) {
-            uint4 a = *reinterpret_cast<const uint4*>(handle + r0), b = *reinterpret_cast<const uint4*>(handle + r0 + 4);
-            h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
-        } else {
+        uint32_t h[ITERS], c[ITERS], off[ITERS], lane_excl[ITERS];
 #pragma unroll
-            for (int k = 0; k < 8; k++) h[k] = r0 + k < n ? handle[r0 + k] : J_NONE;
-        }
-        uint32_t mine = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            uint32_t ck = 0;
-            if (r0 + k < n) {
-                if (h[k] != J_NONE) {
-                    if (csr_mode) { uint4 e = __ldg(&T.entries[h[k]]); ck = e.w; off[k] = e.z; } else ck = 1;
-                } else if (left_join) ck = 1;
+        for (int j = 0; j < ITERS; j++) {
+            const int64_t row = t * J_TILE + j * 256 + threadIdx.x;
+            h[j] = row < n ? handle[row] : J_NONE;
+            uint32_t ck = 0; off[j] = 0;
+            if (row < n) {
+                if (h[j] != J_NONE) { if (csr_mode) { uint4 e = __ldg(&T.entries[h[j]]); ck = e.w; off[j] = e.z; } else ck = 1; }
+                else if (left_join) ck = 1;
             }
-            c[k] = ck; mine += ck;
+            c[j] = ck;
+            uint32_t x = ck;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
+            lane_excl[j] = x - ck;
+            if (lane == 31) seg[j * 8 + warp] = x;
         }
-        uint32_t x = mine;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane_id() >= (unsigned)o) x += y; }
-        if (lane_id() == 31) ws[threadIdx.x >> 5] = x;
         __syncthreads();
-        uint32_t wbase = 0;
-        for (unsigned w = 0; w < (threadIdx.x >> 5); w++) wbase += ws[w];
-        uint64_t pos = tile_off[t] + wbase + x - mine;
+        if (warp == 0) {      // exclusive scan of the 64 segment totals (2 per lane)
+            uint32_t a = seg[2 * lane], b = seg[2 * lane + 1], s2 = a + b, x = s2;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
+            seg[2 * lane] = x - s2; seg[2 * lane + 1] = x - s2 + a;
+        }
+        __syncthreads();
+        const uint64_t base = tile_off[t];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (c[k] == 0) continue;
-            const uint32_t pi = (uint32_t)(r0 + k);
-            if (h[k] == J_NONE) { out_probe[pos] = pi; out_build[pos] = J_NONE; pos++; }
-            else if (!csr_mode) { out_probe[pos] = pi; out_build[pos] = h[k]; pos++; }
-            else for (uint32_t j = 0; j < c[k]; j++) { out_probe[pos] = pi; out_build[pos] = sorted_rows[off[k] + j]; pos++; }
+        for (int j = 0; j < ITERS; j++) {
+            if (c[j] == 0) continue;
+            uint64_t pos = base + seg[j * 8 + warp] + lane_excl[j];
+            const uint32_t pi = (uint32_t)(t * J_TILE + j * 256 + threadIdx.x);
+            if (h[j] == J_NONE) { out_probe[pos] = pi; out_build[pos] = J_NONE; }
+            else if (!csr_mode) { out_probe[pos] = pi; out_build[pos] = h[j]; }
+            else for (uint32_t q = 0; q < c[j]; q++) { out_probe[pos + q] = pi; out_build[pos + q] = sorted_rows[off[j] + q]; }
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------- dense (direct-address) mode
+// When the build keys are integers whose value range is at most a few times the build rows (dense
+// surrogate / primary keys) the hash table degenerates to a perfect hash: slot = key - min.  The
+// table is then 4 bytes per key value (10^7 keys -> 40 MB, L2-resident on B200) and a probe is ONE
+// L2 hit instead of a random HBM sector.  Same outputs as the hashed path; taken only for unique
+// build keys (duplicates fall back to the hashed table + CSR lists).
+__device__ __forceinline__ uint64_t j_ordered(uint64_t raw, int sign_bits) {
+    // order-preserving map to u64: signed types flip the sign bit (32-bit patterns are sign-extended first)
+    if (sign_bits == 64) return raw ^ 0x8000000000000000ULL;
+    if (sign_bits == 32) return (uint64_t)(int64_t)(int32_t)(uint32_t)raw ^ 0x8000000000000000ULL;
+    return raw;
+}
+__global__ void k_join_minmax(const void* __restrict__ keys, const uint32_t* __restrict__ valid, int elem, int sign_bits, int64_t n, unsigned long long* mm) {
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        if (valid != nullptr && !bit_get(valid, r)) continue;
+        uint64_t raw = elem == 8 ? reinterpret_cast<const uint64_t*>(keys)[r] : (uint64_t)reinterpret_cast<const uint32_t*>(keys)[r];
+        unsigned long long k = j_ordered(raw, sign_bits);
+        lo = k < lo ? k : lo; hi = k > hi ? k : hi;
+    }
+    for (int o = 16; o; o >>= 1) {
+        unsigned long long a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = a < lo ? a : lo; hi = b > hi ? b : hi;
+    }
+    if (lane_id() == 0) { atomicMin(&mm[0], lo); atomicMax(&mm[1], hi); }
+}
+__global__ void k_fill_u32j(uint32_t* p, uint32_t v, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void __launch_bounds__(256) k_join_dense_build(uint32_t* __restrict__ table, const void* __restrict__ keys, const uint32_t* __restrict__ valid, int elem, int sign_bits,
+                                                          int64_t n, uint64_t kmin, int* __restrict__ has_dups) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        if (valid != nullptr && !bit_get(valid, r)) continue;
+        uint64_t raw = elem == 8 ? reinterpret_cast<const uint64_t*>(keys)[r] : (uint64_t)reinterpret_cast<const uint32_t*>(keys)[r];
+        const uint32_t old = atomicMin(&table[j_ordered(raw, sign_bits) - kmin], (uint32_t)r);
+        if (old != J_NONE) *has_dups = 1;
+    }
+}
+template <int KEY_ELEM, bool KEY_NULLS>
+__global__ void __launch_bounds__(256) k_join_dense_probe(const uint32_t* __restrict__ table, uint64_t kmin, uint64_t range, int sign_bits, const void* __restrict__ keys,
+                                                          const uint32_t* __restrict__ valid, int64_t n, int left_join, uint32_t* __restrict__ handle,
+                                                          uint32_t* __restrict__ tile_counts, unsigned long long* __restrict__ total) {
+    const int64_t npairs = (n + 1) >> 1;
+    const int64_t rounded = (npairs + 31) / 32 * 32;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < rounded; p += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t kraw[2] = {0, 0};
+        const int64_t r0 = 2 * p;
+        if (r0 + 1 < n) {
+            if (KEY_ELEM == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(keys) + r0); kraw[0] = t.x; kraw[1] = t.y; }
+            else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(keys) + r0); kraw[0] = t.x; kraw[1] = t.y; }
+        } else if (r0 < n) kraw[0] = KEY_ELEM == 8 ? reinterpret_cast<const uint64_t*>(keys)[r0] : (uint64_t)reinterpret_cast<const uint32_t*>(keys)[r0];
+        uint32_t h[2] = {J_NONE, J_NONE};
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int64_t row = r0 + j;
+            if (row >= n) continue;
+            bool v = true;
+            if (KEY_NULLS) v = bit_get(valid, row);
+            const uint64_t d = j_ordered(kraw[j], sign_bits) - kmin;
+            if (v && d < range) h[j] = __ldg(&table[d]);
+            cnt += (h[j] != J_NONE || left_join) ? 1u : 0u;
+        }
+        if (r0 + 1 < n) *reinterpret_cast<uint2*>(handle + r0) = make_uint2(h[0], h[1]);
+        else if (r0 < n) handle[r0] = h[0];
+        uint32_t c = cnt;
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane_id() == 0 && c) { atomicAdd(&tile_counts[r0 / J_TILE], c); atomicAdd(total, (unsigned long long)c); }
     }
 }
 
@@ -241,29 +316,57 @@ JoinResult op_hash_join(const DevCol& left, const DevCol& right, int how, bool n
     const int64_t nb = build.len, np = probe.len;
     Context& c = ctx();
 
-    // ---- build
-    JoinTableDev T; T.cap = (uint64_t)std::max<int64_t>(2 * nb, 16);
-    DevPtr entries = dev_alloc((size_t)(T.cap + 2) * 16);
-    T.entries = as<uint4>(entries);
-    PLB_LAUNCH("k7_join_init", k_join_init, grid_for((int64_t)T.cap + 2, 256), 256, 0, T.entries, (int64_t)T.cap + 2);
-    DevPtr slot_of_row = dev_alloc((size_t)std::max<int64_t>(nb, 1) * 4), has_dups = dev_alloc(4);
-    dev_memset(has_dups->p, 0, 4);
-    if (nb > 0)
-        PLB_LAUNCH("k7_join_build", k_join_build, grid_for(nb, 256), 256, 0, T, build.v(), build.vm(), dt, nb, nulls_equal ? 1 : 0, as<uint32_t>(slot_of_row), as<int>(has_dups));
-    const bool csr = nb > 0 && read_scalar(as<int>(has_dups)) != 0;
-    DevPtr sorted_rows;
-    if (csr) {
-        const int64_t ne = (int64_t)T.cap + 2, ntiles = (ne + J_TILE - 1) / J_TILE;
-        DevPtr sums = dev_alloc((size_t)ntiles * 4), offs = dev_alloc((size_t)ntiles * 8);
-        PLB_LAUNCH("k7_tile_sums", k_join_tile_sums, grid_for(ntiles * 256, 256), 256, 0, T.entries, ne, as<uint32_t>(sums));
-        exclusive_scan_u32_to_u64(as<uint32_t>(sums), as<uint64_t>(offs), ntiles, nullptr);
-        PLB_LAUNCH("k7_csr_offsets", k_join_csr_offsets, grid_for(ntiles * 256, 256), 256, 0, T.entries, ne, as<uint64_t>(offs));
-        // ascending row lists: stable sort of the build rows by entry index (skipped null rows sort last)
-        sorted_rows = dev_alloc((size_t)nb * 4);
-        iota_u32(as<uint32_t>(sorted_rows), nb, 0);
-        sort_pairs_u32(as<uint32_t>(slot_of_row), as<uint32_t>(sorted_rows), nb);
+    trace_point("join:start");
+    // ---- build: dense direct-address table when the build keys are dense unique integers
+    const bool is_int = dtype_is_int(dt);
+    const int elem = dtype_size(dt);
+    const int sign_bits = dtype_is_signed(dt) ? elem * 8 : 0;
+    const char* env_dense = getenv("BL_JOIN_DENSE");
+    bool dense = false; uint64_t kmin = 0, range = 0; DevPtr dense_table;
+    if (is_int && !nulls_equal && nb >= 1024 && !(env_dense && env_dense[0] == '0')) {
+        DevPtr mm = dev_alloc(16);
+        unsigned long long init_mm[2] = {~0ull, 0ull};
+        PLB_CUDA(cudaMemcpyAsync(mm->p, init_mm, 16, cudaMemcpyHostToDevice, c.stream));
+        PLB_LAUNCH("k7_join_minmax", k_join_minmax, grid_for(nb, 256), 256, 0, build.v(), build.vm(), elem, sign_bits, nb, as<unsigned long long>(mm));
+        unsigned long long hmm[2];
+        PLB_CUDA(cudaMemcpyAsync(hmm, mm->p, 16, cudaMemcpyDeviceToHost, c.stream));
+        PLB_CUDA(cudaStreamSynchronize(c.stream));
+        if (hmm[0] <= hmm[1] && hmm[1] - hmm[0] < (unsigned long long)8 * (unsigned long long)nb) {
+            kmin = hmm[0]; range = hmm[1] - hmm[0] + 1;
+            dense_table = dev_alloc((size_t)range * 4 + 16);
+            DevPtr dups = dev_alloc(4); dev_memset(dups->p, 0, 4);
+            PLB_LAUNCH("k7_dense_init", k_fill_u32j, grid_for((int64_t)range, 256), 256, 0, as<uint32_t>(dense_table), J_NONE, (int64_t)range);
+            PLB_LAUNCH("k7_dense_build", k_join_dense_build, grid_for(nb, 256), 256, 0, as<uint32_t>(dense_table), build.v(), build.vm(), elem, sign_bits, nb, (uint64_t)kmin, as<int>(dups));
+            dense = read_scalar(as<int>(dups)) == 0;       // duplicates -> hashed table + CSR lists
+        }
+    }
+    JoinTableDev T; T.cap = (uint64_t)std::max<int64_t>(2 * nb, 16); T.entries = nullptr;
+    DevPtr entries, slot_of_row, sorted_rows;
+    bool csr = false;
+    if (!dense) {
+        entries = dev_alloc((size_t)(T.cap + 2) * 16);
+        T.entries = as<uint4>(entries);
+        PLB_LAUNCH("k7_join_init", k_join_init, grid_for((int64_t)T.cap + 2, 256), 256, 0, T.entries, (int64_t)T.cap + 2);
+        slot_of_row = dev_alloc((size_t)std::max<int64_t>(nb, 1) * 4);
+        DevPtr has_dups = dev_alloc(4);
+        dev_memset(has_dups->p, 0, 4);
+        if (nb > 0)
+            PLB_LAUNCH("k7_join_build", k_join_build, grid_for(nb, 256), 256, 0, T, build.v(), build.vm(), dt, nb, nulls_equal ? 1 : 0, as<uint32_t>(slot_of_row), as<int>(has_dups));
+        csr = nb > 0 && read_scalar(as<int>(has_dups)) != 0;
+        if (csr) {
+            const int64_t ne = (int64_t)T.cap + 2, ntiles_e = (ne + J_TILE - 1) / J_TILE;
+            DevPtr sums = dev_alloc((size_t)ntiles_e * 4), offs = dev_alloc((size_t)ntiles_e * 8);
+            PLB_LAUNCH("k7_tile_sums", k_join_tile_sums, grid_for(ntiles_e * 256, 256), 256, 0, T.entries, ne, as<uint32_t>(sums));
+            exclusive_scan_u32_to_u64(as<uint32_t>(sums), as<uint64_t>(offs), ntiles_e, nullptr);
+            PLB_LAUNCH("k7_csr_offsets", k_join_csr_offsets, grid_for(ntiles_e * 256, 256), 256, 0, T.entries, ne, as<uint64_t>(offs));
+            // ascending row lists: stable sort of the build rows by entry index (skipped null rows sort last)
+            sorted_rows = dev_alloc((size_t)nb * 4);
+            iota_u32(as<uint32_t>(sorted_rows), nb, 0);
+            sort_pairs_u32(as<uint32_t>(slot_of_row), as<uint32_t>(sorted_rows), nb);
+        }
     }
 
+    trace_point("join:build");
     // ---- probe pass 1
     const int64_t ntiles = (np + J_TILE - 1) / J_TILE;
     DevPtr handle = dev_alloc((size_t)std::max<int64_t>(np, 1) * 4 + 16), tc = dev_alloc((size_t)std::max<int64_t>(ntiles, 1) * 4), toff = dev_alloc((size_t)std::max<int64_t>(ntiles, 1) * 8), total = dev_alloc(8);
@@ -274,7 +377,14 @@ JoinResult op_hash_join(const DevCol& left, const DevCol& right, int how, bool n
         const bool kn = probe.validity != nullptr;
         const int left_join = how == BL_JOIN_LEFT ? 1 : 0;
         uint32_t* hp = as<uint32_t>(handle); uint32_t* tcp = as<uint32_t>(tc); unsigned long long* tp = as<unsigned long long>(total);
-        if (dt == BL_FLOAT64) launch_probe<8, 1>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp, tp);
+        if (dense) {
+            const uint32_t* tb = as<uint32_t>(dense_table);
+            if (elem == 8) { if (kn) PLB_LAUNCH("k8_dense_probe", (k_join_dense_probe<8, true>), grid, 256, 0, tb, kmin, range, sign_bits, probe.v(), probe.vm(), np, left_join, hp, tcp, tp);
+                             else PLB_LAUNCH("k8_dense_probe", (k_join_dense_probe<8, false>), grid, 256, 0, tb, kmin, range, sign_bits, probe.v(), probe.vm(), np, left_join, hp, tcp, tp); }
+            else { if (kn) PLB_LAUNCH("k8_dense_probe", (k_join_dense_probe<4, true>), grid, 256, 0, tb, kmin, range, sign_bits, probe.v(), probe.vm(), np, left_join, hp, tcp, tp);
+                   else PLB_LAUNCH("k8_dense_probe", (k_join_dense_probe<4, false>), grid, 256, 0, tb, kmin, range, sign_bits, probe.v(), probe.vm(), np, left_join, hp, tcp, tp); }
+        }
+        else if (dt == BL_FLOAT64) launch_probe<8, 1>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp, tp);
         else if (dt == BL_FLOAT32) launch_probe<4, 2>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp, tp);
         else if (dtype_size(dt) == 8) launch_probe<8, 0>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp, tp);
         else launch_probe<4, 0>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp, tp);
@@ -283,12 +393,14 @@ JoinResult op_hash_join(const DevCol& left, const DevCol& right, int how, bool n
     }
     PLB_REQUIRE(M < 0xFFFFFFFFull, BL_ERR_UNSUPPORTED, "join: result has more than 2^32-2 rows (IdxSize = u32)");
 
+    trace_point("join:probe");
     // ---- probe pass 2
     DevPtr out_probe = dev_alloc((size_t)std::max<uint64_t>(M, 1) * 4 + 16), out_build = dev_alloc((size_t)std::max<uint64_t>(M, 1) * 4 + 16);
     if (M > 0)
         PLB_LAUNCH("k8_join_emit", k_join_emit, (int)std::min<int64_t>(ntiles, (int64_t)c.sm_count * 8), 256, 0, T, as<uint32_t>(handle), np, csr ? 1 : 0, how == BL_JOIN_LEFT ? 1 : 0,
                    as<uint32_t>(sorted_rows), as<uint64_t>(toff), as<uint32_t>(out_probe), as<uint32_t>(out_build));
 
+    trace_point("join:emit");
     JoinResult r;
     r.left = idx_col(swapped ? out_build : out_probe, (int64_t)M, 0);
     r.right = idx_col(swapped ? out_probe : out_build, (int64_t)M, how == BL_JOIN_LEFT ? -1 : 0);
@@ -309,6 +421,7 @@ JoinResult op_hash_join(const DevCol& left, const DevCol& right, int how, bool n
         r.right.validity = m.values;
         r.right.null_count = -1;
     }
+    trace_point("join:done");
     return r;
 }
 

@@ -1,6 +1,8 @@
 // runtime.cu — device context, stream-ordered memory pool, pinned-host cache, per-kernel launch
 // accounting, and the bl_column <-> device-column transfer (pinned DMA, chunk concatenation,
 // bitmap bit-offset normalisation).
+#include <time.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <map>
@@ -85,6 +87,18 @@ void Context::drain_events() {
         event_pool.push_back(p.a); event_pool.push_back(p.b);
     }
     pending.clear();
+}
+
+void trace_point(const char* label) {
+    static int on = -1;
+    static double last = 0;
+    if (on < 0) { const char* e = getenv("BL_TRACE"); on = (e && e[0] == '1') ? 1 : 0; }
+    if (!on) return;
+    cudaStreamSynchronize(ctx().stream);
+    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    fprintf(stderr, "[bl_trace] %-28s +%.3f ms\n", label, last ? now - last : 0.0);
+    last = now;
 }
 
 // ---------------------------------------------------------------------------- memory
