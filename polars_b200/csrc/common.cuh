@@ -153,6 +153,7 @@ void op_gather(const std::vector<DevCol>& cols, const DevCol& idx, bool check_bo
 DevPtr bitmap_and(const uint32_t* a, const uint32_t* b, const uint32_t* c, int64_t bits);
 int64_t bitmap_popcount(const uint32_t* bm, int64_t bits);
 void exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out, int64_t n, uint64_t* total_dev);
+void exclusive_scan_u64(const uint64_t* in, uint64_t* out, int64_t n, uint64_t* total_dev);
 void sort_pairs_u32(uint32_t* keys, uint32_t* vals, int64_t n);   // stable, ascending (device)
 void iota_u32(uint32_t* p, int64_t n, uint32_t base);
 

@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(128) k_mask_tile_counts(const uint32_t* __rest
 }
 
 // single-CTA exclusive scan u32 -> u64 (n up to a few hundred thousand tiles; negligible time)
-__global__ void __launch_bounds__(1024) k_scan_u32_u64(const uint32_t* __restrict__ in, uint64_t* __restrict__ out, int64_t n, uint64_t* total) {
+template <typename TIN>
+__global__ void __launch_bounds__(1024) k_scan_u64(const TIN* __restrict__ in, uint64_t* __restrict__ out, int64_t n, uint64_t* total) {
     __shared__ uint64_t warp_sums[32];
     __shared__ uint64_t carry_s;
     if (threadIdx.x == 0) carry_s = 0;
@@ -70,7 +71,10 @@ __global__ void __launch_bounds__(1024) k_scan_u32_u64(const uint32_t* __restric
     if (threadIdx.x == 0 && total) *total = carry_s;
 }
 void exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out, int64_t n, uint64_t* total_dev) {
-    PLB_LAUNCH("scan_u32_u64", k_scan_u32_u64, 1, 1024, 0, in, out, n, total_dev);
+    PLB_LAUNCH("scan_u32_u64", (k_scan_u64<uint32_t>), 1, 1024, 0, in, out, n, total_dev);
+}
+void exclusive_scan_u64(const uint64_t* in, uint64_t* out, int64_t n, uint64_t* total_dev) {
+    PLB_LAUNCH("scan_u64", (k_scan_u64<uint64_t>), 1, 1024, 0, in, out, n, total_dev);
 }
 
 struct FilterCol { const void* in; void* out; const uint32_t* vin; uint32_t* vout; int elem; int pad; };

@@ -56,22 +56,51 @@ __device__ __forceinline__ uint64_t load_key_rt(const void* keys, int dtype, int
     }
 }
 
-// claim / find the entry of `key`.  nullptr => probe limit hit (table too small): status set.
-__device__ __forceinline__ uint64_t* gb_find_or_insert(const GbTableDev& T, uint64_t key) {
-    uint64_t slot = dirty_hash(key) >> T.shift;
+// ---- L2 cache-policy hints (sm_80+ createpolicy): the hash table is the only data with reuse, the
+//      scanned columns are read once.  hint != 0: table loads / CAS / REDs carry an evict_last policy.
+__device__ __forceinline__ uint64_t make_policy_evict_last() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t tbl_load(const uint64_t* p, uint64_t pol, bool hint) {
+    uint64_t v;
+    if (hint) asm volatile("ld.global.cg.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    else v = __ldcg(reinterpret_cast<const unsigned long long*>(p));
+    return v;
+}
+__device__ __forceinline__ void red_add_u64(uint64_t* p, uint64_t v, uint64_t pol, bool hint) {
+    if (hint) asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" :: "l"(p), "l"(v), "l"(pol) : "memory");
+    else atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+__device__ __forceinline__ void red_add_f64(uint64_t* p, double v, uint64_t pol, bool hint) {
+    if (hint) asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(p), "d"(v), "l"(pol) : "memory");
+    else atomicAdd(reinterpret_cast<double*>(p), v);
+}
+__device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v, uint64_t pol, bool hint) {
+    if (hint) asm volatile("red.global.add.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory");
+    else atomicAdd(p, v);
+}
+
+// claim / find the entry of `key`, continuing from slot `slot` whose key word `k` has already been
+// loaded (the first probes of all rows of an iteration are issued together).
+// nullptr => probe limit hit (table too small): status set.
+__device__ __forceinline__ uint64_t* gb_resolve(const GbTableDev& T, uint64_t key, uint64_t slot, uint64_t k, uint64_t pol, bool hint) {
     const uint64_t mask = T.cap - 1;
     for (int probes = 0; probes < GB_MAX_PROBE; ++probes) {
         uint64_t* e = T.entries + slot * T.stride;
-        uint64_t k = __ldcg(reinterpret_cast<const unsigned long long*>(e));
         if (k == key) return e;
         if (k == GB_EMPTY) {
             unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(e), (unsigned long long)GB_EMPTY, (unsigned long long)key);
             if (old == GB_EMPTY || old == key) return e;
         }
         slot = (slot + 1) & mask;
+        k = tbl_load(T.entries + slot * T.stride, pol, hint);
     }
     *T.status = 1;
     return nullptr;
+}
+__device__ __forceinline__ uint64_t* gb_find_or_insert(const GbTableDev& T, uint64_t key) {
+    const uint64_t slot = dirty_hash(key) >> T.shift;
+    return gb_resolve(T, key, slot, __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + slot * T.stride)), 0, false);
 }
 __device__ __forceinline__ uint64_t* gb_special(const GbTableDev& T, int which) {
     uint64_t* e = T.entries + (T.cap + which) * T.stride;
@@ -94,10 +123,10 @@ __device__ __forceinline__ uint64_t raw_to_int(int dtype, uint64_t raw) {
     return dtype == BL_INT32 ? (uint64_t)(long long)(int)(uint32_t)raw : raw;   // sign-extend i32; u32 already zero-extended
 }
 
-__device__ __forceinline__ void gb_apply(int op, uint64_t* addr, int dtype, uint64_t raw, bool valid) {
+__device__ __forceinline__ void gb_apply(int op, uint64_t* addr, int dtype, uint64_t raw, bool valid, uint64_t pol = 0, bool hint = false) {
     switch (op) {
-        case W_ADD_INT: { uint64_t v = raw_to_int(dtype, raw); if (valid && v) atomicAdd(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)v); break; }
-        case W_ADD_F64: { double f = raw_to_f64(dtype, raw); if (valid && f != 0.0) atomicAdd(reinterpret_cast<double*>(addr), f); break; }
+        case W_ADD_INT: { uint64_t v = raw_to_int(dtype, raw); if (valid && v) red_add_u64(addr, v, pol, hint); break; }
+        case W_ADD_F64: { double f = raw_to_f64(dtype, raw); if (valid && f != 0.0) red_add_f64(addr, f, pol, hint); break; }
         case W_MIN_S64: if (valid) atomicMin(reinterpret_cast<long long*>(addr), (long long)raw_to_int(dtype, raw)); break;
         case W_MAX_S64: if (valid) atomicMax(reinterpret_cast<long long*>(addr), (long long)raw_to_int(dtype, raw)); break;
         case W_MIN_U64: if (valid) atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)raw); break;
@@ -109,51 +138,68 @@ __device__ __forceinline__ void gb_apply(int op, uint64_t* addr, int dtype, uint
 }
 
 // ---------------------------------------------------------------------------- K5 main kernel
-// Each thread owns PAIRS x 2 consecutive-pair rows per iteration: 128-bit loads of the key pair and
-// of every value-column pair (64-bit loads for 4-byte types), then probe + RED per row.
-template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC>
+// Each thread owns PAIRS row pairs per iteration (pair p and p + k * grid stride: every load
+// instruction is a fully coalesced 128-bit access): 128-bit loads of the key pair and of every
+// value-column pair (64-bit loads for 4-byte types), then the first table probe of ALL its rows is
+// issued before any of them is resolved (memory-level parallelism: the kernel is bound by L2
+// latency, not by any throughput unit), then one RED per accumulator.
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC, int PAIRS>
 __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const __grid_constant__ GbBatch B) {
+    constexpr int R = 2 * PAIRS;
     const int64_t npairs = B.n >> 1;
     const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    const bool hint = T.hint != 0;
+    const uint64_t pol = hint ? make_policy_evict_last() : 0;
     int iter = 0;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += gstride) {
+    for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p0 < npairs; p0 += gstride * PAIRS) {
         if (((iter++) & 15) == 0 && *reinterpret_cast<volatile int*>(T.status)) return;
-        uint64_t kraw[2];
-        if (KEY_ELEM == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(B.keys) + 2 * p); kraw[0] = t.x; kraw[1] = t.y; }
-        else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(B.keys) + 2 * p); kraw[0] = t.x; kraw[1] = t.y; }
-        uint64_t raw[MAXC][2];
+        uint64_t kraw[R];
+        uint64_t raw[MAXC][R];
 #pragma unroll
-        for (int c = 0; c < MAXC; c++) {
-            if (c < L.n_cols) {
-                if (B.cols[c].elem == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(B.cols[c].values) + 2 * p); raw[c][0] = t.x; raw[c][1] = t.y; }
-                else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(B.cols[c].values) + 2 * p); raw[c][0] = t.x; raw[c][1] = t.y; }
+        for (int u = 0; u < PAIRS; u++) {
+            const int64_t p = p0 + u * gstride;
+            if (p < npairs) {
+                if (KEY_ELEM == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(B.keys) + 2 * p); kraw[2 * u] = t.x; kraw[2 * u + 1] = t.y; }
+                else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(B.keys) + 2 * p); kraw[2 * u] = t.x; kraw[2 * u + 1] = t.y; }
+#pragma unroll
+                for (int c = 0; c < MAXC; c++) {
+                    if (c < L.n_cols) {
+                        if (B.cols[c].elem == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(B.cols[c].values) + 2 * p); raw[c][2 * u] = t.x; raw[c][2 * u + 1] = t.y; }
+                        else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(B.cols[c].values) + 2 * p); raw[c][2 * u] = t.x; raw[c][2 * u + 1] = t.y; }
+                    }
+                }
             }
         }
-        // issue both table probes before touching the accumulators
-        uint64_t* ent[2];
+        // first probe of every row
+        uint64_t key[R], slot[R], k0[R];
+        int kind[R];   // 0 regular, 1 null-key group, 2 GB_EMPTY-key group, -1 no row
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int64_t row = 2 * p + j;
-            bool kvalid = true;
-            if (KEY_NULLS) kvalid = bit_get(B.key_validity, row);
-            const uint64_t key = canon_key<KEY_CANON>(kraw[j]);
-            if (!kvalid) ent[j] = gb_special(T, 0);
-            else if (key == GB_EMPTY) ent[j] = gb_special(T, 1);
-            else ent[j] = gb_find_or_insert(T, key);
+        for (int r = 0; r < R; r++) {
+            const int64_t p = p0 + (r >> 1) * gstride;
+            kind[r] = -1; key[r] = 0; slot[r] = 0; k0[r] = 0;
+            if (p < npairs) {
+                const int64_t row = 2 * p + (r & 1);
+                bool kvalid = true;
+                if (KEY_NULLS) kvalid = bit_get(B.key_validity, row);
+                key[r] = canon_key<KEY_CANON>(kraw[r]);
+                kind[r] = !kvalid ? 1 : (key[r] == GB_EMPTY ? 2 : 0);
+                if (kind[r] == 0) { slot[r] = dirty_hash(key[r]) >> T.shift; k0[r] = tbl_load(T.entries + slot[r] * T.stride, pol, hint); }
+            }
         }
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            uint64_t* e = ent[j];
+        for (int r = 0; r < R; r++) {
+            if (kind[r] < 0) continue;
+            uint64_t* e = kind[r] == 0 ? gb_resolve(T, key[r], slot[r], k0[r], pol, hint) : gb_special(T, kind[r] - 1);
             if (e == nullptr) continue;
-            const int64_t row = 2 * p + j;
-            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + 1), 1u);
+            const int64_t row = 2 * (p0 + (r >> 1) * gstride) + (r & 1);
+            if (L.need_len) red_add_u32(reinterpret_cast<uint32_t*>(e + 1), 1u, pol, hint);
             if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + 1) + 1, B.row_base + (uint32_t)row);
 #pragma unroll
             for (int c = 0; c < MAXC; c++) {
                 if (c < L.n_cols) {
                     const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
                     const int dt = B.cols[c].dtype;
-                    for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + 2 + L.wslot[k], dt, raw[c][j], valid);
+                    for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + 2 + L.wslot[k], dt, raw[c][r], valid, pol, hint);
                 }
             }
         }
@@ -452,7 +498,8 @@ void GroupByState::alloc_table(uint64_t new_cap) {
     cap = new_cap;
     entries = dev_alloc((size_t)(cap + 2) * L.stride * 8);
     int shift = 64; for (uint64_t c = cap; c > 1; c >>= 1) shift--;
-    T.entries = as<uint64_t>(entries); T.cap = cap; T.shift = shift; T.stride = L.stride; T.status = as<int>(status);
+    static const int hint = [] { const char* e = getenv("BL_K5_HINT"); return e ? atoi(e) : 1; }();
+    T.entries = as<uint64_t>(entries); T.cap = cap; T.shift = shift; T.stride = L.stride; T.status = as<int>(status); T.hint = hint;
     PLB_LAUNCH("k5_table_init", k_gb_init, grid_for((int64_t)(cap + 2) * L.stride, 256), 256, 0, T.entries, (int64_t)(cap + 2), L.stride, L);
     dev_memset(status->p, 0, 4);
 }
@@ -486,12 +533,18 @@ uint64_t GroupByState::choose_cap(const DevCol& key) {
     return pow2_at_least(G / lf);       // load factor <= 0.6 by default
 }
 
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int PAIRS>
+static void launch_consume_p(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int grid) {
+    if (L.n_cols <= 1) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 1, PAIRS>), grid, 256, 0, L, T, B);
+    else if (L.n_cols <= 2) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 2, PAIRS>), grid, 256, 0, L, T, B);
+    else if (L.n_cols <= 4) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 4, PAIRS>), grid, 256, 0, L, T, B);
+    else PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 8, 1>), grid, 256, 0, L, T, B);
+}
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS>
 static void launch_consume(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int grid) {
-    if (L.n_cols <= 1) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 1>), grid, 256, 0, L, T, B);
-    else if (L.n_cols <= 2) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 2>), grid, 256, 0, L, T, B);
-    else if (L.n_cols <= 4) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 4>), grid, 256, 0, L, T, B);
-    else PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 8>), grid, 256, 0, L, T, B);
+    static const int pairs = [] { const char* e = getenv("BL_K5_PAIRS"); int v = e ? atoi(e) : 2; return v == 1 ? 1 : 2; }();
+    if (pairs == 2) launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 2>(L, T, B, grid);
+    else launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 1>(L, T, B, grid);
 }
 
 void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCol*>& values, int64_t row_base) {

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) k_join_csr_offsets(uint4* __restrict__ en
 // handle[i] = unique mode: build row (J_NONE on miss); CSR mode: entry index (J_NONE on miss).
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS>
 __global__ void __launch_bounds__(256) k_join_probe(JoinTableDev T, const void* __restrict__ keys, const uint32_t* __restrict__ valid, int64_t n, int nulls_equal, int csr_mode,
-                                                    int left_join, uint32_t* __restrict__ handle, uint32_t* __restrict__ tile_counts, unsigned long long* __restrict__ total) {
+                                                    int left_join, uint32_t* __restrict__ handle, unsigned long long* __restrict__ tile_counts) {
     const int64_t npairs = (n + 1) >> 1;
     const int64_t rounded = (npairs + 31) / 32 * 32;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < rounded; p += (int64_t)gridDim.x * blockDim.x) {
@@ -167,9 +167,9 @@ __global__ void __launch_bounds__(256) k_join_probe(JoinTableDev T, const void* 
         if (r0 + 1 < n) *reinterpret_cast<uint2*>(handle + r0) = make_uint2(h[0], h[1]);
         else if (r0 < n) handle[r0] = h[0];
         // 32 lanes x 2 rows = 64 consecutive rows: always inside one J_TILE
-        uint32_t c = cnt;
+        unsigned long long c = cnt;
         for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane_id() == 0 && c) { atomicAdd(&tile_counts[(r0) / J_TILE], c); atomicAdd(total, (unsigned long long)c); }
+        if (lane_id() == 0 && c) atomicAdd(&tile_counts[r0 / J_TILE], c);   // one address per 2048-row tile; the grand total comes from the scan
     }
 }
 
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) k_join_dense_build(uint32_t* __restrict__
 template <int KEY_ELEM, bool KEY_NULLS>
 __global__ void __launch_bounds__(256) k_join_dense_probe(const uint32_t* __restrict__ table, uint64_t kmin, uint64_t range, int sign_bits, const void* __restrict__ keys,
                                                           const uint32_t* __restrict__ valid, int64_t n, int left_join, uint32_t* __restrict__ handle,
-                                                          uint32_t* __restrict__ tile_counts, unsigned long long* __restrict__ total) {
+                                                          unsigned long long* __restrict__ tile_counts) {
     const int64_t npairs = (n + 1) >> 1;
     const int64_t rounded = (npairs + 31) / 32 * 32;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < rounded; p += (int64_t)gridDim.x * blockDim.x) {
@@ -288,16 +288,16 @@ __global__ void __launch_bounds__(256) k_join_dense_probe(const uint32_t* __rest
         }
         if (r0 + 1 < n) *reinterpret_cast<uint2*>(handle + r0) = make_uint2(h[0], h[1]);
         else if (r0 < n) handle[r0] = h[0];
-        uint32_t c = cnt;
+        unsigned long long c = cnt;
         for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane_id() == 0 && c) { atomicAdd(&tile_counts[r0 / J_TILE], c); atomicAdd(total, (unsigned long long)c); }
+        if (lane_id() == 0 && c) atomicAdd(&tile_counts[r0 / J_TILE], c);
     }
 }
 
 template <int KEY_ELEM, int KEY_CANON>
-static void launch_probe(bool kn, int grid, JoinTableDev T, const DevCol& probe, int nulls_equal, int csr, int left, uint32_t* handle, uint32_t* tc, unsigned long long* total) {
-    if (kn) PLB_LAUNCH("k8_join_probe", (k_join_probe<KEY_ELEM, KEY_CANON, true>), grid, 256, 0, T, probe.v(), probe.vm(), probe.len, nulls_equal, csr, left, handle, tc, total);
-    else PLB_LAUNCH("k8_join_probe", (k_join_probe<KEY_ELEM, KEY_CANON, false>), grid, 256, 0, T, probe.v(), probe.vm(), probe.len, nulls_equal, csr, left, handle, tc, total);
+static void launch_probe(bool kn, int grid, JoinTableDev T, const DevCol& probe, int nulls_equal, int csr, int left, uint32_t* handle, unsigned long long* tc) {
+    if (kn) PLB_LAUNCH("k8_join_probe", (k_join_probe<KEY_ELEM, KEY_CANON, true>), grid, 256, 0, T, probe.v(), probe.vm(), probe.len, nulls_equal, csr, left, handle, tc);
+    else PLB_LAUNCH("k8_join_probe", (k_join_probe<KEY_ELEM, KEY_CANON, false>), grid, 256, 0, T, probe.v(), probe.vm(), probe.len, nulls_equal, csr, left, handle, tc);
 }
 
 static DevCol idx_col(DevPtr p, int64_t n, int64_t null_count) { DevCol c; c.dtype = BL_UINT32; c.len = n; c.values = p; c.null_count = null_count; return c; }
@@ -369,26 +369,26 @@ JoinResult op_hash_join(const DevCol& left, const DevCol& right, int how, bool n
     trace_point("join:build");
     // ---- probe pass 1
     const int64_t ntiles = (np + J_TILE - 1) / J_TILE;
-    DevPtr handle = dev_alloc((size_t)std::max<int64_t>(np, 1) * 4 + 16), tc = dev_alloc((size_t)std::max<int64_t>(ntiles, 1) * 4), toff = dev_alloc((size_t)std::max<int64_t>(ntiles, 1) * 8), total = dev_alloc(8);
-    dev_memset(tc->p, 0, (size_t)std::max<int64_t>(ntiles, 1) * 4); dev_memset(total->p, 0, 8);
+    DevPtr handle = dev_alloc((size_t)std::max<int64_t>(np, 1) * 4 + 16), tc = dev_alloc((size_t)std::max<int64_t>(ntiles, 1) * 8), toff = dev_alloc((size_t)std::max<int64_t>(ntiles, 1) * 8), total = dev_alloc(8);
+    dev_memset(tc->p, 0, (size_t)std::max<int64_t>(ntiles, 1) * 8); dev_memset(total->p, 0, 8);
     uint64_t M = 0;
     if (np > 0) {
         const int grid = grid_for((np + 1) / 2, 256);
         const bool kn = probe.validity != nullptr;
         const int left_join = how == BL_JOIN_LEFT ? 1 : 0;
-        uint32_t* hp = as<uint32_t>(handle); uint32_t* tcp = as<uint32_t>(tc); unsigned long long* tp = as<unsigned long long>(total);
+        uint32_t* hp = as<uint32_t>(handle); unsigned long long* tcp = as<unsigned long long>(tc);
         if (dense) {
             const uint32_t* tb = as<uint32_t>(dense_table);
-            if (elem == 8) { if (kn) PLB_LAUNCH("k8_dense_probe", (k_join_dense_probe<8, true>), grid, 256, 0, tb, kmin, range, sign_bits, probe.v(), probe.vm(), np, left_join, hp, tcp, tp);
-                             else PLB_LAUNCH("k8_dense_probe", (k_join_dense_probe<8, false>), grid, 256, 0, tb, kmin, range, sign_bits, probe.v(), probe.vm(), np, left_join, hp, tcp, tp); }
-            else { if (kn) PLB_LAUNCH("k8_dense_probe", (k_join_dense_probe<4, true>), grid, 256, 0, tb, kmin, range, sign_bits, probe.v(), probe.vm(), np, left_join, hp, tcp, tp);
-                   else PLB_LAUNCH("k8_dense_probe", (k_join_dense_probe<4, false>), grid, 256, 0, tb, kmin, range, sign_bits, probe.v(), probe.vm(), np, left_join, hp, tcp, tp); }
+            if (elem == 8) { if (kn) PLB_LAUNCH("k8_dense_probe", (k_join_dense_probe<8, true>), grid, 256, 0, tb, kmin, range, sign_bits, probe.v(), probe.vm(), np, left_join, hp, tcp);
+                             else PLB_LAUNCH("k8_dense_probe", (k_join_dense_probe<8, false>), grid, 256, 0, tb, kmin, range, sign_bits, probe.v(), probe.vm(), np, left_join, hp, tcp); }
+            else { if (kn) PLB_LAUNCH("k8_dense_probe", (k_join_dense_probe<4, true>), grid, 256, 0, tb, kmin, range, sign_bits, probe.v(), probe.vm(), np, left_join, hp, tcp);
+                   else PLB_LAUNCH("k8_dense_probe", (k_join_dense_probe<4, false>), grid, 256, 0, tb, kmin, range, sign_bits, probe.v(), probe.vm(), np, left_join, hp, tcp); }
         }
-        else if (dt == BL_FLOAT64) launch_probe<8, 1>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp, tp);
-        else if (dt == BL_FLOAT32) launch_probe<4, 2>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp, tp);
-        else if (dtype_size(dt) == 8) launch_probe<8, 0>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp, tp);
-        else launch_probe<4, 0>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp, tp);
-        exclusive_scan_u32_to_u64(as<uint32_t>(tc), as<uint64_t>(toff), ntiles, nullptr);
+        else if (dt == BL_FLOAT64) launch_probe<8, 1>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp);
+        else if (dt == BL_FLOAT32) launch_probe<4, 2>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp);
+        else if (dtype_size(dt) == 8) launch_probe<8, 0>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp);
+        else launch_probe<4, 0>(kn, grid, T, probe, nulls_equal, csr, left_join, hp, tcp);
+        exclusive_scan_u64(as<uint64_t>(tc), as<uint64_t>(toff), ntiles, as<uint64_t>(total));
         M = read_scalar(as<unsigned long long>(total));
     }
     PLB_REQUIRE(M < 0xFFFFFFFFull, BL_ERR_UNSUPPORTED, "join: result has more than 2^32-2 rows (IdxSize = u32)");
