@@ -372,15 +372,20 @@ int64_t or_group_by(const uint64_t* keys, const uint8_t* key_valid, int64_t n, i
     for (int64_t p = 0; p < G; p++) {
         newpos[fg[p].gid] = (idx_t)p; first[p] = fg[p].first; offsets[p + 1] = offsets[p] + counts[fg[p].gid];
     }
-    /* fill idx lists by one row-order scan => ascending inside each group */
+    /* fill idx lists: every thread scans all rows in order and fills the groups of ITS partition
+     * (the reference pushes into the group's IdxVec during the same T x N scan, hashing.rs:142-153)
+     * => ascending inside each group */
     uint64_t* cursor = (uint64_t*)malloc((size_t)G * sizeof(uint64_t));
     memcpy(cursor, offsets, (size_t)G * sizeof(uint64_t));
-    for (int64_t i = 0; i < n; i++) {
-        int valid = key_valid == NULL || key_valid[i];
-        uint64_t h = valid ? dirty_hash_u64(keys[i]) : 0;
-        int t = P > 1 ? (int)hash_to_partition(h, (uint64_t)P) : 0;
-        idx_t p = newpos[part_base[t] + gid_of_row[i]];
-        idx[cursor[p]++] = (idx_t)i;
+#pragma omp parallel for schedule(static, 1) num_threads(P > 1 ? P : 1) if (P > 1)
+    for (int t = 0; t < P; t++) {
+        for (int64_t i = 0; i < n; i++) {
+            int valid = key_valid == NULL || key_valid[i];
+            uint64_t h = valid ? dirty_hash_u64(keys[i]) : 0;
+            if (P > 1 && (int)hash_to_partition(h, (uint64_t)P) != t) continue;
+            idx_t p = newpos[part_base[t] + gid_of_row[i]];
+            idx[cursor[p]++] = (idx_t)i;
+        }
     }
     for (int t = 0; t < P; t++) { free(part_first[t]); free(part_count[t]); }
     free(part_first); free(part_count); free(part_ngroups); free(part_base);

@@ -266,31 +266,168 @@ __global__ void k_fill_u64(uint64_t* p, uint64_t v, int64_t n) {
 // rows: n_rows x row_words.  table_mode: rows are the slots of another table (stride = row_words,
 // special slots at src_cap, src_cap+1); else exported partial rows whose last word is meta
 // (0 normal, 1 null-key group, 2 GB_EMPTY-key group).
+__device__ __forceinline__ void gb_merge_row(const GbLayout& L, const GbTableDev& T, const uint64_t* src, int meta) {
+    uint64_t* e = meta == 1 ? gb_special(T, 0) : (meta == 2 ? gb_special(T, 1) : gb_find_or_insert(T, src[0]));
+    if (!e) return;
+    const uint64_t lf = src[1];
+    if ((uint32_t)lf) atomicAdd(reinterpret_cast<unsigned*>(e + 1), (uint32_t)lf);
+    if ((uint32_t)(lf >> 32) != 0xFFFFFFFFu) atomicMin(reinterpret_cast<unsigned*>(e + 1) + 1, (uint32_t)(lf >> 32));
+    for (int w = 0; w < L.n_words; w++) {
+        const uint64_t v = src[2 + w];
+        if (v == L.init[w]) continue;
+        uint64_t* a = e + 2 + w;
+        switch (L.slot_op[w]) {
+            case W_ADD_F64: atomicAdd(reinterpret_cast<double*>(a), __longlong_as_double((long long)v)); break;
+            case W_MIN_S64: atomicMin(reinterpret_cast<long long*>(a), (long long)v); break;
+            case W_MAX_S64: atomicMax(reinterpret_cast<long long*>(a), (long long)v); break;
+            case W_MIN_U64: case W_MIN_F64: atomicMin(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v); break;
+            case W_MAX_U64: case W_MAX_F64: atomicMax(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v); break;
+            default: atomicAdd(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v); break;   // ADD_INT, NULLCNT
+        }
+    }
+}
 __global__ void __launch_bounds__(256) k_gb_merge(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const uint64_t* __restrict__ rows, int64_t n_rows, int row_words, int table_mode, int64_t src_cap) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t* src = rows + r * row_words;
-        const uint64_t key = src[0];
         int meta;
-        if (table_mode) { if (key == GB_EMPTY) continue; meta = r == src_cap ? 1 : (r == src_cap + 1 ? 2 : 0); }
+        if (table_mode) { if (src[0] == GB_EMPTY) continue; meta = r == src_cap ? 1 : (r == src_cap + 1 ? 2 : 0); }
         else meta = (int)src[row_words - 1];
-        uint64_t* e = meta == 1 ? gb_special(T, 0) : (meta == 2 ? gb_special(T, 1) : gb_find_or_insert(T, key));
-        if (!e) continue;
-        const uint64_t lf = src[1];
-        if ((uint32_t)lf) atomicAdd(reinterpret_cast<unsigned*>(e + 1), (uint32_t)lf);
-        if ((uint32_t)(lf >> 32) != 0xFFFFFFFFu) atomicMin(reinterpret_cast<unsigned*>(e + 1) + 1, (uint32_t)(lf >> 32));
-        for (int w = 0; w < L.n_words; w++) {
-            const uint64_t v = src[2 + w];
-            if (v == L.init[w]) continue;
-            uint64_t* a = e + 2 + w;
-            switch (L.slot_op[w]) {
-                case W_ADD_F64: atomicAdd(reinterpret_cast<double*>(a), __longlong_as_double((long long)v)); break;
-                case W_MIN_S64: atomicMin(reinterpret_cast<long long*>(a), (long long)v); break;
-                case W_MAX_S64: atomicMax(reinterpret_cast<long long*>(a), (long long)v); break;
-                case W_MIN_U64: case W_MIN_F64: atomicMin(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v); break;
-                case W_MAX_U64: case W_MAX_F64: atomicMax(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v); break;
-                default: atomicAdd(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v); break;   // ADD_INT, NULLCNT
+        gb_merge_row(L, T, src, meta);
+    }
+}
+
+// ---------------------------------------------------------------------------- K5, low-cardinality variant
+// When the sampled estimate says the groups fit a shared-memory table (<= a few thousand), every
+// CTA aggregates into a PRIVATE open-addressing table in shared memory and merges it into the
+// global table once at the end: B200 sustains ~1.2 T shared-memory atomics/s against ~0.2 T L2
+// atomics/s (profiles/r01_ubench_b200.jsonl), so this path is bound by the HBM scan instead of the
+// L2 atomic units.  Shared-memory accumulators: 32-bit native ATOMS; 64-bit integer adds as two
+// 32-bit adds with carry (exact, order-free); f64 add and 64-bit min/max as CAS loops.
+// Rows whose key cannot be placed (table 3/4 full) fall through to the global table, so the
+// result is exact for any input; a wrong estimate only costs speed.
+__device__ __forceinline__ void s_add_u64(uint64_t* a, uint64_t v) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(a);
+    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    const uint32_t old = atomicAdd(w, lo);
+    const uint32_t up = hi + (((uint32_t)(old + lo) < old) ? 1u : 0u);
+    if (up) atomicAdd(w + 1, up);
+}
+__device__ __forceinline__ void gb_apply_smem(int op, uint64_t* addr, int dtype, uint64_t raw, bool valid) {
+    switch (op) {
+        case W_ADD_INT: { uint64_t v = raw_to_int(dtype, raw); if (valid && v) s_add_u64(addr, v); break; }
+        case W_ADD_F64: { double f = raw_to_f64(dtype, raw); if (valid && f != 0.0) atomicAdd(reinterpret_cast<double*>(addr), f); break; }
+        case W_MIN_S64: if (valid) atomicMin(reinterpret_cast<long long*>(addr), (long long)raw_to_int(dtype, raw)); break;
+        case W_MAX_S64: if (valid) atomicMax(reinterpret_cast<long long*>(addr), (long long)raw_to_int(dtype, raw)); break;
+        case W_MIN_U64: if (valid) atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)raw); break;
+        case W_MAX_U64: if (valid) atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)raw); break;
+        case W_MIN_F64: { double f = raw_to_f64(dtype, raw); if (valid && f == f) atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)f64_to_ordered(f)); break; }
+        case W_MAX_F64: { double f = raw_to_f64(dtype, raw); if (valid && f == f) atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)f64_to_ordered(f)); break; }
+        default: if (!valid) atomicAdd(reinterpret_cast<unsigned*>(addr), 1u); break;   // W_NULLCNT (< 2^32 per CTA)
+    }
+}
+
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC>
+__global__ void __launch_bounds__(512) k_gb_consume_smem(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const __grid_constant__ GbBatch B, int scap, int sshift) {
+    extern __shared__ uint64_t stab[];
+    __shared__ int s_used;
+    const int stride = L.stride;
+    const int n_ent = scap + 2;
+    for (int i = threadIdx.x; i < n_ent * stride; i += blockDim.x) {
+        const int w = i % stride;
+        stab[i] = w == 0 ? GB_EMPTY : (w == 1 ? GB_W1_INIT : (w - 2 < L.n_words ? L.init[w - 2] : 0ull));
+    }
+    if (threadIdx.x == 0) s_used = 0;
+    __syncthreads();
+    const int max_used = scap - (scap >> 2);
+    const int64_t npairs = B.n >> 1;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += gstride) {
+        uint64_t kraw[2];
+        if (KEY_ELEM == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(B.keys) + 2 * p); kraw[0] = t.x; kraw[1] = t.y; }
+        else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(B.keys) + 2 * p); kraw[0] = t.x; kraw[1] = t.y; }
+        uint64_t raw[MAXC][2];
+#pragma unroll
+        for (int c = 0; c < MAXC; c++) {
+            if (c < L.n_cols) {
+                if (B.cols[c].elem == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(B.cols[c].values) + 2 * p); raw[c][0] = t.x; raw[c][1] = t.y; }
+                else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(B.cols[c].values) + 2 * p); raw[c][0] = t.x; raw[c][1] = t.y; }
             }
         }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int64_t row = 2 * p + j;
+            bool kvalid = true;
+            if (KEY_NULLS) kvalid = bit_get(B.key_validity, row);
+            const uint64_t key = canon_key<KEY_CANON>(kraw[j]);
+            uint64_t* se = nullptr;     // entry in the CTA's shared table, or nullptr -> global path
+            if (!kvalid || key == GB_EMPTY) {
+                se = stab + (scap + (kvalid ? 1 : 0)) * stride;
+                if (*reinterpret_cast<volatile uint64_t*>(se) == GB_EMPTY) atomicCAS(reinterpret_cast<unsigned long long*>(se), (unsigned long long)GB_EMPTY, kvalid ? 1ull : 0ull);
+            } else {
+                uint32_t slot = (uint32_t)(dirty_hash(key) >> sshift);
+                for (int probes = 0; probes < 32; probes++) {
+                    uint64_t* e = stab + slot * stride;
+                    const uint64_t k = *reinterpret_cast<volatile uint64_t*>(e);
+                    if (k == key) { se = e; break; }
+                    if (k == GB_EMPTY) {
+                        if (*reinterpret_cast<volatile int*>(&s_used) >= max_used) break;
+                        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(e), (unsigned long long)GB_EMPTY, (unsigned long long)key);
+                        if (old == GB_EMPTY) { atomicAdd(&s_used, 1); se = e; break; }
+                        if (old == key) { se = e; break; }
+                    }
+                    slot = (slot + 1) & (uint32_t)(scap - 1);
+                }
+            }
+            if (se != nullptr) {
+                if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(se + 1), 1u);
+                if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(se + 1) + 1, B.row_base + (uint32_t)row);
+#pragma unroll
+                for (int c = 0; c < MAXC; c++) {
+                    if (c < L.n_cols) {
+                        const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
+                        const int dt = B.cols[c].dtype;
+                        for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply_smem(L.wop[k], se + 2 + L.wslot[k], dt, raw[c][j], valid);
+                    }
+                }
+            } else {
+                uint64_t* e = gb_find_or_insert(T, key);
+                if (e != nullptr) {
+                    if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + 1), 1u);
+                    if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + 1) + 1, B.row_base + (uint32_t)row);
+#pragma unroll
+                    for (int c = 0; c < MAXC; c++) {
+                        if (c < L.n_cols) {
+                            const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
+                            const int dt = B.cols[c].dtype;
+                            for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + 2 + L.wslot[k], dt, raw[c][j], valid);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // odd tail row: straight to the global table
+    if ((B.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t row = B.n - 1;
+        bool kvalid = B.key_validity == nullptr || bit_get(B.key_validity, row);
+        uint64_t key = load_key_rt(B.keys, B.key_dtype, row);
+        uint64_t* e = !kvalid ? gb_special(T, 0) : (key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key));
+        if (e) {
+            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + 1), 1u);
+            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + 1) + 1, B.row_base + (uint32_t)row);
+            for (int c = 0; c < L.n_cols; c++) {
+                const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
+                uint64_t raw = B.cols[c].elem == 8 ? reinterpret_cast<const uint64_t*>(B.cols[c].values)[row] : (uint64_t)reinterpret_cast<const uint32_t*>(B.cols[c].values)[row];
+                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + 2 + L.wslot[k], B.cols[c].dtype, raw, valid);
+            }
+        }
+    }
+    __syncthreads();
+    // merge the CTA's partial aggregates into the global table
+    for (int sidx = threadIdx.x; sidx < n_ent; sidx += blockDim.x) {
+        const uint64_t* src = stab + sidx * stride;
+        if (src[0] == GB_EMPTY) continue;
+        gb_merge_row(L, T, src, sidx == scap ? 1 : (sidx == scap + 1 ? 2 : 0));
     }
 }
 
@@ -498,7 +635,7 @@ void GroupByState::alloc_table(uint64_t new_cap) {
     cap = new_cap;
     entries = dev_alloc((size_t)(cap + 2) * L.stride * 8);
     int shift = 64; for (uint64_t c = cap; c > 1; c >>= 1) shift--;
-    static const int hint = [] { const char* e = getenv("BL_K5_HINT"); return e ? atoi(e) : 1; }();
+    static const int hint = [] { const char* e = getenv("BL_K5_HINT"); return e ? atoi(e) : 0; }();
     T.entries = as<uint64_t>(entries); T.cap = cap; T.shift = shift; T.stride = L.stride; T.status = as<int>(status); T.hint = hint;
     PLB_LAUNCH("k5_table_init", k_gb_init, grid_for((int64_t)(cap + 2) * L.stride, 256), 256, 0, T.entries, (int64_t)(cap + 2), L.stride, L);
     dev_memset(status->p, 0, 4);
@@ -529,6 +666,7 @@ uint64_t GroupByState::choose_cap(const DevCol& key) {
         G = estimate_groups((double)d, (double)m, (double)n) * 1.25 + 64;
         if (G > (double)n) G = (double)n;
     }
+    est_groups = (int64_t)G;
     static const double lf = [] { const char* e = getenv("BL_K5_LF"); double v = e ? atof(e) / 100.0 : 0.6; return (v > 0.05 && v < 0.95) ? v : 0.6; }();
     return pow2_at_least(G / lf);       // load factor <= 0.6 by default
 }
@@ -542,9 +680,27 @@ static void launch_consume_p(const GbLayout& L, const GbTableDev& T, const GbBat
 }
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS>
 static void launch_consume(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int grid) {
-    static const int pairs = [] { const char* e = getenv("BL_K5_PAIRS"); int v = e ? atoi(e) : 2; return v == 1 ? 1 : 2; }();
+    static const int pairs = [] { const char* e = getenv("BL_K5_PAIRS"); int v = e ? atoi(e) : 1; return v == 2 ? 2 : 1; }();
     if (pairs == 2) launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 2>(L, T, B, grid);
     else launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 1>(L, T, B, grid);
+}
+
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC>
+static void launch_smem_c(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int scap) {
+    auto kfn = k_gb_consume_smem<KEY_ELEM, KEY_CANON, KEY_NULLS, MAXC>;
+    const size_t smem = (size_t)(scap + 2) * L.stride * 8;
+    PLB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)std::min<size_t>(4, std::max<size_t>(1, (size_t)(220 * 1024) / (smem + 1024)));
+    int sshift = 64; for (int c = scap; c > 1; c >>= 1) sshift--;
+    const int grid = (int)std::min<int64_t>((int64_t)ctx().sm_count * per_sm, std::max<int64_t>(1, (B.n / 2 + 511) / 512));
+    PLB_LAUNCH("k5_groupby_agg_smem", kfn, grid, 512, smem, L, T, B, scap, sshift);
+}
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS>
+static void launch_smem(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int scap) {
+    if (L.n_cols <= 1) launch_smem_c<KEY_ELEM, KEY_CANON, KEY_NULLS, 1>(L, T, B, scap);
+    else if (L.n_cols <= 2) launch_smem_c<KEY_ELEM, KEY_CANON, KEY_NULLS, 2>(L, T, B, scap);
+    else if (L.n_cols <= 4) launch_smem_c<KEY_ELEM, KEY_CANON, KEY_NULLS, 4>(L, T, B, scap);
+    else launch_smem_c<KEY_ELEM, KEY_CANON, KEY_NULLS, 8>(L, T, B, scap);
 }
 
 void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCol*>& values, int64_t row_base) {
@@ -587,8 +743,16 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
     const int elem = dtype_size(key.dtype);
     const int canon = key.dtype == BL_FLOAT64 ? 1 : (key.dtype == BL_FLOAT32 ? 2 : 0);
     // keys must be 16-byte aligned for the 128-bit path (device columns always are)
+    // low-cardinality plan: CTA-private shared-memory tables (largest table that leaves >= 1 CTA per SM)
+    static const int smem_on = [] { const char* e = getenv("BL_K5_SMEM"); return e ? atoi(e) : 1; }();
+    int scap = 0;
+    if (smem_on && est_groups > 0) {
+        int want = 256; while (want < 2 * est_groups && want < (1 << 20)) want <<= 1;
+        if ((size_t)(want + 2) * Lb.stride * 8 <= (size_t)200 * 1024) scap = want;
+    }
 #define GB_DISPATCH(E, C)                                                            \
-    do { if (kn) launch_consume<E, C, true>(Lb, T, B, grid); else launch_consume<E, C, false>(Lb, T, B, grid); } while (0)
+    do { if (scap) { if (kn) launch_smem<E, C, true>(Lb, T, B, scap); else launch_smem<E, C, false>(Lb, T, B, scap); }                       \
+         else if (kn) launch_consume<E, C, true>(Lb, T, B, grid); else launch_consume<E, C, false>(Lb, T, B, grid); } while (0)
     if (elem == 8) { if (canon == 1) GB_DISPATCH(8, 1); else GB_DISPATCH(8, 0); }
     else { if (canon == 2) GB_DISPATCH(4, 2); else GB_DISPATCH(4, 0); }
 #undef GB_DISPATCH

@@ -309,6 +309,27 @@ def test_group_by_high_cardinality_restart(plb):
     assert c.sum() == n and k.size == np.unique(key2).size
 
 
+def test_group_by_smem_plan_overflow_falls_through(plb):
+    # the sampled estimate (~900 groups) selects the shared-memory plan, but the tail holds ~4000
+    # distinct keys: rows that do not fit the CTA-private table must take the global path, exactly
+    n = 400_000
+    rng = np.random.default_rng(21)
+    key = np.where(rng.random(n) < 0.99, 5, rng.integers(10, 10**9, n)).astype(np.int64)
+    vi = rng.integers(-1000, 1000, n).astype(np.int64)
+    vf = rng.uniform(0, 100, n).round(6)
+    valid = rng.random(n) > 0.1
+    aggs = [("sum", vi, valid), ("mean", vf, None), ("len", None, None), ("min", vf, None), ("max", vi, valid)]
+    for order in (True, False):
+        keys, kv, outs = GpuImpl(plb).group_by_agg(key, None, aggs, order)
+        ek, ekv, eouts, _ = oracle.group_by_agg(key, None, aggs, 4, order)
+        if not order:
+            keys, kv, outs = sort_groups(keys, kv, outs)
+            ek, ekv, eouts = sort_groups(ek, ekv, eouts)
+        assert_close(keys, ek, kv, ekv, "keys")
+        for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
+            assert_close(v, ev, m, em, kind)
+
+
 def test_group_by_streaming_and_partials(plb):
     # streaming consume == one shot; export -> merge of partial aggregates == single table
     rng = np.random.default_rng(12)
