@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=20_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU exchange of the partial aggregates")
     return ap.parse_args()
 
 
@@ -178,6 +179,11 @@ def main():
         del key, vi, vf
         spec = [("sum", np.int64), ("mean", np.float64), ("len", None)]
         out_bytes = 0
+        peer_ex = None
+        if world > 1:
+            from polars_b200 import dist as pdist
+            if a.exchange == "p2p":      # window region per source rank: every group of a rank could go to one peer
+                peer_ex = pdist.PeerExchange(plb, rows_per_src=min(a.keys, a.rows) + 1024, row_words=2 + 3)
 
         def step_device():
             nonlocal out_bytes
@@ -185,22 +191,13 @@ def main():
                 ok, outs = plb.group_by_agg(dkey.view(), [("sum", dvi.view()), ("mean", dvf.view()), ("len", None)], False, location=plb.DEVICE)
                 out_bytes = ok.length * (8 + 8 + 8 + 4)
                 return ok.length
-            # partitioned plan: local pre-aggregation -> hash partition of partials -> one all-to-all -> merge
-            g = plb.GroupBy(np.int64, spec)
-            g.consume(dkey.view(), [dvi.view(), dvf.view(), None], row_base=0)
-            ptr, rw, offs = g.export_partials(world)
-            counts = torch.tensor(np.diff(offs), dtype=torch.int64, device="cuda")
-            rcounts = torch.empty_like(counts)
-            dist.all_to_all_single(rcounts, counts)
-            rc = rcounts.cpu().numpy()
-            send = torch.as_tensor(_CudaArray(ptr, int(offs[-1]) * rw), device="cuda") if offs[-1] else torch.empty(0, dtype=torch.int64, device="cuda")
-            recv = torch.empty(int(rc.sum()) * rw, dtype=torch.int64, device="cuda")
-            dist.all_to_all_single(recv, send, output_split_sizes=(rc * rw).tolist(), input_split_sizes=(np.diff(offs) * rw).tolist())
-            torch.cuda.synchronize()
-            f = plb.GroupBy(np.int64, spec, expected_groups=max(int(rc.sum()), 1))
-            f.merge_partials(recv.data_ptr(), int(rc.sum()))
-            ok, outs = f.finish(False, location=plb.DEVICE)
-            plb.dev_free(ptr)
+            # partitioned plan (polars_b200/dist.py): local pre-aggregation -> hash partition of the partial
+            # aggregates -> exchange (fused P2P stores over NVLink, or one NCCL all-to-all) -> merge
+            vals = [dvi.view(), dvf.view(), None]
+            if a.exchange == "p2p":
+                ok, outs = pdist.partitioned_group_by_p2p(plb, peer_ex, dkey.view(), vals, spec, nullable=[False, False, False])
+            else:
+                ok, outs = pdist.partitioned_group_by(plb, dkey.view(), vals, spec, nullable=[False, False, False])
             out_bytes = ok.length * 28
             return ok.length
 
@@ -291,7 +288,7 @@ def main():
         "metric": metric, "value": value, "unit": "rows/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/float64", "data": "synthetic",
         "config": {"workload": wl, "rows_per_gpu": a.rows, "groups_out": int(n_out), "l2_policy": "inputs larger than L2",
-                   "parallelism": "single GPU" if world == 1 else f"hash-partitioned x{world}: local pre-agg + one NCCL all-to-all of partial aggregates + merge"},
+                   "parallelism": "single GPU" if world == 1 else (f"hash-partitioned x{world}: local pre-agg + fused partition/P2P-store exchange over NVLink + merge" if a.exchange == "p2p" else f"hash-partitioned x{world}: local pre-agg + one NCCL all-to-all of partial aggregates + merge")},
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs if peak_gbs else None,
                      "traffic": None, "peak_source": peak_src, "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes_per_row * unit_rows,
                      "kernel_share_of_step": (dom_ms / total_kernel_ms) if total_kernel_ms else None},

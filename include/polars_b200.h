@@ -179,8 +179,10 @@ typedef struct bl_groupby bl_groupby;
 /* key_dtype / value dtypes fix the plan; expected_groups <= 0 lets the library estimate.
  * track_first != 0 records each group's first row index (one extra 32-bit atomic per row); it is
  * required for bl_groupby_finish(maintain_order != 0). */
-bl_status bl_groupby_create(int32_t key_dtype, const int32_t* agg_kinds, const int32_t* value_dtypes, int32_t n_aggs,
-                            int64_t expected_groups, int32_t track_first, bl_groupby** out);
+/* value_nullable[i] == 0 promises that aggregation i's column never carries nulls (saves its null
+ * counter: smaller table entries); NULL = every column may be nullable. */
+bl_status bl_groupby_create(int32_t key_dtype, const int32_t* agg_kinds, const int32_t* value_dtypes, const int32_t* value_nullable,
+                            int32_t n_aggs, int64_t expected_groups, int32_t track_first, bl_groupby** out);
 /* Accumulate one batch: key + one value column per agg (values[i] ignored for LEN).  Columns may
  * be BL_HOST or BL_DEVICE.  row_base = global index of the batch's first row. */
 bl_status bl_groupby_consume(bl_groupby* g, const bl_column* key, const bl_column* values, int64_t row_base);
@@ -193,6 +195,29 @@ bl_status bl_groupby_merge_partials(bl_groupby* g, const void* rows_dev, int64_t
 bl_status bl_groupby_finish(bl_groupby* g, int32_t maintain_order, int32_t out_location, bl_column* out_key, bl_column* out_aggs);
 void bl_groupby_reset(bl_groupby* g);
 void bl_groupby_destroy(bl_groupby* g);
+
+/* ---- peer windows: fused partition + exchange over NVLink (one process per GPU) ----------- */
+/* A window is plain device memory (cudaMalloc) exported with CUDA IPC so that the partition
+ * kernels of the OTHER ranks can store into it directly (P2P stores over NVLink / NVSwitch):
+ * partition and transfer are one kernel, no staging buffer, no NCCL on the data path.
+ * Layout of a window used by bl_groupby_export_partials_p2p: n_ranks regions of
+ * `rows_per_src` rows x row_words 64-bit words; region s is written only by rank s. */
+typedef struct bl_window bl_window;
+#define BL_IPC_HANDLE_BYTES 64
+bl_status bl_window_create(size_t bytes, bl_window** out, void* ipc_handle_out /* BL_IPC_HANDLE_BYTES */);
+void* bl_window_ptr(bl_window* w);
+void bl_window_destroy(bl_window* w);
+/* Maps a peer rank's window into this process (cudaIpcOpenMemHandle). */
+bl_status bl_window_open(const void* ipc_handle, void** peer_ptr_out);
+void bl_window_close(void* peer_ptr);
+/* Fused K6 + exchange for the partitioned group_by: scatters this rank's partial-aggregate rows by
+ * key partition straight into region `my_rank` of the destination rank's window.
+ * windows[p] = device pointer of rank p's window as mapped in THIS process (own window for
+ * p == my_rank).  sent_rows[p] (host) = rows written to rank p; the caller exchanges these counts and
+ * merges region s of its own window with bl_groupby_merge_partials.  Returns after the kernel and
+ * its peer stores have completed. */
+bl_status bl_groupby_export_partials_p2p(bl_groupby* g, int32_t n_ranks, int32_t my_rank, void* const* windows, int64_t rows_per_src,
+                                         int32_t* row_words, int64_t* sent_rows);
 
 /* ---- profiling (CUDA events on the library stream) -------------------------------------- */
 /* enable != 0: every kernel launch is bracketed by events; totals accumulate per kernel name. */

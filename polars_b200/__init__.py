@@ -394,14 +394,15 @@ def hash_partition(key, payload: Sequence, n_partitions: int, location: int = HO
 class GroupBy:
     """Streaming group_by state (bl_groupby_*): consume batches, exchange partial aggregates, finish."""
 
-    def __init__(self, key_dtype, aggs: Sequence, expected_groups: int = 0, track_first: bool = False):
-        """aggs: [(kind, value_dtype | None)]"""
+    def __init__(self, key_dtype, aggs: Sequence, expected_groups: int = 0, track_first: bool = False, nullable: Sequence | None = None):
+        """aggs: [(kind, value_dtype | None)]; nullable[i] = False promises a null-free column (smaller entries)"""
         self.kinds = [AGGS[k] for k, _ in aggs]
         dts = [DTYPES[np.dtype(d)] if d is not None else 3 for _, d in aggs]
         n = len(aggs)
         self.n = n
         self.h = C.c_void_p()
-        _check(lib().bl_groupby_create(C.c_int32(DTYPES[np.dtype(key_dtype)]), (C.c_int32 * max(n, 1))(*self.kinds), (C.c_int32 * max(n, 1))(*dts),
+        nl = None if nullable is None else (C.c_int32 * max(n, 1))(*[int(bool(x)) for x in nullable])
+        _check(lib().bl_groupby_create(C.c_int32(DTYPES[np.dtype(key_dtype)]), (C.c_int32 * max(n, 1))(*self.kinds), (C.c_int32 * max(n, 1))(*dts), nl,
                                        C.c_int32(n), C.c_int64(expected_groups), C.c_int32(int(track_first)), C.byref(self.h)))
 
     def consume(self, key, values: Sequence, row_base: int = 0):
@@ -417,6 +418,16 @@ class GroupBy:
         offs = (C.c_int64 * (n_partitions + 1))()
         _check(lib().bl_groupby_export_partials(self.h, C.c_int32(n_partitions), C.byref(p), C.byref(rw), offs))
         return int(p.value or 0), int(rw.value), np.array(list(offs), dtype=np.int64)
+
+    def export_partials_p2p(self, windows: Sequence[int], my_rank: int, rows_per_src: int):
+        """Fused partition + exchange: stores this rank's partial rows into the peers' windows.
+        -> (row_words, sent_rows[n_ranks])"""
+        n = len(windows)
+        arr = (C.c_void_p * n)(*[C.c_void_p(w) for w in windows])
+        rw = C.c_int32()
+        sent = (C.c_int64 * n)()
+        _check(lib().bl_groupby_export_partials_p2p(self.h, C.c_int32(n), C.c_int32(my_rank), arr, C.c_int64(rows_per_src), C.byref(rw), sent))
+        return int(rw.value), np.array(list(sent), dtype=np.int64)
 
     def merge_partials(self, rows_dev_ptr: int, n_rows: int):
         _check(lib().bl_groupby_merge_partials(self.h, C.c_void_p(rows_dev_ptr), C.c_int64(n_rows)))
@@ -437,6 +448,36 @@ class GroupBy:
                 self.h = None
         except Exception:
             pass
+
+
+class Window:
+    """Device memory exported over CUDA IPC so peer ranks can store into it (bl_window_*)."""
+
+    def __init__(self, nbytes: int):
+        self.h = C.c_void_p()
+        buf = C.create_string_buffer(64)
+        _check(lib().bl_window_create(C.c_size_t(nbytes), C.byref(self.h), buf))
+        self.ipc_handle = bytes(buf.raw)
+        lib().bl_window_ptr.restype = C.c_void_p
+        self.ptr = int(lib().bl_window_ptr(self.h))
+        self.nbytes = nbytes
+
+    @staticmethod
+    def open(ipc_handle: bytes) -> int:
+        p = C.c_void_p()
+        _check(lib().bl_window_open(C.create_string_buffer(ipc_handle, 64), C.byref(p)))
+        return int(p.value)
+
+    @staticmethod
+    def close(ptr: int):
+        lib().bl_window_close.restype = None
+        lib().bl_window_close(C.c_void_p(ptr))
+
+    def destroy(self):
+        if self.h:
+            lib().bl_window_destroy.restype = None
+            lib().bl_window_destroy(self.h)
+            self.h = None
 
 
 def dev_free(ptr: int):

@@ -102,7 +102,9 @@ bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, cons
         vptr[i] = &vals[i];
         dts.push_back(vals[i].dtype);
     }
-    GroupByState st(key.dtype, kinds, dts, 0, maintain_order != 0 || dtype_is_float(key.dtype));
+    std::vector<int> nullable(n_aggs, 0);
+    for (int i = 0; i < n_aggs; i++) nullable[i] = vptr[i] != nullptr && vptr[i]->validity != nullptr;
+    GroupByState st(key.dtype, kinds, dts, nullable, 0, maintain_order != 0 || dtype_is_float(key.dtype));
     st.consume_all(key, vptr);
     DevCol ok; std::vector<DevCol> oa;
     st.finish(maintain_order != 0, &key, ok, oa);
@@ -154,11 +156,13 @@ bl_status bl_hash_partition(const bl_column* key, const bl_column* payload, int3
 // ---- streaming group_by state ---------------------------------------------------------------
 struct bl_groupby { GroupByState* st; };
 
-bl_status bl_groupby_create(int32_t key_dtype, const int32_t* agg_kinds, const int32_t* value_dtypes, int32_t n_aggs, int64_t expected_groups, int32_t track_first, bl_groupby** out) {
+bl_status bl_groupby_create(int32_t key_dtype, const int32_t* agg_kinds, const int32_t* value_dtypes, const int32_t* value_nullable, int32_t n_aggs, int64_t expected_groups, int32_t track_first, bl_groupby** out) {
     BL_TRY
     PLB_REQUIRE(out && (n_aggs == 0 || (agg_kinds && value_dtypes)), BL_ERR_INVALID, "groupby_create: null argument");
     std::vector<int> k(agg_kinds, agg_kinds + n_aggs), d(value_dtypes, value_dtypes + n_aggs);
-    auto* g = new bl_groupby{new GroupByState(key_dtype, k, d, expected_groups, track_first != 0)};
+    std::vector<int> nl;
+    if (value_nullable) nl.assign(value_nullable, value_nullable + n_aggs);
+    auto* g = new bl_groupby{new GroupByState(key_dtype, k, d, nl, expected_groups, track_first != 0)};
     *out = g;
     BL_CATCH
 }
@@ -214,6 +218,41 @@ bl_status bl_groupby_finish(bl_groupby* g, int32_t maintain_order, int32_t out_l
     for (int i = 0; i < n_aggs; i++) out_aggs[i] = ta[i];
     BL_CATCH
 }
+bl_status bl_groupby_export_partials_p2p(bl_groupby* g, int32_t n_ranks, int32_t my_rank, void* const* windows, int64_t rows_per_src, int32_t* row_words, int64_t* sent_rows) {
+    BL_TRY
+    PLB_REQUIRE(g && windows && row_words && sent_rows, BL_ERR_INVALID, "groupby_export_partials_p2p: null argument");
+    int rw = 0;
+    g->st->export_partials_p2p(n_ranks, my_rank, windows, rows_per_src, &rw, sent_rows);
+    *row_words = rw;
+    BL_CATCH
+}
+
+// ---- peer windows (CUDA IPC) -------------------------------------------------------------------
+struct bl_window { void* p; size_t bytes; };
+bl_status bl_window_create(size_t bytes, bl_window** out, void* ipc_handle_out) {
+    BL_TRY
+    PLB_REQUIRE(out && ipc_handle_out && bytes > 0, BL_ERR_INVALID, "window_create: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == BL_IPC_HANDLE_BYTES, "IPC handle size");
+    void* p = nullptr;
+    PLB_CUDA(cudaMalloc(&p, bytes));                       // IPC needs a plain cudaMalloc allocation
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); PLB_CUDA(e); }
+    memcpy(ipc_handle_out, &h, sizeof h);
+    *out = new bl_window{p, bytes};
+    BL_CATCH
+}
+void* bl_window_ptr(bl_window* w) { return w ? w->p : nullptr; }
+void bl_window_destroy(bl_window* w) { if (w) { cudaFree(w->p); delete w; } }
+bl_status bl_window_open(const void* ipc_handle, void** peer_ptr_out) {
+    BL_TRY
+    PLB_REQUIRE(ipc_handle && peer_ptr_out, BL_ERR_INVALID, "window_open: null argument");
+    cudaIpcMemHandle_t h; memcpy(&h, ipc_handle, sizeof h);
+    PLB_CUDA(cudaIpcOpenMemHandle(peer_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    BL_CATCH
+}
+void bl_window_close(void* peer_ptr) { if (peer_ptr) cudaIpcCloseMemHandle(peer_ptr); }
+
 void bl_groupby_reset(bl_groupby* g) { try { if (g) { std::lock_guard<std::recursive_mutex> lk(ctx().mu); g->st->reset(); } } catch (...) {} }
 void bl_groupby_destroy(bl_groupby* g) { try { if (g) { std::lock_guard<std::recursive_mutex> lk(ctx().mu); delete g->st; delete g; } } catch (...) {} }
 

@@ -327,17 +327,24 @@ __device__ __forceinline__ void gb_apply_smem(int op, uint64_t* addr, int dtype,
 }
 
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC>
-__global__ void __launch_bounds__(512) k_gb_consume_smem(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const __grid_constant__ GbBatch B, int scap, int sshift) {
-    extern __shared__ uint64_t stab[];
-    __shared__ int s_used;
+__global__ void __launch_bounds__(512) k_gb_consume_smem(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const __grid_constant__ GbBatch B, int scap, int sshift, int copies) {
+    // `copies` replicas of the table (tiny cardinalities): lane l works on replica l % copies, so the
+    // lanes of a warp that hit the SAME group do not serialise on one shared-memory address.
+    extern __shared__ uint64_t stab_all[];
+    __shared__ int s_used_all[32];
     const int stride = L.stride;
     const int n_ent = scap + 2;
-    for (int i = threadIdx.x; i < n_ent * stride; i += blockDim.x) {
-        const int w = i % stride;
-        stab[i] = w == 0 ? GB_EMPTY : (w == 1 ? GB_W1_INIT : (w - 2 < L.n_words ? L.init[w - 2] : 0ull));
+    const int tab_words = n_ent * stride + 2;          // +2 words: replicas start in different banks
+    for (int i = threadIdx.x; i < copies * tab_words; i += blockDim.x) {
+        const int j = i % tab_words;
+        const int w = j % stride;
+        stab_all[i] = j >= n_ent * stride ? 0ull : (w == 0 ? GB_EMPTY : (w == 1 ? GB_W1_INIT : (w - 2 < L.n_words ? L.init[w - 2] : 0ull)));
     }
-    if (threadIdx.x == 0) s_used = 0;
+    if (threadIdx.x < 32) s_used_all[threadIdx.x] = 0;
     __syncthreads();
+    const int my_copy = (int)(lane_id() % (unsigned)copies);
+    uint64_t* const stab = stab_all + (size_t)my_copy * tab_words;
+    int& s_used = s_used_all[my_copy];
     const int max_used = scap - (scap >> 2);
     const int64_t npairs = B.n >> 1;
     const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
@@ -424,8 +431,9 @@ __global__ void __launch_bounds__(512) k_gb_consume_smem(const __grid_constant__
     }
     __syncthreads();
     // merge the CTA's partial aggregates into the global table
-    for (int sidx = threadIdx.x; sidx < n_ent; sidx += blockDim.x) {
-        const uint64_t* src = stab + sidx * stride;
+    for (int i = threadIdx.x; i < copies * n_ent; i += blockDim.x) {
+        const int sidx = i % n_ent;
+        const uint64_t* src = stab_all + (size_t)(i / n_ent) * tab_words + sidx * stride;
         if (src[0] == GB_EMPTY) continue;
         gb_merge_row(L, T, src, sidx == scap ? 1 : (sidx == scap + 1 ? 2 : 0));
     }
@@ -587,6 +595,43 @@ __global__ void __launch_bounds__(256) k_gb_export_scatter(const uint64_t* __res
     }
 }
 
+// Fused partition + exchange: same block-local reservation as k_gb_export_scatter, but the row is
+// stored straight into the destination rank's window (peer memory over NVLink): partition p's rows
+// land in region `my_rank` of windows[p] at [cursor .. cursor + n).  No staging copy, no collective.
+struct PeerWindows { uint64_t* base[EXP_MAX_PARTS]; };
+__global__ void __launch_bounds__(256) k_gb_export_p2p(const uint64_t* __restrict__ entries, int64_t cap, int stride, int n_words, int P, const __grid_constant__ PeerWindows W,
+                                                       int64_t region_words, int my_rank, int64_t rows_per_src, unsigned long long* part_cursor, int* overflow) {
+    __shared__ unsigned hist[EXP_MAX_PARTS];
+    __shared__ unsigned long long base[EXP_MAX_PARTS];
+    const int row_words = n_words + 3;
+    const int64_t n_entries = cap + 2;
+    const int64_t ntiles = (n_entries + 255) / 256;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        if (threadIdx.x < EXP_MAX_PARTS) hist[threadIdx.x] = 0;
+        __syncthreads();
+        const int64_t s = t * 256 + threadIdx.x;
+        uint64_t key = GB_EMPTY; int p = 0; unsigned local = 0;
+        if (s < n_entries) key = entries[s * stride];
+        if (key != GB_EMPTY) { p = gb_row_partition(key, s, cap, P); local = atomicAdd(&hist[p], 1u); }
+        __syncthreads();
+        if (threadIdx.x < P && hist[threadIdx.x]) base[threadIdx.x] = atomicAdd(&part_cursor[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+        __syncthreads();
+        if (key != GB_EMPTY) {
+            const uint64_t pos = base[p] + local;
+            if ((int64_t)pos >= rows_per_src) *overflow = 1;
+            else {
+                const uint64_t* e = entries + s * stride;
+                uint64_t* dst = W.base[p] + (int64_t)my_rank * region_words + pos * row_words;     // peer store
+                dst[0] = s == cap ? 0 : (s == cap + 1 ? GB_EMPTY : key);
+                dst[1] = e[1];
+                for (int w = 0; w < n_words; w++) dst[2 + w] = e[2 + w];
+                dst[2 + n_words] = s == cap ? 1 : (s == cap + 1 ? 2 : 0);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace plb
 
 // =============================================================================================
@@ -601,7 +646,7 @@ static int sum_out_dtype(int dt) {
     return dt;
 }
 
-GroupByState::GroupByState(int key_dt, const std::vector<int>& kinds, const std::vector<int>& dtypes, int64_t expected, bool track_first)
+GroupByState::GroupByState(int key_dt, const std::vector<int>& kinds, const std::vector<int>& dtypes, const std::vector<int>& nullable, int64_t expected, bool track_first)
     : key_dtype(key_dt), agg_kinds(kinds), agg_dtypes(dtypes), expected_groups(expected) {
     PLB_REQUIRE(key_dt == BL_INT64 || key_dt == BL_UINT64 || key_dt == BL_INT32 || key_dt == BL_UINT32 || key_dt == BL_FLOAT64 || key_dt == BL_FLOAT32,
                 BL_ERR_UNSUPPORTED, std::string("group_by: key dtype ") + dtype_name(key_dt) + " is outside the hot path");
@@ -609,17 +654,21 @@ GroupByState::GroupByState(int key_dt, const std::vector<int>& kinds, const std:
     int nw = 0;
     auto add_word = [&](int op) { PLB_REQUIRE(nw < GB_MAX_WORDS, BL_ERR_UNSUPPORTED, "group_by: too many aggregations for one pass"); L.slot_op[nw] = op; L.init[nw] = word_identity(op); return nw++; };
     for (size_t i = 0; i < kinds.size(); i++) {
-        AggPlan ap; ap.kind = kinds[i]; ap.in_dtype = dtypes[i]; ap.main = -1; ap.nullcnt = -1;
+        AggPlan ap; ap.kind = kinds[i]; ap.in_dtype = dtypes[i]; ap.main = -1; ap.nullcnt = -1; ap.nullable = nullable.empty() || nullable[i] != 0;
         if (ap.kind != BL_AGG_LEN)
             PLB_REQUIRE(ap.in_dtype == BL_INT64 || ap.in_dtype == BL_UINT64 || ap.in_dtype == BL_INT32 || ap.in_dtype == BL_UINT32 || ap.in_dtype == BL_FLOAT64 || ap.in_dtype == BL_FLOAT32,
                         BL_ERR_UNSUPPORTED, std::string("group_by: value dtype ") + dtype_name(ap.in_dtype) + " is outside the hot path");
         const bool flt = dtype_is_float(ap.in_dtype), sgn = dtype_is_signed(ap.in_dtype);
+        // a null counter is only needed when the column can hold nulls (valid count = len - nulls); without it
+        // the C2 entry is key + len|first + 2 accumulators = 32 bytes = one sector
+        const bool nl = nullable.empty() || nullable[i] != 0;
+        auto null_word = [&]() { return nl ? add_word(W_NULLCNT) : -1; };
         switch (ap.kind) {
             case BL_AGG_SUM: ap.main = add_word(flt ? W_ADD_F64 : W_ADD_INT); ap.out_dtype = sum_out_dtype(ap.in_dtype); break;
-            case BL_AGG_MEAN: ap.main = add_word(W_ADD_F64); ap.nullcnt = add_word(W_NULLCNT); ap.out_dtype = ap.in_dtype == BL_FLOAT32 ? BL_FLOAT32 : BL_FLOAT64; L.need_len = 1; break;
-            case BL_AGG_MIN: ap.main = add_word(flt ? W_MIN_F64 : (sgn ? W_MIN_S64 : W_MIN_U64)); ap.nullcnt = add_word(W_NULLCNT); ap.out_dtype = ap.in_dtype; L.need_len = 1; break;
-            case BL_AGG_MAX: ap.main = add_word(flt ? W_MAX_F64 : (sgn ? W_MAX_S64 : W_MAX_U64)); ap.nullcnt = add_word(W_NULLCNT); ap.out_dtype = ap.in_dtype; L.need_len = 1; break;
-            case BL_AGG_COUNT: ap.nullcnt = add_word(W_NULLCNT); ap.out_dtype = BL_UINT32; L.need_len = 1; break;
+            case BL_AGG_MEAN: ap.main = add_word(W_ADD_F64); ap.nullcnt = null_word(); ap.out_dtype = ap.in_dtype == BL_FLOAT32 ? BL_FLOAT32 : BL_FLOAT64; L.need_len = 1; break;
+            case BL_AGG_MIN: ap.main = add_word(flt ? W_MIN_F64 : (sgn ? W_MIN_S64 : W_MIN_U64)); ap.nullcnt = null_word(); ap.out_dtype = ap.in_dtype; L.need_len = 1; break;
+            case BL_AGG_MAX: ap.main = add_word(flt ? W_MAX_F64 : (sgn ? W_MAX_S64 : W_MAX_U64)); ap.nullcnt = null_word(); ap.out_dtype = ap.in_dtype; L.need_len = 1; break;
+            case BL_AGG_COUNT: ap.nullcnt = null_word(); ap.out_dtype = BL_UINT32; L.need_len = 1; break;
             case BL_AGG_LEN: ap.out_dtype = BL_UINT32; L.need_len = 1; break;
             default: fail(BL_ERR_INVALID, "group_by: unknown aggregation kind");
         }
@@ -688,12 +737,14 @@ static void launch_consume(const GbLayout& L, const GbTableDev& T, const GbBatch
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC>
 static void launch_smem_c(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int scap) {
     auto kfn = k_gb_consume_smem<KEY_ELEM, KEY_CANON, KEY_NULLS, MAXC>;
-    const size_t smem = (size_t)(scap + 2) * L.stride * 8;
+    const size_t tab_bytes = ((size_t)(scap + 2) * L.stride + 2) * 8;
+    const int copies = (int)std::min<size_t>(32, std::max<size_t>(1, (size_t)(96 * 1024) / tab_bytes));
+    const size_t smem = tab_bytes * copies;
     PLB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = (int)std::min<size_t>(4, std::max<size_t>(1, (size_t)(220 * 1024) / (smem + 1024)));
     int sshift = 64; for (int c = scap; c > 1; c >>= 1) sshift--;
     const int grid = (int)std::min<int64_t>((int64_t)ctx().sm_count * per_sm, std::max<int64_t>(1, (B.n / 2 + 511) / 512));
-    PLB_LAUNCH("k5_groupby_agg_smem", kfn, grid, 512, smem, L, T, B, scap, sshift);
+    PLB_LAUNCH("k5_groupby_agg_smem", kfn, grid, 512, smem, L, T, B, scap, sshift, copies);
 }
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS>
 static void launch_smem(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int scap) {
@@ -713,6 +764,7 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
         const DevCol* v = values[i];
         PLB_REQUIRE(v != nullptr && v->len == key.len, BL_ERR_INVALID, "group_by: value column length differs from key length");
         PLB_REQUIRE(v->dtype == plans[i].in_dtype, BL_ERR_DTYPE, "group_by: value dtype differs from the plan");
+        PLB_REQUIRE(plans[i].nullable || v->validity == nullptr, BL_ERR_INVALID, "group_by: a column declared non-nullable carries a validity bitmap");
         int c = -1;
         for (size_t j = 0; j < col_ptr.size(); j++) if (col_ptr[j] == v->v() && B.cols[j].validity == v->vm()) c = (int)j;
         if (c < 0) {
@@ -845,6 +897,25 @@ DevPtr GroupByState::export_partials(int n_partitions, int* row_words_out, int64
                    as<unsigned long long>(off), as<unsigned long long>(cursor), as<uint64_t>(rows));
     PLB_CUDA(cudaStreamSynchronize(ctx().stream));   // ho[] is on this stack frame
     return rows;
+}
+
+void GroupByState::export_partials_p2p(int n_ranks, int my_rank, void* const* windows, int64_t rows_per_src, int* row_words_out, int64_t* sent_rows) {
+    PLB_REQUIRE(n_ranks >= 1 && n_ranks <= EXP_MAX_PARTS && my_rank >= 0 && my_rank < n_ranks, BL_ERR_INVALID, "export_partials_p2p: bad rank / world size");
+    const int row_words = L.n_words + 3;
+    *row_words_out = row_words;
+    for (int p = 0; p < n_ranks; p++) sent_rows[p] = 0;
+    if (!entries) return;
+    PeerWindows W; memset(&W, 0, sizeof W);
+    for (int p = 0; p < n_ranks; p++) { PLB_REQUIRE(windows[p] != nullptr, BL_ERR_INVALID, "export_partials_p2p: null window"); W.base[p] = reinterpret_cast<uint64_t*>(windows[p]); }
+    DevPtr cursor = dev_alloc(8 * EXP_MAX_PARTS), ovf = dev_alloc(4);
+    dev_memset(cursor->p, 0, 8 * EXP_MAX_PARTS); dev_memset(ovf->p, 0, 4);
+    PLB_LAUNCH("k6_export_p2p", k_gb_export_p2p, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, L.stride, L.n_words, n_ranks, W,
+               rows_per_src * row_words, my_rank, rows_per_src, as<unsigned long long>(cursor), as<int>(ovf));
+    unsigned long long h[EXP_MAX_PARTS];
+    PLB_CUDA(cudaMemcpyAsync(h, cursor->p, 8 * n_ranks, cudaMemcpyDeviceToHost, ctx().stream));
+    const int o = read_scalar(as<int>(ovf));      // also completes the kernel and its peer stores
+    PLB_REQUIRE(o == 0, BL_ERR_INVALID, "export_partials_p2p: window region too small for the partial aggregates");
+    for (int p = 0; p < n_ranks; p++) sent_rows[p] = (int64_t)h[p];
 }
 
 void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather, DevCol& out_key, std::vector<DevCol>& out_aggs) {

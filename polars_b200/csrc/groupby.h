@@ -28,7 +28,7 @@ struct GbBatch {
 };
 
 
-struct AggPlan { int kind, in_dtype, out_dtype; int main, nullcnt; };
+struct AggPlan { int kind, in_dtype, out_dtype; int main, nullcnt; bool nullable; };
 
 // Host mirror of group_by_helper (crates/polars-mem-engine/src/executors/group_by.rs:60-98): owns
 // the device hash table and the aggregation plan.
@@ -44,11 +44,12 @@ struct GroupByState {
     int64_t rows_seen = 0;
     int64_t est_groups = 0;      // sampled / hinted cardinality; selects the shared-memory plan
 
-    GroupByState(int key_dt, const std::vector<int>& kinds, const std::vector<int>& dtypes, int64_t expected, bool track_first);
+    GroupByState(int key_dt, const std::vector<int>& kinds, const std::vector<int>& dtypes, const std::vector<int>& nullable, int64_t expected, bool track_first);
     void consume_all(const DevCol& key, const std::vector<const DevCol*>& values);
     void consume(const DevCol& key, const std::vector<const DevCol*>& values, int64_t row_base);
     void merge_partials(const uint64_t* rows, int64_t n_rows);
     DevPtr export_partials(int n_partitions, int* row_words_out, int64_t* offsets_host);
+    void export_partials_p2p(int n_ranks, int my_rank, void* const* windows, int64_t rows_per_src, int* row_words_out, int64_t* sent_rows);
     void finish(bool maintain_order, const DevCol* key_col_for_gather, DevCol& out_key, std::vector<DevCol>& out_aggs);
     void reset();
     int64_t count_groups();

@@ -162,7 +162,7 @@ static void run_plugin(PluginOp kind, int op, SeriesExport* inputs, size_t n, Se
             fill_schema(schema, name, format_of(o.dtype));
         } else if (kind == P_GROUP) {
             // inputs: key, value  ->  struct {key, agg} in first-occurrence order
-            GroupByState st(a.dtype, {op}, {b.dtype}, 0, true);
+            GroupByState st(a.dtype, {op}, {b.dtype}, {b.validity != nullptr ? 1 : 0}, 0, true);
             st.consume_all(a, {&b});
             DevCol ok; std::vector<DevCol> oa;
             st.finish(true, &a, ok, oa);

@@ -66,12 +66,12 @@ class CudaWords:
         self.__cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
 
 
-def partitioned_group_by(plb, key_col, value_cols, spec, location=None):
+def partitioned_group_by(plb, key_col, value_cols, spec, location=None, nullable=None):
     """One rank's share of the partitioned group_by: local pre-aggregation (K5) -> hash-partitioned
     export of the partial aggregates (K6) -> one all-to-all -> merge (K5 merge) -> finish.
     Output stays partitioned: this rank owns the groups with hash_to_partition(key) == rank."""
     world = dist.get_world_size()
-    g = plb.GroupBy(np.int64 if key_col is None else plb.NP_OF[key_col.dtype], spec)
+    g = plb.GroupBy(plb.NP_OF[key_col.dtype], spec, nullable=nullable)
     g.consume(key_col, value_cols, row_base=0)
     ptr, rw, offs = g.export_partials(world)
     try:
@@ -79,8 +79,48 @@ def partitioned_group_by(plb, key_col, value_cols, spec, location=None):
         send = torch.as_tensor(CudaWords(ptr, n_send * rw), device="cuda") if n_send else torch.empty(0, dtype=torch.int64, device="cuda")
         recv, rc = all_to_all_rows(send, np.diff(offs), rw)
         torch.cuda.synchronize()
-        f = plb.GroupBy(plb.NP_OF[key_col.dtype], spec, expected_groups=max(int(rc.sum()), 1))
+        f = plb.GroupBy(plb.NP_OF[key_col.dtype], spec, expected_groups=max(int(rc.sum()), 1), nullable=nullable)
         f.merge_partials(recv.data_ptr(), int(rc.sum()))
         return f.finish(False, location=plb.DEVICE if location is None else location)
     finally:
         plb.dev_free(ptr)
+
+
+class PeerExchange:
+    """Peer windows for the fused partition + exchange (K6 stores straight into the destination GPU's
+    memory over NVLink; the only collectives left are a tiny count exchange and a barrier)."""
+
+    def __init__(self, plb, rows_per_src: int, row_words: int):
+        self.plb, self.rows_per_src, self.row_words = plb, int(rows_per_src), int(row_words)
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.win = plb.Window(self.world * self.rows_per_src * self.row_words * 8)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.win.ipc_handle)
+        self.peers = [self.win.ptr if r == self.rank else plb.Window.open(handles[r]) for r in range(self.world)]
+
+    def region_ptr(self, src: int) -> int:
+        return self.win.ptr + src * self.rows_per_src * self.row_words * 8
+
+    def close(self):
+        dist.barrier()
+        for r, p in enumerate(self.peers):
+            if r != self.rank:
+                self.plb.Window.close(p)
+        self.win.destroy()
+
+
+def partitioned_group_by_p2p(plb, ex: PeerExchange, key_col, value_cols, spec, location=None, nullable=None):
+    """Same plan as partitioned_group_by, but the partial aggregates reach their owner by P2P stores from
+    inside the partition kernel (bl_groupby_export_partials_p2p) instead of an NCCL all-to-all."""
+    g = plb.GroupBy(plb.NP_OF[key_col.dtype], spec, nullable=nullable)
+    g.consume(key_col, value_cols, row_base=0)
+    rw, sent = g.export_partials_p2p(ex.peers, ex.rank, ex.rows_per_src)
+    assert rw == ex.row_words
+    recv = exchange_counts(sent, "cuda")          # also orders the peer stores before the merge
+    f = plb.GroupBy(plb.NP_OF[key_col.dtype], spec, expected_groups=max(int(recv.sum()), 1), nullable=nullable)
+    for src in range(ex.world):
+        if recv[src]:
+            f.merge_partials(ex.region_ptr(src), int(recv[src]))
+    out = f.finish(False, location=plb.DEVICE if location is None else location)
+    dist.barrier()                                 # windows may be overwritten by the next step
+    return out

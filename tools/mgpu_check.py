@@ -1,0 +1,55 @@
+"""torchrun --nproc-per-node N tools/mgpu_check.py — correctness of the partitioned group_by on N GPUs
+(both exchanges) against a numpy reduction of the concatenated data."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import polars_b200 as plb  # noqa: E402
+from polars_b200 import dist as pdist  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+plb.init(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+n, K = 2_000_000, 50_000
+
+
+def data(r):
+    rng = np.random.default_rng(7 + r)
+    return rng.integers(-K // 2, K // 2, n).astype(np.int64), rng.integers(-1000, 1000, n).astype(np.int64), rng.uniform(0, 100, n).round(6)
+
+
+key, vi, vf = data(rank)
+dk, dvi, dvf = plb.to_device(key), plb.to_device(vi), plb.to_device(vf)
+spec = [("sum", np.int64), ("mean", np.float64), ("len", None)]
+allk = np.concatenate([data(r)[0] for r in range(world)])
+alli = np.concatenate([data(r)[1] for r in range(world)])
+allf = np.concatenate([data(r)[2] for r in range(world)])
+uk, inv = np.unique(allk, return_inverse=True)
+esum = np.zeros(uk.size, np.int64); np.add.at(esum, inv, alli)
+efs = np.zeros(uk.size); np.add.at(efs, inv, allf)
+ecnt = np.bincount(inv, minlength=uk.size)
+h = (uk.view(np.uint64) * np.uint64(0x55fbfd6bfc5458e9))
+part = np.array([(int(x) * world) >> 64 for x in h])
+ex = pdist.PeerExchange(plb, rows_per_src=K + 1024, row_words=6)  # sum, mean(+null counter), len -> 3 words + key, len|first, meta
+for mode in ("nccl", "p2p", "p2p"):
+    if mode == "nccl":
+        ok, outs = pdist.partitioned_group_by(plb, dk.view(), [dvi.view(), dvf.view(), None], spec)
+    else:
+        ok, outs = pdist.partitioned_group_by_p2p(plb, ex, dk.view(), [dvi.view(), dvf.view(), None], spec)
+    k, _ = ok.to_numpy()
+    s, _ = outs[0].to_numpy(); m, _ = outs[1].to_numpy(); c, _ = outs[2].to_numpy()
+    o = np.argsort(k)
+    sel = part == rank
+    assert np.array_equal(k[o], uk[sel]), f"{mode}: rank {rank} owns the wrong groups ({k.size} vs {sel.sum()})"
+    assert np.array_equal(s[o], esum[sel]) and np.array_equal(c[o], ecnt[sel]), f"{mode}: sums/counts differ"
+    assert np.allclose(m[o], efs[sel] / ecnt[sel], rtol=1e-9), f"{mode}: means differ"
+    dist.barrier()
+    if rank == 0:
+        print(f"mgpu_check {mode}: OK world={world} groups_here={k.size}", flush=True)
+ex.close()
+dist.destroy_process_group()
