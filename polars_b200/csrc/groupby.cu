@@ -799,7 +799,8 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
     static const int smem_on = [] { const char* e = getenv("BL_K5_SMEM"); return e ? atoi(e) : 1; }();
     int scap = 0;
     if (smem_on && est_groups > 0) {
-        int want = 256; while (want < 2 * est_groups && want < (1 << 20)) want <<= 1;
+        // load factor <= 2/3 (probing a shared-memory table is cheap; occupancy is not)
+        int want = 256; while (2 * want < 3 * est_groups && want < (1 << 20)) want <<= 1;
         if ((size_t)(want + 2) * Lb.stride * 8 <= (size_t)200 * 1024) scap = want;
     }
 #define GB_DISPATCH(E, C)                                                            \

@@ -126,50 +126,71 @@ __global__ void __launch_bounds__(256) k_join_csr_offsets(uint4* __restrict__ en
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS>
 __global__ void __launch_bounds__(256) k_join_probe(JoinTableDev T, const void* __restrict__ keys, const uint32_t* __restrict__ valid, int64_t n, int nulls_equal, int csr_mode,
                                                     int left_join, uint32_t* __restrict__ handle, unsigned long long* __restrict__ tile_counts) {
+    // 2 row pairs (4 rows) per thread and iteration; the first table probe of all 4 rows is issued
+    // before any is resolved: the kernel is bound by random-sector latency, so MLP is what counts.
+    constexpr int PAIRS = 2, R = 2 * PAIRS;
     const int64_t npairs = (n + 1) >> 1;
     const int64_t rounded = (npairs + 31) / 32 * 32;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < rounded; p += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t kraw[2] = {0, 0};
-        const int64_t r0 = 2 * p;
-        if (r0 + 1 < n) {
-            if (KEY_ELEM == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(keys) + r0); kraw[0] = t.x; kraw[1] = t.y; }
-            else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(keys) + r0); kraw[0] = t.x; kraw[1] = t.y; }
-        } else if (r0 < n) {
-            kraw[0] = KEY_ELEM == 8 ? reinterpret_cast<const uint64_t*>(keys)[r0] : (uint64_t)reinterpret_cast<const uint32_t*>(keys)[r0];
-        }
-        uint32_t h[2] = {J_NONE, J_NONE};
-        uint32_t cnt = 0;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p0 < rounded; p0 += gstride * PAIRS) {
+        uint64_t key[R]; uint64_t slot[R]; uint4 e[R]; int kind[R];   // kind: 0 hashed, 1 special slot, -1 no lookup (miss / no row)
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int64_t row = r0 + j;
-            if (row >= n) continue;
-            bool v = true;
-            if (KEY_NULLS) v = bit_get(valid, row);
-            uint64_t key = kraw[j];
-            if (KEY_CANON == 1) key = canonical_f64_bits(__longlong_as_double((long long)key));
-            if (KEY_CANON == 2) key = canonical_f32_bits(__uint_as_float((uint32_t)key));
-            uint64_t slot; bool hit = false; uint4 e;
-            if (!v) { slot = T.cap; if (nulls_equal) { e = __ldg(&T.entries[slot]); hit = e.w != 0; } }
-            else if (key == J_EMPTY) { slot = T.cap + 1; e = __ldg(&T.entries[slot]); hit = e.w != 0; }
-            else {
-                slot = __umul64hi(dirty_hash(key), T.cap);
-                while (true) {
-                    e = __ldg(&T.entries[slot]);
-                    const uint64_t k = ((uint64_t)e.y << 32) | e.x;
-                    if (k == key) { hit = true; break; }
-                    if (k == J_EMPTY) break;
-                    if (++slot == T.cap) slot = 0;
-                }
+        for (int u = 0; u < PAIRS; u++) {
+            const int64_t r0 = 2 * (p0 + u * gstride);
+            uint64_t kraw[2] = {0, 0};
+            if (r0 + 1 < n) {
+                if (KEY_ELEM == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(keys) + r0); kraw[0] = t.x; kraw[1] = t.y; }
+                else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(keys) + r0); kraw[0] = t.x; kraw[1] = t.y; }
+            } else if (r0 < n) kraw[0] = KEY_ELEM == 8 ? reinterpret_cast<const uint64_t*>(keys)[r0] : (uint64_t)reinterpret_cast<const uint32_t*>(keys)[r0];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int r = 2 * u + j;
+                const int64_t row = r0 + j;
+                kind[r] = -1; slot[r] = 0; key[r] = 0;
+                if (row >= n) continue;
+                bool v = true;
+                if (KEY_NULLS) v = bit_get(valid, row);
+                uint64_t k = kraw[j];
+                if (KEY_CANON == 1) k = canonical_f64_bits(__longlong_as_double((long long)k));
+                if (KEY_CANON == 2) k = canonical_f32_bits(__uint_as_float((uint32_t)k));
+                key[r] = k;
+                if (!v) { if (nulls_equal) { kind[r] = 1; slot[r] = T.cap; } }
+                else if (k == J_EMPTY) { kind[r] = 1; slot[r] = T.cap + 1; }
+                else { kind[r] = 0; slot[r] = __umul64hi(dirty_hash(k), T.cap); }
+                if (kind[r] >= 0) e[r] = __ldg(&T.entries[slot[r]]);
             }
-            if (hit) { h[j] = csr_mode ? (uint32_t)slot : e.z; cnt += csr_mode ? e.w : 1u; }
-            else if (left_join) cnt += 1u;
         }
-        if (r0 + 1 < n) *reinterpret_cast<uint2*>(handle + r0) = make_uint2(h[0], h[1]);
-        else if (r0 < n) handle[r0] = h[0];
-        // 32 lanes x 2 rows = 64 consecutive rows: always inside one J_TILE
-        unsigned long long c = cnt;
-        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane_id() == 0 && c) atomicAdd(&tile_counts[r0 / J_TILE], c);   // one address per 2048-row tile; the grand total comes from the scan
+#pragma unroll
+        for (int u = 0; u < PAIRS; u++) {
+            const int64_t r0 = 2 * (p0 + u * gstride);
+            if (r0 >= 2 * rounded) continue;                       // warp-uniform
+            uint32_t h[2] = {J_NONE, J_NONE};
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int r = 2 * u + j;
+                if (r0 + j >= n) continue;
+                bool hit = false;
+                if (kind[r] == 1) hit = e[r].w != 0;
+                else if (kind[r] == 0) {
+                    while (true) {
+                        const uint64_t k = ((uint64_t)e[r].y << 32) | e[r].x;
+                        if (k == key[r]) { hit = true; break; }
+                        if (k == J_EMPTY) break;
+                        if (++slot[r] == T.cap) slot[r] = 0;
+                        e[r] = __ldg(&T.entries[slot[r]]);
+                    }
+                }
+                if (hit) { h[j] = csr_mode ? (uint32_t)slot[r] : e[r].z; cnt += csr_mode ? e[r].w : 1u; }
+                else if (left_join) cnt += 1u;
+            }
+            if (r0 + 1 < n) *reinterpret_cast<uint2*>(handle + r0) = make_uint2(h[0], h[1]);
+            else if (r0 < n) handle[r0] = h[0];
+            // 32 lanes x 2 rows = 64 consecutive rows: always inside one J_TILE
+            unsigned long long c = cnt;
+            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane_id() == 0 && c) atomicAdd(&tile_counts[r0 / J_TILE], c);   // one address per 2048-row tile; the grand total comes from the scan
+        }
     }
 }
 
@@ -265,32 +286,49 @@ template <int KEY_ELEM, bool KEY_NULLS>
 __global__ void __launch_bounds__(256) k_join_dense_probe(const uint32_t* __restrict__ table, uint64_t kmin, uint64_t range, int sign_bits, const void* __restrict__ keys,
                                                           const uint32_t* __restrict__ valid, int64_t n, int left_join, uint32_t* __restrict__ handle,
                                                           unsigned long long* __restrict__ tile_counts) {
+    constexpr int PAIRS = 2;
     const int64_t npairs = (n + 1) >> 1;
     const int64_t rounded = (npairs + 31) / 32 * 32;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < rounded; p += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t kraw[2] = {0, 0};
-        const int64_t r0 = 2 * p;
-        if (r0 + 1 < n) {
-            if (KEY_ELEM == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(keys) + r0); kraw[0] = t.x; kraw[1] = t.y; }
-            else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(keys) + r0); kraw[0] = t.x; kraw[1] = t.y; }
-        } else if (r0 < n) kraw[0] = KEY_ELEM == 8 ? reinterpret_cast<const uint64_t*>(keys)[r0] : (uint64_t)reinterpret_cast<const uint32_t*>(keys)[r0];
-        uint32_t h[2] = {J_NONE, J_NONE};
-        uint32_t cnt = 0;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p0 < rounded; p0 += gstride * PAIRS) {
+        uint64_t kraw[PAIRS][2];
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int64_t row = r0 + j;
-            if (row >= n) continue;
-            bool v = true;
-            if (KEY_NULLS) v = bit_get(valid, row);
-            const uint64_t d = j_ordered(kraw[j], sign_bits) - kmin;
-            if (v && d < range) h[j] = __ldg(&table[d]);
-            cnt += (h[j] != J_NONE || left_join) ? 1u : 0u;
+        for (int u = 0; u < PAIRS; u++) {
+            const int64_t r0 = 2 * (p0 + u * gstride);
+            kraw[u][0] = kraw[u][1] = 0;
+            if (r0 + 1 < n) {
+                if (KEY_ELEM == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(keys) + r0); kraw[u][0] = t.x; kraw[u][1] = t.y; }
+                else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(keys) + r0); kraw[u][0] = t.x; kraw[u][1] = t.y; }
+            } else if (r0 < n) kraw[u][0] = KEY_ELEM == 8 ? reinterpret_cast<const uint64_t*>(keys)[r0] : (uint64_t)reinterpret_cast<const uint32_t*>(keys)[r0];
         }
-        if (r0 + 1 < n) *reinterpret_cast<uint2*>(handle + r0) = make_uint2(h[0], h[1]);
-        else if (r0 < n) handle[r0] = h[0];
-        unsigned long long c = cnt;
-        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane_id() == 0 && c) atomicAdd(&tile_counts[r0 / J_TILE], c);
+        uint32_t h[PAIRS][2];
+#pragma unroll
+        for (int u = 0; u < PAIRS; u++) {
+            const int64_t r0 = 2 * (p0 + u * gstride);
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                h[u][j] = J_NONE;
+                const int64_t row = r0 + j;
+                if (row >= n) continue;
+                bool v = true;
+                if (KEY_NULLS) v = bit_get(valid, row);
+                const uint64_t d = j_ordered(kraw[u][j], sign_bits) - kmin;
+                if (v && d < range) h[u][j] = __ldg(&table[d]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PAIRS; u++) {
+            const int64_t r0 = 2 * (p0 + u * gstride);
+            if (r0 >= 2 * rounded) continue;                       // warp-uniform
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int j = 0; j < 2; j++) if (r0 + j < n) cnt += (h[u][j] != J_NONE || left_join) ? 1u : 0u;
+            if (r0 + 1 < n) *reinterpret_cast<uint2*>(handle + r0) = make_uint2(h[u][0], h[u][1]);
+            else if (r0 < n) handle[r0] = h[u][0];
+            unsigned long long c = cnt;
+            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane_id() == 0 && c) atomicAdd(&tile_counts[r0 / J_TILE], c);
+        }
     }
 }
 

@@ -124,3 +124,52 @@ def partitioned_group_by_p2p(plb, ex: PeerExchange, key_col, value_cols, spec, l
     out = f.finish(False, location=plb.DEVICE if location is None else location)
     dist.barrier()                                 # windows may be overwritten by the next step
     return out
+
+
+class _CudaArr:
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def _as_torch(out_col, n: int, typestr: str, dtype):
+    return torch.as_tensor(_CudaArr(out_col.values_ptr, n, typestr), device="cuda") if n else torch.empty(0, dtype=dtype, device="cuda")
+
+
+def all_to_all_1d(send: torch.Tensor, send_counts: np.ndarray):
+    """all-to-all-v of a 1-D tensor whose destination-p slice has send_counts[p] elements."""
+    recv_counts = exchange_counts(np.asarray(send_counts, dtype=np.int64), send.device)
+    recv = torch.empty(int(recv_counts.sum()), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(recv, send, output_split_sizes=recv_counts.tolist(), input_split_sizes=np.asarray(send_counts).tolist())
+    return recv, recv_counts
+
+
+def partitioned_hash_join(plb, left_key, right_key, left_base: int, right_base: int, how: str = "inner"):
+    """Partitioned inner/left hash join on P GPUs: both sides are hash-partitioned on the key
+    (K6, the reference's partition function), exchanged with one all-to-all-v per relation, joined locally
+    (K7/K8) and mapped back to GLOBAL row ids (K4).  left_key/right_key: device Columns of this rank's rows;
+    *_base: global index of this rank's first row.  Returns (left_global_idx, right_global_idx) as torch
+    uint32-valued int32 tensors; the output is partitioned by key."""
+    world = dist.get_world_size()
+    sides = []
+    for key, base in ((left_key, left_base), (right_key, right_base)):
+        n = key.length
+        gid = (torch.arange(n, dtype=torch.int64, device="cuda") + base).to(torch.int32)   # u32 bit pattern
+        torch.cuda.synchronize()
+        gcol = plb.Column(gid.data_ptr(), dtype=np.uint32, length=n, location=plb.DEVICE)
+        kp, [gp], offs = plb.hash_partition(key, [gcol], world, location=plb.DEVICE)
+        counts = np.diff(offs)
+        kt = _as_torch(kp, n, "<i8", torch.int64)
+        gt = _as_torch(gp, n, "<i4", torch.int32)
+        rk, _ = all_to_all_1d(kt, counts)
+        rg, _ = all_to_all_1d(gt, counts)
+        torch.cuda.synchronize()
+        sides.append((rk, rg, kp, gp))
+    (lk, lg, *_), (rk, rg, *_) = sides
+    lcol = plb.Column(lk.data_ptr(), dtype=np.int64, length=lk.numel(), location=plb.DEVICE)
+    rcol = plb.Column(rk.data_ptr(), dtype=np.int64, length=rk.numel(), location=plb.DEVICE)
+    li, ri = plb.hash_join(lcol, rcol, how, False, "none", location=plb.DEVICE)
+    lgc = plb.Column(lg.data_ptr(), dtype=np.uint32, length=lg.numel(), location=plb.DEVICE)
+    rgc = plb.Column(rg.data_ptr(), dtype=np.uint32, length=rg.numel(), location=plb.DEVICE)
+    [gl] = plb.gather([lgc], li.view(), check_bounds=False, location=plb.DEVICE)
+    [gr] = plb.gather([rgc], ri.view(), check_bounds=False, location=plb.DEVICE)
+    return gl, gr

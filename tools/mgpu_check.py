@@ -52,4 +52,23 @@ for mode in ("nccl", "p2p", "p2p"):
     if rank == 0:
         print(f"mgpu_check {mode}: OK world={world} groups_here={k.size}", flush=True)
 ex.close()
+
+# ---- partitioned join: global probe rows x globally-unique build keys
+npr, nbr = 1_000_000, 100_000
+perm = np.random.default_rng(99).permutation(nbr * world * 2)[: nbr * world].astype(np.int64)     # same on every rank
+bkeys = perm[rank * nbr:(rank + 1) * nbr].copy()
+pkeys_all = [np.random.default_rng(500 + r).integers(0, nbr * world * 2, npr).astype(np.int64) for r in range(world)]
+dpk, dbk = plb.to_device(pkeys_all[rank]), plb.to_device(bkeys)
+gl, gr = pdist.partitioned_hash_join(plb, dpk.view(), dbk.view(), rank * npr, rank * nbr)
+l, _ = gl.to_numpy(); r_, _ = gr.to_numpy()
+allp = np.concatenate(pkeys_all)
+assert np.array_equal(allp[l], perm[r_]), "join: keys of the emitted pairs differ"
+kh = (allp[l].view(np.uint64) * np.uint64(0x55fbfd6bfc5458e9))
+assert all(((int(x) * world) >> 64) == rank for x in kh[:2000]), "join: pair on the wrong rank"
+tot = torch.tensor([l.size], dtype=torch.int64, device="cuda"); dist.all_reduce(tot)
+expect = int(np.isin(allp, perm).sum())
+assert int(tot.item()) == expect, f"join: {int(tot.item())} pairs, expected {expect}"
+assert np.unique(l).size == l.size
+if rank == 0:
+    print(f"mgpu_check join: OK world={world} pairs={expect}", flush=True)
 dist.destroy_process_group()
