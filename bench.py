@@ -149,6 +149,7 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------- B200 arm
 def main():
     a = parse()
+    os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")   # NCCL's version banner goes to stdout: keep the JSON line alone
     if a.impl == "reference":
         run_reference(a)
         return

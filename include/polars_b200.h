@@ -192,6 +192,8 @@ bl_status bl_groupby_consume(bl_groupby* g, const bl_column* key, const bl_colum
 bl_status bl_groupby_export_partials(bl_groupby* g, int32_t n_partitions, void** out_rows_dev, int32_t* row_words, int64_t* offsets);
 /* Merge partial rows (from any rank) into this state. */
 bl_status bl_groupby_merge_partials(bl_groupby* g, const void* rows_dev, int64_t n_rows);
+/* Same for several regions (one per source rank) in one launch: rows_dev[i] holds n_rows[i] rows. */
+bl_status bl_groupby_merge_partial_regions(bl_groupby* g, const void* const* rows_dev, const int64_t* n_rows, int32_t n_regions);
 bl_status bl_groupby_finish(bl_groupby* g, int32_t maintain_order, int32_t out_location, bl_column* out_key, bl_column* out_aggs);
 void bl_groupby_reset(bl_groupby* g);
 void bl_groupby_destroy(bl_groupby* g);

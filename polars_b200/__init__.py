@@ -432,6 +432,12 @@ class GroupBy:
     def merge_partials(self, rows_dev_ptr: int, n_rows: int):
         _check(lib().bl_groupby_merge_partials(self.h, C.c_void_p(rows_dev_ptr), C.c_int64(n_rows)))
 
+    def merge_partial_regions(self, ptrs: Sequence[int], counts: Sequence[int]):
+        n = len(ptrs)
+        pa = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in ptrs])
+        ca = (C.c_int64 * n)(*[int(c) for c in counts])
+        _check(lib().bl_groupby_merge_partial_regions(self.h, pa, ca, C.c_int32(n)))
+
     def finish(self, maintain_order: bool = False, location: int = HOST):
         ok, oa = BlColumn(), (BlColumn * max(self.n, 1))()
         _check(lib().bl_groupby_finish(self.h, C.c_int32(int(maintain_order)), C.c_int32(location), C.byref(ok), oa))

@@ -181,9 +181,7 @@ bl_status bl_groupby_consume(bl_groupby* g, const bl_column* key, const bl_colum
         vals[i] = dup >= 0 ? vals[dup] : import_column(&values[i], 1);
         vp[i] = &vals[i];
     }
-    g->st->consume(k, vp, row_base);
-    // inputs may be caller-owned host buffers: finish the batch before returning
-    PLB_CUDA(cudaStreamSynchronize(ctx().stream));
+    g->st->consume(k, vp, row_base);   // reads the overflow flag back: the batch has completed when this returns
     BL_CATCH
 }
 bl_status bl_groupby_export_partials(bl_groupby* g, int32_t n_partitions, void** out_rows_dev, int32_t* row_words, int64_t* offsets) {
@@ -200,7 +198,12 @@ bl_status bl_groupby_merge_partials(bl_groupby* g, const void* rows_dev, int64_t
     BL_TRY
     PLB_REQUIRE(g && (rows_dev || n_rows == 0), BL_ERR_INVALID, "groupby_merge_partials: null argument");
     g->st->merge_partials(reinterpret_cast<const uint64_t*>(rows_dev), n_rows);
-    PLB_CUDA(cudaStreamSynchronize(ctx().stream));
+    BL_CATCH
+}
+bl_status bl_groupby_merge_partial_regions(bl_groupby* g, const void* const* rows_dev, const int64_t* n_rows, int32_t n_regions) {
+    BL_TRY
+    PLB_REQUIRE(g && rows_dev && n_rows, BL_ERR_INVALID, "groupby_merge_partial_regions: null argument");
+    g->st->merge_partial_regions(reinterpret_cast<const uint64_t* const*>(rows_dev), n_rows, n_regions);
     BL_CATCH
 }
 bl_status bl_groupby_finish(bl_groupby* g, int32_t maintain_order, int32_t out_location, bl_column* out_key, bl_column* out_aggs) {

@@ -865,15 +865,38 @@ void GroupByState::reset() {
 }
 
 void GroupByState::merge_partials(const uint64_t* rows, int64_t n_rows) {
+    const uint64_t* ptrs[1] = {rows}; int64_t counts[1] = {n_rows};
+    merge_partial_regions(ptrs, counts, 1);
+}
+
+// Merge several regions of partial rows (one per source rank) with ONE kernel launch and one sync.
+struct MergeRegions { const uint64_t* ptr[EXP_MAX_PARTS]; int64_t end[EXP_MAX_PARTS]; int n; };
+__global__ void __launch_bounds__(256) k_gb_merge_regions(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const __grid_constant__ MergeRegions R, int row_words) {
+    const int64_t total = R.end[R.n - 1];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int r = 0; while (i >= R.end[r]) r++;
+        const int64_t local = i - (r ? R.end[r - 1] : 0);
+        const uint64_t* src = R.ptr[r] + local * row_words;
+        gb_merge_row(L, T, src, (int)src[row_words - 1]);
+    }
+}
+void GroupByState::merge_partial_regions(const uint64_t* const* ptrs, const int64_t* counts, int n_regions) {
+    PLB_REQUIRE(n_regions >= 1 && n_regions <= EXP_MAX_PARTS, BL_ERR_INVALID, "merge_partials: 1..64 regions");
     const int row_words = L.n_words + 3;
-    if (!entries) alloc_table(pow2_at_least((double)std::max<int64_t>(n_rows, 1) / 0.6));
-    else {
+    int64_t n_rows = 0;
+    for (int r = 0; r < n_regions; r++) n_rows += counts[r];
+    if (!entries) alloc_table(pow2_at_least((double)std::max<int64_t>(std::max<int64_t>(n_rows, expected_groups), 1) / 0.6));
+    else if (expected_groups <= 0) {
         int64_t g = count_groups();
         if ((double)(g + n_rows) > 0.6 * (double)cap) grow(pow2_at_least((double)(g + n_rows) / 0.5));
     }
     if (n_rows == 0) return;
-    PLB_LAUNCH("k5_merge_partials", k_gb_merge, grid_for(n_rows, 256), 256, 0, L, T, rows, n_rows, row_words, 0, (int64_t)0);
-    if (read_scalar(as<int>(status)) != 0) fail(BL_ERR_OOM, "group_by: table overflow while merging partial aggregates");
+    MergeRegions R; memset(&R, 0, sizeof R);
+    int64_t acc = 0;
+    for (int r = 0; r < n_regions; r++) { R.ptr[r] = ptrs[r]; acc += counts[r]; R.end[r] = acc; }
+    R.n = n_regions;
+    PLB_LAUNCH("k5_merge_partials", k_gb_merge_regions, grid_for(n_rows, 256), 256, 0, L, T, R, row_words);
+    if (read_scalar(as<int>(status)) != 0) fail(BL_ERR_OOM, "group_by: table overflow while merging partial aggregates (expected_groups too small)");
 }
 
 DevPtr GroupByState::export_partials(int n_partitions, int* row_words_out, int64_t* offsets_host) {

@@ -118,9 +118,7 @@ def partitioned_group_by_p2p(plb, ex: PeerExchange, key_col, value_cols, spec, l
     assert rw == ex.row_words
     recv = exchange_counts(sent, "cuda")          # also orders the peer stores before the merge
     f = plb.GroupBy(plb.NP_OF[key_col.dtype], spec, expected_groups=max(int(recv.sum()), 1), nullable=nullable)
-    for src in range(ex.world):
-        if recv[src]:
-            f.merge_partials(ex.region_ptr(src), int(recv[src]))
+    f.merge_partial_regions([ex.region_ptr(src) for src in range(ex.world)], [int(c) for c in recv])
     out = f.finish(False, location=plb.DEVICE if location is None else location)
     dist.barrier()                                 # windows may be overwritten by the next step
     return out
