@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="groupby", choices=["groupby", "join"])
+    ap.add_argument("--workload", default="groupby", choices=["groupby", "join", "q1"])
     ap.add_argument("--rows", type=int, default=100_000_000)
     ap.add_argument("--keys", type=int, default=1_000_000)
     ap.add_argument("--build-rows", type=int, default=10_000_000)
@@ -107,6 +107,51 @@ def gen_join(rows: int, build_rows: int, seed: int):
     build = rng.permutation(build_rows).astype(np.int64)
     probe = rng.integers(0, build_rows, rows, dtype=np.int64)
     return probe, build
+
+
+def gen_lineitem(rows: int, seed: int):
+    """BASELINE.json configs[3] (C4): PDS-H / TPC-H lineitem columns used by Q1, synthetic with dbgen-like
+    marginals (no dbgen binary here): quantity 1..50, extendedprice = quantity * U(900, 2100), discount
+    0..0.10, tax 0..0.08 (2 decimals), returnflag in {A,N,R} / linestatus in {O,F} as dictionary codes,
+    shipdate uniform over 1992-01-02 .. 1998-12-01 in days since epoch."""
+    rng = np.random.default_rng(seed)
+    qty = rng.integers(1, 51, rows).astype(np.float64)
+    price = (qty * rng.uniform(900.0, 2100.0, rows)).round(2)
+    disc = (rng.integers(0, 11, rows) / 100.0)
+    tax = (rng.integers(0, 9, rows) / 100.0)
+    ship = rng.integers(8036, 10561, rows).astype(np.int64)            # days: 1992-01-02 .. 1998-12-01
+    rf = np.where(ship > 9298, 1, rng.integers(0, 2, rows) * 2).astype(np.int64)   # N after 1995-06-17, else A(0)/R(2)
+    ls = (ship > 9298).astype(np.int64)                                  # O(1) / F(0)
+    return {"qty": qty, "price": price, "disc": disc, "tax": tax, "ship": ship, "rf": rf, "ls": ls}
+
+
+Q1_CUTOFF = 10471   # 1998-09-02
+
+
+def q1_device(plb, d):
+    """PDS-H Q1 through the C ABI on device columns: filter (K2+K3) -> expressions (K1) -> group_by/agg (K5)."""
+    cols = [d["ship"].view(), d["qty"].view(), d["price"].view(), d["disc"].view(), d["tax"].view(), d["rf"].view(), d["ls"].view()]
+    f = plb.filter_cmp(cols, 0, "le", Q1_CUTOFF, location=plb.DEVICE)
+    _, qty, price, disc, tax, rf, ls = f
+    one_minus = plb.elementwise("sub", np.array([1.0]), disc.view(), location=plb.DEVICE)
+    disc_price = plb.elementwise("mul", price.view(), one_minus.view(), location=plb.DEVICE)
+    one_plus = plb.elementwise("add", tax.view(), np.array([1.0]), location=plb.DEVICE)
+    charge = plb.elementwise("mul", disc_price.view(), one_plus.view(), location=plb.DEVICE)
+    key = plb.elementwise("add", plb.elementwise("mul", rf.view(), np.array([256], np.int64), location=plb.DEVICE).view(), ls.view(), location=plb.DEVICE)
+    q, p_, dp, ch, di = qty.view(), price.view(), disc_price.view(), charge.view(), disc.view()
+    return plb.group_by_agg(key.view(), [("sum", q), ("sum", p_), ("sum", dp), ("sum", ch), ("mean", q), ("mean", p_), ("mean", di), ("len", None)], False, location=plb.DEVICE)
+
+
+def q1_numpy(h):
+    m = h["ship"] <= Q1_CUTOFF
+    key = h["rf"][m] * 256 + h["ls"][m]
+    dp = h["price"][m] * (1.0 - h["disc"][m])
+    ch = dp * (h["tax"][m] + 1.0)
+    uk, inv = np.unique(key, return_inverse=True)
+    out = {"key": uk, "len": np.bincount(inv)}
+    for name, v in (("qty", h["qty"][m]), ("price", h["price"][m]), ("dp", dp), ("ch", ch), ("disc", h["disc"][m])):
+        out[name] = np.bincount(inv, weights=v)
+    return out
 
 
 # ------------------------------------------------------------------------------------- reference arm
@@ -212,6 +257,36 @@ def main():
         metric = "group_by_agg_rows_per_sec"
         wl = f"C2 hash group_by {a.rows} rows/GPU, {a.keys} uniform Int64 keys, sum(v_i64)/mean(v_f64)/len; inputs 2.4 GB > L2 (no flush needed)"
         h2d = a.rows * 24
+    elif a.workload == "q1":
+        rows = a.rows if a.rows != 100_000_000 else 60_000_000      # SF10 lineitem ~ 6e7 rows
+        a.rows = rows
+        h = gen_lineitem(rows, 4 + rank)
+        d = {k: plb.to_device(v) for k, v in h.items()}
+        hp = {k: plb.to_pinned(v) for k, v in h.items()}
+        exp = q1_numpy(h)
+        ok, outs = q1_device(plb, d)
+        k, _ = ok.to_numpy(); o = np.argsort(k)
+        assert np.array_equal(k[o], exp["key"]) and np.array_equal(outs[7].to_numpy()[0][o], exp["len"]), "Q1 groups differ"
+        for i, nm in ((0, "qty"), (1, "price"), (2, "dp"), (3, "ch")):
+            assert np.allclose(outs[i].to_numpy()[0][o], exp[nm], rtol=1e-6), "Q1 sums differ: " + nm
+        del h
+
+        def step_device():
+            ok, outs = q1_device(plb, d)
+            return ok.length
+
+        def step_e2e():
+            dd = {k: plb.to_device(v) for k, v in hp.items()}
+            ok, outs = q1_device(plb, dd)
+            res = [ok.to_numpy()[0]] + [o.to_numpy()[0] for o in outs]
+            return res[0].size, sum(r.nbytes for r in res)
+
+        unit_rows = rows
+        alg_bytes_per_row = 8.0 * 6        # K5 reads key + 5 distinct value columns
+        dominant = "k5_groupby_agg_smem"
+        metric = "pdsh_q1_rows_per_sec"
+        wl = f"C4 PDS-H Q1 shape on {rows} synthetic lineitem rows (SF10-sized): filter + 4 expressions + group_by(returnflag,linestatus) with 8 aggregates"
+        h2d = rows * 8 * 7
     else:
         probe, build = gen_join(a.rows, a.build_rows, 2 + rank)
         hp, hb = plb.to_pinned(probe), plb.to_pinned(build)
@@ -300,7 +375,7 @@ def main():
         "e2e": {"value": unit_rows * world / e2e_s if e2e_s else None, "unit": "rows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                 "path": "bl_groupby_agg / bl_hash_join with BL_HOST columns in pinned memory -> BL_HOST outputs"},
     }
-    if world == 1 and not a.no_cpu_baseline:
+    if world == 1 and not a.no_cpu_baseline and a.workload in ("groupby", "join"):
         line["cpu_baseline"] = cpu_baseline(a)
     print(json.dumps(line), flush=True)
     if world > 1:

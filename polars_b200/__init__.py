@@ -230,16 +230,20 @@ class OutColumn:
         if st.location == DEVICE:
             host = BlColumn()
             _check(lib().bl_column_to(C.byref(st), C.c_int32(1), C.c_int32(HOST), C.byref(host)))
-            try:
-                return OutColumn(host).to_numpy()
-            finally:
-                lib().bl_column_free(C.byref(host))
+            return OutColumn(host).to_numpy()      # the returned view keeps the host copy alive
         if st.dtype == BOOL:
             raw = np.ctypeslib.as_array(C.cast(st.values, C.POINTER(C.c_uint8)), shape=((n + 7) // 8 or 1,)) if n else np.zeros(0, np.uint8)
             vals = unpack_bits(raw, n)
         else:
             dt = NP_OF[int(st.dtype)]
-            vals = np.ctypeslib.as_array(C.cast(st.values, C.POINTER(C.c_uint8)), shape=(max(n * dt.itemsize, 1),))[: n * dt.itemsize].view(dt).copy() if n else np.zeros(0, dt)
+            if n:
+                # zero-copy: the array views the library-owned pinned buffer and keeps this OutColumn alive
+                buf = (C.c_char * (n * dt.itemsize)).from_address(st.values)
+                buf._owner = self
+                vals = np.frombuffer(buf, dtype=dt, count=n)
+                self._exported = True
+            else:
+                vals = np.zeros(0, dt)
         valid = None
         if st.validity:
             raw = np.ctypeslib.as_array(C.cast(st.validity, C.POINTER(C.c_uint8)), shape=((n + 7) // 8 or 1,)) if n else np.zeros(0, np.uint8)
@@ -282,7 +286,8 @@ def _finish(outs, location):
     if location == HOST:
         np_res = [r.to_numpy() for r in res]
         for r in res:
-            r.free()
+            if not getattr(r, "_exported", False):
+                r.free()       # value arrays that view the buffer keep their OutColumn alive instead
         return np_res
     return res
 

@@ -82,27 +82,82 @@ bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, cons
     BL_TRY
     PLB_REQUIRE(key_chunks && n_key_chunks >= 1 && out_key, BL_ERR_INVALID, "groupby_agg: null key / output");
     PLB_REQUIRE(n_aggs == 0 || (aggs && out_aggs), BL_ERR_INVALID, "groupby_agg: null aggs / outputs");
-    DevCol key = import_column(key_chunks, n_key_chunks);
     std::vector<int> kinds, dts;
-    std::vector<DevCol> vals(n_aggs);
-    std::vector<const DevCol*> vptr(n_aggs, nullptr);
-    // aggregations over the same chunk list share one device copy
-    std::vector<std::pair<const bl_column*, int>> seen;
     for (int i = 0; i < n_aggs; i++) {
         kinds.push_back(aggs[i].kind);
+        if (aggs[i].kind != BL_AGG_LEN) PLB_REQUIRE(aggs[i].values && aggs[i].n_chunks >= 1, BL_ERR_INVALID, "groupby_agg: aggregation without a value column");
+    }
+    auto same_col = [](const bl_agg& a, const bl_agg& b) {
+        return a.n_chunks == b.n_chunks && (a.values == b.values || (a.n_chunks == 1 && a.values[0].values == b.values[0].values && a.values[0].validity == b.values[0].validity &&
+                                                                    a.values[0].offset == b.values[0].offset && a.values[0].length == b.values[0].length && a.values[0].dtype == b.values[0].dtype));
+    };
+    // Host inputs without nulls: chunked H2D on the copy stream overlapped with K5 on the compute stream.
+    bool pipelined = n_key_chunks == 1 && key_chunks[0].location == BL_HOST && (key_chunks[0].validity == nullptr || key_chunks[0].null_count == 0) &&
+                     key_chunks[0].length >= (int64_t)1 << 22 && dtype_size(key_chunks[0].dtype) >= 4 && key_chunks[0].dtype != BL_BOOL;
+    for (int i = 0; i < n_aggs && pipelined; i++)
+        if (aggs[i].kind != BL_AGG_LEN)
+            pipelined = aggs[i].n_chunks == 1 && aggs[i].values[0].location == BL_HOST && (aggs[i].values[0].validity == nullptr || aggs[i].values[0].null_count == 0) &&
+                        aggs[i].values[0].length == key_chunks[0].length && dtype_size(aggs[i].values[0].dtype) >= 4 && aggs[i].values[0].dtype != BL_BOOL;
+    DevCol key;
+    std::vector<DevCol> vals(n_aggs);
+    std::vector<const DevCol*> vptr(n_aggs, nullptr);
+    std::vector<int> nullable(n_aggs, 0);
+    if (pipelined) {
+        Context& c = ctx();
+        const int64_t n = key_chunks[0].length;
+        key = make_col(key_chunks[0].dtype, n, false);
+        for (int i = 0; i < n_aggs; i++) {
+            if (aggs[i].kind == BL_AGG_LEN) { dts.push_back(BL_INT64); continue; }
+            int dup = -1;
+            for (int j = 0; j < i; j++) if (aggs[j].kind != BL_AGG_LEN && same_col(aggs[j], aggs[i])) { dup = j; break; }
+            if (dup >= 0) vptr[i] = vptr[dup]; else { vals[i] = make_col(aggs[i].values[0].dtype, n, false); vptr[i] = &vals[i]; }
+            dts.push_back(vptr[i]->dtype);
+        }
+        const int64_t chunk_rows = (int64_t)1 << 23;      // 8M rows: 64 MB per 8-byte column
+        const size_t n_chunks = (size_t)((n + chunk_rows - 1) / chunk_rows);
+        std::vector<cudaEvent_t> ready(n_chunks);
+        // the copy stream must not run ahead of the allocation order of the compute stream
+        cudaEvent_t alloc_done; PLB_CUDA(cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming));
+        PLB_CUDA(cudaEventRecord(alloc_done, c.stream));
+        PLB_CUDA(cudaStreamWaitEvent(c.copy_stream, alloc_done, 0));
+        for (size_t ci = 0; ci < n_chunks; ci++) {
+            const int64_t lo = (int64_t)ci * chunk_rows, len = std::min<int64_t>(chunk_rows, n - lo);
+            const int kes = dtype_size(key.dtype);
+            PLB_CUDA(cudaMemcpyAsync((char*)key.values->p + lo * kes, (const char*)key_chunks[0].values + (key_chunks[0].offset + lo) * kes, (size_t)len * kes, cudaMemcpyHostToDevice, c.copy_stream));
+            for (int i = 0; i < n_aggs; i++) {
+                if (vptr[i] != &vals[i]) continue;      // LEN or duplicate column
+                const int ves = dtype_size(vals[i].dtype);
+                PLB_CUDA(cudaMemcpyAsync((char*)vals[i].values->p + lo * ves, (const char*)aggs[i].values[0].values + (aggs[i].values[0].offset + lo) * ves, (size_t)len * ves, cudaMemcpyHostToDevice, c.copy_stream));
+            }
+            PLB_CUDA(cudaEventCreateWithFlags(&ready[ci], cudaEventDisableTiming));
+            PLB_CUDA(cudaEventRecord(ready[ci], c.copy_stream));
+        }
+        GroupByState st(key.dtype, kinds, dts, nullable, 0, maintain_order != 0 || dtype_is_float(key.dtype));
+        try { st.consume_pipelined(key, vptr, chunk_rows, ready); }
+        catch (...) { cudaStreamSynchronize(c.copy_stream); for (auto e : ready) cudaEventDestroy(e); cudaEventDestroy(alloc_done); throw; }
+        for (auto e : ready) cudaEventDestroy(e);
+        cudaEventDestroy(alloc_done);
+        DevCol ok; std::vector<DevCol> oa;
+        st.finish(maintain_order != 0, &key, ok, oa);
+        bl_column tk; std::vector<bl_column> ta(n_aggs);
+        export_column(ok, out_location, &tk);
+        int done = 0;
+        try { for (; done < n_aggs; done++) export_column(oa[done], out_location, &ta[done]); }
+        catch (...) { bl_column_free(&tk); for (int i = 0; i < done; i++) bl_column_free(&ta[i]); throw; }
+        *out_key = tk;
+        for (int i = 0; i < n_aggs; i++) out_aggs[i] = ta[i];
+        return BL_OK;
+    }
+    key = import_column(key_chunks, n_key_chunks);
+    // aggregations over the same chunk list share one device copy
+    for (int i = 0; i < n_aggs; i++) {
         if (aggs[i].kind == BL_AGG_LEN) { dts.push_back(BL_INT64); continue; }
-        PLB_REQUIRE(aggs[i].values && aggs[i].n_chunks >= 1, BL_ERR_INVALID, "groupby_agg: aggregation without a value column");
         int dup = -1;
-        for (int j = 0; j < i; j++)
-            if (aggs[j].kind != BL_AGG_LEN && aggs[j].n_chunks == aggs[i].n_chunks &&
-                (aggs[j].values == aggs[i].values || (aggs[i].n_chunks == 1 && aggs[j].values[0].values == aggs[i].values[0].values && aggs[j].values[0].validity == aggs[i].values[0].validity &&
-                                                      aggs[j].values[0].offset == aggs[i].values[0].offset && aggs[j].values[0].length == aggs[i].values[0].length && aggs[j].values[0].dtype == aggs[i].values[0].dtype)))
-                { dup = j; break; }
+        for (int j = 0; j < i; j++) if (aggs[j].kind != BL_AGG_LEN && same_col(aggs[j], aggs[i])) { dup = j; break; }
         if (dup >= 0) vals[i] = vals[dup]; else vals[i] = import_column(aggs[i].values, aggs[i].n_chunks);
         vptr[i] = &vals[i];
         dts.push_back(vals[i].dtype);
     }
-    std::vector<int> nullable(n_aggs, 0);
     for (int i = 0; i < n_aggs; i++) nullable[i] = vptr[i] != nullptr && vptr[i]->validity != nullptr;
     GroupByState st(key.dtype, kinds, dts, nullable, 0, maintain_order != 0 || dtype_is_float(key.dtype));
     st.consume_all(key, vptr);

@@ -46,6 +46,7 @@ struct GroupByState {
 
     GroupByState(int key_dt, const std::vector<int>& kinds, const std::vector<int>& dtypes, const std::vector<int>& nullable, int64_t expected, bool track_first);
     void consume_all(const DevCol& key, const std::vector<const DevCol*>& values);
+    void consume_pipelined(const DevCol& key, const std::vector<const DevCol*>& values, int64_t chunk_rows, const std::vector<cudaEvent_t>& ready);
     void consume(const DevCol& key, const std::vector<const DevCol*>& values, int64_t row_base);
     void merge_partials(const uint64_t* rows, int64_t n_rows);
     void merge_partial_regions(const uint64_t* const* ptrs, const int64_t* counts, int n_regions);
@@ -57,7 +58,7 @@ struct GroupByState {
 
    private:
     void alloc_table(uint64_t new_cap);
-    uint64_t choose_cap(const DevCol& key);
+    uint64_t choose_cap(const DevCol& key, int64_t n_total);
     void launch_batch(const DevCol& key, const std::vector<const DevCol*>& values, int64_t row_base);
     void grow(uint64_t new_cap);
 };
