@@ -1,0 +1,182 @@
+"""Boundary B2 — post-optimisation IR callback: run Filter→GroupBy and single-key Join
+subtrees of an optimised Polars plan on the B200 library, everything else on Polars' own engine.
+
+    import polars as pl
+    from polars_b200.engine import execute_with_b200
+    out = lf.collect(post_opt_callback=execute_with_b200)        # py-polars/src/polars/lazyframe/frame.py:2191-2192
+
+The reference hands the optimised IR to a Python callable `(NodeTraverser, duration) -> None`
+(crates/polars-python/src/lazyframe/general.rs:57-85).  The callable may inspect nodes
+(`view_current_node`, `get_inputs`, `view_expression`, crates/polars-python/src/lazyframe/visit.rs:110-190)
+and replace the current subtree by a Python UDF with `set_udf` (visit.rs:156-175), which the in-memory
+engine then calls instead of executing the subtree.  This is the seam the reference's own GPU engine uses
+(py-polars/src/polars/lazyframe/engine.py:946-970).
+
+NOT TESTED in this repository: there is no Polars wheel in the authoring image or on the GPU box (no Rust
+toolchain to build one), so this module is written against the reference source only.  It is deliberately
+conservative: any node shape it does not recognise is left untouched (Polars executes it).
+Recognised:
+  * GroupBy(keys=[col], aggs ⊆ {col.sum/mean/min/max/count, len}) over a DataFrameScan, optionally through
+    one Filter(col <cmp> literal)                      -> bl_filter_cmp + bl_groupby_agg
+  * Join(inner|left, one key column per side) of two DataFrameScans -> bl_hash_join + bl_gather
+"""
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+
+_NUMERIC = {"Int32": np.int32, "Int64": np.int64, "UInt32": np.uint32, "UInt64": np.uint64, "Float32": np.float32, "Float64": np.float64}
+_CMP = {"Eq": "eq", "NotEq": "ne", "Lt": "lt", "LtEq": "le", "Gt": "gt", "GtEq": "ge"}
+_AGG = {"sum": "sum", "mean": "mean", "min": "min", "max": "max", "count": "count"}
+
+
+class _Unsupported(Exception):
+    pass
+
+
+def _series_to_column(plb, s):
+    """pl.Series (numeric, any chunking, nulls) -> list of plb.Column chunks over the Arrow buffers (zero copy)."""
+    import pyarrow as pa
+    if str(s.dtype) not in _NUMERIC:
+        raise _Unsupported(f"dtype {s.dtype}")
+    chunks = []
+    arr = s.to_arrow()
+    for ch in (arr.chunks if isinstance(arr, pa.ChunkedArray) else [arr]):
+        bufs = ch.buffers()
+        values = np.frombuffer(bufs[1], dtype=_NUMERIC[str(s.dtype)])
+        valid = None if bufs[0] is None or ch.null_count == 0 else np.frombuffer(bufs[0], dtype=np.uint8)
+        chunks.append(plb.Column(values, valid, offset=ch.offset, length=len(ch), null_count=ch.null_count))
+    return chunks
+
+
+def _column_name(nt, node: int) -> str:
+    e = nt.view_expression(node)
+    if type(e).__name__ != "Column":
+        raise _Unsupported(type(e).__name__)
+    return str(e.name)
+
+
+def _parse_agg(nt, expr_ir):
+    e = nt.view_expression(expr_ir.node)
+    name = type(e).__name__
+    if name == "Len":
+        return "len", None, expr_ir.output_name
+    if name == "Agg" and str(e.name) in _AGG and len(e.arguments) == 1:
+        return _AGG[str(e.name)], _column_name(nt, e.arguments[0]), expr_ir.output_name
+    raise _Unsupported(f"aggregation {name}")
+
+
+def _parse_filter(nt, node):
+    """Filter(input, BinaryExpr(Column, cmp, Literal)) -> (input node id, column, op, python scalar)."""
+    pred = nt.view_expression(node.predicate.node)
+    if type(pred).__name__ != "BinaryExpr":
+        raise _Unsupported("filter predicate")
+    op = str(pred.op).split(".")[-1]
+    if op not in _CMP:
+        raise _Unsupported(f"operator {op}")
+    col = _column_name(nt, pred.left)
+    lit = nt.view_expression(pred.right)
+    if type(lit).__name__ != "Literal":
+        raise _Unsupported("filter rhs")
+    return node.input, col, _CMP[op], lit.value
+
+
+def _scan_frame(nt, node_id):
+    nt.set_node(node_id)
+    n = nt.view_current_node()
+    if type(n).__name__ != "DataFrameScan" or n.selection is not None:
+        raise _Unsupported(type(n).__name__)
+    import polars as pl
+    df = pl.DataFrame._from_pydf(n.df) if hasattr(pl.DataFrame, "_from_pydf") else n.df
+    if n.projection is not None:
+        df = df.select(list(n.projection))
+    return df
+
+
+def _plan_group_by(plb, nt, root_id, node):
+    import polars as pl
+    if len(node.keys) != 1:
+        raise _Unsupported("multi-column keys")
+    key_name = _column_name(nt, node.keys[0].node)
+    aggs = [_parse_agg(nt, a) for a in node.aggs]
+    nt.set_node(node.input)
+    child = nt.view_current_node()
+    flt = None
+    if type(child).__name__ == "Filter":
+        inp, fcol, fop, fval = _parse_filter(nt, child)
+        flt = (fcol, fop, fval)
+        df = _scan_frame(nt, inp)
+    else:
+        df = _scan_frame(nt, node.input)
+    nt.set_node(root_id)
+    maintain_order = bool(node.maintain_order)
+
+    def run(*_args: Any, **_kwargs: Any):
+        needed = [key_name] + [c for _, c, _ in aggs if c is not None]
+        cols = {c: _series_to_column(plb, df.get_column(c)) for c in dict.fromkeys(needed)}
+        if flt is not None:
+            fcol, fop, fval = flt
+            names = list(dict.fromkeys(needed + [fcol]))
+            dev = [plb.to_device(*_concat(df.get_column(c))) for c in names]
+            outs = plb.filter_cmp([d.view() for d in dev], names.index(fcol), fop, fval, location=plb.DEVICE)
+            view = {c: outs[i].view() for i, c in enumerate(names)}
+            key, vals = view[key_name], {c: view[c] for c in needed}
+        else:
+            key, vals = cols[key_name], cols
+        (k, kv), outs = plb.group_by_agg(key, [(kind, None if c is None else vals[c]) for kind, c, _ in aggs], maintain_order)
+        res = {key_name: pl.Series(key_name, k).set(pl.Series(~kv), None) if kv is not None else pl.Series(key_name, k)}
+        for (kind, c, out_name), (v, m) in zip(aggs, outs):
+            s = pl.Series(out_name, v)
+            res[out_name] = s.set(pl.Series(~m), None) if m is not None else s
+        return pl.DataFrame(res)
+
+    return run
+
+
+def _concat(series):
+    a = series.to_numpy()
+    return (a, None) if series.null_count() == 0 else (np.where(series.is_null().to_numpy(), 0, a), ~series.is_null().to_numpy())
+
+
+def _plan_join(plb, nt, root_id, node):
+    import polars as pl
+    how = str(node.options[0]).lower() if isinstance(node.options, (tuple, list)) else str(node.options)
+    how = "inner" if "inner" in how else ("left" if "left" in how else None)
+    if how is None or len(node.left_on) != 1 or len(node.right_on) != 1:
+        raise _Unsupported("join type / multi-key")
+    lkey, rkey = _column_name(nt, node.left_on[0].node), _column_name(nt, node.right_on[0].node)
+    left, right = _scan_frame(nt, node.input_left), _scan_frame(nt, node.input_right)
+    nt.set_node(root_id)
+
+    def run(*_args: Any, **_kwargs: Any):
+        (li, _), (ri, rv) = plb.hash_join(_series_to_column(plb, left.get_column(lkey)), _series_to_column(plb, right.get_column(rkey)), how)
+        ridx = pl.Series(ri) if rv is None else pl.Series(ri).set(pl.Series(~rv), None)
+        out_l = left[pl.Series(li)]
+        out_r = right.drop(rkey)[ridx] if how == "inner" else right.drop(rkey).select(pl.all().gather(ridx))
+        clash = [c for c in out_r.columns if c in out_l.columns]
+        return out_l.hstack(out_r.rename({c: c + "_right" for c in clash}))      # general.rs:17-49
+
+    return run
+
+
+def execute_with_b200(nt: Any, duration_since_start: int | None = None, *, raise_on_fail: bool = False) -> None:
+    """The post-optimisation callback.  Leaves the plan untouched when the root is not a supported shape."""
+    import polars_b200 as plb
+    try:
+        root = nt.view_current_node()
+        kind = type(root).__name__
+        root_id = nt.get_node() if hasattr(nt, "get_node") else None
+        if kind == "GroupBy":
+            fn = _plan_group_by(plb, nt, root_id, root)
+        elif kind == "Join":
+            fn = _plan_join(plb, nt, root_id, root)
+        else:
+            raise _Unsupported(kind)
+        nt.set_udf(fn)
+    except _Unsupported:
+        if raise_on_fail:
+            raise
+    except plb.B200Error:
+        if raise_on_fail:
+            raise

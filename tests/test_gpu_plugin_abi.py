@@ -61,11 +61,12 @@ class Caller:
         exports, arrs = zip(*[self.export(n, ch) for n, ch in inputs])
         arr = (SeriesExport * len(exports))(*exports)
         ret = SeriesExport()
+        before = self.released
         fn = getattr(self.lib, f"_polars_plugin_bl_{op}")
         fn.restype = None
         fn(arr, C.c_size_t(len(exports)), None, C.c_size_t(0), C.byref(ret), None)
         # the callee owns the inputs: every ArrowArray and every SeriesExport must have been released
-        assert self.released == len(exports), "input SeriesExport not released by the plugin"
+        assert self.released - before == len(exports), "input SeriesExport not released by the plugin"
         for group in arrs:
             for a in group:
                 assert not a.release, "input ArrowArray not released by the plugin"
