@@ -34,11 +34,7 @@ static void filter_impl(const bl_column* cols, int32_t n_cols, const DevCol& mas
     std::vector<DevCol> in, o;
     for (int i = 0; i < n_cols; i++) in.push_back(pre ? (*pre)[i] : import_column(&cols[i], 1));
     op_filter(in, mask, o);
-    std::vector<bl_column> tmp(n_cols);
-    int done = 0;
-    try { for (; done < n_cols; done++) export_column(o[done], out_location, &tmp[done]); }
-    catch (...) { for (int i = 0; i < done; i++) bl_column_free(&tmp[i]); throw; }
-    for (int i = 0; i < n_cols; i++) outs[i] = tmp[i];
+    export_many(o, out_location, outs);
 }
 
 bl_status bl_filter(const bl_column* cols, int32_t n_cols, const bl_column* mask, int32_t out_location, bl_column* outs) {
@@ -69,11 +65,7 @@ bl_status bl_gather(const bl_column* cols, int32_t n_cols, const bl_column* idx,
     for (int i = 0; i < n_cols; i++) in.push_back(import_column(&cols[i], 1));
     DevCol ix = import_column(idx, 1);
     op_gather(in, ix, check_bounds != 0, o);
-    std::vector<bl_column> tmp(n_cols);
-    int done = 0;
-    try { for (; done < n_cols; done++) export_column(o[done], out_location, &tmp[done]); }
-    catch (...) { for (int i = 0; i < done; i++) bl_column_free(&tmp[i]); throw; }
-    for (int i = 0; i < n_cols; i++) outs[i] = tmp[i];
+    export_many(o, out_location, outs);
     BL_CATCH
 }
 
@@ -139,13 +131,9 @@ bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, cons
         cudaEventDestroy(alloc_done);
         DevCol ok; std::vector<DevCol> oa;
         st.finish(maintain_order != 0, &key, ok, oa);
-        bl_column tk; std::vector<bl_column> ta(n_aggs);
-        export_column(ok, out_location, &tk);
-        int done = 0;
-        try { for (; done < n_aggs; done++) export_column(oa[done], out_location, &ta[done]); }
-        catch (...) { bl_column_free(&tk); for (int i = 0; i < done; i++) bl_column_free(&ta[i]); throw; }
-        *out_key = tk;
-        for (int i = 0; i < n_aggs; i++) out_aggs[i] = ta[i];
+        { std::vector<DevCol> all{ok}; all.insert(all.end(), oa.begin(), oa.end());
+          std::vector<bl_column> t(all.size()); export_many(all, out_location, t.data());
+          *out_key = t[0]; for (int i = 0; i < n_aggs; i++) out_aggs[i] = t[i + 1]; }
         return BL_OK;
     }
     key = import_column(key_chunks, n_key_chunks);
@@ -163,13 +151,9 @@ bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, cons
     st.consume_all(key, vptr);
     DevCol ok; std::vector<DevCol> oa;
     st.finish(maintain_order != 0, &key, ok, oa);
-    bl_column tk; std::vector<bl_column> ta(n_aggs);
-    export_column(ok, out_location, &tk);
-    int done = 0;
-    try { for (; done < n_aggs; done++) export_column(oa[done], out_location, &ta[done]); }
-    catch (...) { bl_column_free(&tk); for (int i = 0; i < done; i++) bl_column_free(&ta[i]); throw; }
-    *out_key = tk;
-    for (int i = 0; i < n_aggs; i++) out_aggs[i] = ta[i];
+    { std::vector<DevCol> all{ok}; all.insert(all.end(), oa.begin(), oa.end());
+      std::vector<bl_column> t(all.size()); export_many(all, out_location, t.data());
+      *out_key = t[0]; for (int i = 0; i < n_aggs; i++) out_aggs[i] = t[i + 1]; }
     BL_CATCH
 }
 
@@ -181,10 +165,7 @@ bl_status bl_hash_join(const bl_column* left_key, int32_t n_left_chunks, const b
     DevCol l = import_column(left_key, n_left_chunks), r = import_column(right_key, n_right_chunks);
     trace_point("cabi:join imported");
     JoinResult jr = op_hash_join(l, r, how, nulls_equal != 0, maintain_order);
-    bl_column tl, tr;
-    export_column(jr.left, out_location, &tl);
-    try { export_column(jr.right, out_location, &tr); } catch (...) { bl_column_free(&tl); throw; }
-    *out_left_idx = tl; *out_right_idx = tr;
+    { std::vector<DevCol> both{jr.left, jr.right}; bl_column t[2]; export_many(both, out_location, t); *out_left_idx = t[0]; *out_right_idx = t[1]; }
     trace_point("cabi:join exported");
     BL_CATCH
 }
@@ -267,13 +248,9 @@ bl_status bl_groupby_finish(bl_groupby* g, int32_t maintain_order, int32_t out_l
     DevCol ok; std::vector<DevCol> oa;
     g->st->finish(maintain_order != 0, nullptr, ok, oa);
     const int n_aggs = (int)oa.size();
-    bl_column tk; std::vector<bl_column> ta(n_aggs);
-    export_column(ok, out_location, &tk);
-    int done = 0;
-    try { for (; done < n_aggs; done++) export_column(oa[done], out_location, &ta[done]); }
-    catch (...) { bl_column_free(&tk); for (int i = 0; i < done; i++) bl_column_free(&ta[i]); throw; }
-    *out_key = tk;
-    for (int i = 0; i < n_aggs; i++) out_aggs[i] = ta[i];
+    { std::vector<DevCol> all{ok}; all.insert(all.end(), oa.begin(), oa.end());
+      std::vector<bl_column> t(all.size()); export_many(all, out_location, t.data());
+      *out_key = t[0]; for (int i = 0; i < n_aggs; i++) out_aggs[i] = t[i + 1]; }
     BL_CATCH
 }
 bl_status bl_groupby_export_partials_p2p(bl_groupby* g, int32_t n_ranks, int32_t my_rank, void* const* windows, int64_t rows_per_src, int32_t* row_words, int64_t* sent_rows) {

@@ -127,7 +127,8 @@ inline size_t bitmap_bytes(int64_t bits) { return (size_t)((bits + 31) / 32) * 4
 
 // bl_column (host/device, chunked, arbitrary offset)  <->  DevCol
 DevCol import_column(const bl_column* chunks, int n_chunks);
-void export_column(const DevCol& c, int location, bl_column* out);
+void export_column(const DevCol& c, int location, bl_column* out, bool sync = true);
+void export_many(const std::vector<DevCol>& cols, int location, bl_column* outs);   // one sync for all
 DevCol make_col(int dtype, int64_t len, bool with_validity);
 
 // small device scalar readback (sync on compute stream)

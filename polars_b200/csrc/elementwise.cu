@@ -184,11 +184,8 @@ __global__ void __launch_bounds__(256) k_compare(const T* __restrict__ lhs, cons
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const unsigned lane = lane_id();
-    for (int64_t s = warp; s < nsteps; s += nwarps) {
-        int64_t vec = s * 32 + lane;
-        uint4 ta = ld_stream_u32x4(reinterpret_cast<const uint4*>(lhs) + vec);
-        V va = *reinterpret_cast<V*>(&ta), vb;
-        if (!SCALAR) { uint4 tb = ld_stream_u32x4(reinterpret_cast<const uint4*>(rhs) + vec); vb = *reinterpret_cast<V*>(&tb); }
+    constexpr int UNROLL = 4;      // independent 128-bit loads in flight per thread
+    auto emit = [&](int64_t s, const V& va, const V& vb) {
         uint32_t m[VN];
 #pragma unroll
         for (int k = 0; k < VN; k++) m[k] = __ballot_sync(0xffffffffu, cmp_op<T, OP>(va.v[k], SCALAR ? scalar : vb.v[k]));
@@ -200,12 +197,32 @@ __global__ void __launch_bounds__(256) k_compare(const T* __restrict__ lhs, cons
             // 2-spaced 64-bit words, then interleave those.
             uint64_t e = spread_bits(m[0]) | (spread_bits(m[2]) << 1);   // bit 2l+j  <- m[2j] bit l
             uint64_t o = spread_bits(m[1]) | (spread_bits(m[3]) << 1);   // bit 2l+j  <- m[2j+1] bit l
-            // final bit 4l+k with k = 2j+i: from (i ? o : e) bit 2l+j  -> spread each 64->128
             uint64_t e_lo = spread_bits((uint32_t)e), e_hi = spread_bits((uint32_t)(e >> 32));
             uint64_t o_lo = spread_bits((uint32_t)o), o_hi = spread_bits((uint32_t)(o >> 32));
             uint64_t lo = e_lo | (o_lo << 1), hi = e_hi | (o_hi << 1);
             if (lane == 0) *reinterpret_cast<uint4*>(out + s * 4) = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
         }
+    };
+    int64_t s = warp;
+    for (; s + (UNROLL - 1) * nwarps < nsteps; s += UNROLL * nwarps) {
+        uint4 ta[UNROLL], tb[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            ta[u] = ld_stream_u32x4(reinterpret_cast<const uint4*>(lhs) + (s + u * nwarps) * 32 + lane);
+            if (!SCALAR) tb[u] = ld_stream_u32x4(reinterpret_cast<const uint4*>(rhs) + (s + u * nwarps) * 32 + lane);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            V va = *reinterpret_cast<V*>(&ta[u]), vb;
+            if (!SCALAR) vb = *reinterpret_cast<V*>(&tb[u]);
+            emit(s + u * nwarps, va, vb);
+        }
+    }
+    for (; s < nsteps; s += nwarps) {
+        uint4 ta = ld_stream_u32x4(reinterpret_cast<const uint4*>(lhs) + s * 32 + lane);
+        V va = *reinterpret_cast<V*>(&ta), vb;
+        if (!SCALAR) { uint4 tb = ld_stream_u32x4(reinterpret_cast<const uint4*>(rhs) + s * 32 + lane); vb = *reinterpret_cast<V*>(&tb); }
+        emit(s, va, vb);
     }
     // tail rows: one warp, 32 rows per ballot
     if (warp == 0) {

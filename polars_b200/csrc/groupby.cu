@@ -906,7 +906,7 @@ void GroupByState::reset() {
         PLB_LAUNCH("k5_table_init", k_gb_init, grid_for((int64_t)(cap + 2) * L.stride, 256), 256, 0, T.entries, (int64_t)(cap + 2), L.stride, L);
         dev_memset(status->p, 0, 4);
     }
-    rows_seen = 0;
+    rows_seen = 0; merged_rows = 0;
 }
 
 void GroupByState::merge_partials(const uint64_t* rows, int64_t n_rows) {
@@ -940,6 +940,7 @@ void GroupByState::merge_partial_regions(const uint64_t* const* ptrs, const int6
     int64_t acc = 0;
     for (int r = 0; r < n_regions; r++) { R.ptr[r] = ptrs[r]; acc += counts[r]; R.end[r] = acc; }
     R.n = n_regions;
+    merged_rows += n_rows;
     PLB_LAUNCH("k5_merge_partials", k_gb_merge_regions, grid_for(n_rows, 256), 256, 0, L, T, R, row_words);
     if (read_scalar(as<int>(status)) != 0) fail(BL_ERR_OOM, "group_by: table overflow while merging partial aggregates (expected_groups too small)");
 }
@@ -990,16 +991,24 @@ void GroupByState::export_partials_p2p(int n_ranks, int my_rank, void* const* wi
 void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather, DevCol& out_key, std::vector<DevCol>& out_aggs) {
     out_aggs.clear();
     PLB_REQUIRE(!maintain_order || L.need_first, BL_ERR_INVALID, "group_by: maintain_order needs a state created with track_first");
-    int64_t G = entries ? count_groups() : 0;
+    // Extract into buffers sized by an upper bound of the group count, then read the real count and
+    // the null-group position back with ONE 16-byte copy (one host sync for the whole finish).
     const int kelem = dtype_size(key_dtype);
-    DevPtr keys = dev_alloc((size_t)std::max<int64_t>(G, 1) * 8), first = dev_alloc((size_t)std::max<int64_t>(G, 1) * 4), len = dev_alloc((size_t)std::max<int64_t>(G, 1) * 4);
-    DevPtr words = dev_alloc((size_t)std::max<int64_t>(G, 1) * 8 * std::max(L.n_words, 1));
-    DevPtr cursor = dev_alloc(8), nullpos = dev_alloc(8);
-    dev_memset(cursor->p, 0, 8); dev_memset(nullpos->p, 0xFF, 8);
-    if (G > 0)
-        PLB_LAUNCH("k5_extract", k_gb_extract, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, L.stride, L.n_words, as<unsigned long long>(cursor),
-                   as<uint64_t>(keys), as<uint32_t>(first), as<uint32_t>(len), as<uint64_t>(words), G, as<long long>(nullpos));
-    long long null_pos = G > 0 ? read_scalar(as<long long>(nullpos)) : -1;
+    const int64_t Gb = entries ? std::max<int64_t>(1, std::min<int64_t>((int64_t)cap + 2, rows_seen + merged_rows + 2)) : 1;
+    DevPtr keys = dev_alloc((size_t)Gb * 8), first = dev_alloc((size_t)Gb * 4), len = dev_alloc((size_t)Gb * 4);
+    DevPtr words = dev_alloc((size_t)Gb * 8 * std::max(L.n_words, 1));
+    DevPtr ctl = dev_alloc(16);                       // [0] cursor (#groups), [1] null-group position
+    const long long ctl_init[2] = {0, -1};
+    PLB_CUDA(cudaMemcpyAsync(ctl->p, ctl_init, 16, cudaMemcpyHostToDevice, ctx().stream));
+    long long ctl_host[2] = {0, -1};
+    if (entries) {
+        PLB_LAUNCH("k5_extract", k_gb_extract, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, L.stride, L.n_words, as<unsigned long long>(ctl),
+                   as<uint64_t>(keys), as<uint32_t>(first), as<uint32_t>(len), as<uint64_t>(words), Gb, as<long long>(ctl) + 1);
+        PLB_CUDA(cudaMemcpyAsync(ctl_host, ctl->p, 16, cudaMemcpyDeviceToHost, ctx().stream));
+    }
+    PLB_CUDA(cudaStreamSynchronize(ctx().stream));
+    const int64_t G = ctl_host[0];
+    const long long null_pos = ctl_host[1];
     // key column
     out_key = make_col(key_dtype, G, null_pos >= 0);
     if (G > 0)
@@ -1012,8 +1021,8 @@ void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather,
         if (G > 0) {
             FinalizeArgs fa; memset(&fa, 0, sizeof fa);
             fa.kind = ap.kind; fa.in_dtype = ap.in_dtype; fa.out_dtype = ap.out_dtype; fa.G = G;
-            fa.main_word = ap.main >= 0 ? as<uint64_t>(words) + (int64_t)ap.main * G : nullptr;
-            fa.nullcnt_word = ap.nullcnt >= 0 ? as<uint64_t>(words) + (int64_t)ap.nullcnt * G : nullptr;
+            fa.main_word = ap.main >= 0 ? as<uint64_t>(words) + (int64_t)ap.main * Gb : nullptr;
+            fa.nullcnt_word = ap.nullcnt >= 0 ? as<uint64_t>(words) + (int64_t)ap.nullcnt * Gb : nullptr;
             fa.len = as<uint32_t>(len); fa.out = o.values->p; fa.out_valid = as<uint32_t>(o.validity);
             PLB_LAUNCH("k5_finalize", k_gb_finalize, grid_for(G, 256), 256, 0, fa);
         }

@@ -42,6 +42,7 @@ struct GroupByState {
     DevPtr entries, status;
     uint64_t cap = 0;
     int64_t rows_seen = 0;
+    int64_t merged_rows = 0;     // partial-aggregate rows merged in (bounds the group count together with rows_seen)
     int64_t est_groups = 0;      // sampled / hinted cardinality; selects the shared-memory plan
 
     GroupByState(int key_dt, const std::vector<int>& kinds, const std::vector<int>& dtypes, const std::vector<int>& nullable, int64_t expected, bool track_first);

@@ -289,7 +289,7 @@ DevCol import_column(const bl_column* chunks, int n_chunks) {
 
 struct ColOwner { DevPtr values, validity; void* hv = nullptr; void* hm = nullptr; };
 
-void export_column(const DevCol& col, int location, bl_column* out) {
+void export_column(const DevCol& col, int location, bl_column* out, bool sync) {
     PLB_REQUIRE(out != nullptr, BL_ERR_INVALID, "null output column");
     Context& c = ctx();
     auto* own = new ColOwner();
@@ -305,17 +305,28 @@ void export_column(const DevCol& col, int location, bl_column* out) {
             // borrowed inputs must not escape as outputs: copy them
             if (col.values && !col.values->owned) { DevPtr t = dev_alloc(vb + 16); PLB_CUDA(cudaMemcpyAsync(t->p, col.values->p, vb, cudaMemcpyDeviceToDevice, c.stream)); own->values = t; r.values = t->p; }
             if (col.validity && !col.validity->owned) { DevPtr t = dev_alloc(mb + 16); PLB_CUDA(cudaMemcpyAsync(t->p, col.validity->p, mb, cudaMemcpyDeviceToDevice, c.stream)); own->validity = t; r.validity = (const uint8_t*)t->p; }
-            PLB_CUDA(cudaStreamSynchronize(c.stream));
+            if (sync) PLB_CUDA(cudaStreamSynchronize(c.stream));
         } else {
             own->hv = pinned_alloc_raw(vb + 16);
             if (vb) PLB_CUDA(cudaMemcpyAsync(own->hv, col.values->p, vb, cudaMemcpyDeviceToHost, c.stream));
             if (col.validity) { own->hm = pinned_alloc_raw(mb + 16); PLB_CUDA(cudaMemcpyAsync(own->hm, col.validity->p, mb, cudaMemcpyDeviceToHost, c.stream)); }
-            PLB_CUDA(cudaStreamSynchronize(c.stream));
+            if (sync) PLB_CUDA(cudaStreamSynchronize(c.stream));
             r.values = own->hv; r.validity = (const uint8_t*)own->hm;
         }
     } catch (...) { pinned_free_raw(own->hv); pinned_free_raw(own->hm); delete own; throw; }
     r.owner = own;
     *out = r;
+}
+
+// Export several columns with ONE stream synchronisation (all copies are queued first).
+void export_many(const std::vector<DevCol>& cols, int location, bl_column* outs) {
+    std::vector<bl_column> tmp(cols.size());
+    size_t done = 0;
+    try {
+        for (; done < cols.size(); done++) export_column(cols[done], location, &tmp[done], false);
+        PLB_CUDA(cudaStreamSynchronize(ctx().stream));
+    } catch (...) { cudaStreamSynchronize(ctx().stream); for (size_t i = 0; i < done; i++) bl_column_free(&tmp[i]); throw; }
+    for (size_t i = 0; i < cols.size(); i++) outs[i] = tmp[i];
 }
 
 }  // namespace plb

@@ -88,18 +88,30 @@ def partitioned_group_by(plb, key_col, value_cols, spec, location=None, nullable
 
 class PeerExchange:
     """Peer windows for the fused partition + exchange (K6 stores straight into the destination GPU's
-    memory over NVLink; the only collectives left are a tiny count exchange and a barrier)."""
+    memory over NVLink; the only collective left on the step is a tiny count exchange).
+    Two window halves alternate between steps, so a fast rank that already runs step k+1 writes into the
+    other half than the one a slow rank is still merging from step k; the count exchange of step k+1
+    cannot complete before every rank has finished merging step k, so two halves are enough and no
+    barrier is needed."""
 
     def __init__(self, plb, rows_per_src: int, row_words: int):
         self.plb, self.rows_per_src, self.row_words = plb, int(rows_per_src), int(row_words)
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
-        self.win = plb.Window(self.world * self.rows_per_src * self.row_words * 8)
+        self.half_bytes = self.world * self.rows_per_src * self.row_words * 8
+        self.win = plb.Window(2 * self.half_bytes)
         handles = [None] * self.world
         dist.all_gather_object(handles, self.win.ipc_handle)
         self.peers = [self.win.ptr if r == self.rank else plb.Window.open(handles[r]) for r in range(self.world)]
+        self.half = 0
+
+    def flip(self):
+        self.half ^= 1
+
+    def peer_ptrs(self):
+        return [p + self.half * self.half_bytes for p in self.peers]
 
     def region_ptr(self, src: int) -> int:
-        return self.win.ptr + src * self.rows_per_src * self.row_words * 8
+        return self.win.ptr + self.half * self.half_bytes + src * self.rows_per_src * self.row_words * 8
 
     def close(self):
         dist.barrier()
@@ -114,14 +126,13 @@ def partitioned_group_by_p2p(plb, ex: PeerExchange, key_col, value_cols, spec, l
     inside the partition kernel (bl_groupby_export_partials_p2p) instead of an NCCL all-to-all."""
     g = plb.GroupBy(plb.NP_OF[key_col.dtype], spec, nullable=nullable)
     g.consume(key_col, value_cols, row_base=0)
-    rw, sent = g.export_partials_p2p(ex.peers, ex.rank, ex.rows_per_src)
+    ex.flip()
+    rw, sent = g.export_partials_p2p(ex.peer_ptrs(), ex.rank, ex.rows_per_src)
     assert rw == ex.row_words
     recv = exchange_counts(sent, "cuda")          # also orders the peer stores before the merge
     f = plb.GroupBy(plb.NP_OF[key_col.dtype], spec, expected_groups=max(int(recv.sum()), 1), nullable=nullable)
     f.merge_partial_regions([ex.region_ptr(src) for src in range(ex.world)], [int(c) for c in recv])
-    out = f.finish(False, location=plb.DEVICE if location is None else location)
-    dist.barrier()                                 # windows may be overwritten by the next step
-    return out
+    return f.finish(False, location=plb.DEVICE if location is None else location)
 
 
 class _CudaArr:
