@@ -194,7 +194,10 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------- B200 arm
 def main():
     a = parse()
-    os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")   # NCCL's version banner goes to stdout: keep the JSON line alone
+    # NCCL prints its version banner to STDOUT for any NCCL_DEBUG level: keep the JSON line alone on stdout
+    os.environ.pop("NCCL_DEBUG", None)
+    if os.environ.get("BENCH_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
     if a.impl == "reference":
         run_reference(a)
         return

@@ -332,6 +332,118 @@ __global__ void __launch_bounds__(256) k_join_dense_probe(const uint32_t* __rest
     }
 }
 
+// ---------------------------------------------------------------------------- K8 fused probe + emit
+// Unique build keys (dense table or hashed table without duplicates): every probe row yields at most
+// one tuple, so probe and emission fuse into ONE pass with a decoupled look-back scan over 2048-row
+// tiles (tiles are handed out by an atomic counter, so every predecessor of a tile is already
+// running: the look-back cannot wait on an unscheduled CTA).  HBM traffic: 8 B key in + 8 B tuple out
+// per match — exactly the algorithmic 16 B/row, instead of 24 B/row for the two-pass form.
+// status[t]: bits 63..62 = 0 empty / 1 tile aggregate / 2 inclusive prefix, bits 61..0 = value.
+constexpr unsigned long long LB_AGG = 1ull << 62, LB_INC = 2ull << 62, LB_VAL = (1ull << 62) - 1;
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, bool DENSE>
+__global__ void __launch_bounds__(256) k_join_probe_emit(JoinTableDev T, const uint32_t* __restrict__ dense_table, uint64_t kmin, uint64_t range, int sign_bits,
+                                                         const void* __restrict__ keys, const uint32_t* __restrict__ valid, int64_t n, int nulls_equal, int left_join,
+                                                         unsigned long long* __restrict__ status, unsigned int* __restrict__ tile_counter, int* __restrict__ error,
+                                                         uint32_t* __restrict__ out_probe, uint32_t* __restrict__ out_build) {
+    constexpr int ITERS = J_TILE / 256;
+    __shared__ uint32_t seg[ITERS * 8];
+    __shared__ long long s_tile;
+    __shared__ unsigned long long s_prefix;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const int64_t ntiles = (n + J_TILE - 1) / J_TILE;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = (long long)atomicAdd(tile_counter, 1u);
+        __syncthreads();
+        const int64_t t = s_tile;
+        if (t >= ntiles) break;
+        uint32_t h[ITERS], lane_excl[ITERS]; bool emit[ITERS];
+        uint64_t kraw[ITERS];
+#pragma unroll
+        for (int j = 0; j < ITERS; j++) {        // all key loads of the tile first (coalesced, 8 in flight per thread)
+            const int64_t row = t * J_TILE + j * 256 + threadIdx.x;
+            kraw[j] = 0;
+            if (row < n) kraw[j] = KEY_ELEM == 8 ? __ldcs(reinterpret_cast<const unsigned long long*>(keys) + row) : (uint64_t)__ldcs(reinterpret_cast<const unsigned int*>(keys) + row);
+        }
+#pragma unroll
+        for (int j = 0; j < ITERS; j++) {
+            const int64_t row = t * J_TILE + j * 256 + threadIdx.x;
+            h[j] = J_NONE;
+            if (row < n) {
+                bool v = true;
+                if (KEY_NULLS) v = bit_get(valid, row);
+                if (DENSE) {
+                    const uint64_t d = j_ordered(kraw[j], sign_bits) - kmin;
+                    if (v && d < range) h[j] = __ldg(&dense_table[d]);
+                } else {
+                    uint64_t key = kraw[j];
+                    if (KEY_CANON == 1) key = canonical_f64_bits(__longlong_as_double((long long)key));
+                    if (KEY_CANON == 2) key = canonical_f32_bits(__uint_as_float((uint32_t)key));
+                    uint4 e;
+                    if (!v) { if (nulls_equal) { e = __ldg(&T.entries[T.cap]); if (e.w) h[j] = e.z; } }
+                    else if (key == J_EMPTY) { e = __ldg(&T.entries[T.cap + 1]); if (e.w) h[j] = e.z; }
+                    else {
+                        uint64_t slot = __umul64hi(dirty_hash(key), T.cap);
+                        while (true) {
+                            e = __ldg(&T.entries[slot]);
+                            const uint64_t k = ((uint64_t)e.y << 32) | e.x;
+                            if (k == key) { h[j] = e.z; break; }
+                            if (k == J_EMPTY) break;
+                            if (++slot == T.cap) slot = 0;
+                        }
+                    }
+                }
+            }
+            emit[j] = row < n && (h[j] != J_NONE || left_join);
+            const uint32_t b = __ballot_sync(0xffffffffu, emit[j]);
+            lane_excl[j] = __popc(b & lanemask_lt());
+            if (lane == 0) seg[j * 8 + warp] = __popc(b);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // exclusive scan of the 64 segment counts; tile total
+            uint32_t a = seg[2 * lane], b2 = seg[2 * lane + 1], s2 = a + b2, x = s2;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
+            seg[2 * lane] = x - s2; seg[2 * lane + 1] = x - s2 + a;
+            const unsigned long long tile_total = __shfl_sync(0xffffffffu, x, 31);
+            // decoupled look-back
+            if (lane == 0) atomicExch(&status[t], (t == 0 ? LB_INC : LB_AGG) | tile_total);
+            unsigned long long exclusive = 0;
+            if (t > 0) {
+                int64_t look = t - 1;
+                while (true) {
+                    const int64_t idx = look - lane;
+                    unsigned long long st = LB_INC;          // virtual predecessor before tile 0: inclusive 0
+                    int spins = 0;
+                    if (idx >= 0) st = *reinterpret_cast<volatile unsigned long long*>(&status[idx]);
+                    while (__any_sync(0xffffffffu, (st >> 62) == 0)) {
+                        if (idx >= 0 && (st >> 62) == 0) st = *reinterpret_cast<volatile unsigned long long*>(&status[idx]);
+                        if (++spins > (1 << 22) || ((spins & 1023) == 0 && *reinterpret_cast<volatile int*>(error))) { *error = 1; break; }   // never hang the device
+                    }
+                    const unsigned inc = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+                    const unsigned upto = inc ? (unsigned)(__ffs(inc) - 1) : 31u;     // nearest inclusive predecessor
+                    unsigned long long v = lane <= upto ? (st & LB_VAL) : 0ull;
+                    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    exclusive += v;
+                    if (inc || *reinterpret_cast<volatile int*>(error)) break;
+                    look -= 32;
+                }
+                if (lane == 0) atomicExch(&status[t], LB_INC | ((exclusive + tile_total) & LB_VAL));
+            }
+            if (lane == 0) s_prefix = exclusive;
+        }
+        __syncthreads();
+        const uint64_t base = s_prefix;
+#pragma unroll
+        for (int j = 0; j < ITERS; j++) {
+            if (!emit[j]) continue;
+            const uint64_t pos = base + seg[j * 8 + warp] + lane_excl[j];
+            out_probe[pos] = (uint32_t)(t * J_TILE + j * 256 + threadIdx.x);
+            out_build[pos] = h[j];
+        }
+        __syncthreads();
+    }
+}
+
 template <int KEY_ELEM, int KEY_CANON>
 static void launch_probe(bool kn, int grid, JoinTableDev T, const DevCol& probe, int nulls_equal, int csr, int left, uint32_t* handle, unsigned long long* tc) {
     if (kn) PLB_LAUNCH("k8_join_probe", (k_join_probe<KEY_ELEM, KEY_CANON, true>), grid, 256, 0, T, probe.v(), probe.vm(), probe.len, nulls_equal, csr, left, handle, tc);
@@ -405,11 +517,41 @@ JoinResult op_hash_join(const DevCol& left, const DevCol& right, int how, bool n
     }
 
     trace_point("join:build");
-    // ---- probe pass 1
+    // ---- unique build keys: fused single-pass probe + emit
+    static const int fused_on = [] { const char* e = getenv("BL_JOIN_FUSED"); return e ? atoi(e) : 1; }();
     const int64_t ntiles = (np + J_TILE - 1) / J_TILE;
+    uint64_t M = 0;
+    DevPtr out_probe, out_build;
+    bool done = false;
+    if (fused_on && !csr && np > 0) {
+        out_probe = dev_alloc((size_t)np * 4 + 16); out_build = dev_alloc((size_t)np * 4 + 16);
+        DevPtr st = dev_alloc((size_t)ntiles * 8 + 16), ctl = dev_alloc(8);
+        dev_memset(st->p, 0, (size_t)ntiles * 8 + 16); dev_memset(ctl->p, 0, 8);
+        const bool kn = probe.validity != nullptr;
+        const int left_join = how == BL_JOIN_LEFT ? 1 : 0;
+        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c.sm_count * 6);
+        unsigned long long* stp = as<unsigned long long>(st); unsigned* cnt = as<unsigned>(ctl); int* err = as<int>(ctl) + 1;
+        const uint32_t* tb = as<uint32_t>(dense_table);
+#define PE_LAUNCH(E, C, D)                                                                                                                          \
+        do { if (kn) PLB_LAUNCH("k8_join_probe_emit", (k_join_probe_emit<E, C, true, D>), grid, 256, 0, T, tb, kmin, range, sign_bits, probe.v(), probe.vm(), np, nulls_equal ? 1 : 0, left_join, stp, cnt, err, as<uint32_t>(out_probe), as<uint32_t>(out_build)); \
+             else PLB_LAUNCH("k8_join_probe_emit", (k_join_probe_emit<E, C, false, D>), grid, 256, 0, T, tb, kmin, range, sign_bits, probe.v(), probe.vm(), np, nulls_equal ? 1 : 0, left_join, stp, cnt, err, as<uint32_t>(out_probe), as<uint32_t>(out_build)); } while (0)
+        if (dense) { if (elem == 8) PE_LAUNCH(8, 0, true); else PE_LAUNCH(4, 0, true); }
+        else if (dt == BL_FLOAT64) PE_LAUNCH(8, 1, false);
+        else if (dt == BL_FLOAT32) PE_LAUNCH(4, 2, false);
+        else if (elem == 8) PE_LAUNCH(8, 0, false);
+        else PE_LAUNCH(4, 0, false);
+#undef PE_LAUNCH
+        unsigned long long last = 0; int herr[2] = {0, 0};
+        PLB_CUDA(cudaMemcpyAsync(&last, stp + (ntiles - 1), 8, cudaMemcpyDeviceToHost, c.stream));
+        PLB_CUDA(cudaMemcpyAsync(herr, ctl->p, 8, cudaMemcpyDeviceToHost, c.stream));
+        PLB_CUDA(cudaStreamSynchronize(c.stream));
+        if (herr[1] == 0) { M = last & LB_VAL; done = true; }     // else: look-back gave up -> two-pass path below
+    }
+    trace_point("join:probe");
+    if (!done) {
+    // ---- probe pass 1
     DevPtr handle = dev_alloc((size_t)std::max<int64_t>(np, 1) * 4 + 16), tc = dev_alloc((size_t)std::max<int64_t>(ntiles, 1) * 8), toff = dev_alloc((size_t)std::max<int64_t>(ntiles, 1) * 8), total = dev_alloc(8);
     dev_memset(tc->p, 0, (size_t)std::max<int64_t>(ntiles, 1) * 8); dev_memset(total->p, 0, 8);
-    uint64_t M = 0;
     if (np > 0) {
         const int grid = grid_for((np + 1) / 2, 256);
         const bool kn = probe.validity != nullptr;
@@ -430,14 +572,13 @@ JoinResult op_hash_join(const DevCol& left, const DevCol& right, int how, bool n
         M = read_scalar(as<unsigned long long>(total));
     }
     PLB_REQUIRE(M < 0xFFFFFFFFull, BL_ERR_UNSUPPORTED, "join: result has more than 2^32-2 rows (IdxSize = u32)");
-
-    trace_point("join:probe");
     // ---- probe pass 2
-    DevPtr out_probe = dev_alloc((size_t)std::max<uint64_t>(M, 1) * 4 + 16), out_build = dev_alloc((size_t)std::max<uint64_t>(M, 1) * 4 + 16);
+    out_probe = dev_alloc((size_t)std::max<uint64_t>(M, 1) * 4 + 16); out_build = dev_alloc((size_t)std::max<uint64_t>(M, 1) * 4 + 16);
     if (M > 0)
         PLB_LAUNCH("k8_join_emit", k_join_emit, (int)std::min<int64_t>(ntiles, (int64_t)c.sm_count * 8), 256, 0, T, as<uint32_t>(handle), np, csr ? 1 : 0, how == BL_JOIN_LEFT ? 1 : 0,
                    as<uint32_t>(sorted_rows), as<uint64_t>(toff), as<uint32_t>(out_probe), as<uint32_t>(out_build));
-
+    }
+    if (!out_probe) { out_probe = dev_alloc(16); out_build = dev_alloc(16); }
     trace_point("join:emit");
     JoinResult r;
     r.left = idx_col(swapped ? out_build : out_probe, (int64_t)M, 0);
