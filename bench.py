@@ -359,6 +359,13 @@ def main():
         return
     if a.workload == "join":      # hashed or dense probe, whichever ran
         dominant = max((k for k in prof if k.startswith("k8_") and "probe" in k), key=lambda k: prof[k]["ms"], default=dominant)
+    traffic = None      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(f"{a.workload}:{a.rows}:{a.keys if a.workload == 'groupby' else a.build_rows}", {})
+            traffic = t.get(dominant)
+    except Exception:
+        pass
     dom = prof.get(dominant, {"launches": 0, "ms": 0.0})
     dom_ms = dom["ms"] / max(dom["launches"], 1)
     achieved = (alg_bytes_per_row * unit_rows / 1e9) / (dom_ms / 1e3) if dom_ms > 0 else 0.0
@@ -369,7 +376,7 @@ def main():
         "config": {"workload": wl, "rows_per_gpu": a.rows, "groups_out": int(n_out), "l2_policy": "inputs larger than L2",
                    "parallelism": "single GPU" if world == 1 else (f"hash-partitioned x{world}: local pre-agg + fused partition/P2P-store exchange over NVLink + merge" if a.exchange == "p2p" else f"hash-partitioned x{world}: local pre-agg + one NCCL all-to-all of partial aggregates + merge")},
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs if peak_gbs else None,
-                     "traffic": None, "peak_source": peak_src, "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes_per_row * unit_rows,
+                     "traffic": traffic, "peak_source": peak_src, "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes_per_row * unit_rows,
                      "kernel_share_of_step": (dom_ms / total_kernel_ms) if total_kernel_ms else None},
         "kernels_ms_per_step": {k: v["ms"] / a.steps for k, v in prof.items()},
         "gpu_launches": int(launches),

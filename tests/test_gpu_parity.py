@@ -489,3 +489,49 @@ def test_large_properties_groupby_join(plb):
     l_idx, _ = li.to_numpy()
     assert np.array_equal(a, b) and a.size == int((pkey < nb).sum())
     assert np.all(np.diff(l_idx.astype(np.int64)) > 0)       # probe order, unique build keys
+
+
+# ------------------------------------------------------------------ boundary behaviour
+def test_join_chunked_sliced_nullable_keys(plb):
+    # chunked ChunkedArray inputs with arbitrary validity bit offsets on both sides
+    # (reference regression: crates/polars/tests/it/core/joins.rs:651-684 test_4_threads_bit_offset)
+    rng = np.random.default_rng(31)
+    nl, nr = 7001, 2503
+    lk = rng.integers(0, 900, nl + 13).astype(np.int64)
+    rk = rng.integers(0, 900, nr + 5).astype(np.int64)
+    lv = rng.random(nl + 13) > 0.2
+    rv = rng.random(nr + 5) > 0.2
+    cuts_l = [0, 1, 64, 1999, nl]
+    lch = [plb.Column(lk, lv, offset=13 + a, length=b - a) for a, b in zip(cuts_l[:-1], cuts_l[1:])]
+    rch = [plb.Column(rk, rv, offset=5, length=1000), plb.Column(rk, rv, offset=1005, length=nr - 1000)]
+    for how in ("inner", "left"):
+        (li, _), (ri, _) = plb.hash_join(lch, rch, how)
+        eli, eri = oracle.hash_join(lk[13:13 + nl], rk[5:5 + nr], lv[13:13 + nl], rv[5:5 + nr], how, False, "none", 3)
+        assert np.array_equal(li, eli) and np.array_equal(ri, eri), how
+
+
+def test_error_paths(plb):
+    a = np.arange(10, dtype=np.int64)
+    with pytest.raises(plb.B200Error) as e:
+        plb.elementwise("add", a, np.arange(7, dtype=np.int64))           # lengths do not broadcast
+    assert e.value.status == 1
+    with pytest.raises(plb.ComputeError):
+        plb.elementwise("add", a, a.astype(np.float64))                   # dtype mismatch
+    with pytest.raises(plb.B200Error) as e:
+        plb.group_by_agg(a.astype(np.int8), [("len", None)])              # dtype outside the hot path
+    assert e.value.status == 4
+    with pytest.raises(plb.B200Error):
+        plb.filter([a], np.ones(9, bool))                                 # mask length mismatch
+    # the library stays usable after errors
+    out, _ = plb.elementwise("mul", a, np.array([3], np.int64))
+    assert np.array_equal(out, a * 3)
+
+
+def test_null_scalar_and_empty_inputs(plb):
+    a = np.arange(5, dtype=np.float64)
+    out, v = plb.elementwise("add", a, plb.Column(np.array([1.0]), np.array([False])))    # null scalar -> all null (arity.rs:916-922)
+    assert v is not None and not v.any() and out.size == 5
+    (k, _), outs = plb.group_by_agg(np.zeros(0, np.int64), [("sum", np.zeros(0, np.int64)), ("mean", np.zeros(0)), ("len", None)], True)
+    assert k.size == 0 and all(o[0].size == 0 for o in outs)
+    (li, _), (ri, _) = plb.hash_join(np.zeros(0, np.int64), np.arange(3, dtype=np.int64), "left")
+    assert li.size == 0 and ri.size == 0

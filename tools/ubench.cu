@@ -35,6 +35,17 @@ __global__ void k_red(uint64_t* table, uint64_t mask, int64_t nops, int stride_w
         }
     }
 }
+// SoA variant of mode 2: key load from keys[slot], REDs into three separate dense arrays
+__global__ void k_red_soa(const uint64_t* keys, unsigned* len, uint64_t* si, double* sf, uint64_t mask, int64_t nops) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nops; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t slot = mix((uint64_t)i) & mask;
+        unsigned long long k = __ldcg((const unsigned long long*)(keys + slot));
+        if (k == 0xdeadbeefULL) continue;
+        atomicAdd(len + slot, 1u);
+        atomicAdd((unsigned long long*)(si + slot), (unsigned long long)i);
+        atomicAdd(sf + slot, 1.5);
+    }
+}
 __global__ void k_smem_atom(int64_t nops, int use64, unsigned long long* out) {
     __shared__ unsigned long long t[4096];   // 32 KB
     for (int i = threadIdx.x; i < 4096; i += blockDim.x) t[i] = 0;
@@ -91,6 +102,14 @@ int main() {
         printf("{\"test\": \"red_random\", \"log2_entries\": %d, \"dense_u64_Gops\": %.2f, \"stride32_u64_Gops\": %.2f, \"keyload_plus_3red_Grows\": %.2f, \"table_MB_stride32\": %.1f}\n",
                lg, nops / ms0 / 1e6, nops / ms1 / 1e6, nops / ms2 / 1e6, n * 32 / 1048576.0);
         cudaFree(t);
+    }
+    for (int lg : {20, 21, 22}) {
+        uint64_t n = 1ull << lg; uint64_t *keys, *si; unsigned* len; double* sf;
+        CK(cudaMalloc(&keys, n * 8)); CK(cudaMalloc(&si, n * 8)); CK(cudaMalloc(&sf, n * 8)); CK(cudaMalloc(&len, n * 4));
+        CK(cudaMemset(keys, 0, n * 8)); CK(cudaMemset(si, 0, n * 8)); CK(cudaMemset(sf, 0, n * 8)); CK(cudaMemset(len, 0, n * 4));
+        float ms = timeit([&] { k_red_soa<<<grid, block>>>(keys, len, si, sf, n - 1, nops); });
+        printf("{\"test\": \"keyload_plus_3red_SoA\", \"log2_entries\": %d, \"Grows\": %.2f, \"total_MB\": %.1f}\n", lg, nops / ms / 1e6, n * 28 / 1048576.0);
+        cudaFree(keys); cudaFree(si); cudaFree(sf); cudaFree(len);
     }
     {
         float ms = timeit([&] { k_smem_atom<<<grid, block>>>(nops, 0, sink); });
