@@ -86,24 +86,24 @@ __device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v, uint64_t po
 __device__ __forceinline__ uint64_t* gb_resolve(const GbTableDev& T, uint64_t key, uint64_t slot, uint64_t k, uint64_t pol, bool hint) {
     const uint64_t mask = T.cap - 1;
     for (int probes = 0; probes < GB_MAX_PROBE; ++probes) {
-        uint64_t* e = T.entries + slot * T.stride;
+        uint64_t* e = T.entries + slot * T.es;
         if (k == key) return e;
         if (k == GB_EMPTY) {
             unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(e), (unsigned long long)GB_EMPTY, (unsigned long long)key);
             if (old == GB_EMPTY || old == key) return e;
         }
         slot = (slot + 1) & mask;
-        k = tbl_load(T.entries + slot * T.stride, pol, hint);
+        k = tbl_load(T.entries + slot * T.es, pol, hint);
     }
     *T.status = 1;
     return nullptr;
 }
 __device__ __forceinline__ uint64_t* gb_find_or_insert(const GbTableDev& T, uint64_t key) {
     const uint64_t slot = dirty_hash(key) >> T.shift;
-    return gb_resolve(T, key, slot, __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + slot * T.stride)), 0, false);
+    return gb_resolve(T, key, slot, __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + slot * T.es)), 0, false);
 }
 __device__ __forceinline__ uint64_t* gb_special(const GbTableDev& T, int which) {
-    uint64_t* e = T.entries + (T.cap + which) * T.stride;
+    uint64_t* e = T.entries + (T.cap + which) * T.es;
     if (__ldcg(reinterpret_cast<const unsigned long long*>(e)) == GB_EMPTY)
         atomicCAS(reinterpret_cast<unsigned long long*>(e), (unsigned long long)GB_EMPTY, (unsigned long long)which);
     return e;
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
                 if (KEY_NULLS) kvalid = bit_get(B.key_validity, row);
                 key[r] = canon_key<KEY_CANON>(kraw[r]);
                 kind[r] = !kvalid ? 1 : (key[r] == GB_EMPTY ? 2 : 0);
-                if (kind[r] == 0) { slot[r] = dirty_hash(key[r]) >> T.shift; k0[r] = tbl_load(T.entries + slot[r] * T.stride, pol, hint); }
+                if (kind[r] == 0) { slot[r] = dirty_hash(key[r]) >> T.shift; k0[r] = tbl_load(T.entries + slot[r] * T.es, pol, hint); }
             }
         }
 #pragma unroll
@@ -192,14 +192,14 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
             uint64_t* e = kind[r] == 0 ? gb_resolve(T, key[r], slot[r], k0[r], pol, hint) : gb_special(T, kind[r] - 1);
             if (e == nullptr) continue;
             const int64_t row = 2 * (p0 + (r >> 1) * gstride) + (r & 1);
-            if (L.need_len) red_add_u32(reinterpret_cast<uint32_t*>(e + 1), 1u, pol, hint);
-            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + 1) + 1, B.row_base + (uint32_t)row);
+            if (L.need_len) red_add_u32(reinterpret_cast<uint32_t*>(e + T.ws), 1u, pol, hint);
+            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + T.ws) + 1, B.row_base + (uint32_t)row);
 #pragma unroll
             for (int c = 0; c < MAXC; c++) {
                 if (c < L.n_cols) {
                     const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
                     const int dt = B.cols[c].dtype;
-                    for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + 2 + L.wslot[k], dt, raw[c][r], valid, pol, hint);
+                    for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + (2 + L.wslot[k]) * T.ws, dt, raw[c][r], valid, pol, hint);
                 }
             }
         }
@@ -211,21 +211,22 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
         uint64_t key = load_key_rt(B.keys, B.key_dtype, row);
         uint64_t* e = !kvalid ? gb_special(T, 0) : (key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key));
         if (e) {
-            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + 1), 1u);
-            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + 1) + 1, B.row_base + (uint32_t)row);
+            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + T.ws), 1u);
+            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + T.ws) + 1, B.row_base + (uint32_t)row);
             for (int c = 0; c < L.n_cols; c++) {
                 const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
                 uint64_t raw = B.cols[c].elem == 8 ? reinterpret_cast<const uint64_t*>(B.cols[c].values)[row] : (uint64_t)reinterpret_cast<const uint32_t*>(B.cols[c].values)[row];
-                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + 2 + L.wslot[k], B.cols[c].dtype, raw, valid);
+                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + (2 + L.wslot[k]) * T.ws, B.cols[c].dtype, raw, valid);
             }
         }
     }
 }
 
-__global__ void k_gb_init(uint64_t* entries, int64_t n_entries, int stride, const __grid_constant__ GbLayout L) {
+// word w of entry s lives at entries[s * es + w * ws]: AoS (es = stride, ws = 1) or word-major planes (es = 1, ws = n_entries)
+__global__ void k_gb_init(uint64_t* entries, int64_t n_entries, int stride, int soa, const __grid_constant__ GbLayout L) {
     const int64_t total = n_entries * stride;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int w = (int)(i % stride);
+        int w = soa ? (int)(i / n_entries) : (int)(i % stride);
         uint64_t v = 0;
         if (w == 0) v = GB_EMPTY; else if (w == 1) v = GB_W1_INIT; else if (w - 2 < L.n_words) v = L.init[w - 2];
         entries[i] = v;
@@ -266,16 +267,16 @@ __global__ void k_fill_u64(uint64_t* p, uint64_t v, int64_t n) {
 // rows: n_rows x row_words.  table_mode: rows are the slots of another table (stride = row_words,
 // special slots at src_cap, src_cap+1); else exported partial rows whose last word is meta
 // (0 normal, 1 null-key group, 2 GB_EMPTY-key group).
-__device__ __forceinline__ void gb_merge_row(const GbLayout& L, const GbTableDev& T, const uint64_t* src, int meta) {
+__device__ __forceinline__ void gb_merge_row(const GbLayout& L, const GbTableDev& T, const uint64_t* src, int meta, int64_t sws = 1) {
     uint64_t* e = meta == 1 ? gb_special(T, 0) : (meta == 2 ? gb_special(T, 1) : gb_find_or_insert(T, src[0]));
     if (!e) return;
-    const uint64_t lf = src[1];
-    if ((uint32_t)lf) atomicAdd(reinterpret_cast<unsigned*>(e + 1), (uint32_t)lf);
-    if ((uint32_t)(lf >> 32) != 0xFFFFFFFFu) atomicMin(reinterpret_cast<unsigned*>(e + 1) + 1, (uint32_t)(lf >> 32));
+    const uint64_t lf = src[sws];
+    if ((uint32_t)lf) atomicAdd(reinterpret_cast<unsigned*>(e + T.ws), (uint32_t)lf);
+    if ((uint32_t)(lf >> 32) != 0xFFFFFFFFu) atomicMin(reinterpret_cast<unsigned*>(e + T.ws) + 1, (uint32_t)(lf >> 32));
     for (int w = 0; w < L.n_words; w++) {
-        const uint64_t v = src[2 + w];
+        const uint64_t v = src[(2 + w) * sws];
         if (v == L.init[w]) continue;
-        uint64_t* a = e + 2 + w;
+        uint64_t* a = e + (2 + w) * T.ws;
         switch (L.slot_op[w]) {
             case W_ADD_F64: atomicAdd(reinterpret_cast<double*>(a), __longlong_as_double((long long)v)); break;
             case W_MIN_S64: atomicMin(reinterpret_cast<long long*>(a), (long long)v); break;
@@ -286,13 +287,13 @@ __device__ __forceinline__ void gb_merge_row(const GbLayout& L, const GbTableDev
         }
     }
 }
-__global__ void __launch_bounds__(256) k_gb_merge(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const uint64_t* __restrict__ rows, int64_t n_rows, int row_words, int table_mode, int64_t src_cap) {
+__global__ void __launch_bounds__(256) k_gb_merge(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const uint64_t* __restrict__ rows, int64_t n_rows, int64_t src_es, int64_t src_ws, int table_mode, int64_t src_cap) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
-        const uint64_t* src = rows + r * row_words;
+        const uint64_t* src = rows + r * src_es;
         int meta;
         if (table_mode) { if (src[0] == GB_EMPTY) continue; meta = r == src_cap ? 1 : (r == src_cap + 1 ? 2 : 0); }
-        else meta = (int)src[row_words - 1];
-        gb_merge_row(L, T, src, meta);
+        else meta = (int)src[(L.n_words + 2) * src_ws];
+        gb_merge_row(L, T, src, meta, src_ws);
     }
 }
 
@@ -399,14 +400,14 @@ __global__ void __launch_bounds__(512) k_gb_consume_smem(const __grid_constant__
             } else {
                 uint64_t* e = gb_find_or_insert(T, key);
                 if (e != nullptr) {
-                    if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + 1), 1u);
-                    if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + 1) + 1, B.row_base + (uint32_t)row);
+                    if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + T.ws), 1u);
+                    if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + T.ws) + 1, B.row_base + (uint32_t)row);
 #pragma unroll
                     for (int c = 0; c < MAXC; c++) {
                         if (c < L.n_cols) {
                             const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
                             const int dt = B.cols[c].dtype;
-                            for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + 2 + L.wslot[k], dt, raw[c][j], valid);
+                            for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + (2 + L.wslot[k]) * T.ws, dt, raw[c][j], valid);
                         }
                     }
                 }
@@ -420,12 +421,12 @@ __global__ void __launch_bounds__(512) k_gb_consume_smem(const __grid_constant__
         uint64_t key = load_key_rt(B.keys, B.key_dtype, row);
         uint64_t* e = !kvalid ? gb_special(T, 0) : (key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key));
         if (e) {
-            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + 1), 1u);
-            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + 1) + 1, B.row_base + (uint32_t)row);
+            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + T.ws), 1u);
+            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + T.ws) + 1, B.row_base + (uint32_t)row);
             for (int c = 0; c < L.n_cols; c++) {
                 const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
                 uint64_t raw = B.cols[c].elem == 8 ? reinterpret_cast<const uint64_t*>(B.cols[c].values)[row] : (uint64_t)reinterpret_cast<const uint32_t*>(B.cols[c].values)[row];
-                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + 2 + L.wslot[k], B.cols[c].dtype, raw, valid);
+                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + (2 + L.wslot[k]) * T.ws, B.cols[c].dtype, raw, valid);
             }
         }
     }
@@ -440,10 +441,10 @@ __global__ void __launch_bounds__(512) k_gb_consume_smem(const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------- extraction
-__global__ void k_gb_count_used(const uint64_t* entries, int64_t n_entries, int stride, unsigned long long* count) {
+__global__ void k_gb_count_used(const uint64_t* entries, int64_t n_entries, int64_t es, unsigned long long* count) {
     unsigned long long c = 0;
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_entries; s += (int64_t)gridDim.x * blockDim.x)
-        c += entries[s * stride] != GB_EMPTY;
+        c += entries[s * es] != GB_EMPTY;
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane_id() == 0 && c) atomicAdd(count, c);
 }
@@ -451,7 +452,7 @@ __global__ void k_gb_count_used(const uint64_t* entries, int64_t n_entries, int 
 // Dense SoA extraction.  Group order = slot order within 256-slot tiles, tiles in atomic-arrival
 // order (unspecified, like the reference's hashbrown iteration order).
 // out_words: n_words arrays of G u64.  null_pos: position of the null-key group or -1.
-__global__ void __launch_bounds__(256) k_gb_extract(const uint64_t* __restrict__ entries, int64_t cap, int stride, int n_words, unsigned long long* cursor,
+__global__ void __launch_bounds__(256) k_gb_extract(const uint64_t* __restrict__ entries, int64_t cap, int64_t es, int64_t ws, int n_words, unsigned long long* cursor,
                                                     uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_first, uint32_t* __restrict__ out_len,
                                                     uint64_t* __restrict__ out_words, int64_t G, long long* null_pos) {
     const int64_t n_entries = cap + 2;
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(256) k_gb_extract(const uint64_t* __restrict__
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t s = t * 256 + threadIdx.x;
         uint64_t key = GB_EMPTY;
-        if (s < n_entries) key = entries[s * stride];
+        if (s < n_entries) key = entries[s * es];
         const bool used = key != GB_EMPTY;
         const unsigned b = __ballot_sync(0xffffffffu, used);
         if (lane_id() == 0) warp_cnt[threadIdx.x >> 5] = __popc(b);
@@ -474,15 +475,15 @@ __global__ void __launch_bounds__(256) k_gb_extract(const uint64_t* __restrict__
         __syncthreads();
         if (used) {
             const int64_t pos = (int64_t)tile_base + warp_cnt[threadIdx.x >> 5] + __popc(b & lanemask_lt());
-            const uint64_t* e = entries + s * stride;
+            const uint64_t* e = entries + s * es;
             uint64_t kout = key;
             if (s == cap) { kout = 0; *null_pos = pos; }
             else if (s == cap + 1) kout = GB_EMPTY;
             out_keys[pos] = kout;
-            const uint64_t lf = e[1];
+            const uint64_t lf = e[ws];
             out_len[pos] = (uint32_t)lf;
             out_first[pos] = (uint32_t)(lf >> 32);
-            for (int w = 0; w < n_words; w++) out_words[(int64_t)w * G + pos] = e[2 + w];
+            for (int w = 0; w < n_words; w++) out_words[(int64_t)w * G + pos] = e[(2 + w) * ws];
         }
         __syncthreads();
     }
@@ -555,18 +556,18 @@ __device__ __forceinline__ int gb_row_partition(uint64_t key, int64_t s, int64_t
     if (s == cap) return 0;                                            // null key -> partition 0 (hashing.rs:113-115)
     return (int)hash_to_partition(dirty_hash(s == cap + 1 ? GB_EMPTY : key), (uint32_t)P);
 }
-__global__ void __launch_bounds__(256) k_gb_export_count(const uint64_t* __restrict__ entries, int64_t cap, int stride, int P, unsigned long long* part_counts) {
+__global__ void __launch_bounds__(256) k_gb_export_count(const uint64_t* __restrict__ entries, int64_t cap, int64_t es, int P, unsigned long long* part_counts) {
     __shared__ unsigned hist[EXP_MAX_PARTS];
     if (threadIdx.x < EXP_MAX_PARTS) hist[threadIdx.x] = 0;
     __syncthreads();
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap + 2; s += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t key = entries[s * stride];
+        uint64_t key = entries[s * es];
         if (key != GB_EMPTY) atomicAdd(&hist[gb_row_partition(key, s, cap, P)], 1u);
     }
     __syncthreads();
     if (threadIdx.x < P && hist[threadIdx.x]) atomicAdd(&part_counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
 }
-__global__ void __launch_bounds__(256) k_gb_export_scatter(const uint64_t* __restrict__ entries, int64_t cap, int stride, int n_words, int P,
+__global__ void __launch_bounds__(256) k_gb_export_scatter(const uint64_t* __restrict__ entries, int64_t cap, int64_t es, int64_t ws, int n_words, int P,
                                                            const unsigned long long* __restrict__ part_off, unsigned long long* part_cursor, uint64_t* __restrict__ rows) {
     __shared__ unsigned hist[EXP_MAX_PARTS];
     __shared__ unsigned long long base[EXP_MAX_PARTS];
@@ -578,17 +579,17 @@ __global__ void __launch_bounds__(256) k_gb_export_scatter(const uint64_t* __res
         __syncthreads();
         const int64_t s = t * 256 + threadIdx.x;
         uint64_t key = GB_EMPTY; int p = 0; unsigned local = 0;
-        if (s < n_entries) key = entries[s * stride];
+        if (s < n_entries) key = entries[s * es];
         if (key != GB_EMPTY) { p = gb_row_partition(key, s, cap, P); local = atomicAdd(&hist[p], 1u); }
         __syncthreads();
         if (threadIdx.x < P && hist[threadIdx.x]) base[threadIdx.x] = part_off[threadIdx.x] + atomicAdd(&part_cursor[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
         __syncthreads();
         if (key != GB_EMPTY) {
-            const uint64_t* e = entries + s * stride;
+            const uint64_t* e = entries + s * es;
             uint64_t* dst = rows + (base[p] + local) * row_words;
             dst[0] = s == cap ? 0 : (s == cap + 1 ? GB_EMPTY : key);
-            dst[1] = e[1];
-            for (int w = 0; w < n_words; w++) dst[2 + w] = e[2 + w];
+            dst[1] = e[ws];
+            for (int w = 0; w < n_words; w++) dst[2 + w] = e[(2 + w) * ws];
             dst[2 + n_words] = s == cap ? 1 : (s == cap + 1 ? 2 : 0);
         }
         __syncthreads();
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(256) k_gb_export_scatter(const uint64_t* __res
 // stored straight into the destination rank's window (peer memory over NVLink): partition p's rows
 // land in region `my_rank` of windows[p] at [cursor .. cursor + n).  No staging copy, no collective.
 struct PeerWindows { uint64_t* base[EXP_MAX_PARTS]; };
-__global__ void __launch_bounds__(256) k_gb_export_p2p(const uint64_t* __restrict__ entries, int64_t cap, int stride, int n_words, int P, const __grid_constant__ PeerWindows W,
+__global__ void __launch_bounds__(256) k_gb_export_p2p(const uint64_t* __restrict__ entries, int64_t cap, int64_t es, int64_t ws, int n_words, int P, const __grid_constant__ PeerWindows W,
                                                        int64_t region_words, int my_rank, int64_t rows_per_src, unsigned long long* part_cursor, int* overflow) {
     __shared__ unsigned hist[EXP_MAX_PARTS];
     __shared__ unsigned long long base[EXP_MAX_PARTS];
@@ -611,7 +612,7 @@ __global__ void __launch_bounds__(256) k_gb_export_p2p(const uint64_t* __restric
         __syncthreads();
         const int64_t s = t * 256 + threadIdx.x;
         uint64_t key = GB_EMPTY; int p = 0; unsigned local = 0;
-        if (s < n_entries) key = entries[s * stride];
+        if (s < n_entries) key = entries[s * es];
         if (key != GB_EMPTY) { p = gb_row_partition(key, s, cap, P); local = atomicAdd(&hist[p], 1u); }
         __syncthreads();
         if (threadIdx.x < P && hist[threadIdx.x]) base[threadIdx.x] = atomicAdd(&part_cursor[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
@@ -620,11 +621,11 @@ __global__ void __launch_bounds__(256) k_gb_export_p2p(const uint64_t* __restric
             const uint64_t pos = base[p] + local;
             if ((int64_t)pos >= rows_per_src) *overflow = 1;
             else {
-                const uint64_t* e = entries + s * stride;
+                const uint64_t* e = entries + s * es;
                 uint64_t* dst = W.base[p] + (int64_t)my_rank * region_words + pos * row_words;     // peer store
                 dst[0] = s == cap ? 0 : (s == cap + 1 ? GB_EMPTY : key);
-                dst[1] = e[1];
-                for (int w = 0; w < n_words; w++) dst[2 + w] = e[2 + w];
+                dst[1] = e[ws];
+                for (int w = 0; w < n_words; w++) dst[2 + w] = e[(2 + w) * ws];
                 dst[2 + n_words] = s == cap ? 1 : (s == cap + 1 ? 2 : 0);
             }
         }
@@ -685,8 +686,11 @@ void GroupByState::alloc_table(uint64_t new_cap) {
     entries = dev_alloc((size_t)(cap + 2) * L.stride * 8);
     int shift = 64; for (uint64_t c = cap; c > 1; c >>= 1) shift--;
     static const int hint = [] { const char* e = getenv("BL_K5_HINT"); return e ? atoi(e) : 0; }();
-    T.entries = as<uint64_t>(entries); T.cap = cap; T.shift = shift; T.stride = L.stride; T.status = as<int>(status); T.hint = hint;
-    PLB_LAUNCH("k5_table_init", k_gb_init, grid_for((int64_t)(cap + 2) * L.stride, 256), 256, 0, T.entries, (int64_t)(cap + 2), L.stride, L);
+    // word-major planes by default: the REDs of one row then hit different sectors / L2 slices (ubench: 54 vs 38 G rows/s)
+    static const int soa = [] { const char* e = getenv("BL_K5_SOA"); return e ? atoi(e) : 1; }();
+    T.entries = as<uint64_t>(entries); T.cap = cap; T.shift = shift; T.status = as<int>(status); T.hint = hint;
+    T.es = soa ? 1 : L.stride; T.ws = soa ? (int64_t)(cap + 2) : 1; T.soa = soa;
+    PLB_LAUNCH("k5_table_init", k_gb_init, grid_for((int64_t)(cap + 2) * L.stride, 256), 256, 0, T.entries, (int64_t)(cap + 2), L.stride, soa, L);
     dev_memset(status->p, 0, 4);
 }
 
@@ -815,14 +819,14 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
 
 void GroupByState::grow(uint64_t new_cap) {
     // rehash: merge the old table's entries into a bigger one
-    DevPtr old = entries; const uint64_t old_cap = cap;
+    DevPtr old = entries; const uint64_t old_cap = cap; const int64_t old_es = T.es, old_ws = T.ws;
     alloc_table(new_cap);
-    if (old) PLB_LAUNCH("k5_rehash", k_gb_merge, grid_for((int64_t)old_cap + 2, 256), 256, 0, L, T, as<uint64_t>(old), (int64_t)old_cap + 2, L.stride, 1, (int64_t)old_cap);
+    if (old) PLB_LAUNCH("k5_rehash", k_gb_merge, grid_for((int64_t)old_cap + 2, 256), 256, 0, L, T, as<uint64_t>(old), (int64_t)old_cap + 2, old_es, old_ws, 1, (int64_t)old_cap);
 }
 
 int64_t GroupByState::count_groups() {
     DevPtr c = dev_alloc(8); dev_memset(c->p, 0, 8);
-    PLB_LAUNCH("k5_count_used", k_gb_count_used, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap + 2, L.stride, as<unsigned long long>(c));
+    PLB_LAUNCH("k5_count_used", k_gb_count_used, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap + 2, T.es, as<unsigned long long>(c));
     return (int64_t)read_scalar(as<unsigned long long>(c));
 }
 
@@ -903,7 +907,7 @@ void GroupByState::consume(const DevCol& key, const std::vector<const DevCol*>& 
 
 void GroupByState::reset() {
     if (entries) {
-        PLB_LAUNCH("k5_table_init", k_gb_init, grid_for((int64_t)(cap + 2) * L.stride, 256), 256, 0, T.entries, (int64_t)(cap + 2), L.stride, L);
+        PLB_LAUNCH("k5_table_init", k_gb_init, grid_for((int64_t)(cap + 2) * L.stride, 256), 256, 0, T.entries, (int64_t)(cap + 2), L.stride, T.soa, L);
         dev_memset(status->p, 0, 4);
     }
     rows_seen = 0; merged_rows = 0;
@@ -952,7 +956,7 @@ DevPtr GroupByState::export_partials(int n_partitions, int* row_words_out, int64
     if (!entries) { for (int p = 0; p <= n_partitions; p++) offsets_host[p] = 0; return dev_alloc(16); }
     DevPtr counts = dev_alloc(8 * EXP_MAX_PARTS), cursor = dev_alloc(8 * EXP_MAX_PARTS), off = dev_alloc(8 * EXP_MAX_PARTS);
     dev_memset(counts->p, 0, 8 * EXP_MAX_PARTS); dev_memset(cursor->p, 0, 8 * EXP_MAX_PARTS);
-    PLB_LAUNCH("k6_export_count", k_gb_export_count, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, L.stride, n_partitions, as<unsigned long long>(counts));
+    PLB_LAUNCH("k6_export_count", k_gb_export_count, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, T.es, n_partitions, as<unsigned long long>(counts));
     unsigned long long h[EXP_MAX_PARTS];
     PLB_CUDA(cudaMemcpyAsync(h, counts->p, 8 * n_partitions, cudaMemcpyDeviceToHost, ctx().stream));
     PLB_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -963,7 +967,7 @@ DevPtr GroupByState::export_partials(int n_partitions, int* row_words_out, int64
     const int64_t G = (int64_t)ho[n_partitions];
     DevPtr rows = dev_alloc((size_t)std::max<int64_t>(G, 1) * row_words * 8);
     if (G > 0)
-        PLB_LAUNCH("k6_export_scatter", k_gb_export_scatter, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, L.stride, L.n_words, n_partitions,
+        PLB_LAUNCH("k6_export_scatter", k_gb_export_scatter, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, L.n_words, n_partitions,
                    as<unsigned long long>(off), as<unsigned long long>(cursor), as<uint64_t>(rows));
     PLB_CUDA(cudaStreamSynchronize(ctx().stream));   // ho[] is on this stack frame
     return rows;
@@ -979,7 +983,7 @@ void GroupByState::export_partials_p2p(int n_ranks, int my_rank, void* const* wi
     for (int p = 0; p < n_ranks; p++) { PLB_REQUIRE(windows[p] != nullptr, BL_ERR_INVALID, "export_partials_p2p: null window"); W.base[p] = reinterpret_cast<uint64_t*>(windows[p]); }
     DevPtr cursor = dev_alloc(8 * EXP_MAX_PARTS), ovf = dev_alloc(4);
     dev_memset(cursor->p, 0, 8 * EXP_MAX_PARTS); dev_memset(ovf->p, 0, 4);
-    PLB_LAUNCH("k6_export_p2p", k_gb_export_p2p, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, L.stride, L.n_words, n_ranks, W,
+    PLB_LAUNCH("k6_export_p2p", k_gb_export_p2p, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, L.n_words, n_ranks, W,
                rows_per_src * row_words, my_rank, rows_per_src, as<unsigned long long>(cursor), as<int>(ovf));
     unsigned long long h[EXP_MAX_PARTS];
     PLB_CUDA(cudaMemcpyAsync(h, cursor->p, 8 * n_ranks, cudaMemcpyDeviceToHost, ctx().stream));
@@ -1002,7 +1006,7 @@ void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather,
     PLB_CUDA(cudaMemcpyAsync(ctl->p, ctl_init, 16, cudaMemcpyHostToDevice, ctx().stream));
     long long ctl_host[2] = {0, -1};
     if (entries) {
-        PLB_LAUNCH("k5_extract", k_gb_extract, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, L.stride, L.n_words, as<unsigned long long>(ctl),
+        PLB_LAUNCH("k5_extract", k_gb_extract, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, L.n_words, as<unsigned long long>(ctl),
                    as<uint64_t>(keys), as<uint32_t>(first), as<uint32_t>(len), as<uint64_t>(words), Gb, as<long long>(ctl) + 1);
         PLB_CUDA(cudaMemcpyAsync(ctl_host, ctl->p, 16, cudaMemcpyDeviceToHost, ctx().stream));
     }
