@@ -313,10 +313,14 @@ __device__ __forceinline__ void s_add_u64(uint64_t* a, uint64_t v) {
     const uint32_t up = hi + (((uint32_t)(old + lo) < old) ? 1u : 0u);
     if (up) atomicAdd(w + 1, up);
 }
+// FAST: every value column is 8 bytes wide and has no validity bitmap (the common analytic case): the
+// dtype dispatch collapses to one select and the null checks disappear (this kernel is issue-bound).
+template <bool FAST>
 __device__ __forceinline__ void gb_apply_smem(int op, uint64_t* addr, int dtype, uint64_t raw, bool valid) {
     switch (op) {
-        case W_ADD_INT: { uint64_t v = raw_to_int(dtype, raw); if (valid && v) s_add_u64(addr, v); break; }
-        case W_ADD_F64: { double f = raw_to_f64(dtype, raw); if (valid && f != 0.0) atomicAdd(reinterpret_cast<double*>(addr), f); break; }
+        case W_ADD_INT: { uint64_t v = FAST ? raw : raw_to_int(dtype, raw); if (valid && v) s_add_u64(addr, v); break; }
+        case W_ADD_F64: { double f = FAST ? (dtype == BL_FLOAT64 ? __longlong_as_double((long long)raw) : (dtype == BL_INT64 ? (double)(long long)raw : (double)(unsigned long long)raw)) : raw_to_f64(dtype, raw);
+                          if (valid && f != 0.0) atomicAdd(reinterpret_cast<double*>(addr), f); break; }
         case W_MIN_S64: if (valid) atomicMin(reinterpret_cast<long long*>(addr), (long long)raw_to_int(dtype, raw)); break;
         case W_MAX_S64: if (valid) atomicMax(reinterpret_cast<long long*>(addr), (long long)raw_to_int(dtype, raw)); break;
         case W_MIN_U64: if (valid) atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)raw); break;
@@ -327,7 +331,7 @@ __device__ __forceinline__ void gb_apply_smem(int op, uint64_t* addr, int dtype,
     }
 }
 
-template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC>
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC, bool FAST>
 __global__ void __launch_bounds__(512) k_gb_consume_smem(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const __grid_constant__ GbBatch B, int scap, int sshift, int copies) {
     // `copies` replicas of the table (tiny cardinalities): lane l works on replica l % copies, so the
     // lanes of a warp that hit the SAME group do not serialise on one shared-memory address.
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(512) k_gb_consume_smem(const __grid_constant__
 #pragma unroll
         for (int c = 0; c < MAXC; c++) {
             if (c < L.n_cols) {
-                if (B.cols[c].elem == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(B.cols[c].values) + 2 * p); raw[c][0] = t.x; raw[c][1] = t.y; }
+                if (FAST || B.cols[c].elem == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(B.cols[c].values) + 2 * p); raw[c][0] = t.x; raw[c][1] = t.y; }
                 else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(B.cols[c].values) + 2 * p); raw[c][0] = t.x; raw[c][1] = t.y; }
             }
         }
@@ -392,9 +396,9 @@ __global__ void __launch_bounds__(512) k_gb_consume_smem(const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < MAXC; c++) {
                     if (c < L.n_cols) {
-                        const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
+                        const bool valid = FAST || B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
                         const int dt = B.cols[c].dtype;
-                        for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply_smem(L.wop[k], se + 2 + L.wslot[k], dt, raw[c][j], valid);
+                        for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply_smem<FAST>(L.wop[k], se + 2 + L.wslot[k], dt, raw[c][j], valid);
                     }
                 }
             } else {
@@ -722,7 +726,13 @@ uint64_t GroupByState::choose_cap(const DevCol& key, int64_t n_total) {
     }
     est_groups = (int64_t)G;
     static const double lf = [] { const char* e = getenv("BL_K5_LF"); double v = e ? atof(e) / 100.0 : 0.6; return (v > 0.05 && v < 0.95) ? v : 0.6; }();
-    return pow2_at_least(G / lf);       // load factor <= 0.6 by default
+    uint64_t c = pow2_at_least(G / lf);       // load factor <= 0.6 by default
+    // keep the table inside L2 when a load factor <= 0.85 allows it: past ~55 % of L2 the REDs miss and the
+    // kernel slows down ~3x (measured: 67 MB table 1.95 ms, 134 MB table 5.8 ms), while linear probing over
+    // word-major key planes (4 keys per sector) stays cheap at higher load factors
+    const double l2_budget = 0.55 * (double)ctx().l2_bytes;
+    if ((double)c * L.stride * 8 > l2_budget && G / ((double)c / 2) <= 0.85 && c > 1024) c >>= 1;
+    return c;
 }
 
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int PAIRS>
@@ -739,9 +749,9 @@ static void launch_consume(const GbLayout& L, const GbTableDev& T, const GbBatch
     else launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 1>(L, T, B, grid);
 }
 
-template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC>
-static void launch_smem_c(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int scap) {
-    auto kfn = k_gb_consume_smem<KEY_ELEM, KEY_CANON, KEY_NULLS, MAXC>;
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC, bool FAST>
+static void launch_smem_cf(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int scap) {
+    auto kfn = k_gb_consume_smem<KEY_ELEM, KEY_CANON, KEY_NULLS, MAXC, FAST>;
     const size_t tab_bytes = ((size_t)(scap + 2) * L.stride + 2) * 8;
     const int copies = (int)std::min<size_t>(32, std::max<size_t>(1, (size_t)(96 * 1024) / tab_bytes));
     const size_t smem = tab_bytes * copies;
@@ -750,6 +760,13 @@ static void launch_smem_c(const GbLayout& L, const GbTableDev& T, const GbBatch&
     int sshift = 64; for (int c = scap; c > 1; c >>= 1) sshift--;
     const int grid = (int)std::min<int64_t>((int64_t)ctx().sm_count * per_sm, std::max<int64_t>(1, (B.n / 2 + 511) / 512));
     PLB_LAUNCH("k5_groupby_agg_smem", kfn, grid, 512, smem, L, T, B, scap, sshift, copies);
+}
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC>
+static void launch_smem_c(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int scap) {
+    bool fast = true;
+    for (int c = 0; c < L.n_cols; c++) fast = fast && B.cols[c].elem == 8 && B.cols[c].validity == nullptr;
+    if (fast) launch_smem_cf<KEY_ELEM, KEY_CANON, KEY_NULLS, MAXC, true>(L, T, B, scap);
+    else launch_smem_cf<KEY_ELEM, KEY_CANON, KEY_NULLS, MAXC, false>(L, T, B, scap);
 }
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS>
 static void launch_smem(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int scap) {

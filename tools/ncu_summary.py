@@ -19,5 +19,6 @@ for r in rows[2:]:
     for k in KEEP:
         if k in d:
             print(f"| {k} | {d[k]} | {units[hdr.index(k)]} |")
-    dr = float(d.get("dram__bytes_read.sum", "0").replace(",", "")) + float(d.get("dram__bytes_write.sum", "0").replace(",", ""))
-    print(f"\nDRAM traffic (read+write, unit as above): {dr:.3f}\n")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    dr = sum(float(d.get(k, "0").replace(",", "")) * scale.get(units[hdr.index(k)], 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum") if k in d)
+    print(f"\nDRAM traffic (read + write): {dr / 1e9:.3f} GB\n")
