@@ -731,7 +731,7 @@ uint64_t GroupByState::choose_cap(const DevCol& key, int64_t n_total) {
     // kernel slows down ~3x (measured: 67 MB table 1.95 ms, 134 MB table 5.8 ms), while linear probing over
     // word-major key planes (4 keys per sector) stays cheap at higher load factors
     const double l2_budget = 0.55 * (double)ctx().l2_bytes;
-    if ((double)c * L.stride * 8 > l2_budget && G / ((double)c / 2) <= 0.85 && c > 1024) c >>= 1;
+    if ((double)c * L.stride * 8 > l2_budget && G / ((double)c / 2) <= 0.9 && c > 1024) c >>= 1;   // G already carries a 1.25x safety margin
     return c;
 }
 
