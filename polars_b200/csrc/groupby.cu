@@ -61,9 +61,13 @@ __device__ __forceinline__ uint64_t load_key_rt(const void* keys, int dtype, int
 __device__ __forceinline__ uint64_t make_policy_evict_last() {
     uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
 }
-__device__ __forceinline__ uint64_t tbl_load(const uint64_t* p, uint64_t pol, bool hint) {
+// Key-plane loads.  hint bit 1: L1-cached (ld.ca) — safe because a key word only ever changes EMPTY -> key: a
+// stale EMPTY from L1 is caught by the CAS that follows (it returns the real key), a non-EMPTY value is final.
+// The second linear probe usually falls into the sector the first one fetched (4 keys per sector).
+__device__ __forceinline__ uint64_t tbl_load(const uint64_t* p, uint64_t pol, int hint) {
     uint64_t v;
-    if (hint) asm volatile("ld.global.cg.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    if (hint & 2) asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    else if (hint & 1) asm volatile("ld.global.cg.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
     else v = __ldcg(reinterpret_cast<const unsigned long long*>(p));
     return v;
 }
@@ -83,7 +87,7 @@ __device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v, uint64_t po
 // claim / find the entry of `key`, continuing from slot `slot` whose key word `k` has already been
 // loaded (the first probes of all rows of an iteration are issued together).
 // nullptr => probe limit hit (table too small): status set.
-__device__ __forceinline__ uint64_t* gb_resolve(const GbTableDev& T, uint64_t key, uint64_t slot, uint64_t k, uint64_t pol, bool hint) {
+__device__ __forceinline__ uint64_t* gb_resolve(const GbTableDev& T, uint64_t key, uint64_t slot, uint64_t k, uint64_t pol, int hint) {
     const uint64_t mask = T.cap - 1;
     for (int probes = 0; probes < GB_MAX_PROBE; ++probes) {
         uint64_t* e = T.entries + slot * T.es;
@@ -100,7 +104,7 @@ __device__ __forceinline__ uint64_t* gb_resolve(const GbTableDev& T, uint64_t ke
 }
 __device__ __forceinline__ uint64_t* gb_find_or_insert(const GbTableDev& T, uint64_t key) {
     const uint64_t slot = dirty_hash(key) >> T.shift;
-    return gb_resolve(T, key, slot, __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + slot * T.es)), 0, false);
+    return gb_resolve(T, key, slot, __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + slot * T.es)), 0, 0);
 }
 __device__ __forceinline__ uint64_t* gb_special(const GbTableDev& T, int which) {
     uint64_t* e = T.entries + (T.cap + which) * T.es;
@@ -148,7 +152,8 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
     constexpr int R = 2 * PAIRS;
     const int64_t npairs = B.n >> 1;
     const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
-    const bool hint = T.hint != 0;
+    const int khint = T.hint;                 // key-load flavour (bit 0: evict_last policy, bit 1: L1-cached)
+    const bool hint = (T.hint & 1) != 0;      // evict_last policy on the REDs
     const uint64_t pol = hint ? make_policy_evict_last() : 0;
     int iter = 0;
     for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p0 < npairs; p0 += gstride * PAIRS) {
@@ -183,13 +188,13 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
                 if (KEY_NULLS) kvalid = bit_get(B.key_validity, row);
                 key[r] = canon_key<KEY_CANON>(kraw[r]);
                 kind[r] = !kvalid ? 1 : (key[r] == GB_EMPTY ? 2 : 0);
-                if (kind[r] == 0) { slot[r] = dirty_hash(key[r]) >> T.shift; k0[r] = tbl_load(T.entries + slot[r] * T.es, pol, hint); }
+                if (kind[r] == 0) { slot[r] = dirty_hash(key[r]) >> T.shift; k0[r] = tbl_load(T.entries + slot[r] * T.es, pol, khint); }
             }
         }
 #pragma unroll
         for (int r = 0; r < R; r++) {
             if (kind[r] < 0) continue;
-            uint64_t* e = kind[r] == 0 ? gb_resolve(T, key[r], slot[r], k0[r], pol, hint) : gb_special(T, kind[r] - 1);
+            uint64_t* e = kind[r] == 0 ? gb_resolve(T, key[r], slot[r], k0[r], pol, khint) : gb_special(T, kind[r] - 1);
             if (e == nullptr) continue;
             const int64_t row = 2 * (p0 + (r >> 1) * gstride) + (r & 1);
             if (L.need_len) red_add_u32(reinterpret_cast<uint32_t*>(e + T.ws), 1u, pol, hint);
