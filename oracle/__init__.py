@@ -253,4 +253,7 @@ def hash_join(left_keys, right_keys, left_valid=None, right_valid=None, how: str
             lib().or_stable_sort_pairs(_p(li), _p(ri), C.c_int64(m), C.c_int(1))
         else:
             raise ValueError(maintain_order)
+    if how == "left" and maintain_order in ("right", "right_left"):
+        # polars-ops/src/frame/join/dispatch_left_right.rs:142-170: stable sort on the right idx (null = u32::MAX last)
+        lib().or_stable_sort_pairs(_p(li), _p(ri), C.c_int64(m), C.c_int(1))
     return li, ri

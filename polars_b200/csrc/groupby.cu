@@ -715,8 +715,8 @@ static double estimate_groups(double d, double m, double n) {
 }
 
 uint64_t GroupByState::choose_cap(const DevCol& key, int64_t n_total) {
-    double G;
-    if (expected_groups > 0) G = (double)expected_groups;
+    double G, G_raw;
+    if (expected_groups > 0) G = G_raw = (double)expected_groups;
     else {
         const int64_t n = key.len, m = std::min<int64_t>(n, 65536);
         const uint64_t scap = 1 << 18;
@@ -726,8 +726,10 @@ uint64_t GroupByState::choose_cap(const DevCol& key, int64_t n_total) {
         PLB_LAUNCH("k5_estimate", k_gb_estimate, grid_for(m, 256), 256, 0, key.v(), key.vm(), key.dtype, n, m, as<uint64_t>(scratch), scap, 64 - 18, as<unsigned>(cnt));
         unsigned d = read_scalar(as<unsigned>(cnt));
         const double nt = (double)std::max<int64_t>(n_total, n);
-        G = estimate_groups((double)d, (double)m, nt) * 1.25 + 64;
+        G_raw = estimate_groups((double)d, (double)m, nt);
+        G = G_raw * 1.25 + 64;
         if (G > nt) G = nt;
+        if (G_raw > nt) G_raw = nt;
     }
     est_groups = (int64_t)G;
     static const double lf = [] { const char* e = getenv("BL_K5_LF"); double v = e ? atof(e) / 100.0 : 0.6; return (v > 0.05 && v < 0.95) ? v : 0.6; }();
@@ -736,7 +738,7 @@ uint64_t GroupByState::choose_cap(const DevCol& key, int64_t n_total) {
     // kernel slows down ~3x (measured: 67 MB table 1.95 ms, 134 MB table 5.8 ms), while linear probing over
     // word-major key planes (4 keys per sector) stays cheap at higher load factors
     const double l2_budget = 0.55 * (double)ctx().l2_bytes;
-    if ((double)c * L.stride * 8 > l2_budget && G / ((double)c / 2) <= 0.9 && c > 1024) c >>= 1;   // G already carries a 1.25x safety margin
+    if ((double)c * L.stride * 8 > l2_budget && G_raw / ((double)c / 2) <= 0.8 && c > 1024) c >>= 1;   // an under-estimate costs one restart
     return c;
 }
 

@@ -590,6 +590,10 @@ JoinResult op_hash_join(const DevCol& left, const DevCol& right, int how, bool n
         if (by_left && !left_sorted) sort_pairs_u32(as<uint32_t>(r.left.values), as<uint32_t>(r.right.values), (int64_t)M);
         else if (!by_left && !swapped) sort_pairs_u32(as<uint32_t>(r.right.values), as<uint32_t>(r.left.values), (int64_t)M);
     }
+    // left join: only Right / RightLeft reorder (stable sort on the right idx, unmatched rows = u32::MAX last;
+    // dispatch_left_right.rs:142-170); the probe order already is the left order
+    if (how == BL_JOIN_LEFT && (maintain_order == BL_ORDER_RIGHT || maintain_order == BL_ORDER_RIGHT_LEFT) && M > 1)
+        sort_pairs_u32(as<uint32_t>(r.right.values), as<uint32_t>(r.left.values), (int64_t)M);
     if (how == BL_JOIN_LEFT && M > 0) {
         // Arrow-proper validity for the nullable right index: bit = (idx != BL_IDX_NULL)
         DevCol none = make_col(BL_UINT32, 1, false);

@@ -397,7 +397,7 @@ def test_join_vs_oracle(plb, nl, nr, krange, dups, key_dtype):
     impl = GpuImpl(plb)
     for nulls_equal in (False, True):
         for how in ("inner", "left"):
-            orders = ["none", "left", "right", "left_right"] if how == "inner" else ["none"]
+            orders = ["none", "left", "right", "left_right"] if how == "inner" else ["none", "left", "right", "right_left"]
             for order in orders:
                 li, ri = impl.plb.hash_join(plb.Column(lk, lv), plb.Column(rk, rv), how, nulls_equal, order)
                 li, ri = li[0], ri[0]
