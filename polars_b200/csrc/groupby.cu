@@ -188,7 +188,10 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
                 if (KEY_NULLS) kvalid = bit_get(B.key_validity, row);
                 key[r] = canon_key<KEY_CANON>(kraw[r]);
                 kind[r] = !kvalid ? 1 : (key[r] == GB_EMPTY ? 2 : 0);
-                if (kind[r] == 0) { slot[r] = dirty_hash(key[r]) >> T.shift; k0[r] = tbl_load(T.entries + slot[r] * T.es, pol, khint); }
+                const uint64_t hsh = dirty_hash(key[r]);
+                // multi-pass mode (tables larger than L2): this launch only owns the slot sub-range `pass_id`
+                if (T.pass_bits && (kind[r] == 0 ? (int)(hsh >> (64 - T.pass_bits)) != T.pass_id : T.pass_id != 0)) kind[r] = -1;
+                if (kind[r] == 0) { slot[r] = hsh >> T.shift; k0[r] = tbl_load(T.entries + slot[r] * T.es, pol, khint); }
             }
         }
 #pragma unroll
@@ -214,7 +217,9 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
         const int64_t row = B.n - 1;
         bool kvalid = B.key_validity == nullptr || bit_get(B.key_validity, row);
         uint64_t key = load_key_rt(B.keys, B.key_dtype, row);
-        uint64_t* e = !kvalid ? gb_special(T, 0) : (key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key));
+        const bool regular = kvalid && key != GB_EMPTY;
+        const bool mine = !T.pass_bits || (regular ? (int)(dirty_hash(key) >> (64 - T.pass_bits)) == T.pass_id : T.pass_id == 0);
+        uint64_t* e = !mine ? nullptr : (!kvalid ? gb_special(T, 0) : (key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key)));
         if (e) {
             if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + T.ws), 1u);
             if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + T.ws) + 1, B.row_base + (uint32_t)row);
@@ -698,7 +703,7 @@ void GroupByState::alloc_table(uint64_t new_cap) {
     // word-major planes by default: the REDs of one row then hit different sectors / L2 slices (ubench: 54 vs 38 G rows/s)
     static const int soa = [] { const char* e = getenv("BL_K5_SOA"); return e ? atoi(e) : 1; }();
     T.entries = as<uint64_t>(entries); T.cap = cap; T.shift = shift; T.status = as<int>(status); T.hint = hint;
-    T.es = soa ? 1 : L.stride; T.ws = soa ? (int64_t)(cap + 2) : 1; T.soa = soa;
+    T.es = soa ? 1 : L.stride; T.ws = soa ? (int64_t)(cap + 2) : 1; T.soa = soa; T.pass_bits = 0; T.pass_id = 0;
     PLB_LAUNCH("k5_table_init", k_gb_init, grid_for((int64_t)(cap + 2) * L.stride, 256), 256, 0, T.entries, (int64_t)(cap + 2), L.stride, soa, L);
     dev_memset(status->p, 0, 4);
 }
@@ -833,12 +838,24 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
         // beyond ~72 KB of table per CTA the occupancy loss outweighs the cheaper atomics (measured: 2000 keys)
         if ((size_t)(want + 2) * Lb.stride * 8 <= (size_t)72 * 1024) scap = want;
     }
+    // tables that cannot stay L2-resident are filled in several passes over the batch: pass h only touches the
+    // slot sub-range h of every plane (slot = top hash bits), so each pass works on an L2-sized slice
+    int pass_bits = 0;
+    if (!scap) {
+        static const int mp = [] { const char* e = getenv("BL_K5_MULTIPASS"); return e ? atoi(e) : 1; }();
+        const double tbl = (double)(cap + 2) * L.stride * 8, budget = 0.55 * (double)ctx().l2_bytes;
+        while (mp && pass_bits < 4 && tbl / (double)(1 << pass_bits) > budget) pass_bits++;
+    }
+    GbTableDev Tp = T;
+#define GB_LAUNCH_ALL(E, C, KN)                                                      \
+    do { for (int h = 0; h < (1 << pass_bits); h++) { Tp.pass_bits = pass_bits; Tp.pass_id = h; launch_consume<E, C, KN>(Lb, Tp, B, grid); } } while (0)
 #define GB_DISPATCH(E, C)                                                            \
     do { if (scap) { if (kn) launch_smem<E, C, true>(Lb, T, B, scap); else launch_smem<E, C, false>(Lb, T, B, scap); }                       \
-         else if (kn) launch_consume<E, C, true>(Lb, T, B, grid); else launch_consume<E, C, false>(Lb, T, B, grid); } while (0)
+         else if (kn) GB_LAUNCH_ALL(E, C, true); else GB_LAUNCH_ALL(E, C, false); } while (0)
     if (elem == 8) { if (canon == 1) GB_DISPATCH(8, 1); else GB_DISPATCH(8, 0); }
     else { if (canon == 2) GB_DISPATCH(4, 2); else GB_DISPATCH(4, 0); }
 #undef GB_DISPATCH
+#undef GB_LAUNCH_ALL
 }
 
 void GroupByState::grow(uint64_t new_cap) {

@@ -22,7 +22,7 @@ struct GbLayout {
     uint64_t init[GB_MAX_WORDS];      // word index -> identity
 };
 // word w of entry s: entries[s * es + w * ws]  (AoS: es = stride, ws = 1;  word-major planes: es = 1, ws = cap + 2)
-struct GbTableDev { uint64_t* entries; uint64_t cap; int64_t es, ws; int32_t shift; int32_t soa; int32_t* status; int32_t hint; int32_t pad; };
+struct GbTableDev { uint64_t* entries; uint64_t cap; int64_t es, ws; int32_t shift; int32_t soa; int32_t* status; int32_t hint; int32_t pass_bits; int32_t pass_id; int32_t pad; };
 struct GbBatch {
     const void* keys; const uint32_t* key_validity; int64_t n; uint32_t row_base; int32_t key_dtype;
     GbColDev cols[GB_MAX_COLS];

@@ -535,3 +535,22 @@ def test_null_scalar_and_empty_inputs(plb):
     assert k.size == 0 and all(o[0].size == 0 for o in outs)
     (li, _), (ri, _) = plb.hash_join(np.zeros(0, np.int64), np.arange(3, dtype=np.int64), "left")
     assert li.size == 0 and ri.size == 0
+
+
+def test_group_by_multipass_beyond_l2(plb):
+    # ~3.5e6 groups: the table (268 MB) cannot stay L2-resident, K5 runs several passes over slot sub-ranges;
+    # null keys and the sentinel key (i64::MIN) must be handled by exactly one pass
+    rng = np.random.default_rng(77)
+    n = 5_000_001
+    key = (rng.integers(0, 3_500_000, n) * 7919 - 10**9).astype(np.int64)
+    key[::1000] = -2**63
+    kvalid = rng.random(n) > 0.001
+    vi = rng.integers(-1000, 1000, n).astype(np.int64)
+    vf = rng.uniform(0, 100, n).round(6)
+    (k, kv), outs = plb.group_by_agg(plb.Column(key, kvalid), [("sum", plb.Column(vi)), ("mean", plb.Column(vf)), ("len", None)], False)
+    ek, ekv, eouts, _ = oracle.group_by_agg(key, kvalid, [("sum", vi, None), ("mean", vf, None), ("len", None, None)], 8, False)
+    k, kv, outs = sort_groups(k, kv, outs)
+    ek, ekv, eouts = sort_groups(ek, ekv, eouts)
+    assert_close(k, ek, kv, ekv, "keys")
+    for name, (v, m), (ev, em) in zip(("sum", "mean", "len"), outs, eouts):
+        assert_close(v, ev, m, em, name)
