@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -232,7 +232,15 @@ def main():
         if world > 1:
             from polars_b200 import dist as pdist
             if a.exchange == "p2p":      # window region per source rank: every group of a rank could go to one peer
-                peer_ex = pdist.PeerExchange(plb, rows_per_src=min(a.keys, a.rows) + 1024, row_words=2 + 3)
+                try:
+                    peer_ex = pdist.PeerExchange(plb, rows_per_src=min(a.keys, a.rows) + 1024, row_words=2 + 3)
+                    ok_all = torch.tensor([1], device="cuda")
+                except Exception as e:      # CUDA IPC unavailable (container policy): use the NCCL all-to-all instead
+                    print(f"[bench] peer windows unavailable ({e}); falling back to --exchange nccl", file=sys.stderr)
+                    ok_all = torch.tensor([0], device="cuda")
+                dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+                if int(ok_all.item()) == 0:
+                    a.exchange, peer_ex = "nccl", None
 
         def step_device():
             nonlocal out_bytes
@@ -328,7 +336,6 @@ def main():
         e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     prof = plb.profile()
     launches = plb.launch_count()
     plb.profile_enable(False)
@@ -352,6 +359,7 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
+    clocks = sampler.stop() if rank == 0 else None      # sampled over the timed region and the e2e steps that follow it
 
     if rank != 0:
         if world > 1:

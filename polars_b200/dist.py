@@ -98,10 +98,27 @@ class PeerExchange:
         self.plb, self.rows_per_src, self.row_words = plb, int(rows_per_src), int(row_words)
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         self.half_bytes = self.world * self.rows_per_src * self.row_words * 8
-        self.win = plb.Window(2 * self.half_bytes)
+        # every collective below is reached by every rank even if a local step fails (no rank may hang)
+        try:
+            self.win, err = plb.Window(2 * self.half_bytes), None
+        except Exception as e:
+            self.win, err = None, str(e)
         handles = [None] * self.world
-        dist.all_gather_object(handles, self.win.ipc_handle)
-        self.peers = [self.win.ptr if r == self.rank else plb.Window.open(handles[r]) for r in range(self.world)]
+        dist.all_gather_object(handles, None if self.win is None else self.win.ipc_handle)
+        self.peers = []
+        if all(h is not None for h in handles):
+            try:
+                self.peers = [self.win.ptr if r == self.rank else plb.Window.open(handles[r]) for r in range(self.world)]
+            except Exception as e:
+                err = str(e)
+        else:
+            err = err or "a peer could not create its window"
+        flags = [None] * self.world
+        dist.all_gather_object(flags, err)
+        if any(f is not None for f in flags):
+            if self.win is not None:
+                self.win.destroy()
+            raise RuntimeError("peer windows unavailable: " + "; ".join(str(f) for f in flags if f))
         self.half = 0
 
     def flip(self):

@@ -538,11 +538,11 @@ def test_null_scalar_and_empty_inputs(plb):
 
 
 def test_group_by_multipass_beyond_l2(plb):
-    # ~3.5e6 groups: the table (268 MB) cannot stay L2-resident, K5 runs several passes over slot sub-ranges;
+    # ~1.4e6 groups in 2e6 rows: the table (134 MB) cannot stay L2-resident, K5 runs two passes over slot sub-ranges;
     # null keys and the sentinel key (i64::MIN) must be handled by exactly one pass
     rng = np.random.default_rng(77)
-    n = 5_000_001
-    key = (rng.integers(0, 3_500_000, n) * 7919 - 10**9).astype(np.int64)
+    n = 2_000_001
+    key = (rng.integers(0, 3_000_000, n) * 7919 - 10**9).astype(np.int64)
     key[::1000] = -2**63
     kvalid = rng.random(n) > 0.001
     vi = rng.integers(-1000, 1000, n).astype(np.int64)
