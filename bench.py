@@ -223,7 +223,7 @@ def main():
 
     if a.workload == "groupby":
         key, vi, vf = gen_groupby(a.rows, a.keys, 1 + rank)
-        hkey, hvi, hvf = plb.to_pinned(key), plb.to_pinned(vi), plb.to_pinned(vf)
+        hkey, hvi, hvf = (plb.to_pinned(key), plb.to_pinned(vi), plb.to_pinned(vf)) if a.e2e_steps > 0 else (None, None, None)
         dkey, dvi, dvf = plb.to_device(key), plb.to_device(vi), plb.to_device(vf)
         del key, vi, vf
         spec = [("sum", np.int64), ("mean", np.float64), ("len", None)]

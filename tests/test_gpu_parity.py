@@ -388,14 +388,16 @@ def test_join_vs_oracle(plb, nl, nr, krange, dups, key_dtype):
     rk = np.concatenate([rk, rng.integers(0, krange, nr - rk.size)]).astype(key_dtype)
     rng.shuffle(rk)
     if np.dtype(key_dtype).kind == "f" and nl > 10 and nr > 10:
-        lk[::13] = np.nan
-        rk[::17] = np.nan
-        lk[1::13] = -0.0
-        rk[1::17] = 0.0
+        step_l, step_r = (13, 17) if nl <= 3000 else (nl // 40, nr // 30)     # NaN joins NaN: keep the cross product small
+        lk[::step_l] = np.nan
+        rk[::step_r] = np.nan
+        lk[1::step_l] = -0.0
+        rk[1::step_r] = 0.0
     lv = rng.random(nl) > 0.1
     rv = rng.random(nr) > 0.1
     impl = GpuImpl(plb)
-    for nulls_equal in (False, True):
+    # nulls_equal joins every null key with every null key: quadratic output, small inputs only
+    for nulls_equal in ((False, True) if nl <= 3000 else (False,)):
         for how in ("inner", "left"):
             orders = ["none", "left", "right", "left_right"] if how == "inner" else ["none", "left", "right", "right_left"]
             for order in orders:
