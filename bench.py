@@ -49,6 +49,11 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=20_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skew", default="uniform", choices=["uniform", "zipf"], help="group_by key distribution (SURVEY.md 8(d) C2 variants)")
+    ap.add_argument("--null-frac", type=float, default=0.0, help="group_by: fraction of null rows in each value column")
+    ap.add_argument("--hit-frac", type=float, default=1.0, help="join: fraction of probe rows with a match (C3 variant: 0.5)")
+    ap.add_argument("--dup", type=int, default=1, help="join: copies of every build key (C3 variant: 4)")
+    ap.add_argument("--acero-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU exchange of the partial aggregates")
     return ap.parse_args()
 
@@ -92,20 +97,26 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def gen_groupby(rows: int, keys: int, seed: int):
-    """uniform keys, v_i64 in [-1000,1000), v_f64 = U(0,100).round(6) (h2oai v3)."""
+def gen_groupby(rows: int, keys: int, seed: int, skew: str = "uniform"):
+    """uniform keys (or the Zipf(1.1) variant folded into [0, keys)), v_i64 in
+    [-1000,1000), v_f64 = U(0,100).round(6) (h2oai v3)."""
     rng = np.random.default_rng(seed)
-    key = rng.integers(0, keys, rows, dtype=np.int64)
+    if skew == "zipf":
+        key = (rng.zipf(1.1, rows) % keys).astype(np.int64)
+    else:
+        key = rng.integers(0, keys, rows, dtype=np.int64)
     vi = rng.integers(-1000, 1000, rows, dtype=np.int64)
     vf = rng.uniform(0, 100, rows).round(6)
     return key, vi, vf
 
 
-def gen_join(rows: int, build_rows: int, seed: int):
-    """C3: build = permutation(build_rows) (unique keys), probe keys uniform in [0, build_rows): 100 % hit."""
+def gen_join(rows: int, build_rows: int, seed: int, hit_frac: float = 1.0, dup: int = 1):
+    """C3: build = permutation (unique keys, or `dup` copies of each), probe keys uniform over
+    [0, distinct build keys / hit_frac): 100 % hit by default; variants 50 % hit and 4 duplicates per key."""
     rng = np.random.default_rng(seed)
-    build = rng.permutation(build_rows).astype(np.int64)
-    probe = rng.integers(0, build_rows, rows, dtype=np.int64)
+    distinct = max(1, build_rows // dup)
+    build = rng.permutation(distinct * dup).astype(np.int64) % distinct if dup > 1 else rng.permutation(build_rows).astype(np.int64)
+    probe = rng.integers(0, max(1, int(distinct / hit_frac)), rows, dtype=np.int64)
     return probe, build
 
 
@@ -164,14 +175,14 @@ def run_reference(a):
     cores = oracle.max_threads()
     sample = min(a.rows, a.cpu_sample)
     if a.workload == "groupby":
-        key, vi, vf = gen_groupby(sample, a.keys, 1)
+        key, vi, vf = gen_groupby(sample, a.keys, 1, a.skew)
         aggs = [("sum", vi, None), ("mean", vf, None), ("len", None, None)]
         fn = lambda: oracle.group_by_agg(key, None, aggs, cores, False)   # noqa: E731
         unit_rows = sample
         metric, wl = "group_by_agg_rows_per_sec", f"C2 hash group_by {a.rows} rows, {a.keys} Int64 keys, sum(i64)/mean(f64)/len"
     else:
         build_rows = max(1, int(a.build_rows * sample / a.rows))
-        probe, build = gen_join(sample, build_rows, 2)
+        probe, build = gen_join(sample, build_rows, 2, a.hit_frac, a.dup)
         fn = lambda: oracle.hash_join(probe, build, None, None, "inner", False, "none", cores)   # noqa: E731
         unit_rows = sample
         metric, wl = "hash_join_probe_rows_per_sec", f"C3 inner hash join {a.rows} x {a.build_rows} Int64"
@@ -198,6 +209,9 @@ def main():
     os.environ.pop("NCCL_DEBUG", None)
     if os.environ.get("BENCH_NCCL_DEBUG"):
         os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
+    if a.acero_child:
+        acero_child(a)
+        return
     if a.impl == "reference":
         run_reference(a)
         return
@@ -222,9 +236,13 @@ def main():
         plb.sync()
 
     if a.workload == "groupby":
-        key, vi, vf = gen_groupby(a.rows, a.keys, 1 + rank)
+        key, vi, vf = gen_groupby(a.rows, a.keys, 1 + rank, a.skew)
         hkey, hvi, hvf = (plb.to_pinned(key), plb.to_pinned(vi), plb.to_pinned(vf)) if a.e2e_steps > 0 else (None, None, None)
-        dkey, dvi, dvf = plb.to_device(key), plb.to_device(vi), plb.to_device(vf)
+        val_i = val_f = None
+        if a.null_frac > 0:      # the "+5 % nulls" variant: independent validity bitmaps on both value columns
+            nrng = np.random.default_rng(100 + rank)
+            val_i, val_f = (plb.pack_bits(nrng.random(a.rows) >= a.null_frac) for _ in range(2))      # Arrow LSB bitmaps
+        dkey, dvi, dvf = plb.to_device(key), plb.to_device(vi, val_i), plb.to_device(vf, val_f)
         del key, vi, vf
         spec = [("sum", np.int64), ("mean", np.float64), ("len", None)]
         out_bytes = 0
@@ -259,14 +277,15 @@ def main():
             return ok.length
 
         def step_e2e():
-            (k, _), outs = plb.group_by_agg(plb.Column(hkey), [("sum", plb.Column(hvi)), ("mean", plb.Column(hvf)), ("len", None)], False, location=plb.HOST)
+            (k, _), outs = plb.group_by_agg(plb.Column(hkey), [("sum", plb.Column(hvi, val_i)), ("mean", plb.Column(hvf, val_f)), ("len", None)], False, location=plb.HOST)
             return k.size, k.nbytes + sum(o[0].nbytes for o in outs)
 
         unit_rows = a.rows
         alg_bytes_per_row = 24.0
         dominant = "k5_groupby_agg"
         metric = "group_by_agg_rows_per_sec"
-        wl = f"C2 hash group_by {a.rows} rows/GPU, {a.keys} uniform Int64 keys, sum(v_i64)/mean(v_f64)/len; inputs 2.4 GB > L2 (no flush needed)"
+        wl = (f"C2 hash group_by {a.rows} rows/GPU, {a.keys} {'Zipf(1.1)-skewed' if a.skew == 'zipf' else 'uniform'} Int64 keys, sum(v_i64)/mean(v_f64)/len"
+              + (f", {a.null_frac:.0%} nulls per value column" if a.null_frac > 0 else "") + "; inputs 2.4 GB > L2 (no flush needed)")
         h2d = a.rows * 24
     elif a.workload == "q1":
         rows = a.rows if a.rows != 100_000_000 else 60_000_000      # SF10 lineitem ~ 6e7 rows
@@ -299,7 +318,7 @@ def main():
         wl = f"C4 PDS-H Q1 shape on {rows} synthetic lineitem rows (SF10-sized): filter + 4 expressions + group_by(returnflag,linestatus) with 8 aggregates"
         h2d = rows * 8 * 7
     else:
-        probe, build = gen_join(a.rows, a.build_rows, 2 + rank)
+        probe, build = gen_join(a.rows, a.build_rows, 2 + rank, a.hit_frac, a.dup)
         hp, hb = plb.to_pinned(probe), plb.to_pinned(build)
         dp, db = plb.to_device(probe), plb.to_device(build)
         del probe, build
@@ -313,10 +332,11 @@ def main():
             return li.size, li.nbytes + ri.nbytes
 
         unit_rows = a.rows
-        alg_bytes_per_row = 16.0
+        alg_bytes_per_row = 8.0 + 8.0 * a.hit_frac * a.dup      # probe key + (left_idx, right_idx) u32 per match
         dominant = "k8_join_probe"
         metric = "hash_join_probe_rows_per_sec"
-        wl = f"C3 inner hash join: probe {a.rows} x build {a.build_rows} unique Int64 keys, 100% hit; outputs (left_idx,right_idx) u32"
+        wl = (f"C3 inner hash join: probe {a.rows} x build {a.build_rows} Int64 keys ({'unique' if a.dup == 1 else str(a.dup) + ' copies of each'}), "
+              f"{a.hit_frac:.0%} hit; outputs (left_idx,right_idx) u32")
         h2d = (a.rows + a.build_rows) * 8
 
     # ---- warm-up, then the timed region (device-resident inputs)
@@ -407,24 +427,60 @@ class _CudaArray:
         self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (ptr, False), "version": 2}
 
 
+def acero_child(a):
+    """Child process of `acero_baseline`: times the query on pyarrow's Acero engine and prints one JSON object."""
+    import pyarrow as pa
+    if a.workload == "groupby":
+        key, vi, vf = gen_groupby(a.rows, a.keys, 1, a.skew)
+        t = pa.table({"key": key, "vi": vi, "vf": vf})
+        t0 = time.perf_counter()
+        t.group_by("key", use_threads=True).aggregate([("vi", "sum"), ("vf", "mean"), ([], "count_all")])
+        dt = time.perf_counter() - t0
+    else:
+        probe, build = gen_join(a.rows, a.build_rows, 2, a.hit_frac, a.dup)
+        lt, rt = pa.table({"key": probe}), pa.table({"key": build, "r": np.arange(build.size, dtype=np.int64)})
+        t0 = time.perf_counter()
+        lt.join(rt, keys="key", join_type="inner", use_threads=True)
+        dt = time.perf_counter() - t0
+    print(json.dumps({"engine": f"pyarrow-acero {pa.__version__}", "value": a.rows / dt, "unit": "rows/s", "threads": pa.cpu_count()}), flush=True)
+    os._exit(0)      # Acero's worker threads occasionally abort the interpreter during static destruction
+
+
+def acero_baseline(a, sample: int, build_rows: int):
+    """Second, independent CPU reference: the same query on pyarrow's Acero engine with
+    its default thread pool, in a child process.  Reported beside the oracle port; neither is the target."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--acero-child", "--workload", a.workload, "--rows", str(sample), "--keys", str(a.keys),
+           "--build-rows", str(build_rows), "--skew", a.skew, "--hit-frac", str(a.hit_frac), "--dup", str(a.dup)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:      # optional evidence, never a reason to lose the bench line
+        return {"engine": "pyarrow-acero", "unavailable": f"{type(e).__name__}: {e}"[:160]}
+
+
 def cpu_baseline(a):
     import oracle
     oracle.build()
     cores = oracle.max_threads()
     sample = min(a.rows, a.cpu_sample)
     if a.workload == "groupby":
-        key, vi, vf = gen_groupby(sample, a.keys, 1)
+        key, vi, vf = gen_groupby(sample, a.keys, 1, a.skew)
         aggs = [("sum", vi, None), ("mean", vf, None), ("len", None, None)]
         t0 = time.perf_counter()
         oracle.group_by_agg(key, None, aggs, cores, False)
         dt = time.perf_counter() - t0
+        second = acero_baseline(a, sample, a.build_rows)
     else:
-        probe, build = gen_join(sample, max(1, int(a.build_rows * sample / a.rows)), 2)
+        build_rows = max(1, int(a.build_rows * sample / a.rows))
+        probe, build = gen_join(sample, build_rows, 2, a.hit_frac, a.dup)
         t0 = time.perf_counter()
         oracle.hash_join(probe, build, None, None, "inner", False, "none", cores)
         dt = time.perf_counter() - t0
+        second = acero_baseline(a, sample, build_rows)
     return {"value": sample / dt, "unit": "rows/s", "cores": cores, "kind": "port",
-            "sample": f"{sample} rows of the same workload, one pass; oracle = C/OpenMP restatement of the reference's partitioned algorithm (the Rust reference cannot be built here)"}
+            "sample": f"{sample} rows of the same workload, one pass; oracle = C/OpenMP restatement of the reference's partitioned algorithm (the Rust reference cannot be built here)",
+            "second_reference": second}
 
 
 if __name__ == "__main__":

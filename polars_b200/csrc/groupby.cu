@@ -243,31 +243,47 @@ __global__ void k_gb_init(uint64_t* entries, int64_t n_entries, int stride, int 
     }
 }
 
-// cardinality sample: insert m strided keys into a scratch key table, count distinct
-__global__ void k_gb_estimate(const void* keys, const uint32_t* key_validity, int key_dtype, int64_t n, int64_t m, uint64_t* scratch, uint64_t cap, int shift, unsigned* distinct) {
+// cardinality sample: insert m strided keys into a scratch key table with per-slot multiplicities.
+// stats[0] = distinct keys, stats[3] = sampled rows whose successor row carries the same key
+// (collision rate of neighbouring rows: skew / sortedness); stats[1], stats[2] are filled by
+// k_gb_estimate_stats (keys seen exactly once / exactly twice in the sample).
+struct GbSampleStats { unsigned distinct, f1, f2, adjacent; };
+__global__ void k_gb_estimate(const void* keys, const uint32_t* key_validity, int key_dtype, int64_t n, int64_t m, uint64_t* scratch, unsigned* mult, uint64_t cap, int shift, GbSampleStats* stats) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t row = (int64_t)(((unsigned __int128)i * (unsigned __int128)n) / (unsigned __int128)m);
-        bool ins = false;
+        bool ins = false, adj = false;
         if (key_validity == nullptr || bit_get(key_validity, row)) {
             uint64_t key = load_key_rt(keys, key_dtype, row);
+            adj = row + 1 < n && load_key_rt(keys, key_dtype, row + 1) == key;
             if (key != GB_EMPTY) {
                 uint64_t slot = dirty_hash(key) >> shift;
                 for (int pr = 0; pr < (int)cap; pr++) {
                     uint64_t k = __ldcg(reinterpret_cast<const unsigned long long*>(scratch + slot));
-                    if (k == key) break;
                     if (k == GB_EMPTY) {
                         unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(scratch + slot), (unsigned long long)GB_EMPTY, (unsigned long long)key);
-                        if (old == GB_EMPTY) { ins = true; break; }
-                        if (old == key) break;
+                        if (old == GB_EMPTY) { ins = true; k = key; } else k = old;
                     }
+                    if (k == key) { atomicAdd(mult + slot, 1u); break; }
                     slot = (slot + 1) & (cap - 1);
                 }
             }
         }
         unsigned act = __activemask();
-        unsigned b = __ballot_sync(act, ins);
-        if (b && lane_id() == (unsigned)(__ffs(act) - 1)) atomicAdd(distinct, (unsigned)__popc(b));
+        unsigned b = __ballot_sync(act, ins), a = __ballot_sync(act, adj);
+        if (lane_id() == (unsigned)(__ffs(act) - 1)) {
+            if (b) atomicAdd(&stats->distinct, (unsigned)__popc(b));
+            if (a) atomicAdd(&stats->adjacent, (unsigned)__popc(a));
+        }
     }
+}
+__global__ void k_gb_estimate_stats(const unsigned* mult, int64_t cap, GbSampleStats* stats) {
+    unsigned f1 = 0, f2 = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned c = mult[i];
+        f1 += c == 1; f2 += c == 2;
+    }
+    f1 = __reduce_add_sync(0xffffffffu, f1); f2 = __reduce_add_sync(0xffffffffu, f2);
+    if (lane_id() == 0) { if (f1) atomicAdd(&stats->f1, f1); if (f2) atomicAdd(&stats->f2, f2); }
 }
 __global__ void k_fill_u64(uint64_t* p, uint64_t v, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
@@ -725,13 +741,23 @@ uint64_t GroupByState::choose_cap(const DevCol& key, int64_t n_total) {
     else {
         const int64_t n = key.len, m = std::min<int64_t>(n, 65536);
         const uint64_t scap = 1 << 18;
-        DevPtr scratch = dev_alloc(scap * 8), cnt = dev_alloc(4);
+        DevPtr scratch = dev_alloc(scap * 8), mult = dev_alloc(scap * 4 + sizeof(GbSampleStats));
+        GbSampleStats* dstats = reinterpret_cast<GbSampleStats*>(as<unsigned>(mult) + scap);
         PLB_LAUNCH("k5_fill", k_fill_u64, grid_for(scap, 256), 256, 0, as<uint64_t>(scratch), GB_EMPTY, (int64_t)scap);
-        dev_memset(cnt->p, 0, 4);
-        PLB_LAUNCH("k5_estimate", k_gb_estimate, grid_for(m, 256), 256, 0, key.v(), key.vm(), key.dtype, n, m, as<uint64_t>(scratch), scap, 64 - 18, as<unsigned>(cnt));
-        unsigned d = read_scalar(as<unsigned>(cnt));
+        dev_memset(mult->p, 0, scap * 4 + sizeof(GbSampleStats));
+        PLB_LAUNCH("k5_estimate", k_gb_estimate, grid_for(m, 256), 256, 0, key.v(), key.vm(), key.dtype, n, m, as<uint64_t>(scratch), as<unsigned>(mult), scap, 64 - 18, dstats);
+        PLB_LAUNCH("k5_estimate", k_gb_estimate_stats, grid_for(scap, 256), 256, 0, as<unsigned>(mult), (int64_t)scap, dstats);
+        const GbSampleStats st = read_scalar(dstats);
         const double nt = (double)std::max<int64_t>(n_total, n);
-        G_raw = estimate_groups((double)d, (double)m, nt);
+        G_raw = estimate_groups((double)st.distinct, (double)m, nt);
+        // skewed keys: the uniform inversion collapses onto the hot head of the distribution.  Chao's
+        // estimator (distinct + f1^2 / 2 f2, from the keys sampled exactly once / twice) recovers the
+        // long tail; take the larger of the two (an under-estimate costs a restart, an over-estimate L2 misses)
+        if (m < n && st.f1 > 0) {
+            const double chao = (double)st.distinct + (double)st.f1 * ((double)st.f1 - 1.0) / (2.0 * ((double)st.f2 + 1.0));
+            if (chao > G_raw) G_raw = chao;
+        }
+        sample_adjacent = m > 0 ? (double)st.adjacent / (double)m : 0.0;
         G = G_raw * 1.25 + 64;
         if (G > nt) G = nt;
         if (G_raw > nt) G_raw = nt;
@@ -838,6 +864,11 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
         // beyond ~72 KB of table per CTA the occupancy loss outweighs the cheaper atomics (measured: 2000 keys)
         if ((size_t)(want + 2) * Lb.stride * 8 <= (size_t)72 * 1024) scap = want;
     }
+    // hot-table mode (experimental knob): run the shared-memory kernel with BL_K5_HOT slots even though the
+    // groups do not fit; the first keys a CTA sees (the hot head of a skewed distribution) aggregate in shared
+    // memory, everything else falls through to the global table
+    const int hot_slots = [] { const char* e = getenv("BL_K5_HOT"); int v = e ? atoi(e) : 0; int c = 0; if (v > 0) { c = 16; while (c < v && c < 2048) c <<= 1; } return c; }();
+    if (!scap && hot_slots) scap = hot_slots;
     // tables that cannot stay L2-resident are filled in several passes over the batch: pass h only touches the
     // slot sub-range h of every plane (slot = top hash bits), so each pass works on an L2-sized slice
     int pass_bits = 0;

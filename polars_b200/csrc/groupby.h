@@ -45,6 +45,7 @@ struct GroupByState {
     int64_t rows_seen = 0;
     int64_t merged_rows = 0;     // partial-aggregate rows merged in (bounds the group count together with rows_seen)
     int64_t est_groups = 0;      // sampled / hinted cardinality; selects the shared-memory plan
+    double sample_adjacent = 0;  // sampled fraction of rows whose successor carries the same key (skew / sortedness)
 
     GroupByState(int key_dt, const std::vector<int>& kinds, const std::vector<int>& dtypes, const std::vector<int>& nullable, int64_t expected, bool track_first);
     void consume_all(const DevCol& key, const std::vector<const DevCol*>& values);

@@ -330,6 +330,28 @@ def test_group_by_smem_plan_overflow_falls_through(plb):
             assert_close(v, ev, m, em, kind)
 
 
+@pytest.mark.parametrize("hot", [0, 64, 1024])
+def test_group_by_skewed_keys(plb, monkeypatch, hot):
+    # Zipf(1.1) keys (SURVEY 8(d) C2 skew variant): a hot head plus a long tail of singletons.  The sampled
+    # estimate (uniform inversion vs Chao's tail correction) only steers table sizing; the result must be
+    # exact either way, also with the hot-table detour (BL_K5_HOT) and for sorted keys (runs of equal keys)
+    if hot:
+        monkeypatch.setenv("BL_K5_HOT", str(hot))
+    n = 600_000
+    rng = np.random.default_rng(33)
+    key = (rng.zipf(1.1, n) % 200_000).astype(np.int64)
+    vi = rng.integers(-1000, 1000, n).astype(np.int64)
+    vf = rng.uniform(0, 100, n).round(6)
+    valid = rng.random(n) > 0.05
+    aggs = [("sum", vi, valid), ("mean", vf, None), ("len", None, None), ("min", vf, None), ("max", vi, valid)]
+    for k_in in (key, np.sort(key)):
+        keys, kv, outs = GpuImpl(plb).group_by_agg(k_in, None, aggs, True)
+        ek, ekv, eouts, _ = oracle.group_by_agg(k_in, None, aggs, 4, True)
+        assert_close(keys, ek, kv, ekv, "keys")
+        for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
+            assert_close(v, ev, m, em, kind)
+
+
 def test_group_by_streaming_and_partials(plb):
     # streaming consume == one shot; export -> merge of partial aggregates == single table
     rng = np.random.default_rng(12)
