@@ -152,6 +152,14 @@ typedef struct bl_agg {
 bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, const bl_agg* aggs, int32_t n_aggs,
                          int32_t maintain_order, int32_t out_location, bl_column* out_key, bl_column* out_aggs);
 
+/* Group tuples: the reference's GroupsIdx{first, all} (polars-core/src/frame/group_by/position.rs:16-22)
+ * as built by group_by_threaded_slice with sorted = true (hashing.rs:116-167, finish_group_order :41-63),
+ * for aggregations outside the fused set above.  Groups come in first-occurrence order; group g owns
+ * out_all[out_offsets[g] .. out_offsets[g+1]) (row indices ascending), out_first[g] = its first row.
+ * All three outputs are BL_UINT32 (IdxSize); out_offsets has n_groups + 1 entries.  Null key = own group. */
+bl_status bl_group_tuples(const bl_column* key_chunks, int32_t n_key_chunks, int32_t out_location,
+                          bl_column* out_first, bl_column* out_offsets, bl_column* out_all);
+
 /* ---- K7/K8: hash join on one numeric key ----------------------------------------------- */
 /* (build_tables single_keys.rs:16-167, probe_inner single_keys_inner.rs:11-149,
  *  hash_join_tuples_left single_keys_left.rs:106-195) */

@@ -373,6 +373,18 @@ def group_by_agg(key, aggs: Sequence, maintain_order: bool = False, location: in
     return res[0], res[1:]
 
 
+def group_tuples(key, location: int = HOST):
+    """GroupsIdx of the reference (first, offsets, all): groups in first-occurrence order, rows ascending."""
+    kch = [_as_col(c) for c in (key if isinstance(key, list) else [key])]
+    ka = _col_array(kch)
+    of, oo, oa = BlColumn(), BlColumn(), BlColumn()
+    _check(lib().bl_group_tuples(ka, C.c_int32(len(kch)), C.c_int32(location), C.byref(of), C.byref(oo), C.byref(oa)))
+    res = _finish([of, oo, oa], location)
+    if location == HOST:
+        return res[0][0], res[1][0], res[2][0]
+    return res[0], res[1], res[2]
+
+
 def hash_join(left_key, right_key, how: str = "inner", nulls_equal: bool = False, maintain_order: str = "none", location: int = HOST):
     lch = [_as_col(c) for c in (left_key if isinstance(left_key, list) else [left_key])]
     rch = [_as_col(c) for c in (right_key if isinstance(right_key, list) else [right_key])]

@@ -157,6 +157,16 @@ bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, cons
     BL_CATCH
 }
 
+bl_status bl_group_tuples(const bl_column* key_chunks, int32_t n_key_chunks, int32_t out_location, bl_column* out_first, bl_column* out_offsets, bl_column* out_all) {
+    BL_TRY
+    PLB_REQUIRE(key_chunks && n_key_chunks >= 1 && out_first && out_offsets && out_all, BL_ERR_INVALID, "group_tuples: null argument");
+    DevCol key = import_column(key_chunks, n_key_chunks);
+    DevCol first, offsets, all;
+    op_group_tuples(key, first, offsets, all);
+    { std::vector<DevCol> cols{first, offsets, all}; bl_column t[3]; export_many(cols, out_location, t); *out_first = t[0]; *out_offsets = t[1]; *out_all = t[2]; }
+    BL_CATCH
+}
+
 bl_status bl_hash_join(const bl_column* left_key, int32_t n_left_chunks, const bl_column* right_key, int32_t n_right_chunks, int32_t how, int32_t nulls_equal,
                        int32_t maintain_order, int32_t out_location, bl_column* out_left_idx, bl_column* out_right_idx) {
     BL_TRY

@@ -1132,4 +1132,73 @@ void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather,
     }
 }
 
+// ---------------------------------------------------------------------------- group tuples (GroupsIdx)
+// The reference's group_by materialises GroupsIdx{first, all} (position.rs:16-22) in
+// group_by_threaded_slice (hashing.rs:116-167); finish_group_order (hashing.rs:41-63) orders the groups
+// by first row.  The fused aggregation path above never needs the index lists; this entry point builds
+// them for callers that do (aggregations outside the fused set evaluate per group over `all`):
+//   1. K5 with no accumulators: table of (key, len, first row)
+//   2. row -> first row of its group (a lookup; the first row is the group's identity)
+//   3. stable radix sort of (first-of-group, row): groups in first-occurrence order, rows ascending
+//   4. run starts of the sorted keys -> offsets, first = all[offsets]
+__global__ void __launch_bounds__(256) k_gb_lookup_first(const __grid_constant__ GbTableDev T, const void* keys, const uint32_t* key_validity, int key_dtype, int64_t n, uint32_t* __restrict__ out) {
+    const uint64_t mask = T.cap - 1;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        const bool kvalid = key_validity == nullptr || bit_get(key_validity, row);
+        const uint64_t key = load_key_rt(keys, key_dtype, row);
+        uint64_t slot;
+        if (!kvalid) slot = T.cap;
+        else if (key == GB_EMPTY) slot = T.cap + 1;
+        else {
+            slot = dirty_hash(key) >> T.shift;
+            for (int probes = 0; probes < GB_MAX_PROBE; ++probes) {
+                if (__ldcg(reinterpret_cast<const unsigned long long*>(T.entries + slot * T.es)) == key) break;
+                slot = (slot + 1) & mask;
+            }
+        }
+        const uint64_t w1 = __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + slot * T.es + T.ws));
+        out[row] = (uint32_t)(w1 >> 32);
+    }
+}
+// bit i of the mask = sorted[i] starts a run (i == 0 or sorted[i] != sorted[i-1]); n_round = n rounded up to 32
+__global__ void __launch_bounds__(256) k_run_starts(const uint32_t* __restrict__ sorted, int64_t n, int64_t n_round, uint32_t* __restrict__ mask_words) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool start = i < n && (i == 0 || sorted[i] != sorted[i - 1]);
+        const unsigned b = __ballot_sync(0xffffffffu, start);
+        if ((threadIdx.x & 31) == 0) mask_words[i >> 5] = b;
+    }
+}
+
+void op_group_tuples(const DevCol& key, DevCol& out_first, DevCol& out_offsets, DevCol& out_all) {
+    const int64_t n = key.len;
+    PLB_REQUIRE(n <= 0x7FFFFFFFll, BL_ERR_UNSUPPORTED, "group_tuples: more than 2^31-1 rows");
+    out_all = make_col(BL_UINT32, n, false);
+    if (n == 0) {
+        out_first = make_col(BL_UINT32, 0, false);
+        out_offsets = make_col(BL_UINT32, 1, false);
+        dev_memset(out_offsets.values->p, 0, 4);
+        return;
+    }
+    GroupByState st(key.dtype, {}, {}, {}, 0, true);
+    st.consume_all(key, {});
+    DevPtr gid = dev_alloc((size_t)n * 4);
+    PLB_LAUNCH("k5_lookup_first", k_gb_lookup_first, grid_for(n, 256, 16), 256, 0, st.T, key.v(), key.vm(), key.dtype, n, as<uint32_t>(gid));
+    iota_u32(as<uint32_t>(out_all.values), n, 0);
+    sort_pairs_u32(as<uint32_t>(gid), as<uint32_t>(out_all.values), n);
+    DevCol starts = make_col(BL_BOOL, n, false);
+    const int64_t n_round = (n + 31) / 32 * 32;
+    PLB_LAUNCH("k5_run_starts", k_run_starts, grid_for(n_round, 256, 16), 256, 0, as<uint32_t>(gid), n, n_round, as<uint32_t>(starts.values));
+    DevCol pos = make_col(BL_UINT32, n, false);
+    iota_u32(as<uint32_t>(pos.values), n, 0);
+    std::vector<DevCol> in{pos, out_all}, outv;
+    op_filter(in, starts, outv);
+    const int64_t G = outv[0].len;
+    out_first = outv[1];
+    out_offsets = make_col(BL_UINT32, G + 1, false);
+    PLB_CUDA(cudaMemcpyAsync(out_offsets.values->p, outv[0].values->p, (size_t)G * 4, cudaMemcpyDeviceToDevice, ctx().stream));
+    const uint32_t n32 = (uint32_t)n;
+    PLB_CUDA(cudaMemcpyAsync((char*)out_offsets.values->p + (size_t)G * 4, &n32, 4, cudaMemcpyHostToDevice, ctx().stream));
+    PLB_CUDA(cudaStreamSynchronize(ctx().stream));      // n32 lives on this frame
+}
+
 }  // namespace plb

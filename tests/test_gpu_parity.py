@@ -352,6 +352,23 @@ def test_group_by_skewed_keys(plb, monkeypatch, hot):
             assert_close(v, ev, m, em, kind)
 
 
+@pytest.mark.parametrize("n,k,nulls,dtype", [(0, 1, False, np.int64), (1, 1, False, np.int64), (33, 4, True, np.int64), (5000, 37, True, np.float64),
+                                             (200_000, 5000, True, np.int64), (300_001, 250_000, False, np.int32), (1_000_000, 3, False, np.uint64)])
+def test_group_tuples_vs_oracle(plb, n, k, nulls, dtype):
+    # GroupsIdx{first, all} with sorted = true (hashing.rs:41-63,116-167): bit-exact first / offsets / index lists
+    rng = np.random.default_rng(n + k)
+    key = rng.integers(0, k, n).astype(dtype)
+    if n > 10 and np.dtype(dtype).kind == "f":
+        key[::7] = np.nan; key[1::11] = -0.0; key[2::11] = 0.0
+    kvalid = (rng.random(n) > 0.1) if nulls else None
+    g = oracle.group_by(key, kvalid, 4, True)
+    first, offsets, all_ = plb.group_tuples(plb.Column(key, kvalid))
+    assert first.dtype == np.uint32 and offsets.dtype == np.uint32 and all_.dtype == np.uint32
+    assert np.array_equal(first, g.first)
+    assert np.array_equal(offsets.astype(np.uint64), g.offsets)
+    assert np.array_equal(all_, g.idx)
+
+
 def test_group_by_streaming_and_partials(plb):
     # streaming consume == one shot; export -> merge of partial aggregates == single table
     rng = np.random.default_rng(12)
