@@ -173,6 +173,16 @@ bl_status bl_hash_join(const bl_column* left_key, int32_t n_left_chunks, const b
                        int32_t how, int32_t nulls_equal, int32_t maintain_order, int32_t out_location,
                        bl_column* out_left_idx, bl_column* out_right_idx);
 
+/* Join + materialisation (_finish_join, polars-ops/src/frame/join/general.rs:17-49; JoinExec,
+ * polars-mem-engine/src/executors/join.rs:39-120): bl_hash_join on the key columns followed by one K4
+ * gather per side, the tuples never leaving the device.  out_left_cols[i] = left_cols[i] taken at the left
+ * idx, out_right_cols[j] = right_cols[j] taken at the right idx (left join: unmatched rows are null).
+ * Column naming (the `_right` suffix, dropping the right key) is the caller's metadata.  One chunk per column. */
+bl_status bl_join(const bl_column* left_key, const bl_column* right_key,
+                  const bl_column* left_cols, int32_t n_left_cols, const bl_column* right_cols, int32_t n_right_cols,
+                  int32_t how, int32_t nulls_equal, int32_t maintain_order, int32_t out_location,
+                  bl_column* out_left_cols, bl_column* out_right_cols);
+
 /* ---- K6: radix hash partition (multi-GPU exchange step) --------------------------------- */
 /* partition id = hash_to_partition(dirty_hash(key), n_partitions)
  *              = ((key * 0x55fbfd6bfc5458e9 mod 2^64) * n_partitions) >> 64   (hashing.rs:62-69,132-142),

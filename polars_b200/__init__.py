@@ -396,6 +396,20 @@ def hash_join(left_key, right_key, how: str = "inner", nulls_equal: bool = False
     return res[0], res[1]
 
 
+def join(left_key, right_key, left_cols: Sequence, right_cols: Sequence, how: str = "inner", nulls_equal: bool = False,
+         maintain_order: str = "none", location: int = HOST):
+    """hash_join + gather of both sides on the device (the reference's _finish_join).  Returns
+    (left outputs, right outputs), each a list like `gather` returns."""
+    lk, rk = _as_col(left_key), _as_col(right_key)
+    lc, rc = [_as_col(c) for c in left_cols], [_as_col(c) for c in right_cols]
+    lks, rks = lk.struct(), rk.struct()
+    la, ra = (_col_array(lc) if lc else None), (_col_array(rc) if rc else None)
+    lo, ro = (BlColumn * max(len(lc), 1))(), (BlColumn * max(len(rc), 1))()
+    _check(lib().bl_join(C.byref(lks), C.byref(rks), la, C.c_int32(len(lc)), ra, C.c_int32(len(rc)), C.c_int32(JOINS[how]), C.c_int32(int(nulls_equal)),
+                         C.c_int32(ORDERS[maintain_order]), C.c_int32(location), lo, ro))
+    return _finish(list(lo)[:len(lc)], location), _finish(list(ro)[:len(rc)], location)
+
+
 def hash_partition(key, payload: Sequence, n_partitions: int, location: int = HOST):
     k = _as_col(key)
     ps = [_as_col(p) for p in payload]

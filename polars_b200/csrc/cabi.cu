@@ -137,12 +137,22 @@ bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, cons
         return BL_OK;
     }
     key = import_column(key_chunks, n_key_chunks);
+    // 8/16-bit integers: keys are grouped on their zero-extended bit pattern, value columns aggregate as Int64
+    // (series/implementations/mod.rs:145-154); key / min / max outputs are narrowed back below
+    const int key_in_dtype = key.dtype;
+    if (dtype_is_small_int(key_in_dtype)) key = op_cast_small_int(key, BL_UINT32, true);
+    std::vector<int> val_in_dtype(n_aggs, -1);
     // aggregations over the same chunk list share one device copy
     for (int i = 0; i < n_aggs; i++) {
         if (aggs[i].kind == BL_AGG_LEN) { dts.push_back(BL_INT64); continue; }
         int dup = -1;
         for (int j = 0; j < i; j++) if (aggs[j].kind != BL_AGG_LEN && same_col(aggs[j], aggs[i])) { dup = j; break; }
-        if (dup >= 0) vals[i] = vals[dup]; else vals[i] = import_column(aggs[i].values, aggs[i].n_chunks);
+        if (dup >= 0) { vals[i] = vals[dup]; val_in_dtype[i] = val_in_dtype[dup]; }
+        else {
+            vals[i] = import_column(aggs[i].values, aggs[i].n_chunks);
+            val_in_dtype[i] = vals[i].dtype;
+            if (dtype_is_small_int(vals[i].dtype)) vals[i] = op_cast_small_int(vals[i], BL_INT64, false);
+        }
         vptr[i] = &vals[i];
         dts.push_back(vals[i].dtype);
     }
@@ -151,6 +161,9 @@ bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, cons
     st.consume_all(key, vptr);
     DevCol ok; std::vector<DevCol> oa;
     st.finish(maintain_order != 0, &key, ok, oa);
+    if (dtype_is_small_int(key_in_dtype)) ok = op_cast_small_int(ok, key_in_dtype, true);
+    for (int i = 0; i < n_aggs; i++)
+        if ((aggs[i].kind == BL_AGG_MIN || aggs[i].kind == BL_AGG_MAX) && dtype_is_small_int(val_in_dtype[i])) oa[i] = op_cast_small_int(oa[i], val_in_dtype[i], false);
     { std::vector<DevCol> all{ok}; all.insert(all.end(), oa.begin(), oa.end());
       std::vector<bl_column> t(all.size()); export_many(all, out_location, t.data());
       *out_key = t[0]; for (int i = 0; i < n_aggs; i++) out_aggs[i] = t[i + 1]; }
@@ -161,6 +174,7 @@ bl_status bl_group_tuples(const bl_column* key_chunks, int32_t n_key_chunks, int
     BL_TRY
     PLB_REQUIRE(key_chunks && n_key_chunks >= 1 && out_first && out_offsets && out_all, BL_ERR_INVALID, "group_tuples: null argument");
     DevCol key = import_column(key_chunks, n_key_chunks);
+    if (dtype_is_small_int(key.dtype)) key = op_cast_small_int(key, BL_UINT32, true);
     DevCol first, offsets, all;
     op_group_tuples(key, first, offsets, all);
     { std::vector<DevCol> cols{first, offsets, all}; bl_column t[3]; export_many(cols, out_location, t); *out_first = t[0]; *out_offsets = t[1]; *out_all = t[2]; }
@@ -173,10 +187,36 @@ bl_status bl_hash_join(const bl_column* left_key, int32_t n_left_chunks, const b
     PLB_REQUIRE(left_key && right_key && out_left_idx && out_right_idx, BL_ERR_INVALID, "hash_join: null argument");
     PLB_REQUIRE(maintain_order >= BL_ORDER_NONE && maintain_order <= BL_ORDER_RIGHT_LEFT, BL_ERR_INVALID, "hash_join: unknown maintain_order");
     DevCol l = import_column(left_key, n_left_chunks), r = import_column(right_key, n_right_chunks);
+    PLB_REQUIRE(l.dtype == r.dtype, BL_ERR_DTYPE, "hash_join: key dtypes differ");
+    if (dtype_is_small_int(l.dtype)) { l = op_cast_small_int(l, BL_UINT32, true); r = op_cast_small_int(r, BL_UINT32, true); }
     trace_point("cabi:join imported");
     JoinResult jr = op_hash_join(l, r, how, nulls_equal != 0, maintain_order);
     { std::vector<DevCol> both{jr.left, jr.right}; bl_column t[2]; export_many(both, out_location, t); *out_left_idx = t[0]; *out_right_idx = t[1]; }
     trace_point("cabi:join exported");
+    BL_CATCH
+}
+
+bl_status bl_join(const bl_column* left_key, const bl_column* right_key, const bl_column* left_cols, int32_t n_left_cols, const bl_column* right_cols, int32_t n_right_cols,
+                  int32_t how, int32_t nulls_equal, int32_t maintain_order, int32_t out_location, bl_column* out_left_cols, bl_column* out_right_cols) {
+    BL_TRY
+    PLB_REQUIRE(left_key && right_key, BL_ERR_INVALID, "join: null key");
+    PLB_REQUIRE((n_left_cols == 0 || (left_cols && out_left_cols)) && (n_right_cols == 0 || (right_cols && out_right_cols)) && n_left_cols >= 0 && n_right_cols >= 0, BL_ERR_INVALID, "join: null payload / output");
+    PLB_REQUIRE(maintain_order >= BL_ORDER_NONE && maintain_order <= BL_ORDER_RIGHT_LEFT, BL_ERR_INVALID, "join: unknown maintain_order");
+    DevCol l = import_column(left_key, 1), r = import_column(right_key, 1);
+    PLB_REQUIRE(l.dtype == r.dtype, BL_ERR_DTYPE, "join: key dtypes differ");
+    if (dtype_is_small_int(l.dtype)) { l = op_cast_small_int(l, BL_UINT32, true); r = op_cast_small_int(r, BL_UINT32, true); }
+    std::vector<DevCol> lin, rin, lout, rout;
+    for (int i = 0; i < n_left_cols; i++) { lin.push_back(import_column(&left_cols[i], 1)); PLB_REQUIRE(lin.back().len == l.len, BL_ERR_INVALID, "join: left payload length differs from the key"); }
+    for (int i = 0; i < n_right_cols; i++) { rin.push_back(import_column(&right_cols[i], 1)); PLB_REQUIRE(rin.back().len == r.len, BL_ERR_INVALID, "join: right payload length differs from the key"); }
+    // tuples stay on the device: _finish_join (join/general.rs:17-49) = one gather per side
+    JoinResult jr = op_hash_join(l, r, how, nulls_equal != 0, maintain_order);
+    if (!lin.empty()) op_gather(lin, jr.left, false, lout);
+    if (!rin.empty()) op_gather(rin, jr.right, false, rout);
+    std::vector<DevCol> all(lout); all.insert(all.end(), rout.begin(), rout.end());
+    std::vector<bl_column> t(all.size());
+    if (!all.empty()) export_many(all, out_location, t.data());
+    for (int i = 0; i < n_left_cols; i++) out_left_cols[i] = t[i];
+    for (int i = 0; i < n_right_cols; i++) out_right_cols[i] = t[n_left_cols + i];
     BL_CATCH
 }
 

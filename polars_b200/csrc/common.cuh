@@ -151,6 +151,8 @@ DevCol op_compare(int op, const DevCol& lhs, const DevCol& rhs, bool missing);
 void op_filter(const std::vector<DevCol>& cols, const DevCol& mask, std::vector<DevCol>& outs);
 DevCol op_cmp_scalar_mask(const DevCol& col, int cmp_op, const DevCol& scalar);
 void op_gather(const std::vector<DevCol>& cols, const DevCol& idx, bool check_bounds, std::vector<DevCol>& outs);
+bool dtype_is_small_int(int dt);
+DevCol op_cast_small_int(const DevCol& in, int to_dtype, bool bits);
 void op_group_tuples(const DevCol& key, DevCol& out_first, DevCol& out_offsets, DevCol& out_all);
 DevPtr bitmap_and(const uint32_t* a, const uint32_t* b, const uint32_t* c, int64_t bits);
 int64_t bitmap_popcount(const uint32_t* bm, int64_t bits);

@@ -385,4 +385,42 @@ DevCol op_cmp_scalar_mask(const DevCol& col, int cmp_op, const DevCol& scalar) {
     return m;
 }
 
+// ---------------------------------------------------------------------------- small-integer casts
+// The reference aggregates Int8/16 and UInt8/16 columns after a cast to Int64
+// (polars-core/src/series/implementations/mod.rs:145-154) and groups / joins integer keys on their
+// zero-extended bit representation (into_groups.rs:178-185 `to_bit_repr`).  The hot kernels only
+// take 4- and 8-byte elements, so the operator entry points widen such columns first and narrow
+// key / min / max outputs back (truncation restores the original bit pattern exactly).
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) k_cast_int(const S* __restrict__ in, D* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (D)in[i];
+}
+template <typename S, typename D> static void launch_cast(const DevCol& in, DevCol& out) {
+    if (in.len > 0) PLB_LAUNCH("k1_cast_int", (k_cast_int<S, D>), grid_for(in.len, 256, 16), 256, 0, reinterpret_cast<const S*>(in.v()), reinterpret_cast<D*>(out.values->p), in.len);
+}
+bool dtype_is_small_int(int dt) { return dt == BL_INT8 || dt == BL_INT16 || dt == BL_UINT8 || dt == BL_UINT16; }
+
+// small int -> BL_UINT32 (`bits`: zero-extended bit pattern, for keys) or BL_INT64 (numeric value, for
+// aggregated columns); BL_UINT32 / BL_INT64 -> small int (truncation).  The validity bitmap is shared.
+DevCol op_cast_small_int(const DevCol& in, int to_dtype, bool bits) {
+    DevCol out = make_col(to_dtype, in.len, false);
+    out.validity = in.validity; out.null_count = in.null_count;
+    const int from = in.dtype;
+    if (to_dtype == BL_UINT32 && bits) {
+        if (dtype_size(from) == 1) launch_cast<uint8_t, uint32_t>(in, out); else launch_cast<uint16_t, uint32_t>(in, out);
+    } else if (to_dtype == BL_INT64 && dtype_is_small_int(from)) {
+        switch (from) {
+            case BL_INT8: launch_cast<int8_t, int64_t>(in, out); break;
+            case BL_INT16: launch_cast<int16_t, int64_t>(in, out); break;
+            case BL_UINT8: launch_cast<uint8_t, int64_t>(in, out); break;
+            default: launch_cast<uint16_t, int64_t>(in, out); break;
+        }
+    } else if (from == BL_UINT32 && dtype_is_small_int(to_dtype)) {
+        if (dtype_size(to_dtype) == 1) launch_cast<uint32_t, uint8_t>(in, out); else launch_cast<uint32_t, uint16_t>(in, out);
+    } else if (from == BL_INT64 && dtype_is_small_int(to_dtype)) {
+        if (dtype_size(to_dtype) == 1) launch_cast<int64_t, uint8_t>(in, out); else launch_cast<int64_t, uint16_t>(in, out);
+    } else fail(BL_ERR_UNSUPPORTED, std::string("cast ") + dtype_name(from) + " -> " + dtype_name(to_dtype) + " is outside the hot path");
+    return out;
+}
+
 }  // namespace plb

@@ -232,6 +232,196 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
     }
 }
 
+__device__ __forceinline__ void gb_merge_row(const GbLayout& L, const GbTableDev& T, const uint64_t* src, int meta, int64_t sws = 1);
+
+// ---------------------------------------------------------------------------- K5, heavy-hitter variant
+// Skewed keys: all rows of a hot key hit ONE entry, and same-address L2 atomics retire serially
+// (~4.6 ns each on B200: Zipf(1.1) keys cost 44 ms per 1e8 rows in k_gb_consume against 2.0 ms for
+// uniform keys).  Here the keys the sample flagged as heavy hitters (plus the null / GB_EMPTY key
+// groups when those are frequent) never touch the global table row by row: a warp groups its lanes
+// by hot key (__match_any_sync), reduces each group with shuffles and lets the group's first lane
+// update a WARP-PRIVATE accumulator row in shared memory with plain loads/stores — no atomics at
+// all.  The rows are merged into the global table once per warp at the end.  Cold keys take the
+// same path as in k_gb_consume.
+__device__ __forceinline__ uint64_t hot_contrib(int op, int dtype, uint64_t raw, bool valid) {
+    switch (op) {
+        case W_ADD_INT: return valid ? raw_to_int(dtype, raw) : 0ull;
+        case W_ADD_F64: return valid ? (uint64_t)__double_as_longlong(raw_to_f64(dtype, raw)) : 0ull;
+        case W_MIN_S64: case W_MAX_S64: return valid ? raw_to_int(dtype, raw) : word_identity(op);
+        case W_MIN_U64: case W_MAX_U64: return valid ? raw : word_identity(op);
+        case W_MIN_F64: case W_MAX_F64: { const double f = raw_to_f64(dtype, raw); return (valid && f == f) ? (uint64_t)f64_to_ordered(f) : word_identity(op); }
+        default: return valid ? 0ull : 1ull;   // W_NULLCNT
+    }
+}
+__device__ __forceinline__ uint64_t hot_combine(int op, uint64_t a, uint64_t b) {
+    switch (op) {
+        case W_ADD_F64: return (uint64_t)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)b));
+        case W_MIN_S64: return (long long)a < (long long)b ? a : b;
+        case W_MAX_S64: return (long long)a > (long long)b ? a : b;
+        case W_MIN_U64: case W_MIN_F64: return a < b ? a : b;
+        case W_MAX_U64: case W_MAX_F64: return a > b ? a : b;
+        default: return a + b;                  // W_ADD_INT, W_NULLCNT
+    }
+}
+// reduction over the lanes of `peers` (every lane of the group calls this with the same mask)
+__device__ __forceinline__ uint64_t hot_group_reduce(int op, unsigned peers, uint64_t v) {
+    unsigned m = peers;
+    int src = __ffs(m) - 1;
+    uint64_t acc = __shfl_sync(peers, (unsigned long long)v, src);
+    for (m &= m - 1; m; m &= m - 1) {
+        src = __ffs(m) - 1;
+        acc = hot_combine(op, acc, __shfl_sync(peers, (unsigned long long)v, src));
+    }
+    return acc;
+}
+
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC>
+__global__ void __launch_bounds__(256) k_gb_consume_hot(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const __grid_constant__ GbBatch B, const __grid_constant__ GbHotDev H) {
+    // shared memory: [GB_HOT_SLOTS lookup keys][8 warps x H.rows x row_words accumulator rows][GB_HOT_SLOTS dense row indices]
+    // accumulator row = [key, len | first << 32, words...]: the source-row format of gb_merge_row
+    extern __shared__ uint64_t hot_smem[];
+    const int row_words = 2 + L.n_words;
+    uint64_t* const s_keys = hot_smem;
+    uint64_t* const s_acc = hot_smem + GB_HOT_SLOTS;
+    uint8_t* const s_idx = reinterpret_cast<uint8_t*>(s_acc + 8 * H.rows * row_words);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < GB_HOT_SLOTS; i += blockDim.x) { s_keys[i] = H.keys[i]; s_idx[i] = H.idx[i]; }
+    for (int i = threadIdx.x; i < 8 * H.rows * row_words; i += blockDim.x) {
+        const int w = i % row_words;
+        s_acc[i] = w == 0 ? 0ull : (w == 1 ? GB_W1_INIT : L.init[w - 2]);
+    }
+    __syncthreads();
+    uint64_t* const wacc = s_acc + warp * H.rows * row_words;
+    const int64_t npairs = B.n >> 1;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    const int khint = T.hint & 2;
+    int iter = 0;
+    // warp-uniform trip count: the hot path is warp-collective
+    for (int64_t pb = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); pb < npairs; pb += gstride) {
+        if (((iter++) & 15) == 0) {
+            const int st = *reinterpret_cast<volatile int*>(T.status);
+            if (__any_sync(0xffffffffu, st != 0)) break;
+        }
+        const int64_t p = pb + lane;
+        const bool in = p < npairs;
+        uint64_t kraw[2] = {0, 0};
+        uint64_t raw[MAXC][2];
+        if (in) {
+            if (KEY_ELEM == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(B.keys) + 2 * p); kraw[0] = t.x; kraw[1] = t.y; }
+            else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(B.keys) + 2 * p); kraw[0] = t.x; kraw[1] = t.y; }
+#pragma unroll
+            for (int c = 0; c < MAXC; c++) {
+                if (c < L.n_cols) {
+                    if (B.cols[c].elem == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(B.cols[c].values) + 2 * p); raw[c][0] = t.x; raw[c][1] = t.y; }
+                    else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(B.cols[c].values) + 2 * p); raw[c][0] = t.x; raw[c][1] = t.y; }
+                }
+            }
+        }
+        uint64_t key[2], slot[2], k0[2];
+        int kind[2], hidx[2];   // kind: 0 regular, 1 null-key group, 2 GB_EMPTY-key group, -1 no row;  hidx: accumulator row or -1 (cold)
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            kind[r] = -1; hidx[r] = -1; key[r] = 0; slot[r] = 0; k0[r] = 0;
+            if (in) {
+                const int64_t row = 2 * p + r;
+                bool kvalid = true;
+                if (KEY_NULLS) kvalid = bit_get(B.key_validity, row);
+                key[r] = canon_key<KEY_CANON>(kraw[r]);
+                kind[r] = !kvalid ? 1 : (key[r] == GB_EMPTY ? 2 : 0);
+                const uint64_t hsh = dirty_hash(key[r]);
+                if (T.pass_bits && (kind[r] == 0 ? (int)(hsh >> (64 - T.pass_bits)) != T.pass_id : T.pass_id != 0)) kind[r] = -1;
+                if (kind[r] == 0) {
+                    unsigned hs = (unsigned)(hsh >> (64 - GB_HOT_BITS));
+                    for (;;) {
+                        const uint64_t hk = s_keys[hs];
+                        if (hk == key[r]) { hidx[r] = (int)s_idx[hs]; break; }
+                        if (hk == GB_EMPTY) break;
+                        hs = (hs + 1) & (GB_HOT_SLOTS - 1);
+                    }
+                    if (hidx[r] < 0) { slot[r] = hsh >> T.shift; k0[r] = tbl_load(T.entries + slot[r] * T.es, 0, khint); }
+                } else if (kind[r] == 1) { if (H.null_hot) hidx[r] = H.n_hot; }
+                else if (kind[r] == 2) { if (H.empty_hot) hidx[r] = H.n_hot + 1; }
+            }
+        }
+        // hot rows: group lanes by accumulator row, reduce, first lane of the group updates the warp's row
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            if (__ballot_sync(0xffffffffu, hidx[r] >= 0) == 0) continue;      // warp-uniform
+            const unsigned peers = __match_any_sync(0xffffffffu, hidx[r]);
+            if (hidx[r] >= 0) {
+                const bool lead = lane == __ffs(peers) - 1;
+                uint64_t* const arow = wacc + hidx[r] * row_words;
+                const int64_t row = 2 * p + r;
+                if (lead) {
+                    const uint64_t w1 = arow[1];
+                    const uint32_t len = (uint32_t)w1 + (uint32_t)__popc(peers);
+                    uint32_t first = (uint32_t)(w1 >> 32);
+                    // lanes hold ascending rows: the group's first lane owns its smallest row
+                    if (L.need_first) first = min(first, B.row_base + (uint32_t)row);
+                    arow[0] = key[r];
+                    arow[1] = ((uint64_t)first << 32) | len;
+                }
+#pragma unroll
+                for (int c = 0; c < MAXC; c++) {
+                    if (c < L.n_cols) {
+                        const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
+                        const int dt = B.cols[c].dtype;
+                        for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) {
+                            const int op = L.wop[k];
+                            const uint64_t tot = hot_group_reduce(op, peers, hot_contrib(op, dt, raw[c][r], valid));
+                            if (lead) { uint64_t* a = arow + 2 + L.wslot[k]; *a = hot_combine(op, *a, tot); }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // cold rows: the global table, as in k_gb_consume
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            if (kind[r] < 0 || hidx[r] >= 0) continue;
+            uint64_t* e = kind[r] == 0 ? gb_resolve(T, key[r], slot[r], k0[r], 0, khint) : gb_special(T, kind[r] - 1);
+            if (e == nullptr) continue;
+            const int64_t row = 2 * p + r;
+            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + T.ws), 1u);
+            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + T.ws) + 1, B.row_base + (uint32_t)row);
+#pragma unroll
+            for (int c = 0; c < MAXC; c++) {
+                if (c < L.n_cols) {
+                    const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
+                    const int dt = B.cols[c].dtype;
+                    for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + (2 + L.wslot[k]) * T.ws, dt, raw[c][r], valid);
+                }
+            }
+        }
+    }
+    // odd tail row: straight to the global table
+    if ((B.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t row = B.n - 1;
+        bool kvalid = B.key_validity == nullptr || bit_get(B.key_validity, row);
+        uint64_t key = load_key_rt(B.keys, B.key_dtype, row);
+        const bool regular = kvalid && key != GB_EMPTY;
+        const bool mine = !T.pass_bits || (regular ? (int)(dirty_hash(key) >> (64 - T.pass_bits)) == T.pass_id : T.pass_id == 0);
+        uint64_t* e = !mine ? nullptr : (!kvalid ? gb_special(T, 0) : (key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key)));
+        if (e) {
+            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + T.ws), 1u);
+            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + T.ws) + 1, B.row_base + (uint32_t)row);
+            for (int c = 0; c < L.n_cols; c++) {
+                const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
+                uint64_t raw = B.cols[c].elem == 8 ? reinterpret_cast<const uint64_t*>(B.cols[c].values)[row] : (uint64_t)reinterpret_cast<const uint32_t*>(B.cols[c].values)[row];
+                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + (2 + L.wslot[k]) * T.ws, B.cols[c].dtype, raw, valid);
+            }
+        }
+    }
+    // merge the warp's accumulator rows into the global table (rows no lane touched keep len == 0)
+    __syncwarp();
+    for (int h = lane; h < H.rows; h += 32) {
+        const uint64_t* arow = wacc + h * row_words;
+        if ((uint32_t)arow[1] == 0) continue;
+        gb_merge_row(L, T, arow, h == H.n_hot ? 1 : (h == H.n_hot + 1 ? 2 : 0));
+    }
+}
+
 // word w of entry s lives at entries[s * es + w * ws]: AoS (es = stride, ws = 1) or word-major planes (es = 1, ws = n_entries)
 __global__ void k_gb_init(uint64_t* entries, int64_t n_entries, int stride, int soa, const __grid_constant__ GbLayout L) {
     const int64_t total = n_entries * stride;
@@ -247,14 +437,16 @@ __global__ void k_gb_init(uint64_t* entries, int64_t n_entries, int stride, int 
 // stats[0] = distinct keys, stats[3] = sampled rows whose successor row carries the same key
 // (collision rate of neighbouring rows: skew / sortedness); stats[1], stats[2] are filled by
 // k_gb_estimate_stats (keys seen exactly once / exactly twice in the sample).
-struct GbSampleStats { unsigned distinct, f1, f2, adjacent; };
+constexpr int GB_CAND_MAX = 1024;
+struct GbSampleStats { unsigned distinct, f1, f2, adjacent, nulls, empties, n_cand, pad; };
+struct GbCandidate { uint64_t key; uint64_t mult; };
 __global__ void k_gb_estimate(const void* keys, const uint32_t* key_validity, int key_dtype, int64_t n, int64_t m, uint64_t* scratch, unsigned* mult, uint64_t cap, int shift, GbSampleStats* stats) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t row = (int64_t)(((unsigned __int128)i * (unsigned __int128)n) / (unsigned __int128)m);
-        bool ins = false, adj = false;
+        bool ins = false, adj = false, isnull = false, isempty = false;
         if (key_validity == nullptr || bit_get(key_validity, row)) {
             uint64_t key = load_key_rt(keys, key_dtype, row);
-            adj = row + 1 < n && load_key_rt(keys, key_dtype, row + 1) == key;
+            adj = row + 1 < n && load_key_rt(keys, key_dtype, row + 1) == key && (key_validity == nullptr || bit_get(key_validity, row + 1));
             if (key != GB_EMPTY) {
                 uint64_t slot = dirty_hash(key) >> shift;
                 for (int pr = 0; pr < (int)cap; pr++) {
@@ -266,21 +458,31 @@ __global__ void k_gb_estimate(const void* keys, const uint32_t* key_validity, in
                     if (k == key) { atomicAdd(mult + slot, 1u); break; }
                     slot = (slot + 1) & (cap - 1);
                 }
-            }
+            } else isempty = true;
+        } else {
+            isnull = true;
+            adj = row + 1 < n && !bit_get(key_validity, row + 1);
         }
         unsigned act = __activemask();
-        unsigned b = __ballot_sync(act, ins), a = __ballot_sync(act, adj);
+        unsigned b = __ballot_sync(act, ins), a = __ballot_sync(act, adj), bn = __ballot_sync(act, isnull), be = __ballot_sync(act, isempty);
         if (lane_id() == (unsigned)(__ffs(act) - 1)) {
             if (b) atomicAdd(&stats->distinct, (unsigned)__popc(b));
             if (a) atomicAdd(&stats->adjacent, (unsigned)__popc(a));
+            if (bn) atomicAdd(&stats->nulls, (unsigned)__popc(bn));
+            if (be) atomicAdd(&stats->empties, (unsigned)__popc(be));
         }
     }
 }
-__global__ void k_gb_estimate_stats(const unsigned* mult, int64_t cap, GbSampleStats* stats) {
+// f1 / f2 (keys sampled exactly once / twice) and the heavy-hitter candidates (multiplicity >= hot_thr)
+__global__ void k_gb_estimate_stats(const uint64_t* scratch, const unsigned* mult, int64_t cap, unsigned hot_thr, GbSampleStats* stats, GbCandidate* cand) {
     unsigned f1 = 0, f2 = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
         const unsigned c = mult[i];
         f1 += c == 1; f2 += c == 2;
+        if (c >= hot_thr) {
+            const unsigned at = atomicAdd(&stats->n_cand, 1u);
+            if (at < GB_CAND_MAX) { cand[at].key = scratch[i]; cand[at].mult = c; }
+        }
     }
     f1 = __reduce_add_sync(0xffffffffu, f1); f2 = __reduce_add_sync(0xffffffffu, f2);
     if (lane_id() == 0) { if (f1) atomicAdd(&stats->f1, f1); if (f2) atomicAdd(&stats->f2, f2); }
@@ -293,7 +495,7 @@ __global__ void k_fill_u64(uint64_t* p, uint64_t v, int64_t n) {
 // rows: n_rows x row_words.  table_mode: rows are the slots of another table (stride = row_words,
 // special slots at src_cap, src_cap+1); else exported partial rows whose last word is meta
 // (0 normal, 1 null-key group, 2 GB_EMPTY-key group).
-__device__ __forceinline__ void gb_merge_row(const GbLayout& L, const GbTableDev& T, const uint64_t* src, int meta, int64_t sws = 1) {
+__device__ __forceinline__ void gb_merge_row(const GbLayout& L, const GbTableDev& T, const uint64_t* src, int meta, int64_t sws) {
     uint64_t* e = meta == 1 ? gb_special(T, 0) : (meta == 2 ? gb_special(T, 1) : gb_find_or_insert(T, src[0]));
     if (!e) return;
     const uint64_t lf = src[sws];
@@ -735,20 +937,58 @@ static double estimate_groups(double d, double m, double n) {
     return hi;
 }
 
+// Heavy hitters -> device lookup table for k_gb_consume_hot (keys at their hashed slot, dense row index per slot).
+void GroupByState::build_hot_list(const void* cand_v, int n_cand, bool null_hot, bool empty_hot, double m) {
+    const GbCandidate* cand = static_cast<const GbCandidate*>(cand_v);
+    hot = GbHotDev{}; hot_share = 0; hot_buf.reset();
+    const int on = [] { const char* e = getenv("BL_K5_HOTKEYS"); return e ? atoi(e) : 1; }();
+    if (!on || (n_cand <= 0 && !null_hot && !empty_hot)) return;
+    std::vector<GbCandidate> c(cand, cand + std::max(n_cand, 0));
+    std::sort(c.begin(), c.end(), [](const GbCandidate& a, const GbCandidate& b) { return a.mult > b.mult || (a.mult == b.mult && a.key < b.key); });
+    const int row_words = 2 + L.n_words;
+    int n_hot = std::min<int>((int)c.size(), std::min(GB_HOT_MAX, 512 / row_words - 2));     // <= 4 KB of accumulator rows per warp
+    if (n_hot < 0) n_hot = 0;
+    if (!c.empty()) hot_share = (double)c[0].mult / m;
+    std::vector<unsigned char> h(GB_HOT_SLOTS * 8 + GB_HOT_SLOTS, 0);
+    uint64_t* hk = reinterpret_cast<uint64_t*>(h.data());
+    unsigned char* hi = h.data() + GB_HOT_SLOTS * 8;
+    for (int i = 0; i < GB_HOT_SLOTS; i++) hk[i] = GB_EMPTY;
+    for (int i = 0; i < n_hot; i++) {
+        unsigned sl = (unsigned)(dirty_hash(c[i].key) >> (64 - GB_HOT_BITS));
+        while (hk[sl] != GB_EMPTY) sl = (sl + 1) & (GB_HOT_SLOTS - 1);
+        hk[sl] = c[i].key; hi[sl] = (unsigned char)i;
+    }
+    hot_buf = dev_alloc(h.size());
+    PLB_CUDA(cudaMemcpyAsync(hot_buf->p, h.data(), h.size(), cudaMemcpyHostToDevice, ctx().stream));
+    PLB_CUDA(cudaStreamSynchronize(ctx().stream));      // `h` lives on this frame
+    hot.keys = as<uint64_t>(hot_buf); hot.idx = reinterpret_cast<const uint8_t*>(hot_buf->p) + GB_HOT_SLOTS * 8;
+    hot.n_hot = n_hot; hot.null_hot = null_hot ? 1 : 0; hot.empty_hot = empty_hot ? 1 : 0; hot.rows = n_hot + 2;
+}
+
 uint64_t GroupByState::choose_cap(const DevCol& key, int64_t n_total) {
     double G, G_raw;
     if (expected_groups > 0) G = G_raw = (double)expected_groups;
     else {
         const int64_t n = key.len, m = std::min<int64_t>(n, 65536);
         const uint64_t scap = 1 << 18;
-        DevPtr scratch = dev_alloc(scap * 8), mult = dev_alloc(scap * 4 + sizeof(GbSampleStats));
+        // one allocation: multiplicities | stats | heavy-hitter candidates (read back with one copy)
+        const size_t tail_bytes = sizeof(GbSampleStats) + sizeof(GbCandidate) * GB_CAND_MAX;
+        DevPtr scratch = dev_alloc(scap * 8), mult = dev_alloc(scap * 4 + tail_bytes);
         GbSampleStats* dstats = reinterpret_cast<GbSampleStats*>(as<unsigned>(mult) + scap);
+        GbCandidate* dcand = reinterpret_cast<GbCandidate*>(dstats + 1);
+        const double nt = (double)std::max<int64_t>(n_total, n);
+        // a key is "hot" when its rows would serialise on one L2 address for >~0.15 ms (~4.6 ns per same-address RED)
+        const double hot_rows = [] { const char* e = getenv("BL_K5_HOT_ROWS"); double v = e ? atof(e) : 30000.0; return v >= 0 ? v : 30000.0; }();
+        const unsigned hot_thr = (unsigned)std::max(12.0, std::ceil(hot_rows * (double)m / nt));
         PLB_LAUNCH("k5_fill", k_fill_u64, grid_for(scap, 256), 256, 0, as<uint64_t>(scratch), GB_EMPTY, (int64_t)scap);
         dev_memset(mult->p, 0, scap * 4 + sizeof(GbSampleStats));
         PLB_LAUNCH("k5_estimate", k_gb_estimate, grid_for(m, 256), 256, 0, key.v(), key.vm(), key.dtype, n, m, as<uint64_t>(scratch), as<unsigned>(mult), scap, 64 - 18, dstats);
-        PLB_LAUNCH("k5_estimate", k_gb_estimate_stats, grid_for(scap, 256), 256, 0, as<unsigned>(mult), (int64_t)scap, dstats);
-        const GbSampleStats st = read_scalar(dstats);
-        const double nt = (double)std::max<int64_t>(n_total, n);
+        PLB_LAUNCH("k5_estimate", k_gb_estimate_stats, grid_for(scap, 256), 256, 0, as<uint64_t>(scratch), as<unsigned>(mult), (int64_t)scap, hot_thr, dstats, dcand);
+        std::vector<unsigned char> hbuf(tail_bytes);
+        PLB_CUDA(cudaMemcpyAsync(hbuf.data(), dstats, tail_bytes, cudaMemcpyDeviceToHost, ctx().stream));
+        PLB_CUDA(cudaStreamSynchronize(ctx().stream));
+        GbSampleStats st; memcpy(&st, hbuf.data(), sizeof st);
+        const GbCandidate* cand = reinterpret_cast<const GbCandidate*>(hbuf.data() + sizeof(GbSampleStats));
         G_raw = estimate_groups((double)st.distinct, (double)m, nt);
         // skewed keys: the uniform inversion collapses onto the hot head of the distribution.  Chao's
         // estimator (distinct + f1^2 / 2 f2, from the keys sampled exactly once / twice) recovers the
@@ -757,10 +997,18 @@ uint64_t GroupByState::choose_cap(const DevCol& key, int64_t n_total) {
             const double chao = (double)st.distinct + (double)st.f1 * ((double)st.f1 - 1.0) / (2.0 * ((double)st.f2 + 1.0));
             if (chao > G_raw) G_raw = chao;
         }
+        // sorted / clustered keys: every group is at least one run of equal neighbours, so groups <= runs
+        // = rows * (1 - P[next row has the same key]) — a strided sample of such data looks all-distinct
         sample_adjacent = m > 0 ? (double)st.adjacent / (double)m : 0.0;
+        if (m < n && sample_adjacent > 0.5) {
+            const double q = 1.0 - sample_adjacent;
+            const double runs = nt * std::min(1.0, q + 3.0 * std::sqrt(q * sample_adjacent / (double)m) + 2.0 / (double)m) + 1.0;
+            if (runs < G_raw) G_raw = runs;
+        }
         G = G_raw * 1.25 + 64;
         if (G > nt) G = nt;
         if (G_raw > nt) G_raw = nt;
+        build_hot_list(cand, (int)std::min<unsigned>(st.n_cand, GB_CAND_MAX), st.nulls >= hot_thr, st.empties >= hot_thr, (double)m);
     }
     est_groups = (int64_t)(G_raw * 1.25) + 2;      // for the shared-memory plan (overflow falls through to the global table)
     static const double lf = [] { const char* e = getenv("BL_K5_LF"); double v = e ? atof(e) / 100.0 : 0.6; return (v > 0.05 && v < 0.95) ? v : 0.6; }();
@@ -785,6 +1033,21 @@ static void launch_consume(const GbLayout& L, const GbTableDev& T, const GbBatch
     static const int pairs = [] { const char* e = getenv("BL_K5_PAIRS"); int v = e ? atoi(e) : 1; return v == 2 ? 2 : 1; }();
     if (pairs == 2) launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 2>(L, T, B, grid);
     else launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 1>(L, T, B, grid);
+}
+
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC>
+static void launch_hot_c(const GbLayout& L, const GbTableDev& T, const GbBatch& B, const GbHotDev& H, int grid) {
+    auto kfn = k_gb_consume_hot<KEY_ELEM, KEY_CANON, KEY_NULLS, MAXC>;
+    const size_t smem = (size_t)GB_HOT_SLOTS * 8 + (size_t)8 * H.rows * (2 + L.n_words) * 8 + GB_HOT_SLOTS;
+    PLB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PLB_LAUNCH("k5_groupby_agg_hot", kfn, grid, 256, smem, L, T, B, H);
+}
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS>
+static void launch_hot(const GbLayout& L, const GbTableDev& T, const GbBatch& B, const GbHotDev& H, int grid) {
+    if (L.n_cols <= 1) launch_hot_c<KEY_ELEM, KEY_CANON, KEY_NULLS, 1>(L, T, B, H, grid);
+    else if (L.n_cols <= 2) launch_hot_c<KEY_ELEM, KEY_CANON, KEY_NULLS, 2>(L, T, B, H, grid);
+    else if (L.n_cols <= 4) launch_hot_c<KEY_ELEM, KEY_CANON, KEY_NULLS, 4>(L, T, B, H, grid);
+    else launch_hot_c<KEY_ELEM, KEY_CANON, KEY_NULLS, 8>(L, T, B, H, grid);
 }
 
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC, bool FAST>
@@ -864,6 +1127,14 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
         // beyond ~72 KB of table per CTA the occupancy loss outweighs the cheaper atomics (measured: 2000 keys)
         if ((size_t)(want + 2) * Lb.stride * 8 <= (size_t)72 * 1024) scap = want;
     }
+    // skewed keys: the CTA-private tables serialise on the hot key's shared-memory address as soon as more than a
+    // few of the CTA's 512 threads work on it (measured: Zipf keys 112 ms); with too few replicas to spread
+    // that load, take the global table + warp-private heavy-hitter rows instead
+    if (scap && hot.rows > 0) {
+        const size_t tab_bytes = ((size_t)(scap + 2) * Lb.stride + 2) * 8;
+        const double copies = (double)std::min<size_t>(32, std::max<size_t>(1, (size_t)(96 * 1024) / tab_bytes));
+        if (hot_share * 512.0 / copies > 4.0) scap = 0;
+    }
     // hot-table mode (experimental knob): run the shared-memory kernel with BL_K5_HOT slots even though the
     // groups do not fit; the first keys a CTA sees (the hot head of a skewed distribution) aggregate in shared
     // memory, everything else falls through to the global table
@@ -881,8 +1152,10 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
         if (pass_bits > 2) pass_bits = 0;
     }
     GbTableDev Tp = T;
+    const bool use_hot = hot.rows > 0;
 #define GB_LAUNCH_ALL(E, C, KN)                                                      \
-    do { for (int h = 0; h < (1 << pass_bits); h++) { Tp.pass_bits = pass_bits; Tp.pass_id = h; launch_consume<E, C, KN>(Lb, Tp, B, grid); } } while (0)
+    do { for (int h = 0; h < (1 << pass_bits); h++) { Tp.pass_bits = pass_bits; Tp.pass_id = h;                                              \
+             if (use_hot) launch_hot<E, C, KN>(Lb, Tp, B, hot, grid); else launch_consume<E, C, KN>(Lb, Tp, B, grid); } } while (0)
 #define GB_DISPATCH(E, C)                                                            \
     do { if (scap) { if (kn) launch_smem<E, C, true>(Lb, T, B, scap); else launch_smem<E, C, false>(Lb, T, B, scap); }                       \
          else if (kn) GB_LAUNCH_ALL(E, C, true); else GB_LAUNCH_ALL(E, C, false); } while (0)

@@ -58,7 +58,7 @@ KATS = {
         {
             "cite": "py-polars/tests/unit/operations/test_group_by.py:689-702 (test_group_by_signed_transmutes)",
             "note": "negative keys keep value + order under maintain_order (median of singletons == the value; we check min/max/mean)",
-            "key": [-1, -2, -3, -4, -5], "key_dtype": "int64", "maintain_order": True,
+            "key": [-1, -2, -3, -4, -5], "key_dtype": "int64", "key_dtypes": ["int8", "int16", "int32", "int64"], "maintain_order": True,
             "aggs": [{"col": [500, 600, 700, 800, 900], "dtype": "int64", "kind": "mean", "expect": [500.0, 600.0, 700.0, 800.0, 900.0]},
                      {"col": [500, 600, 700, 800, 900], "dtype": "int64", "kind": "min", "expect": [500, 600, 700, 800, 900]},
                      {"col": [500, 600, 700, 800, 900], "dtype": "int64", "kind": "max", "expect": [500, 600, 700, 800, 900]}],
@@ -99,7 +99,7 @@ KATS = {
         {
             "cite": "py-polars/tests/unit/operations/test_join.py:131-153 (test_join_negative_integers)",
             "note": "check_row_order=False; expected a=[-6,-1,0] => pairs as a multiset",
-            "left_key": [-1, -6, -3, 0], "right_key": [-6, -1, -4, -2, 0], "key_dtype": "int64", "how": "inner",
+            "left_key": [-1, -6, -3, 0], "right_key": [-6, -1, -4, -2, 0], "key_dtype": "int64", "key_dtypes": ["int8", "int16", "int32", "int64"], "how": "inner",
             "maintain_order": "none", "threads": [1, 4],
             "expect_pairs_sorted": [[0, 1], [1, 0], [3, 4]], "exact_order": False,
         },

@@ -67,6 +67,12 @@ def sort_groups(keys, key_valid, outs):
 
 
 def run_group_by_kat(impl, case):
+    # a KAT the reference runs "for dt in [Int8, Int16, Int32, Int64]" lists those widths in key_dtypes
+    for kdt in case.get("key_dtypes", [case["key_dtype"]]):
+        _run_group_by_kat_one(impl, dict(case, key_dtype=kdt))
+
+
+def _run_group_by_kat_one(impl, case):
     if case.get("generated") == "overflow_mean":
         key = np.array([1, 2] * 50_000, dtype=case["key_dtype"])
         kvalid = None
@@ -90,6 +96,11 @@ def run_group_by_kat(impl, case):
 
 
 def run_join_kat(impl, case, set_threads=None):
+    for kdt in case.get("key_dtypes", [case["key_dtype"]]):
+        _run_join_kat_one(impl, dict(case, key_dtype=kdt), set_threads)
+
+
+def _run_join_kat_one(impl, case, set_threads=None):
     lk, lv = col(case["left_key"], case["key_dtype"])
     rk, rv = col(case["right_key"], case["key_dtype"])
     for t in case.get("threads", [None]):

@@ -279,6 +279,62 @@ def test_group_by_dtypes(plb, key_dtype, val_dtype):
         assert_close(v, ev, m, em, kind)
 
 
+@pytest.mark.parametrize("key_dtype,val_dtype", [("int8", "int8"), ("int16", "uint16"), ("uint8", "int16"), ("uint16", "uint8"), ("int64", "int8")])
+def test_group_by_small_ints(plb, key_dtype, val_dtype):
+    # Int8/16, UInt8/16 value columns aggregate as Int64 (series/implementations/mod.rs:145-154): sum -> Int64,
+    # min/max keep the dtype, mean -> Float64; small integer keys group on their bit pattern (into_groups.rs:178-185)
+    rng = np.random.default_rng(9)
+    n = 30_000
+    ki, vi = np.iinfo(key_dtype), np.iinfo(val_dtype)
+    key = rng.integers(max(ki.min, -60), min(ki.max, 60) + 1, n).astype(key_dtype)
+    val = rng.integers(vi.min, int(vi.max) + 1, n).astype(val_dtype)
+    vvalid = rng.random(n) > 0.1
+    kvalid = rng.random(n) > 0.02
+    aggs = [("sum", val, vvalid), ("mean", val, vvalid), ("min", val, vvalid), ("max", val, vvalid), ("count", val, vvalid), ("len", None, None)]
+    keys, kv, outs = GpuImpl(plb).group_by_agg(key, kvalid, aggs, True)
+    wide = val.astype(np.int64)
+    eaggs = [(k, None if v is None else wide, m) for (k, v, m) in aggs]
+    ek, ekv, eouts, _ = oracle.group_by_agg(key, kvalid, eaggs, 1, True)
+    assert keys.dtype == np.dtype(key_dtype)
+    assert_close(keys, ek, kv, ekv, "keys")
+    exp_dtype = {"sum": np.int64, "mean": np.float64, "min": val_dtype, "max": val_dtype, "count": np.uint32, "len": np.uint32}
+    for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
+        assert v.dtype == np.dtype(exp_dtype[kind]), (kind, v.dtype)
+        assert_close(v, ev.astype(v.dtype), m, em, kind)
+
+
+@pytest.mark.parametrize("how,order", [("inner", "none"), ("inner", "left_right"), ("left", "none"), ("left", "right_left")])
+def test_join_materialised_payloads(plb, how, order):
+    # _finish_join (join/general.rs:17-49): both sides gathered at the join tuples; left-join misses are null rows
+    rng = np.random.default_rng(44)
+    nl, nr = 40_000, 9_000
+    lk, rk = rng.integers(0, 12_000, nl).astype(np.int64), rng.integers(0, 12_000, nr).astype(np.int64)
+    lvalid, rvalid = rng.random(nl) > 0.03, rng.random(nr) > 0.03
+    lp, rp = rng.normal(size=nl), rng.integers(-9, 9, nr).astype(np.int32)
+    rp_valid = rng.random(nr) > 0.2
+    (lo_k, lo_p), (ro_p,) = plb.join(plb.Column(lk, lvalid), plb.Column(rk, rvalid), [plb.Column(lk, lvalid), plb.Column(lp)], [plb.Column(rp, rp_valid)],
+                                     how=how, maintain_order=order)
+    li, ri = oracle.hash_join(lk, rk, lvalid, rvalid, how, False, order, 4)
+    assert np.array_equal(lo_k[0], lk[li]) and np.array_equal(lo_k[1] if lo_k[1] is not None else np.ones(li.size, bool), lvalid[li])
+    assert np.array_equal(lo_p[0].view(np.uint64), lp[li].view(np.uint64))
+    hit = ri != plb.IDX_NULL
+    exp_valid = np.zeros(ri.size, bool); exp_valid[hit] = rp_valid[ri[hit]]
+    got_valid = ro_p[1] if ro_p[1] is not None else np.ones(ri.size, bool)
+    assert np.array_equal(got_valid, exp_valid)
+    assert np.array_equal(ro_p[0][exp_valid], rp[ri[exp_valid]])
+
+
+def test_join_small_int_keys(plb):
+    rng = np.random.default_rng(10)
+    lk = rng.integers(-128, 128, 5000).astype(np.int8)
+    rk = rng.integers(-128, 128, 300).astype(np.int8)
+    lv, rv = rng.random(5000) > 0.05, rng.random(300) > 0.05
+    for how in ("inner", "left"):
+        li, ri = GpuImpl(plb).hash_join(lk, rk, lv, rv, how=how)
+        eli, eri = oracle.hash_join(lk, rk, lv, rv, how, False, "none", 4)
+        assert np.array_equal(li, eli) and np.array_equal(ri, eri)
+
+
 def test_group_by_edge_semantics(plb):
     key = np.array([0, 0, 1, 1, 2, 2, 3, -2**63, -2**63], np.int64)
     vi = np.array([2**62, 2**62, 1, 2, 5, 6, 7, 1, 1], np.int64)
@@ -367,6 +423,62 @@ def test_group_tuples_vs_oracle(plb, n, k, nulls, dtype):
     assert np.array_equal(first, g.first)
     assert np.array_equal(offsets.astype(np.uint64), g.offsets)
     assert np.array_equal(all_, g.idx)
+
+
+def _hot_case(rng, n, kind):
+    """Keys with heavy hitters (warp-private accumulator rows in k_gb_consume_hot), incl. hot null / i64::MIN groups."""
+    if kind == "zipf_i64":
+        key = (rng.zipf(1.1, n) % 50_000).astype(np.int64)
+        key[rng.random(n) < 0.15] = np.iinfo(np.int64).min          # the GB_EMPTY bit pattern as a frequent key
+        kvalid = rng.random(n) > 0.2                                  # frequent null keys
+    elif kind == "f64":
+        key = (rng.zipf(1.3, n) % 1000).astype(np.float64)
+        key[rng.random(n) < 0.1] = np.nan
+        key[rng.random(n) < 0.1] = -0.0
+        key[rng.random(n) < 0.1] = 0.0
+        kvalid = None
+    else:
+        key = (rng.zipf(1.2, n) % 3000).astype(np.int32) - 7
+        kvalid = rng.random(n) > 0.01
+    return key, kvalid
+
+
+@pytest.mark.parametrize("kind", ["zipf_i64", "f64", "i32"])
+@pytest.mark.parametrize("hot_rows", [None, "0"])
+def test_group_by_heavy_hitters(plb, monkeypatch, kind, hot_rows):
+    # hot_rows "0": every key sampled >= 12 times is treated as a heavy hitter (exercises up to 62 rows per warp)
+    if hot_rows is not None:
+        monkeypatch.setenv("BL_K5_HOT_ROWS", hot_rows)
+    rng = np.random.default_rng(77)
+    n = 700_001
+    key, kvalid = _hot_case(rng, n, kind)
+    vi = rng.integers(-1000, 1000, n).astype(np.int32 if kind == "i32" else np.int64)
+    vf = rng.uniform(-50, 100, n).round(6)
+    vf[::97] = np.nan
+    ivalid, fvalid = rng.random(n) > 0.1, rng.random(n) > 0.3
+    aggs = [("sum", vi, ivalid), ("mean", vf, fvalid), ("len", None, None), ("min", vf, fvalid), ("max", vi, ivalid), ("count", vi, ivalid), ("max", vf, None), ("min", vi, None)]
+    for order in (True, False):
+        keys, kv, outs = GpuImpl(plb).group_by_agg(key, kvalid, aggs, order)
+        ek, ekv, eouts, _ = oracle.group_by_agg(key, kvalid, aggs, 4, order)
+        if not order:
+            keys, kv, outs = sort_groups(keys, kv, outs)
+            ek, ekv, eouts = sort_groups(ek, ekv, eouts)
+        assert_close(keys, ek, kv, ekv, "keys")
+        for (k_, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
+            assert_close(v, ev, m, em, k_)
+    # the same keys through the group-tuple path (hot rows carry len/first only) and a streamed two-batch consume
+    g = oracle.group_by(key, kvalid, 4, True)
+    first, offsets, all_ = plb.group_tuples(plb.Column(key, kvalid))
+    assert np.array_equal(first, g.first) and np.array_equal(offsets.astype(np.uint64), g.offsets) and np.array_equal(all_, g.idx)
+    st = plb.GroupBy(key.dtype, [("sum", vi.dtype), ("len", None)], track_first=True)
+    half = n // 2 + 1
+    for a, b in ((0, half), (half, n)):
+        st.consume(plb.Column(key[a:b], None if kvalid is None else kvalid[a:b]), [plb.Column(vi[a:b], ivalid[a:b]), None], row_base=a)
+    (k2, kv2), outs2 = st.finish(maintain_order=True)
+    ek, ekv, eouts, _ = oracle.group_by_agg(key, kvalid, [("sum", vi, ivalid), ("len", None, None)], 4, True)
+    assert_close(k2, ek, kv2, ekv, "stream keys")
+    assert_close(outs2[0][0], eouts[0][0], outs2[0][1], eouts[0][1], "stream sum")
+    assert_close(outs2[1][0], eouts[1][0], outs2[1][1], eouts[1][1], "stream len")
 
 
 def test_group_by_streaming_and_partials(plb):

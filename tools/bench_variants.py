@@ -1,6 +1,6 @@
 """C2 / C3 workload variants of SURVEY.md 8(d) in one process (device-resident inputs, CUDA-event-free wall
 timing around synchronised steps): Zipf(1.1) keys, 5 % nulls, 50 % hit rate, 4 duplicates per build key,
-plus the experimental hot-table knob (BL_K5_HOT) on the skewed keys.  Prints one JSON object per line."""
+with the heavy-hitter path on and off, sorted keys, frequent null keys.  Prints one JSON object per line."""
 import json
 import os
 import sys
@@ -48,12 +48,15 @@ def main():
     del nvi, nvf
     zkey = plb.to_device(bench.gen_groupby(ROWS, KEYS, 1, "zipf")[0])
     timed(gb(zkey, dvi, dvf), "groupby Zipf(1.1) keys", ROWS)
-    for hot in (256, 1024, 2048):
-        os.environ["BL_K5_HOT"] = str(hot)
-        timed(gb(zkey, dvi, dvf), f"groupby Zipf(1.1) keys, hot table {hot} slots/CTA", ROWS, {"BL_K5_HOT": hot})
-    os.environ["BL_K5_HOT"] = "1024"
-    timed(gb(dkey, dvi, dvf), "groupby uniform, hot table 1024 slots/CTA (cost of the detour)", ROWS, {"BL_K5_HOT": 1024})
-    os.environ.pop("BL_K5_HOT")
+    os.environ["BL_K5_HOTKEYS"] = "0"
+    timed(gb(zkey, dvi, dvf), "groupby Zipf(1.1) keys, heavy-hitter rows off (BL_K5_HOTKEYS=0)", ROWS, {"BL_K5_HOTKEYS": 0})
+    os.environ.pop("BL_K5_HOTKEYS")
+    z3 = plb.to_device((np.random.default_rng(5).zipf(1.1, ROWS) % 1000).astype(np.int64))
+    timed(gb(z3, dvi, dvf), "groupby Zipf(1.1) keys folded into 1000 groups", ROWS)
+    del z3
+    nk = plb.to_device(key, np.random.default_rng(6).random(ROWS) >= 0.1)
+    timed(gb(nk, dvi, dvf), "groupby uniform keys, 10% null keys (one hot null group)", ROWS)
+    del nk
     skey = plb.to_device(np.sort(key))
     timed(gb(skey, dvi, dvf), "groupby sorted keys (runs of ~100 equal keys)", ROWS)
     del dkey, dvi, dvf, zkey, skey, key, vi, vf
