@@ -163,12 +163,13 @@ bl_status bl_group_tuples(const bl_column* key_chunks, int32_t n_key_chunks, int
 /* ---- K7/K8: hash join on one numeric key ----------------------------------------------- */
 /* (build_tables single_keys.rs:16-167, probe_inner single_keys_inner.rs:11-149,
  *  hash_join_tuples_left single_keys_left.rs:106-195) */
-enum { BL_JOIN_INNER = 0, BL_JOIN_LEFT = 1 };
+enum { BL_JOIN_INNER = 0, BL_JOIN_LEFT = 1, BL_JOIN_SEMI = 2, BL_JOIN_ANTI = 3 };
 enum { BL_ORDER_NONE = 0, BL_ORDER_LEFT = 1, BL_ORDER_LEFT_RIGHT = 2, BL_ORDER_RIGHT = 3, BL_ORDER_RIGHT_LEFT = 4 };
 /* Returns the join tuples as two UINT32 columns.  BL_ORDER_NONE reproduces the in-memory engine's
  * order (probe = longer relation, tie -> right probes; probe-row order; matches ascending build
  * idx — hash_join/mod.rs:41-50).  Null keys match only if nulls_equal.  Left join: unmatched
- * right idx = BL_IDX_NULL (and a null slot). */
+ * right idx = BL_IDX_NULL (and a null slot).  BL_JOIN_SEMI / BL_JOIN_ANTI (single_keys_semi_anti.rs:41-140):
+ * out_left_idx = the left rows, in row order, with / without a match; out_right_idx is an empty column. */
 bl_status bl_hash_join(const bl_column* left_key, int32_t n_left_chunks, const bl_column* right_key, int32_t n_right_chunks,
                        int32_t how, int32_t nulls_equal, int32_t maintain_order, int32_t out_location,
                        bl_column* out_left_idx, bl_column* out_right_idx);

@@ -232,8 +232,20 @@ def group_by_agg(keys, key_valid, aggs, n_partitions=None, maintain_order=True):
 # ------------------------------------------------------------------ join
 def hash_join(left_keys, right_keys, left_valid=None, right_valid=None, how: str = "inner", nulls_equal: bool = False,
               maintain_order: str = "none", n_threads: int | None = None):
-    """Returns (left_idx u32, right_idx u32); unmatched right idx (left join) = IDX_NULL."""
+    """Returns (left_idx u32, right_idx u32); unmatched right idx (left join) = IDX_NULL.
+    how = "semi" / "anti": (left_idx, empty)."""
     lk, rk = key_bits(left_keys), key_bits(right_keys)
+    if how in ("semi", "anti"):
+        # polars-ops/src/frame/join/hash_join/single_keys_semi_anti.rs:8-140: a hash SET of the right keys (null keys
+        # only when nulls_equal, :27-29); every left row, in row order, is kept when the set holds (semi) / does not
+        # hold (anti) its key.  Restated as set membership on the canonical key bits.
+        lv = np.ones(lk.size, np.bool_) if left_valid is None else np.asarray(left_valid, np.bool_)
+        rv = np.ones(rk.size, np.bool_) if right_valid is None else np.asarray(right_valid, np.bool_)
+        match = lv & np.isin(lk, rk[rv])
+        if nulls_equal and (~rv).any():
+            match |= ~lv
+        idx = np.nonzero(match if how == "semi" else ~match)[0].astype(np.uint32)
+        return idx, np.zeros(0, np.uint32)
     T = n_threads if n_threads is not None else max_threads()
     pl, pr = C.c_void_p(), C.c_void_p()
     m = lib().or_hash_join(_p(lk), _p(_valid(left_valid, lk.size)), C.c_int64(lk.size), _p(rk),

@@ -27,7 +27,7 @@ BOOL = 10
 OPS = {"add": 0, "sub": 1, "mul": 2, "floordiv": 3, "mod": 4, "truediv": 5}
 CMPS = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5}
 AGGS = {"sum": 0, "mean": 1, "min": 2, "max": 3, "count": 4, "len": 5}
-JOINS = {"inner": 0, "left": 1}
+JOINS = {"inner": 0, "left": 1, "semi": 2, "anti": 3}
 ORDERS = {"none": 0, "left": 1, "left_right": 2, "right": 3, "right_left": 4}
 STATUS = {1: "INVALID", 2: "CUDA", 3: "OOM", 4: "UNSUPPORTED", 5: "DTYPE", 6: "BOUNDS"}
 

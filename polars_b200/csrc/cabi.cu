@@ -208,6 +208,7 @@ bl_status bl_join(const bl_column* left_key, const bl_column* right_key, const b
     std::vector<DevCol> lin, rin, lout, rout;
     for (int i = 0; i < n_left_cols; i++) { lin.push_back(import_column(&left_cols[i], 1)); PLB_REQUIRE(lin.back().len == l.len, BL_ERR_INVALID, "join: left payload length differs from the key"); }
     for (int i = 0; i < n_right_cols; i++) { rin.push_back(import_column(&right_cols[i], 1)); PLB_REQUIRE(rin.back().len == r.len, BL_ERR_INVALID, "join: right payload length differs from the key"); }
+    PLB_REQUIRE((how != BL_JOIN_SEMI && how != BL_JOIN_ANTI) || n_right_cols == 0, BL_ERR_INVALID, "join: semi / anti joins produce no right-hand columns");
     // tuples stay on the device: _finish_join (join/general.rs:17-49) = one gather per side
     JoinResult jr = op_hash_join(l, r, how, nulls_equal != 0, maintain_order);
     if (!lin.empty()) op_gather(lin, jr.left, false, lout);

@@ -24,6 +24,7 @@
 // (1 key load + 1 RED per accumulator per row).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -966,7 +967,7 @@ void GroupByState::build_hot_list(const void* cand_v, int n_cand, bool null_hot,
 }
 
 uint64_t GroupByState::choose_cap(const DevCol& key, int64_t n_total) {
-    double G, G_raw;
+    double G, G_raw, G_upper = 0;
     if (expected_groups > 0) G = G_raw = (double)expected_groups;
     else {
         const int64_t n = key.len, m = std::min<int64_t>(n, 65536);
@@ -1008,6 +1009,10 @@ uint64_t GroupByState::choose_cap(const DevCol& key, int64_t n_total) {
         G = G_raw * 1.25 + 64;
         if (G > nt) G = nt;
         if (G_raw > nt) G_raw = nt;
+        // Good-Turing: a fraction f1/m of the rows carries keys the sample has not seen; if every such row were a
+        // new key the table would need distinct + (f1/m) * rows entries.  Heavy-tailed keys sit between the two
+        // (Zipf(1.1): Chao 2.6e5, truth 1e6), so the table takes whatever the L2 budget allows up to that bound.
+        G_upper = std::min(nt, (double)st.distinct + (double)st.f1 / (double)m * nt);
         build_hot_list(cand, (int)std::min<unsigned>(st.n_cand, GB_CAND_MAX), st.nulls >= hot_thr, st.empties >= hot_thr, (double)m);
     }
     est_groups = (int64_t)(G_raw * 1.25) + 2;      // for the shared-memory plan (overflow falls through to the global table)
@@ -1018,6 +1023,12 @@ uint64_t GroupByState::choose_cap(const DevCol& key, int64_t n_total) {
     // word-major key planes (4 keys per sector) stays cheap at higher load factors
     const double l2_budget = 0.55 * (double)ctx().l2_bytes;
     if ((double)c * L.stride * 8 > l2_budget && G_raw / ((double)c / 2) <= 0.8 && c > 1024) c >>= 1;   // an under-estimate costs one restart
+    // spare L2 is free insurance against an under-estimate (load factors 0.15-0.6 run at the same speed; a table at
+    // 95 % load ran 7x slower): grow towards the Good-Turing bound while the table stays inside the L2 budget
+    while (G_upper / lf > (double)c && (double)(2 * c) * L.stride * 8 <= l2_budget) c <<= 1;
+    if (getenv("BL_K5_DEBUG"))
+        fprintf(stderr, "[k5] rows=%lld est_groups=%.0f upper=%.0f cap=%llu (%.1f MB) hot_keys=%d null_hot=%d empty_hot=%d hot_share=%.4f adjacent=%.3f\n", (long long)n_total, G_raw, G_upper,
+                (unsigned long long)c, (double)c * L.stride * 8 / 1e6, hot.n_hot, hot.null_hot, hot.empty_hot, hot_share, sample_adjacent);
     return c;
 }
 

@@ -452,8 +452,45 @@ static void launch_probe(bool kn, int grid, JoinTableDev T, const DevCol& probe,
 
 static DevCol idx_col(DevPtr p, int64_t n, int64_t null_count) { DevCol c; c.dtype = BL_UINT32; c.len = n; c.values = p; c.null_count = null_count; return c; }
 
+// ---------------------------------------------------------------------------- semi / anti
+// hash_join_tuples_left_semi / _anti (polars-ops/src/frame/join/hash_join/single_keys_semi_anti.rs:41-140):
+// the left rows, in row order, that have (semi) / do not have (anti) a key match on the right; a null left key
+// never matches unless nulls_equal.  Derived from the left-join tuples, which already come in left-row order with
+// BL_IDX_NULL for misses: anti keeps the misses, semi the first tuple of every matched left row.
+__global__ void __launch_bounds__(256) k_semi_anti_mask(const uint32_t* __restrict__ li, const uint32_t* __restrict__ ri, int64_t M, int64_t m_round, int anti, uint32_t* __restrict__ mask_words) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m_round; i += (int64_t)gridDim.x * blockDim.x) {
+        bool keep = false;
+        if (i < M) {
+            const bool miss = ri[i] == J_NONE;
+            keep = anti ? miss : (!miss && (i == 0 || li[i] != li[i - 1]));
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        if ((threadIdx.x & 31) == 0) mask_words[i >> 5] = b;
+    }
+}
+
+static JoinResult hash_join_inner_left(const DevCol& left, const DevCol& right, int how, bool nulls_equal, int maintain_order);
+
 JoinResult op_hash_join(const DevCol& left, const DevCol& right, int how, bool nulls_equal, int maintain_order) {
-    PLB_REQUIRE(how == BL_JOIN_INNER || how == BL_JOIN_LEFT, BL_ERR_UNSUPPORTED, "join: only inner and left joins are on the hot path");
+    if (how != BL_JOIN_SEMI && how != BL_JOIN_ANTI) return hash_join_inner_left(left, right, how, nulls_equal, maintain_order);
+    JoinResult lj = hash_join_inner_left(left, right, BL_JOIN_LEFT, nulls_equal, BL_ORDER_NONE);
+    const int64_t M = lj.left.len;
+    JoinResult r;
+    r.right = idx_col(dev_alloc(16), 0, 0);
+    if (M == 0) { r.left = idx_col(dev_alloc(16), 0, 0); return r; }
+    DevCol mask = make_col(BL_BOOL, M, false);
+    const int64_t m_round = (M + 31) / 32 * 32;
+    PLB_LAUNCH("k8_semi_anti_mask", k_semi_anti_mask, grid_for(m_round, 256, 16), 256, 0, as<uint32_t>(lj.left.values), as<uint32_t>(lj.right.values), M, m_round, how == BL_JOIN_ANTI ? 1 : 0,
+               as<uint32_t>(mask.values));
+    DevCol li = idx_col(lj.left.values, M, 0);
+    std::vector<DevCol> in{li}, out;
+    op_filter(in, mask, out);
+    r.left = out[0];
+    return r;
+}
+
+static JoinResult hash_join_inner_left(const DevCol& left, const DevCol& right, int how, bool nulls_equal, int maintain_order) {
+    PLB_REQUIRE(how == BL_JOIN_INNER || how == BL_JOIN_LEFT, BL_ERR_UNSUPPORTED, "join: only inner, left, semi and anti joins are on the hot path");
     PLB_REQUIRE(left.dtype == right.dtype, BL_ERR_DTYPE, std::string("join: key dtypes differ (") + dtype_name(left.dtype) + " vs " + dtype_name(right.dtype) + ")");   // join/mod.rs:231-241
     const int dt = left.dtype;
     PLB_REQUIRE(dt == BL_INT64 || dt == BL_UINT64 || dt == BL_INT32 || dt == BL_UINT32 || dt == BL_FLOAT64 || dt == BL_FLOAT32, BL_ERR_UNSUPPORTED,

@@ -97,6 +97,18 @@ KATS = {
             "expect_left_idx": [0, 1, 2, 3, 4], "expect_right_idx": [N, 0, 1, N, N], "exact_order": True,
         },
         {
+            "cite": "py-polars/tests/unit/operations/test_join.py:29-41 (test_semi_anti_join, anti)",
+            "note": "df_a.key [1,2,3] vs df_b.key [3,4,5,None]: anti keeps rows 0,1 (key 1,2)",
+            "left_key": [1, 2, 3], "right_key": [3, 4, 5, N], "key_dtype": "int64", "how": "anti", "maintain_order": "none",
+            "expect_left_idx": [0, 1], "expect_right_idx": [], "exact_order": True,
+        },
+        {
+            "cite": "py-polars/tests/unit/operations/test_join.py:29-41 (test_semi_anti_join, semi)",
+            "note": "semi keeps row 2 (key 3); the right null key matches nothing",
+            "left_key": [1, 2, 3], "right_key": [3, 4, 5, N], "key_dtype": "int64", "how": "semi", "maintain_order": "none",
+            "expect_left_idx": [2], "expect_right_idx": [], "exact_order": True,
+        },
+        {
             "cite": "py-polars/tests/unit/operations/test_join.py:131-153 (test_join_negative_integers)",
             "note": "check_row_order=False; expected a=[-6,-1,0] => pairs as a multiset",
             "left_key": [-1, -6, -3, 0], "right_key": [-6, -1, -4, -2, 0], "key_dtype": "int64", "key_dtypes": ["int8", "int16", "int32", "int64"], "how": "inner",

@@ -324,6 +324,23 @@ def test_join_materialised_payloads(plb, how, order):
     assert np.array_equal(ro_p[0][exp_valid], rp[ri[exp_valid]])
 
 
+@pytest.mark.parametrize("dtype", [np.int64, np.float64, np.uint32])
+@pytest.mark.parametrize("nulls_equal", [False, True])
+def test_semi_anti_join_vs_oracle(plb, dtype, nulls_equal):
+    # single_keys_semi_anti.rs:41-140: left rows in order with / without a match; duplicates on either side, nulls
+    rng = np.random.default_rng(3)
+    for nl, nr, kr in ((0, 5, 3), (7, 0, 3), (5000, 700, 1500), (200_000, 30_000, 50_000)):
+        lk, rk = rng.integers(0, kr, nl).astype(dtype), rng.integers(0, kr, nr).astype(dtype)
+        if np.dtype(dtype).kind == "f" and nl > 10:
+            lk[::7] = np.nan; rk[::5] = np.nan; lk[1::9] = -0.0; rk[1::9] = 0.0
+        lv, rv = rng.random(nl) > 0.1, rng.random(nr) > 0.1
+        for how in ("semi", "anti"):
+            li, ri = GpuImpl(plb).hash_join(lk, rk, lv, rv, how=how, nulls_equal=nulls_equal)
+            eli, _ = oracle.hash_join(lk, rk, lv, rv, how, nulls_equal, "none", 4)
+            assert ri.size == 0 and li.dtype == np.uint32
+            assert np.array_equal(li, eli), (how, nl, nr)
+
+
 def test_join_small_int_keys(plb):
     rng = np.random.default_rng(10)
     lk = rng.integers(-128, 128, 5000).astype(np.int8)
@@ -671,7 +688,7 @@ def test_error_paths(plb):
     with pytest.raises(plb.ComputeError):
         plb.elementwise("add", a, a.astype(np.float64))                   # dtype mismatch
     with pytest.raises(plb.B200Error) as e:
-        plb.group_by_agg(a.astype(np.int8), [("len", None)])              # dtype outside the hot path
+        plb.group_by_agg(a > 4, [("len", None)])                          # Boolean keys are outside the hot path
     assert e.value.status == 4
     with pytest.raises(plb.B200Error):
         plb.filter([a], np.ones(9, bool))                                 # mask length mismatch
