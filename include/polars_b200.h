@@ -152,6 +152,13 @@ typedef struct bl_agg {
 bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, const bl_agg* aggs, int32_t n_aggs,
                          int32_t maintain_order, int32_t out_location, bl_column* out_key, bl_column* out_aggs);
 
+/* Several key columns (DataFrame::group_by_with_series routes them through row encoding,
+ * polars-core/src/frame/group_by/mod.rs:88-94; polars-row/src/fixed/numeric.rs:100-145): numeric columns of the
+ * dtypes above plus Int8/16, UInt8/16, one chunk each.  Equality per column as for a single key (null == null,
+ * -0 == +0, NaN == NaN).  out_keys[i] = keys[i] taken at each group's first row; the rest as bl_groupby_agg. */
+bl_status bl_groupby_agg_keys(const bl_column* keys, int32_t n_keys, const bl_agg* aggs, int32_t n_aggs,
+                              int32_t maintain_order, int32_t out_location, bl_column* out_keys, bl_column* out_aggs);
+
 /* Group tuples: the reference's GroupsIdx{first, all} (polars-core/src/frame/group_by/position.rs:16-22)
  * as built by group_by_threaded_slice with sorted = true (hashing.rs:116-167, finish_group_order :41-63),
  * for aggregations outside the fused set above.  Groups come in first-occurrence order; group g owns

@@ -184,6 +184,43 @@ def group_by(keys, key_valid=None, n_partitions: int | None = None, maintain_ord
     return Groups(first[:G].copy(), offsets[:G + 1].copy(), idx[:n])
 
 
+def group_by_multi(keys_list, valids_list=None, maintain_order: bool = True) -> Groups:
+    """Several key columns.  The reference row-encodes the columns (polars-core/src/frame/group_by/mod.rs:88-94,
+    polars-row/src/fixed/numeric.rs:100-145: canonical float bits, a validity sentinel per column) and groups on
+    the encoded rows; two rows fall in one group iff every column agrees under that encoding.  Restated with
+    numpy: per-column (validity, canonical key bits) pairs -> np.unique over the stacked rows; groups ordered by
+    first occurrence (hashing.rs:41-63), row lists ascending."""
+    n = np.ascontiguousarray(keys_list[0]).size
+    valids_list = valids_list or [None] * len(keys_list)
+    cols = []
+    for k, v in zip(keys_list, valids_list):
+        bits = key_bits(k)
+        vv = (np.ones(n, np.uint64) if v is None else _valid(v, n).astype(np.uint64))
+        cols += [vv, np.where(vv != 0, bits, np.uint64(0))]
+    if n == 0:
+        return Groups(np.zeros(0, np.uint32), np.zeros(1, np.uint64), np.zeros(0, np.uint32))
+    rows = np.stack(cols, axis=1)
+    _, first, inverse, counts = np.unique(rows, axis=0, return_index=True, return_inverse=True, return_counts=True)
+    order = np.argsort(first, kind="stable")                   # groups by first occurrence
+    rank = np.empty_like(order); rank[order] = np.arange(order.size)
+    gid = rank[np.asarray(inverse).reshape(-1)]
+    idx = np.argsort(gid, kind="stable").astype(np.uint32)    # rows grouped, ascending inside a group
+    offsets = np.concatenate([[0], np.cumsum(counts[order])]).astype(np.uint64)
+    return Groups(first[order].astype(np.uint32), offsets, idx)
+
+
+def group_by_agg_multi(keys_list, valids_list, aggs, maintain_order=True):
+    """-> ([(key values, key valid|None) per key column], [(vals, valid)...], Groups); key output = take(first)."""
+    g = group_by_multi(keys_list, valids_list, maintain_order)
+    valids_list = valids_list or [None] * len(keys_list)
+    kouts = []
+    for k, v in zip(keys_list, valids_list):
+        k = np.ascontiguousarray(k)
+        kouts.append((k[g.first], None if v is None else np.asarray(v, np.bool_)[g.first]))
+    outs = [agg(kind, vals, valid, g) for (kind, vals, valid) in aggs]
+    return kouts, outs, g
+
+
 def agg(kind: str, values, valid, groups: Groups):
     """kind in sum/mean/min/max/count/len.  Returns (values, valid|None) per group."""
     G = len(groups)

@@ -373,6 +373,31 @@ def group_by_agg(key, aggs: Sequence, maintain_order: bool = False, location: in
     return res[0], res[1:]
 
 
+def group_by_agg_keys(keys: Sequence, aggs: Sequence, maintain_order: bool = False, location: int = HOST):
+    """Several key columns (one chunk each); aggs as in group_by_agg.  Returns ([key_outs], [agg_outs])."""
+    kcols = [_as_col(c) for c in keys]
+    karr = _col_array(kcols)
+    keep, agg_structs = [], []
+    cache = {}
+    for kind, vals in aggs:
+        if kind == "len" or vals is None:
+            agg_structs.append(BlAgg(AGGS[kind], 0, None))
+            continue
+        ident = id(vals)
+        if ident not in cache:
+            chunks = [_as_col(c) for c in (vals if isinstance(vals, list) else [vals])]
+            cache[ident] = (chunks, _col_array(chunks))
+        chunks, arr = cache[ident]
+        keep.append((chunks, arr))
+        agg_structs.append(BlAgg(AGGS[kind], len(chunks), C.cast(arr, C.POINTER(BlColumn))))
+    aarr = (BlAgg * max(len(agg_structs), 1))(*agg_structs)
+    out_keys, out_aggs = (BlColumn * len(kcols))(), (BlColumn * max(len(agg_structs), 1))()
+    _check(lib().bl_groupby_agg_keys(karr, C.c_int32(len(kcols)), aarr, C.c_int32(len(agg_structs)), C.c_int32(int(maintain_order)), C.c_int32(location),
+                                     out_keys, out_aggs))
+    res = _finish(list(out_keys) + list(out_aggs)[: len(agg_structs)], location)
+    return res[: len(kcols)], res[len(kcols):]
+
+
 def group_tuples(key, location: int = HOST):
     """GroupsIdx of the reference (first, offsets, all): groups in first-occurrence order, rows ascending."""
     kch = [_as_col(c) for c in (key if isinstance(key, list) else [key])]

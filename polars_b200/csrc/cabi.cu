@@ -170,6 +170,59 @@ bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, cons
     BL_CATCH
 }
 
+bl_status bl_groupby_agg_keys(const bl_column* keys, int32_t n_keys, const bl_agg* aggs, int32_t n_aggs, int32_t maintain_order, int32_t out_location,
+                              bl_column* out_keys, bl_column* out_aggs) {
+    BL_TRY
+    PLB_REQUIRE(keys && n_keys >= 1 && out_keys, BL_ERR_INVALID, "groupby_agg_keys: null keys / output");
+    PLB_REQUIRE(n_aggs == 0 || (aggs && out_aggs), BL_ERR_INVALID, "groupby_agg_keys: null aggs / outputs");
+    std::vector<DevCol> kcols;
+    for (int i = 0; i < n_keys; i++) kcols.push_back(import_column(&keys[i], 1));
+    DevCol packed = op_pack_keys(kcols);
+    auto same_col = [](const bl_agg& a, const bl_agg& b) {
+        return a.n_chunks == b.n_chunks && (a.values == b.values || (a.n_chunks == 1 && a.values[0].values == b.values[0].values && a.values[0].validity == b.values[0].validity &&
+                                                                    a.values[0].offset == b.values[0].offset && a.values[0].length == b.values[0].length && a.values[0].dtype == b.values[0].dtype));
+    };
+    std::vector<int> kinds, dts, nullable(n_aggs, 0), val_in_dtype(n_aggs, -1);
+    std::vector<DevCol> vals(n_aggs);
+    std::vector<const DevCol*> vptr(n_aggs, nullptr);
+    for (int i = 0; i < n_aggs; i++) {
+        kinds.push_back(aggs[i].kind);
+        if (aggs[i].kind == BL_AGG_LEN) { dts.push_back(BL_INT64); continue; }
+        PLB_REQUIRE(aggs[i].values && aggs[i].n_chunks >= 1, BL_ERR_INVALID, "groupby_agg_keys: aggregation without a value column");
+        int dup = -1;
+        for (int j = 0; j < i; j++) if (aggs[j].kind != BL_AGG_LEN && same_col(aggs[j], aggs[i])) { dup = j; break; }
+        if (dup >= 0) { vals[i] = vals[dup]; val_in_dtype[i] = val_in_dtype[dup]; }
+        else {
+            vals[i] = import_column(aggs[i].values, aggs[i].n_chunks);
+            val_in_dtype[i] = vals[i].dtype;
+            if (dtype_is_small_int(vals[i].dtype)) vals[i] = op_cast_small_int(vals[i], BL_INT64, false);
+        }
+        vptr[i] = &vals[i];
+        dts.push_back(vals[i].dtype);
+        nullable[i] = vals[i].validity != nullptr;
+    }
+    GroupByState st(BL_UINT64, kinds, dts, nullable, 0, true);
+    st.consume_all(packed, vptr);
+    DevCol ok, first; std::vector<DevCol> oa;
+    st.finish(maintain_order != 0, nullptr, ok, oa, &first);
+    for (int i = 0; i < n_aggs; i++)
+        if ((aggs[i].kind == BL_AGG_MIN || aggs[i].kind == BL_AGG_MAX) && dtype_is_small_int(val_in_dtype[i])) oa[i] = op_cast_small_int(oa[i], val_in_dtype[i], false);
+    // key output = every key column taken at the group's first row (group_by/mod.rs:258-266)
+    std::vector<DevCol> all;
+    for (int i = 0; i < n_keys; i++) {
+        if (dtype_size(kcols[i].dtype) >= 4) { std::vector<DevCol> in{kcols[i]}, o; op_gather(in, first, false, o); all.push_back(o[0]); }
+        else {      // K4 takes 4- and 8-byte elements: gather the widened bit pattern, narrow it back
+            std::vector<DevCol> in{op_cast_small_int(kcols[i], BL_UINT32, true)}, o; op_gather(in, first, false, o);
+            all.push_back(op_cast_small_int(o[0], kcols[i].dtype, true));
+        }
+    }
+    all.insert(all.end(), oa.begin(), oa.end());
+    std::vector<bl_column> t(all.size()); export_many(all, out_location, t.data());
+    for (int i = 0; i < n_keys; i++) out_keys[i] = t[i];
+    for (int i = 0; i < n_aggs; i++) out_aggs[i] = t[n_keys + i];
+    BL_CATCH
+}
+
 bl_status bl_group_tuples(const bl_column* key_chunks, int32_t n_key_chunks, int32_t out_location, bl_column* out_first, bl_column* out_offsets, bl_column* out_all) {
     BL_TRY
     PLB_REQUIRE(key_chunks && n_key_chunks >= 1 && out_first && out_offsets && out_all, BL_ERR_INVALID, "group_tuples: null argument");

@@ -153,6 +153,8 @@ DevCol op_cmp_scalar_mask(const DevCol& col, int cmp_op, const DevCol& scalar);
 void op_gather(const std::vector<DevCol>& cols, const DevCol& idx, bool check_bounds, std::vector<DevCol>& outs);
 bool dtype_is_small_int(int dt);
 DevCol op_cast_small_int(const DevCol& in, int to_dtype, bool bits);
+DevCol op_group_first_ids(const DevCol& key);
+DevCol op_pack_keys(const std::vector<DevCol>& keys);
 void op_group_tuples(const DevCol& key, DevCol& out_first, DevCol& out_offsets, DevCol& out_all);
 DevPtr bitmap_and(const uint32_t* a, const uint32_t* b, const uint32_t* c, int64_t bits);
 int64_t bitmap_popcount(const uint32_t* bm, int64_t bits);

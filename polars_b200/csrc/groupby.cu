@@ -1351,7 +1351,7 @@ void GroupByState::export_partials_p2p(int n_ranks, int my_rank, void* const* wi
     for (int p = 0; p < n_ranks; p++) sent_rows[p] = (int64_t)h[p];
 }
 
-void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather, DevCol& out_key, std::vector<DevCol>& out_aggs) {
+void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather, DevCol& out_key, std::vector<DevCol>& out_aggs, DevCol* out_first) {
     out_aggs.clear();
     PLB_REQUIRE(!maintain_order || L.need_first, BL_ERR_INVALID, "group_by: maintain_order needs a state created with track_first");
     // Extract into buffers sized by an upper bound of the group count, then read the real count and
@@ -1410,10 +1410,13 @@ void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather,
         DevCol pidx; pidx.dtype = BL_UINT32; pidx.len = G; pidx.values = perm; pidx.null_count = 0;
         std::vector<DevCol> in{out_key}, outv;
         for (auto& a : out_aggs) in.push_back(a);
+        if (out_first) in.push_back(first_col);
         op_gather(in, pidx, false, outv);
         out_key = outv[0];
         for (size_t i = 0; i < out_aggs.size(); i++) out_aggs[i] = outv[i + 1];
+        if (out_first) first_col = outv.back();
     }
+    if (out_first) *out_first = first_col;
 }
 
 // ---------------------------------------------------------------------------- group tuples (GroupsIdx)
@@ -1453,6 +1456,68 @@ __global__ void __launch_bounds__(256) k_run_starts(const uint32_t* __restrict__
     }
 }
 
+// row -> first row index of the row's group (u32): a group id that needs no renumbering
+DevCol op_group_first_ids(const DevCol& key) {
+    const int64_t n = key.len;
+    DevCol ids = make_col(BL_UINT32, n, false);
+    if (n == 0) return ids;
+    GroupByState st(key.dtype, {}, {}, {}, 0, true);
+    st.consume_all(key, {});
+    PLB_LAUNCH("k5_lookup_first", k_gb_lookup_first, grid_for(n, 256, 16), 256, 0, st.T, key.v(), key.vm(), key.dtype, n, as<uint32_t>(ids.values));
+    return ids;
+}
+
+// ---------------------------------------------------------------------------- multi-column keys
+// The reference row-encodes several key columns into one binary key (group_by/mod.rs:88-94,
+// polars-row/src/fixed/numeric.rs:100-145: floats canonicalised, one validity sentinel per column) and groups
+// on that.  Fixed-width columns pack into ONE 64-bit key instead: each column contributes its (canonical) bit
+// pattern plus a validity bit when it can hold nulls; when the next column does not fit, the key so far is
+// replaced by its 32-bit group id (first row of its group: one K5 build + lookup), so any number of columns
+// of any hot-path dtype works and narrow keys (Q1's two flag bytes, two Int32s) need no extra pass at all.
+__global__ void __launch_bounds__(256) k_pack_append(const uint64_t* __restrict__ acc, int shift, const void* __restrict__ values, const uint32_t* __restrict__ validity, int dtype, int vbits,
+                                                     int64_t n, uint64_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t rep = 0;
+        const bool valid = validity == nullptr || bit_get(validity, i);
+        if (valid) {
+            switch (dtype) {
+                case BL_INT8: case BL_UINT8: rep = reinterpret_cast<const uint8_t*>(values)[i]; break;
+                case BL_INT16: case BL_UINT16: rep = reinterpret_cast<const uint16_t*>(values)[i]; break;
+                default: rep = load_key_rt(values, dtype, i); break;      // canonical float bits / zero-extended 32-bit pattern / 64-bit pattern
+            }
+            if (validity != nullptr) rep |= 1ull << vbits;                 // validity bit above the value bits (never reached for 64-bit values: those are id-compressed first)
+        }
+        out[i] = (acc ? acc[i] : 0ull) | (rep << shift);
+    }
+}
+
+// Packs the key columns into one BL_UINT64 key column (no validity: nulls are part of the packed value).
+DevCol op_pack_keys(const std::vector<DevCol>& keys) {
+    PLB_REQUIRE(!keys.empty(), BL_ERR_INVALID, "group_by: no key columns");
+    const int64_t n = keys[0].len;
+    DevCol acc; bool have = false; int used = 0;
+    for (const DevCol& k0 : keys) {
+        PLB_REQUIRE(k0.len == n, BL_ERR_INVALID, "group_by: key columns differ in length");
+        PLB_REQUIRE(k0.dtype != BL_BOOL, BL_ERR_UNSUPPORTED, "group_by: Boolean keys are outside the hot path");
+        DevCol k = k0;
+        int vbits = dtype_size(k.dtype) * 8;
+        int w = vbits + (k.validity ? 1 : 0);
+        if (w > 64 || (w > 32 && have && used + w > 64)) {      // wide column that cannot sit beside the rest: use its group id
+            k = op_group_first_ids(k); vbits = 32; w = 32;
+        }
+        if (have && used + w > 64) {                              // key so far -> its 32-bit group id
+            DevCol ids = op_group_first_ids(acc);
+            DevCol wide = make_col(BL_UINT64, n, false);
+            if (n) PLB_LAUNCH("k5_pack_keys", k_pack_append, grid_for(n, 256, 16), 256, 0, (const uint64_t*)nullptr, 0, ids.v(), ids.vm(), BL_UINT32, 32, n, as<uint64_t>(wide.values));
+            acc = wide; used = 32;
+        }
+        DevCol out = make_col(BL_UINT64, n, false);
+        if (n) PLB_LAUNCH("k5_pack_keys", k_pack_append, grid_for(n, 256, 16), 256, 0, have ? as<uint64_t>(acc.values) : (const uint64_t*)nullptr, used, k.v(), k.vm(), k.dtype, vbits, n, as<uint64_t>(out.values));
+        acc = out; have = true; used += w;
+    }
+    return acc;
+}
+
 void op_group_tuples(const DevCol& key, DevCol& out_first, DevCol& out_offsets, DevCol& out_all) {
     const int64_t n = key.len;
     PLB_REQUIRE(n <= 0x7FFFFFFFll, BL_ERR_UNSUPPORTED, "group_tuples: more than 2^31-1 rows");
@@ -1463,10 +1528,8 @@ void op_group_tuples(const DevCol& key, DevCol& out_first, DevCol& out_offsets, 
         dev_memset(out_offsets.values->p, 0, 4);
         return;
     }
-    GroupByState st(key.dtype, {}, {}, {}, 0, true);
-    st.consume_all(key, {});
-    DevPtr gid = dev_alloc((size_t)n * 4);
-    PLB_LAUNCH("k5_lookup_first", k_gb_lookup_first, grid_for(n, 256, 16), 256, 0, st.T, key.v(), key.vm(), key.dtype, n, as<uint32_t>(gid));
+    DevCol ids = op_group_first_ids(key);
+    DevPtr gid = ids.values;
     iota_u32(as<uint32_t>(out_all.values), n, 0);
     sort_pairs_u32(as<uint32_t>(gid), as<uint32_t>(out_all.values), n);
     DevCol starts = make_col(BL_BOOL, n, false);

@@ -66,7 +66,7 @@ struct GroupByState {
     void merge_partial_regions(const uint64_t* const* ptrs, const int64_t* counts, int n_regions);
     DevPtr export_partials(int n_partitions, int* row_words_out, int64_t* offsets_host);
     void export_partials_p2p(int n_ranks, int my_rank, void* const* windows, int64_t rows_per_src, int* row_words_out, int64_t* sent_rows);
-    void finish(bool maintain_order, const DevCol* key_col_for_gather, DevCol& out_key, std::vector<DevCol>& out_aggs);
+    void finish(bool maintain_order, const DevCol* key_col_for_gather, DevCol& out_key, std::vector<DevCol>& out_aggs, DevCol* out_first = nullptr);
     void reset();
     int64_t count_groups();
 

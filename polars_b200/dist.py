@@ -199,3 +199,25 @@ def partitioned_hash_join(plb, left_key, right_key, left_base: int, right_base: 
     [gl] = plb.gather([lgc], li.view(), check_bounds=False, location=plb.DEVICE)
     [gr] = plb.gather([rgc], ri.view(), check_bounds=False, location=plb.DEVICE)
     return gl, gr
+
+
+def broadcast_hash_join(plb, left_key, right_key, left_base: int, how: str = "inner"):
+    """Small-build-side alternative: every rank gathers the WHOLE build (right) key column with
+    one all-gather and joins its own probe (left) rows against it — no probe-side exchange at all (C3: 80 MB of
+    build keys against 175 MB of probe rows per GPU).  Rank r's build rows must be rows [r*n_r, (r+1)*n_r) of the
+    global build relation (equal n_r on every rank), so the gathered order IS the global row id and the tuples
+    come back in global ids directly.  Returns (left_global_idx, right_global_idx) device columns; the output
+    stays distributed by probe row (rank r holds the matches of its own rows, in the reference's probe order)."""
+    world = dist.get_world_size()
+    n_r = right_key.length
+    mine = _as_torch(right_key, n_r, "<i8", torch.int64) if hasattr(right_key, "values_ptr") else \
+        torch.as_tensor(_CudaArr(right_key._vptr, n_r, "<i8"), device="cuda")
+    full = torch.empty(n_r * world, dtype=torch.int64, device="cuda")
+    dist.all_gather_into_tensor(full, mine)
+    torch.cuda.synchronize()
+    rcol = plb.Column(full.data_ptr(), dtype=np.int64, length=full.numel(), location=plb.DEVICE)
+    li, ri = plb.hash_join(left_key, rcol, how, False, "none", location=plb.DEVICE)
+    # local probe idx -> global: add this rank's base (K1)
+    base = plb.Column(np.array([left_base], np.uint32))
+    gl = plb.elementwise("add", li.view(), base, location=plb.DEVICE)
+    return gl, ri

@@ -79,6 +79,26 @@ KATS = {
             "expect_key": [1, 2, 3],
         },
     ],
+    "group_by_multi": [
+        {
+            "cite": "crates/polars-core/src/frame/group_by/mod.rs:1009-1047 (test_static_group_by_by_12_columns)",
+            "note": "12 key columns (strings dictionary-encoded by first appearance, bool as 0/1); N_sum sorted == [1,2,2,6]",
+            "keys": [[0, 0, 1, 1, 2], [0, 1, 2, 2, 1], [0, 1, 2, 2, 3], [0, 1, 2, 2, 3], [0, 1, 2, 2, 3], [0, 1, 1, 1, 0], [0, 1, 2, 2, 3],
+                     [0, 1, 2, 2, 3], [1, 2, 3, 3, 4], [0, 1, 2, 2, 3], [0, 1, 2, 2, 3], [0, 1, 2, 2, 3]],
+            "key_dtype": "int32", "col": [1, 2, 2, 4, 2], "dtype": "int32", "kind": "sum", "expect_sorted": [1, 2, 2, 6],
+        },
+        {
+            "cite": "py-polars/tests/unit/operations/test_group_by.py:1122-1132 (test_group_by_with_null)",
+            "note": "a all null, b [1,1,2,2], maintain_order: groups (null,1),(null,2) with 2 rows each; c lists -> len",
+            "keys": [[N, N, N, N], [1, 1, 2, 2]], "key_dtype": "int64", "kind": "len", "expect": [2, 2],
+            "expect_keys": [[N, N], [1, 2]],
+        },
+        {
+            "cite": "py-polars/tests/unit/operations/test_group_by.py:1012-1017 (test_group_by_partitioned_ending_cast)",
+            "note": "a=[1]*5, b=[1]*5 -> one group, len 5",
+            "keys": [[1, 1, 1, 1, 1], [1, 1, 1, 1, 1]], "key_dtype": "int64", "kind": "len", "expect": [5], "expect_keys": [[1], [1]],
+        },
+    ],
     "join": [
         {
             "cite": "crates/polars/tests/it/core/joins.rs:40-78 (test_inner_join, POLARS_MAX_THREADS 1..7)",

@@ -131,3 +131,23 @@ def pairs_sorted(li, ri):
     p = (li.astype(np.uint64) << np.uint64(32)) | ri.astype(np.uint64)
     p.sort()
     return p
+
+
+def run_group_by_multi_kat(group_by_agg_multi, case):
+    """group_by_agg_multi(keys_list, valids_list, aggs, maintain_order) -> ([(key, valid)...], [(vals, valid)...])"""
+    kv = [col(k, case["key_dtype"]) for k in case["keys"]]
+    keys, valids = [k for k, _ in kv], [v for _, v in kv]
+    if case["kind"] == "len":
+        aggs = [("len", None, None)]
+    else:
+        c, cvalid = col(case["col"], case["dtype"])
+        aggs = [(case["kind"], c, cvalid)]
+    kouts, outs = group_by_agg_multi(keys, valids, aggs, True)
+    vals = outs[0][0]
+    if "expect_sorted" in case:
+        assert sorted(vals.tolist()) == case["expect_sorted"], case["cite"]
+    else:
+        assert vals.tolist() == case["expect"], case["cite"]
+    for (kvals, kvalid), exp in zip(kouts, case.get("expect_keys", [])):
+        e, em = col(exp, case["key_dtype"])
+        assert_close(kvals, e, kvalid, em, what=case["cite"] + " keys")

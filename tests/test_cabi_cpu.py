@@ -18,7 +18,7 @@ def declared_symbols():
 
 def test_header_declares_the_hot_path():
     syms = declared_symbols()
-    for s in ("bl_elementwise", "bl_compare", "bl_filter", "bl_filter_cmp", "bl_gather", "bl_groupby_agg", "bl_group_tuples", "bl_hash_join", "bl_join",
+    for s in ("bl_elementwise", "bl_compare", "bl_filter", "bl_filter_cmp", "bl_gather", "bl_groupby_agg", "bl_groupby_agg_keys", "bl_group_tuples", "bl_hash_join", "bl_join",
               "bl_hash_partition", "bl_groupby_create", "bl_groupby_consume", "bl_groupby_export_partials",
               "bl_groupby_merge_partials", "bl_groupby_finish", "bl_last_error", "bl_init", "bl_alloc_pinned"):
         assert s in syms

@@ -498,6 +498,56 @@ def test_group_by_heavy_hitters(plb, monkeypatch, kind, hot_rows):
     assert_close(outs2[1][0], eouts[1][0], outs2[1][1], eouts[1][1], "stream len")
 
 
+def _gpu_group_by_multi(plb):
+    def run(keys, valids, aggs, order):
+        kouts, outs = plb.group_by_agg_keys([plb.Column(k, v) for k, v in zip(keys, valids)], [(kind, None if vals is None else plb.Column(vals, valid)) for kind, vals, valid in aggs], order)
+        return kouts, outs
+    return run
+
+
+def test_group_by_multi_kats(plb, kats):
+    from helpers import run_group_by_multi_kat
+    for case in kats["group_by_multi"]:
+        run_group_by_multi_kat(_gpu_group_by_multi(plb), case)
+
+
+@pytest.mark.parametrize("shape", ["two_i32", "u8_u8", "i64_f64_i16", "f32_i64_i64_u16", "nullable_wide"])
+def test_group_by_multi_vs_oracle(plb, shape):
+    # several key columns (row-encoding equality, group_by/mod.rs:88-94): packed into one 64-bit key when the widths
+    # fit, otherwise through 32-bit group ids of the key so far; outputs = every key column at the group's first row
+    rng = np.random.default_rng(len(shape))
+    n = 150_001
+    spec = {"two_i32": [(np.int32, 40, False), (np.int32, 30, True)],
+            "u8_u8": [(np.uint8, 3, False), (np.uint8, 2, False)],
+            "i64_f64_i16": [(np.int64, 50, False), (np.float64, 6, True), (np.int16, 4, False)],
+            "f32_i64_i64_u16": [(np.float32, 5, False), (np.int64, 20, True), (np.int64, 7, False), (np.uint16, 3, True)],
+            "nullable_wide": [(np.uint64, 9, True), (np.float64, 9, True), (np.int64, 9, True)]}[shape]
+    keys, valids = [], []
+    for dt, card, nullable in spec:
+        k = rng.integers(-card // 2, card - card // 2, n) if np.dtype(dt).kind in "if" else rng.integers(0, card, n)
+        k = k.astype(dt)
+        if np.dtype(dt).kind == "f":
+            k[rng.random(n) < 0.05] = np.nan; k[rng.random(n) < 0.05] = -0.0
+        keys.append(k); valids.append((rng.random(n) > 0.1) if nullable else None)
+    vi = rng.integers(-1000, 1000, n).astype(np.int64)
+    vf = rng.uniform(0, 10, n)
+    ivalid = rng.random(n) > 0.2
+    aggs = [("sum", vi, ivalid), ("mean", vf, None), ("len", None, None), ("min", vi, ivalid), ("max", vf, None), ("count", vi, ivalid)]
+    ekouts, eouts, _ = oracle.group_by_agg_multi(keys, valids, aggs, True)
+    kouts, outs = _gpu_group_by_multi(plb)(keys, valids, aggs, True)
+    for (k, kv), (ek, ekv) in zip(kouts, ekouts):
+        assert k.dtype == ek.dtype
+        assert_close(k, ek, kv, ekv, "keys")
+        if k.dtype.kind == "f":      # first-occurrence bit patterns (-0.0 vs 0.0, NaN payload) survive
+            ok = np.ones(k.size, bool) if ekv is None else ekv
+            assert np.array_equal(k[ok].view(np.uint8), ek[ok].view(np.uint8))
+    for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
+        assert_close(v, ev, m, em, kind)
+    # unordered variant: same groups as a set
+    kouts2, outs2 = _gpu_group_by_multi(plb)(keys, valids, [("len", None, None)], False)
+    assert outs2[0][0].size == eouts[2][0].size and int(outs2[0][0].sum()) == n
+
+
 def test_group_by_streaming_and_partials(plb):
     # streaming consume == one shot; export -> merge of partial aggregates == single table
     rng = np.random.default_rng(12)

@@ -251,3 +251,25 @@ def test_filter_gather_kat():
     iv = np.array([1, 1, 0, 1, 1], bool)
     out, ov = oracle.gather(vals, valid, idx, iv)
     assert out.tolist() == [13.5, 0.0, 0.0, 4.5, 10.5] and ov.tolist() == [False, False, False, False, True]
+
+
+def test_group_by_multi_kats(kats):
+    from helpers import run_group_by_multi_kat
+    for case in kats["group_by_multi"]:
+        run_group_by_multi_kat(lambda k, v, a, o: oracle.group_by_agg_multi(k, v, a, o)[:2], case)
+
+
+def test_group_by_multi_matches_single_key_and_pyarrow():
+    import pyarrow as pa
+    rng = np.random.default_rng(8)
+    n = 20_000
+    a, b = rng.integers(0, 30, n).astype(np.int32), rng.integers(-5, 5, n).astype(np.int64)
+    av = rng.random(n) > 0.1
+    v = rng.integers(-100, 100, n).astype(np.int64)
+    g1, g2 = oracle.group_by(a, av, 4, True), oracle.group_by_multi([a], [av], True)
+    assert np.array_equal(g1.first, g2.first) and np.array_equal(g1.offsets, g2.offsets) and np.array_equal(g1.idx, g2.idx)
+    kouts, outs, _ = oracle.group_by_agg_multi([a, b], [av, None], [("sum", v, None), ("len", None, None)], True)
+    t = pa.table({"a": pa.array(a, mask=~av), "b": b, "v": v}).group_by(["a", "b"]).aggregate([("v", "sum"), ([], "count_all")]).to_pydict()
+    exp = {(x, y): (s, c) for x, y, s, c in zip(t["a"], t["b"], t["v_sum"], t["count_all"])}
+    got = {(None if (kouts[0][1] is not None and not kouts[0][1][i]) else int(kouts[0][0][i]), int(kouts[1][0][i])): (int(outs[0][0][i]), int(outs[1][0][i])) for i in range(len(outs[0][0]))}
+    assert got == exp

@@ -71,4 +71,13 @@ assert int(tot.item()) == expect, f"join: {int(tot.item())} pairs, expected {exp
 assert np.unique(l).size == l.size
 if rank == 0:
     print(f"mgpu_check join: OK world={world} pairs={expect}", flush=True)
+
+# ---- broadcast-build join: same relation, no probe-side exchange; rank r keeps the matches of its own probe rows
+gl2, gr2 = pdist.broadcast_hash_join(plb, dpk.view(), dbk.view(), rank * npr)
+l2, _ = gl2.to_numpy(); r2, rv2 = gr2.to_numpy()
+assert np.array_equal(allp[l2], perm[r2]), "broadcast join: keys of the emitted pairs differ"
+assert l2.size == int(np.isin(pkeys_all[rank], perm).sum()) and (l2.size == 0 or (l2.min() >= rank * npr and l2.max() < (rank + 1) * npr))
+assert np.all(np.diff(l2.astype(np.int64)) > 0), "broadcast join: probe order lost"
+if rank == 0:
+    print(f"mgpu_check broadcast join: OK world={world}", flush=True)
 dist.destroy_process_group()
