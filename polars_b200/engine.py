@@ -12,8 +12,9 @@ and replace the current subtree by a Python UDF with `set_udf` (visit.rs:156-175
 engine then calls instead of executing the subtree.  This is the seam the reference's own GPU engine uses
 (py-polars/src/polars/lazyframe/engine.py:946-970).
 
-NOT TESTED in this repository: there is no Polars wheel in the authoring image or on the GPU box (no Rust
-toolchain to build one), so this module is written against the reference source only.  It is deliberately
+There is no Polars wheel in the authoring image or on the GPU box (no Rust toolchain to build one), so the
+UDF bodies are written against the reference source only; the plan matcher (which shapes are taken, which are
+left to Polars) is tested with a mock NodeTraverser in tests/test_engine_matcher.py.  It is deliberately
 conservative: any node shape it does not recognise is left untouched (Polars executes it).
 Recognised:
   * GroupBy(keys=[col], aggs ⊆ {col.sum/mean/min/max/count, len}) over a DataFrameScan, optionally through
@@ -83,19 +84,22 @@ def _parse_filter(nt, node):
 
 
 def _scan_frame(nt, node_id):
+    """DataFrameScan node -> a thunk producing the pl.DataFrame (polars is imported only when the UDF runs)."""
     nt.set_node(node_id)
     n = nt.view_current_node()
     if type(n).__name__ != "DataFrameScan" or n.selection is not None:
         raise _Unsupported(type(n).__name__)
-    import polars as pl
-    df = pl.DataFrame._from_pydf(n.df) if hasattr(pl.DataFrame, "_from_pydf") else n.df
-    if n.projection is not None:
-        df = df.select(list(n.projection))
-    return df
+    pydf, projection = n.df, n.projection
+
+    def frame():
+        import polars as pl
+        df = pl.DataFrame._from_pydf(pydf) if hasattr(pl.DataFrame, "_from_pydf") else pydf
+        return df.select(list(projection)) if projection is not None else df
+
+    return frame
 
 
 def _plan_group_by(plb, nt, root_id, node):
-    import polars as pl
     if len(node.keys) != 1:
         raise _Unsupported("multi-column keys")
     key_name = _column_name(nt, node.keys[0].node)
@@ -106,13 +110,15 @@ def _plan_group_by(plb, nt, root_id, node):
     if type(child).__name__ == "Filter":
         inp, fcol, fop, fval = _parse_filter(nt, child)
         flt = (fcol, fop, fval)
-        df = _scan_frame(nt, inp)
+        frame = _scan_frame(nt, inp)
     else:
-        df = _scan_frame(nt, node.input)
+        frame = _scan_frame(nt, node.input)
     nt.set_node(root_id)
     maintain_order = bool(node.maintain_order)
 
     def run(*_args: Any, **_kwargs: Any):
+        import polars as pl
+        df = frame()
         needed = [key_name] + [c for _, c, _ in aggs if c is not None]
         cols = {c: _series_to_column(plb, df.get_column(c)) for c in dict.fromkeys(needed)}
         if flt is not None:
@@ -140,16 +146,17 @@ def _concat(series):
 
 
 def _plan_join(plb, nt, root_id, node):
-    import polars as pl
     how = str(node.options[0]).lower() if isinstance(node.options, (tuple, list)) else str(node.options)
     how = "inner" if "inner" in how else ("left" if "left" in how else None)
     if how is None or len(node.left_on) != 1 or len(node.right_on) != 1:
         raise _Unsupported("join type / multi-key")
     lkey, rkey = _column_name(nt, node.left_on[0].node), _column_name(nt, node.right_on[0].node)
-    left, right = _scan_frame(nt, node.input_left), _scan_frame(nt, node.input_right)
+    left_frame, right_frame = _scan_frame(nt, node.input_left), _scan_frame(nt, node.input_right)
     nt.set_node(root_id)
 
     def run(*_args: Any, **_kwargs: Any):
+        import polars as pl
+        left, right = left_frame(), right_frame()
         (li, _), (ri, rv) = plb.hash_join(_series_to_column(plb, left.get_column(lkey)), _series_to_column(plb, right.get_column(rkey)), how)
         ridx = pl.Series(ri) if rv is None else pl.Series(ri).set(pl.Series(~rv), None)
         out_l = left[pl.Series(li)]

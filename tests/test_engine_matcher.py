@@ -1,0 +1,97 @@
+"""Boundary B2: the post-optimisation callback must take exactly the plan shapes the library
+covers and leave everything else to Polars.  Polars itself is not installable here, so the IR is mocked with
+classes named like the reference's node/expression views (crates/polars-python/src/lazyframe/visitor/nodes.rs,
+visitor/expr_nodes.rs); only the matcher runs — no kernel is launched."""
+import types
+
+import pytest
+
+from polars_b200 import engine
+
+
+def make(_kind, **fields):
+    obj = type(_kind, (), {})()
+    for k, v in fields.items():
+        setattr(obj, k, v)
+    return obj
+
+
+class FakeTraverser:
+    """node ids -> IR nodes, expression ids -> expression nodes; records set_udf."""
+
+    def __init__(self, nodes, exprs, root):
+        self.nodes, self.exprs, self.cur, self.udf = nodes, exprs, root, None
+
+    def view_current_node(self):
+        return self.nodes[self.cur]
+
+    def set_node(self, n):
+        self.cur = n
+
+    def get_node(self):
+        return self.cur
+
+    def view_expression(self, e):
+        return self.exprs[e]
+
+    def set_udf(self, fn):
+        self.udf = fn
+
+
+def expr_ir(node, name):
+    return types.SimpleNamespace(node=node, output_name=name)
+
+
+def group_by_plan(agg_name="sum", n_keys=1, with_filter=True, rhs_literal=True, scan_selection=None):
+    exprs = {0: make("Column", name="key"), 1: make("Column", name="x"), 2: make("Agg", name=agg_name, arguments=[1]), 3: make("Len"),
+             4: make("BinaryExpr", left=1, op="Operator.Gt", right=5), 5: make("Literal", value=0) if rhs_literal else make("Column", name="y"),
+             6: make("Column", name="key2")}
+    scan = make("DataFrameScan", df=object(), projection=None, selection=scan_selection)
+    nodes = {10: scan}
+    child = 10
+    if with_filter:
+        nodes[11] = make("Filter", input=10, predicate=expr_ir(4, "p"))
+        child = 11
+    keys = [expr_ir(0, "key")] + ([expr_ir(6, "key2")] if n_keys == 2 else [])
+    nodes[12] = make("GroupBy", input=child, keys=keys, aggs=[expr_ir(2, "x"), expr_ir(3, "len")], maintain_order=True)
+    return FakeTraverser(nodes, exprs, 12)
+
+
+def test_filter_group_by_is_taken():
+    for with_filter in (True, False):
+        nt = group_by_plan(with_filter=with_filter)
+        engine.execute_with_b200(nt)
+        assert callable(nt.udf) and nt.cur == 12          # the traverser is left on the replaced root
+
+
+@pytest.mark.parametrize("kwargs", [dict(agg_name="median"), dict(n_keys=2), dict(rhs_literal=False), dict(scan_selection=object())])
+def test_unsupported_group_by_shapes_are_left_to_polars(kwargs):
+    nt = group_by_plan(**kwargs)
+    engine.execute_with_b200(nt)
+    assert nt.udf is None
+    with pytest.raises(Exception):
+        engine.execute_with_b200(group_by_plan(**kwargs), raise_on_fail=True)
+
+
+def join_plan(how="Inner", n_keys=1):
+    exprs = {0: make("Column", name="k"), 1: make("Column", name="k"), 2: make("Column", name="k2")}
+    nodes = {20: make("DataFrameScan", df=object(), projection=None, selection=None), 21: make("DataFrameScan", df=object(), projection=["k", "r"], selection=None)}
+    on = [expr_ir(0, "k")] + ([expr_ir(2, "k2")] if n_keys == 2 else [])
+    nodes[22] = make("Join", input_left=20, input_right=21, left_on=on, right_on=[expr_ir(1, "k")] + on[1:], options=(how, False))
+    return FakeTraverser(nodes, exprs, 22)
+
+
+def test_single_key_joins_are_taken_and_others_left():
+    for how in ("Inner", "Left"):
+        nt = join_plan(how)
+        engine.execute_with_b200(nt)
+        assert callable(nt.udf) and nt.cur == 22
+    for nt in (join_plan("Full"), join_plan("Cross"), join_plan("Inner", n_keys=2)):
+        engine.execute_with_b200(nt)
+        assert nt.udf is None
+
+
+def test_other_roots_are_untouched():
+    nt = FakeTraverser({1: make("Sort", input=0)}, {}, 1)
+    engine.execute_with_b200(nt)
+    assert nt.udf is None
