@@ -236,6 +236,11 @@ def agg(kind: str, values, valid, groups: Groups):
         out = np.empty(G, np.uint32)
         L.or_agg_count(_p(v), _p(off), _p(idx), C.c_int64(G), _p(out))
         return out, None
+    if values.dtype in (np.dtype("int8"), np.dtype("int16"), np.dtype("uint8"), np.dtype("uint16")):
+        # 8/16-bit integers aggregate after a cast to Int64 (polars-core/src/series/implementations/mod.rs:145-154);
+        # sum stays Int64, mean is Float64 (aggregations/mod.rs:1227-1296), min/max return the input dtype
+        out, ov = agg(kind, values.astype(np.int64), valid, groups)
+        return (out.astype(values.dtype) if kind in ("min", "max") else out), ov
     sfx = _SUFFIX[values.dtype]
     if kind == "sum":
         out = np.empty(G, values.dtype)

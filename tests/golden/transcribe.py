@@ -78,6 +78,20 @@ KATS = {
             "aggs": [{"col": [1] * 10 + [N] * 20, "dtype": "int64", "kind": "mean", "expect": [1.0, N, N]}],
             "expect_key": [1, 2, 3],
         },
+        {
+            "cite": "py-polars/tests/unit/operations/test_group_by.py:82-92,155-177 (test_group_by_mean_by_dtype, 8/16-bit rows)",
+            "note": "key a,a,a,b -> 0,0,0,1; input [1,2,3,4] in every numeric dtype; mean [2,4] as Float64 (Float32 stays Float32)",
+            "key": [0, 0, 0, 1], "key_dtype": "int64", "maintain_order": True,
+            "aggs": [{"col": [1, 2, 3, 4], "dtype": dt, "kind": "mean", "expect": [2.0, 4.0]} for dt in ("uint8", "int8", "uint16", "int16")],
+            "expect_key": [0, 1],
+        },
+        {
+            "cite": "py-polars/tests/unit/operations/test_group_by.py:82-92,155-177 (test_group_by_mean_by_dtype, 32/64-bit rows)",
+            "note": "same table, wider dtypes (two cases so that one call stays within 8 distinct value columns)",
+            "key": [0, 0, 0, 1], "key_dtype": "int64", "maintain_order": True,
+            "aggs": [{"col": [1, 2, 3, 4], "dtype": dt, "kind": "mean", "expect": [2.0, 4.0]} for dt in ("uint32", "int32", "uint64", "float32", "float64")],
+            "expect_key": [0, 1],
+        },
     ],
     "group_by_multi": [
         {
@@ -115,6 +129,24 @@ KATS = {
             "left_key": [0, 1, 2, 3, 4], "right_key": [1, 2], "key_dtype": "int32", "how": "left", "maintain_order": "none",
             "threads": [1, 2, 3, 4, 5, 6, 7],
             "expect_left_idx": [0, 1, 2, 3, 4], "expect_right_idx": [N, 0, 1, N, N], "exact_order": True,
+        },
+        {
+            "cite": "crates/polars/tests/it/core/joins.rs:172-200 (test_join_with_nulls)",
+            "note": "left dates 20..28 (no 26), right = dates[3..]; left join keeps every left row, the first three unmatched",
+            "left_key": [20, 21, 22, 23, 24, 25, 27, 28], "right_key": [23, 24, 25, 27, 28], "key_dtype": "int32", "how": "left", "maintain_order": "none",
+            "expect_left_idx": [0, 1, 2, 3, 4, 5, 6, 7], "expect_right_idx": [N, N, N, 0, 1, 2, 3, 4], "exact_order": True,
+        },
+        {
+            "cite": "crates/polars/tests/it/core/joins.rs:474-494 (test_joins_with_duplicates, inner)",
+            "note": "duplicates on both sides: left [1,1,2] x right [1,1,1,1,1,3] -> height 10, no nulls",
+            "left_key": [1, 1, 2], "right_key": [1, 1, 1, 1, 1, 3], "key_dtype": "int32", "how": "inner", "maintain_order": "none",
+            "expect_height": 10, "expect_right_nulls": 0, "exact_order": False,
+        },
+        {
+            "cite": "crates/polars/tests/it/core/joins.rs:496-504 (test_joins_with_duplicates, left)",
+            "note": "left join: height 11, exactly one unmatched row (dbl_col null_count == 1)",
+            "left_key": [1, 1, 2], "right_key": [1, 1, 1, 1, 1, 3], "key_dtype": "int32", "how": "left", "maintain_order": "none",
+            "expect_height": 11, "expect_right_nulls": 1, "exact_order": False,
         },
         {
             "cite": "py-polars/tests/unit/operations/test_join.py:29-41 (test_semi_anti_join, anti)",

@@ -113,6 +113,11 @@ def _run_join_kat_one(impl, case, set_threads=None):
             er = np.array([IDX_NULL if x is None else x for x in case["expect_right_idx"]], np.uint32)
             assert np.array_equal(li, el), f"{case['cite']} threads={t}: left idx {li} != {el}"
             assert np.array_equal(ri, er), f"{case['cite']} threads={t}: right idx {ri} != {er}"
+        elif "expect_height" in case:
+            assert li.size == case["expect_height"] and ri.size == li.size, f"{case['cite']}: height {li.size}"
+            assert int((ri == IDX_NULL).sum()) == case["expect_right_nulls"], case["cite"]
+            hit = ri != IDX_NULL
+            assert np.array_equal(lk[li[hit]], rk[ri[hit]]), f"{case['cite']}: joined keys differ"
         else:
             got = sorted(zip(li.tolist(), ri.tolist()))
             assert got == [tuple(p) for p in case["expect_pairs_sorted"]], f"{case['cite']}: {got}"
