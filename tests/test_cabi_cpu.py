@@ -62,3 +62,24 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
                 assert "liboracle" not in txt and "oracle.c" not in txt and "or_group_by" not in txt, f
+
+
+def _build_c_demo(tmp_path):
+    import shutil
+    import subprocess
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    import polars_b200 as plb
+    plb.lib()                                     # builds the library if needed
+    libdir = os.path.join(ROOT, "polars_b200", "_lib")
+    exe = str(tmp_path / "c_abi_demo")
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_abi_demo.c"),
+                        "-L" + libdir, "-lpolars_b200", "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    # the boundary must be consumable from C99 (no C++ / torch types): compile + link examples/c_abi_demo.c
+    _build_c_demo(tmp_path)

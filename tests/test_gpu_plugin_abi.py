@@ -128,3 +128,25 @@ def test_plugin_filter_gather_group_join(caller):
 def test_plugin_error_channel(caller):
     with pytest.raises(RuntimeError, match="dtypes differ"):
         caller.call("add", [("x", [pa.array([1, 2, 3])]), ("y", [pa.array([1.0, 2.0, 3.0])])])
+
+
+@pytest.mark.gpu
+def test_plain_c_caller(tmp_path):
+    # examples/c_abi_demo.c: filter -> group_by/agg -> join through the C ABI from a C99 program (no Python in the loop)
+    import subprocess
+    from test_cabi_cpu import _build_c_demo
+    exe = _build_c_demo(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    key, x = np.arange(1000) % 7, (np.arange(1000) % 11) - 5
+    m = x > 0
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "groups: 7"
+    order = []
+    for k in key[m]:
+        if k not in order:
+            order.append(int(k))
+    for ln, k in zip(lines[1:8], order):
+        sel = m & (key == k)
+        assert ln.split() == ["key", str(k), "sum", str(int(x[sel].sum())), "mean", f"{x[sel].mean():.4f}", "len", str(int(sel.sum()))], ln
+    assert lines[8].startswith("join rows: 1000 (first: key 0 payload 4.5)"), lines[8]
