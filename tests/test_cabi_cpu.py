@@ -83,3 +83,15 @@ def _build_c_demo(tmp_path):
 def test_header_is_plain_c_and_links(tmp_path):
     # the boundary must be consumable from C99 (no C++ / torch types): compile + link examples/c_abi_demo.c
     _build_c_demo(tmp_path)
+
+
+def test_rust_sys_declarations_match_the_header():
+    # integration/polars_b200_sys.rs (boundary B3, documentation: no Rust toolchain here) is generated from the header;
+    # it must declare every exported entry point with the header's current signature
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "integration", "gen_rust_sys.py"), "--check"])
+    assert r.returncode == 0, "integration/polars_b200_sys.rs is stale: run python integration/gen_rust_sys.py"
+    rs = open(os.path.join(ROOT, "integration", "polars_b200_sys.rs")).read()
+    for sym in declared_symbols():
+        assert f"pub fn {sym}(" in rs, sym
