@@ -190,6 +190,7 @@ void op_filter(const std::vector<DevCol>& cols, const DevCol& mask, std::vector<
 // (maintain_order, duplicate build keys), never on the headline path.  CUB radix sort (library).
 void sort_pairs_u32(uint32_t* keys, uint32_t* vals, int64_t n) {
     if (n <= 1) return;
+    PLB_REQUIRE(n <= 0x7FFFFFFFll, BL_ERR_UNSUPPORTED, "ordered output with more than 2^31-1 rows (radix sort item count)");
     Context& c = ctx();
     DevPtr k2 = dev_alloc((size_t)n * 4), v2 = dev_alloc((size_t)n * 4);
     size_t tmp_bytes = 0;

@@ -221,3 +221,52 @@ def broadcast_hash_join(plb, left_key, right_key, left_base: int, how: str = "in
     base = plb.Column(np.array([left_base], np.uint32))
     gl = plb.elementwise("add", li.view(), base, location=plb.DEVICE)
     return gl, ri
+
+
+def exchange_columns(cols, send_counts: np.ndarray):
+    """all-to-all-v of several 1-D tensors that share one destination-major row layout (partition p's rows are
+    contiguous in every column): ONE count exchange, then one all-to-all per column.  Backend-agnostic (NCCL on
+    GPUs, isend/irecv pairs under gloo).  Returns ([received columns], recv_counts)."""
+    send_counts = np.asarray(send_counts, dtype=np.int64)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    recv_counts = exchange_counts(send_counts, cols[0].device if cols else "cpu")
+    so, ro = np.concatenate([[0], np.cumsum(send_counts)]), np.concatenate([[0], np.cumsum(recv_counts)])
+    outs = []
+    for send in cols:
+        assert send.numel() == int(send_counts.sum())
+        recv = torch.empty(int(recv_counts.sum()), dtype=send.dtype, device=send.device)
+        if dist.get_backend() == "nccl":
+            dist.all_to_all_single(recv, send, output_split_sizes=recv_counts.tolist(), input_split_sizes=send_counts.tolist())
+        else:
+            recv[ro[rank]:ro[rank + 1]] = send[so[rank]:so[rank + 1]]
+            reqs = []
+            for p in range(world):
+                if p == rank:
+                    continue
+                if recv_counts[p]:
+                    reqs.append(dist.irecv(recv[ro[p]:ro[p + 1]], src=p))
+                if send_counts[p]:
+                    reqs.append(dist.isend(send[so[p]:so[p + 1]].contiguous(), dst=p))
+            for r in reqs:
+                r.wait()
+        outs.append(recv)
+    return outs, recv_counts
+
+
+def partitioned_group_by_rows(plb, key_col, value_cols, aggs, location=None):
+    """High-cardinality plan: when local pre-aggregation would not shrink the data (groups ~
+    rows), the RAW rows are hash-partitioned on the key (K6: key + value columns scattered together), exchanged with
+    one all-to-all-v per column, and aggregated once on the owning rank (K5).  `aggs`: [(kind, index into value_cols
+    | None)].  8-byte key and value columns without nulls.  Output stays partitioned by key."""
+    world = dist.get_world_size()
+    n = key_col.length
+    kp, vps, offs = plb.hash_partition(key_col, value_cols, world, location=plb.DEVICE)
+    counts = np.diff(offs)
+    key_t = _as_torch(kp, n, "<i8", torch.int64)
+    val_t = [_as_torch(v, n, "<i8", torch.int64) for v in vps]
+    recv, rc = exchange_columns([key_t] + val_t, counts)
+    torch.cuda.synchronize()
+    m = int(rc.sum())
+    kcol = plb.Column(recv[0].data_ptr(), dtype=plb.NP_OF[key_col.dtype], length=m, location=plb.DEVICE)
+    vcols = [plb.Column(r.data_ptr(), dtype=plb.NP_OF[v.dtype], length=m, location=plb.DEVICE) for r, v in zip(recv[1:], value_cols)]
+    return plb.group_by_agg(kcol, [(kind, None if i is None else vcols[i]) for kind, i in aggs], False, location=plb.DEVICE if location is None else location)

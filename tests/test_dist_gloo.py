@@ -85,3 +85,53 @@ def test_partitioned_exchange_world2():
         assert np.array_equal(ks, ek[sel][order]), f"rank {p} owns the wrong groups"
         assert np.array_equal(ln, outs[2][0][sel][order].astype(np.int64)) and np.array_equal(si, outs[0][0][sel][order])
         assert np.allclose(sf, outs[1][0][sel][order], rtol=1e-9)
+
+
+def _worker_rows(rank, world, port, q):
+    """High-cardinality plan (ii): raw rows partitioned on the key, exchanged column by column, aggregated on the owner."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from polars_b200.dist import exchange_columns
+    key, vi, vf = _data(rank, n=30_000, k=40_000)           # groups ~ rows: pre-aggregation would not shrink anything
+    part = oracle.hash_to_partition(oracle.dirty_hash(oracle.key_bits(key)), world).astype(np.int64)
+    order = np.argsort(part, kind="stable")                  # what K6 does: stable scatter by partition
+    counts = np.bincount(part, minlength=world)
+    (rk, ri, rf, r32), rc = exchange_columns([torch.from_numpy(key[order]), torch.from_numpy(vi[order]), torch.from_numpy(vf[order]),
+                                              torch.from_numpy(vi[order].astype(np.int32))], counts)
+    assert rk.numel() == rc.sum() and np.array_equal(r32.numpy(), ri.numpy().astype(np.int32))
+    owner = oracle.hash_to_partition(oracle.dirty_hash(oracle.key_bits(rk.numpy())), world)
+    assert (owner == rank).all()
+    ek, _, outs, _ = oracle.group_by_agg(rk.numpy(), None, [("sum", ri.numpy(), None), ("mean", rf.numpy(), None), ("len", None, None)], 1, True)
+    q.put((rank, ek, outs[0][0], outs[1][0], outs[2][0]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_raw_row_exchange_world2():
+    import oracle
+    world, port = 2, 31500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_rows, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r = q.get(timeout=240)
+        res[r[0]] = r[1:]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    key = np.concatenate([_data(r, n=30_000, k=40_000)[0] for r in range(world)])
+    vi = np.concatenate([_data(r, n=30_000, k=40_000)[1] for r in range(world)])
+    vf = np.concatenate([_data(r, n=30_000, k=40_000)[2] for r in range(world)])
+    ek, _, outs, _ = oracle.group_by_agg(key, None, [("sum", vi, None), ("mean", vf, None), ("len", None, None)], 4, True)
+    got_k = np.concatenate([res[r][0] for r in range(world)])
+    o, eo = np.argsort(got_k), np.argsort(ek)
+    assert np.array_equal(got_k[o], ek[eo])                   # every group on exactly one rank
+    assert np.array_equal(np.concatenate([res[r][1] for r in range(world)])[o], outs[0][0][eo])
+    assert np.allclose(np.concatenate([res[r][2] for r in range(world)])[o], outs[1][0][eo], rtol=1e-9)
+    assert np.array_equal(np.concatenate([res[r][3] for r in range(world)])[o], outs[2][0][eo])

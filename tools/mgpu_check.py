@@ -80,4 +80,21 @@ assert l2.size == int(np.isin(pkeys_all[rank], perm).sum()) and (l2.size == 0 or
 assert np.all(np.diff(l2.astype(np.int64)) > 0), "broadcast join: probe order lost"
 if rank == 0:
     print(f"mgpu_check broadcast join: OK world={world}", flush=True)
+
+# ---- high-cardinality plan (ii): raw rows partitioned + exchanged, one aggregation on the owning rank
+hk = [np.random.default_rng(900 + r).integers(0, 5_000_000, 400_000).astype(np.int64) for r in range(world)]
+hv = [np.random.default_rng(950 + r).integers(-1000, 1000, 400_000).astype(np.int64) for r in range(world)]
+dk, dv = plb.to_device(hk[rank]), plb.to_device(hv[rank])
+okey, oaggs = pdist.partitioned_group_by_rows(plb, dk.view(), [dv.view()], [("sum", 0), ("len", None)])
+k_, _ = okey.to_numpy(); s_, _ = oaggs[0].to_numpy(); l_, _ = oaggs[1].to_numpy()
+allk, allv = np.concatenate(hk), np.concatenate(hv)
+uk, inv = np.unique(allk, return_inverse=True)
+es, el = np.zeros(uk.size, np.int64), np.bincount(inv)
+np.add.at(es, inv, allv)
+pos = np.searchsorted(uk, k_)
+assert np.array_equal(uk[pos], k_) and np.array_equal(es[pos], s_) and np.array_equal(el[pos], l_), "raw-row plan: aggregates differ"
+tot = torch.tensor([k_.size], dtype=torch.int64, device="cuda"); dist.all_reduce(tot)
+assert int(tot.item()) == uk.size, "raw-row plan: a group is missing or owned twice"
+if rank == 0:
+    print(f"mgpu_check raw-row group_by: OK world={world} groups={uk.size}", flush=True)
 dist.destroy_process_group()
