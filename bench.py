@@ -470,6 +470,10 @@ def cpu_baseline(a):
         t0 = time.perf_counter()
         oracle.group_by_agg(key, None, aggs, cores, False)
         dt = time.perf_counter() - t0
+        n1 = min(sample, 4_000_000)      # single-thread point of the same port (all cores and 1 core)
+        t1 = time.perf_counter()
+        oracle.group_by_agg(key[:n1], None, [(k, None if v is None else v[:n1], m) for k, v, m in aggs], 1, False)
+        one = n1 / (time.perf_counter() - t1)
         second = acero_baseline(a, sample, a.build_rows)
     else:
         build_rows = max(1, int(a.build_rows * sample / a.rows))
@@ -477,9 +481,14 @@ def cpu_baseline(a):
         t0 = time.perf_counter()
         oracle.hash_join(probe, build, None, None, "inner", False, "none", cores)
         dt = time.perf_counter() - t0
+        n1 = min(sample, 4_000_000)
+        t1 = time.perf_counter()
+        oracle.hash_join(probe[:n1], build, None, None, "inner", False, "none", 1)
+        one = n1 / (time.perf_counter() - t1)
         second = acero_baseline(a, sample, build_rows)
     return {"value": sample / dt, "unit": "rows/s", "cores": cores, "kind": "port",
             "sample": f"{sample} rows of the same workload, one pass; oracle = C/OpenMP restatement of the reference's partitioned algorithm (the Rust reference cannot be built here)",
+            "single_thread": {"value": one, "unit": "rows/s", "cores": 1, "sample": f"{n1} rows"},
             "second_reference": second}
 
 
