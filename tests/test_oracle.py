@@ -273,3 +273,42 @@ def test_group_by_multi_matches_single_key_and_pyarrow():
     exp = {(x, y): (s, c) for x, y, s, c in zip(t["a"], t["b"], t["v_sum"], t["count_all"])}
     got = {(None if (kouts[0][1] is not None and not kouts[0][1][i]) else int(kouts[0][0][i]), int(kouts[1][0][i])): (int(outs[0][0][i]), int(outs[1][0][i])) for i in range(len(outs[0][0]))}
     assert got == exp
+
+
+@pytest.mark.parametrize("nulls_equal", [False, True])
+def test_semi_anti_vs_bruteforce_and_acero(nulls_equal):
+    # single_keys_semi_anti.rs:41-140 restated as set membership; cross-checked against a brute-force loop and Acero
+    import pyarrow as pa
+    rng = np.random.default_rng(17)
+    nl, nr = 600, 90
+    lk, rk = rng.integers(0, 120, nl).astype(np.int64), rng.integers(0, 120, nr).astype(np.int64)
+    lv, rv = rng.random(nl) > 0.1, rng.random(nr) > 0.1
+    right_has_null = bool((~rv).any())
+    exp = np.array([(lv[i] and bool(((rk == lk[i]) & rv).any())) or (nulls_equal and not lv[i] and right_has_null) for i in range(nl)])
+    semi, _ = oracle.hash_join(lk, rk, lv, rv, "semi", nulls_equal, "none", 4)
+    anti, _ = oracle.hash_join(lk, rk, lv, rv, "anti", nulls_equal, "none", 4)
+    assert np.array_equal(semi, np.nonzero(exp)[0]) and np.array_equal(anti, np.nonzero(~exp)[0])
+    if not nulls_equal:      # Acero's semi/anti joins never match nulls
+        lt = pa.table({"k": pa.array(lk, mask=~lv), "i": np.arange(nl)})
+        rt = pa.table({"k": pa.array(rk, mask=~rv)})
+        for how, got in (("left semi", semi), ("left anti", anti)):
+            idx = np.sort(lt.join(rt, keys="k", join_type=how).column("i").to_numpy())
+            assert np.array_equal(idx, got), how
+
+
+@pytest.mark.parametrize("dtype", ["int8", "uint8", "int16", "uint16"])
+def test_small_int_aggregation_rules(dtype):
+    # series/implementations/mod.rs:145-154: 8/16-bit sums are computed (and returned) as Int64 — no wrap-around
+    rng = np.random.default_rng(23)
+    info = np.iinfo(dtype)
+    n = 50_000
+    key = rng.integers(0, 4, n).astype(np.int64)
+    val = rng.integers(info.min, int(info.max) + 1, n).astype(dtype)
+    valid = rng.random(n) > 0.2
+    ek, _, outs, _ = oracle.group_by_agg(key, None, [("sum", val, valid), ("mean", val, valid), ("min", val, valid), ("max", val, valid)], 2, True)
+    for g, k in enumerate(ek):
+        sel = (key == k) & valid
+        wide = val[sel].astype(np.int64)
+        assert outs[0][0].dtype == np.int64 and outs[0][0][g] == wide.sum()
+        assert outs[1][0].dtype == np.float64 and abs(outs[1][0][g] - wide.mean()) < 1e-9
+        assert outs[2][0].dtype == np.dtype(dtype) and outs[2][0][g] == wide.min() and outs[3][0][g] == wide.max()
