@@ -311,3 +311,31 @@ def hash_join(left_keys, right_keys, left_valid=None, right_valid=None, how: str
         # polars-ops/src/frame/join/dispatch_left_right.rs:142-170: stable sort on the right idx (null = u32::MAX last)
         lib().or_stable_sort_pairs(_p(li), _p(ri), C.c_int64(m), C.c_int(1))
     return li, ri
+
+
+def hash_join_multi(left_keys, right_keys, left_valids=None, right_valids=None, how: str = "inner", nulls_equal: bool = False,
+                    maintain_order: str = "none", n_threads: int | None = None):
+    """Several key columns per side.  The reference canonicalises float keys, row-encodes the columns of each side
+    into one binary key (polars-ops/src/frame/join/mod.rs:658-678 `prepare_keys_multiple`) and runs the SAME
+    single-key machinery on it; with nulls_equal = false a null in ANY key column makes the whole encoded key null
+    (`encode_rows_vertical_par_unordered_broadcast_nulls`, :676), with nulls_equal = true nulls are part of the key.
+    Restated: one dense id per distinct (validity, canonical bits) row over BOTH relations, then `hash_join`."""
+    nl, nr = np.ascontiguousarray(left_keys[0]).size, np.ascontiguousarray(right_keys[0]).size
+    left_valids = left_valids or [None] * len(left_keys)
+    right_valids = right_valids or [None] * len(right_keys)
+    cols, all_valid = [], np.ones(nl + nr, np.bool_)
+    for lk, rk, lv, rv in zip(left_keys, right_keys, left_valids, right_valids):
+        if np.asarray(lk).dtype != np.asarray(rk).dtype:
+            raise TypeError("join key dtypes differ")                      # join/mod.rs:231-241
+        bits = np.concatenate([key_bits(lk), key_bits(rk)])
+        vv = np.concatenate([np.ones(nl, np.bool_) if lv is None else _valid(lv, nl), np.ones(nr, np.bool_) if rv is None else _valid(rv, nr)])
+        all_valid &= vv
+        cols += [vv.astype(np.uint64), np.where(vv, bits, np.uint64(0))]
+    if nl + nr == 0:
+        ids = np.zeros(0, np.uint64)
+    else:
+        _, inverse = np.unique(np.stack(cols, axis=1), axis=0, return_inverse=True)
+        ids = np.asarray(inverse).reshape(-1).astype(np.uint64)
+    row_valid = None if nulls_equal else all_valid
+    return hash_join(ids[:nl], ids[nl:], None if row_valid is None else row_valid[:nl], None if row_valid is None else row_valid[nl:],
+                     how, nulls_equal, maintain_order, n_threads)

@@ -113,6 +113,21 @@ KATS = {
             "keys": [[1, 1, 1, 1, 1], [1, 1, 1, 1, 1]], "key_dtype": "int64", "kind": "len", "expect": [5], "expect_keys": [[1], [1]],
         },
     ],
+    "join_multi": [
+        {
+            "cite": "crates/polars/tests/it/core/joins.rs:602-628 (test_join_floats)",
+            "note": "left join on (a, c) = (foo, bar), Float64 keys: ham == [None, 'var', None, None] -> right idx [N, 1, N, N]",
+            "left_keys": [[1.0, 2.0, 1.0, 1.0], [0.0, 1.0, 2.0, 3.0]], "right_keys": [[1.0, 2.0, 1.0], [1.0, 1.0, 1.0]], "key_dtype": "float64",
+            "how": "left", "nulls_equal": False, "expect_left_idx": [0, 1, 2, 3], "expect_right_idx": [N, 1, N, N],
+        },
+        {
+            "cite": "crates/polars/tests/it/core/joins.rs:651-684 (test_4_threads_bit_offset)",
+            "note": "inner join on (a, b) with join_nulls(true): left b = None on even rows else 0, right a = 1..8, b = None where a % 3 == 0 else 1; "
+                    "only (6, None) matches -> shape (1, 2)",
+            "left_keys": [[0, 1, 2, 3, 4, 5, 6, 7], [N, 0, N, 0, N, 0, N, 0]], "right_keys": [[1, 2, 3, 4, 5, 6, 7, 8], [1, 1, N, 1, 1, N, 1, 1]],
+            "key_dtype": "int64", "how": "inner", "nulls_equal": True, "expect_left_idx": [6], "expect_right_idx": [5],
+        },
+    ],
     "join": [
         {
             "cite": "crates/polars/tests/it/core/joins.rs:40-78 (test_inner_join, POLARS_MAX_THREADS 1..7)",

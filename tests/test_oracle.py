@@ -312,3 +312,29 @@ def test_small_int_aggregation_rules(dtype):
         assert outs[0][0].dtype == np.int64 and outs[0][0][g] == wide.sum()
         assert outs[1][0].dtype == np.float64 and abs(outs[1][0][g] - wide.mean()) < 1e-9
         assert outs[2][0].dtype == np.dtype(dtype) and outs[2][0][g] == wide.min() and outs[3][0][g] == wide.max()
+
+
+def test_join_multi_kats(kats):
+    # multi-column join keys are not on the GPU path yet (NEXT.md); the oracle restatement is pinned already
+    from helpers import col
+    for case in kats["join_multi"]:
+        lk = [col(k, case["key_dtype"]) for k in case["left_keys"]]
+        rk = [col(k, case["key_dtype"]) for k in case["right_keys"]]
+        for threads in (1, 4):
+            li, ri = oracle.hash_join_multi([k for k, _ in lk], [k for k, _ in rk], [v for _, v in lk], [v for _, v in rk], case["how"], case["nulls_equal"], "none", threads)
+            assert li.tolist() == case["expect_left_idx"], case["cite"]
+            assert ri.tolist() == [IDX_NULL if x is None else x for x in case["expect_right_idx"]], case["cite"]
+
+
+def test_join_multi_matches_acero():
+    rng = np.random.default_rng(31)
+    nl, nr = 3000, 800
+    la, lb = rng.integers(0, 40, nl).astype(np.int64), rng.integers(0, 6, nl).astype(np.int32)
+    ra, rb = rng.integers(0, 40, nr).astype(np.int64), rng.integers(0, 6, nr).astype(np.int32)
+    lbv, rbv = rng.random(nl) > 0.1, rng.random(nr) > 0.1
+    li, ri = oracle.hash_join_multi([la, lb], [ra, rb], [None, lbv], [None, rbv], "inner", False, "none", 4)
+    lt = pa.table({"a": la, "b": pa.array(lb, mask=~lbv), "i": np.arange(nl)})
+    rt = pa.table({"a": ra, "b": pa.array(rb, mask=~rbv), "j": np.arange(nr)})
+    j = lt.join(rt, keys=["a", "b"], join_type="inner")
+    exp = sorted(zip(j.column("i").to_pylist(), j.column("j").to_pylist()))
+    assert sorted(zip(li.tolist(), ri.tolist())) == exp
