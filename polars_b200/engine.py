@@ -17,9 +17,9 @@ UDF bodies are written against the reference source only; the plan matcher (whic
 left to Polars) is tested with a mock NodeTraverser in tests/test_engine_matcher.py.  It is deliberately
 conservative: any node shape it does not recognise is left untouched (Polars executes it).
 Recognised:
-  * GroupBy(keys=[col], aggs ⊆ {col.sum/mean/min/max/count, len}) over a DataFrameScan, optionally through
-    one Filter(col <cmp> literal)                      -> bl_filter_cmp + bl_groupby_agg
-  * Join(inner|left, one key column per side) of two DataFrameScans -> bl_hash_join + bl_gather
+  * GroupBy(keys=[col, ...], aggs ⊆ {col.sum/mean/min/max/count, len}) over a DataFrameScan, optionally through
+    one Filter(col <cmp> literal)                      -> bl_filter_cmp + bl_groupby_agg / bl_groupby_agg_keys
+  * Join(inner|left|semi|anti, one key column per side) of two DataFrameScans -> bl_hash_join + bl_gather
 """
 from __future__ import annotations
 
@@ -100,9 +100,10 @@ def _scan_frame(nt, node_id):
 
 
 def _plan_group_by(plb, nt, root_id, node):
-    if len(node.keys) != 1:
-        raise _Unsupported("multi-column keys")
-    key_name = _column_name(nt, node.keys[0].node)
+    if len(node.keys) < 1:
+        raise _Unsupported("group_by without keys")
+    key_names = [_column_name(nt, k.node) for k in node.keys]       # several plain columns -> bl_groupby_agg_keys
+    key_name = key_names[0]
     aggs = [_parse_agg(nt, a) for a in node.aggs]
     nt.set_node(node.input)
     child = nt.view_current_node()
@@ -119,7 +120,7 @@ def _plan_group_by(plb, nt, root_id, node):
     def run(*_args: Any, **_kwargs: Any):
         import polars as pl
         df = frame()
-        needed = [key_name] + [c for _, c, _ in aggs if c is not None]
+        needed = key_names + [c for _, c, _ in aggs if c is not None]
         cols = {c: _series_to_column(plb, df.get_column(c)) for c in dict.fromkeys(needed)}
         if flt is not None:
             fcol, fop, fval = flt
@@ -127,11 +128,20 @@ def _plan_group_by(plb, nt, root_id, node):
             dev = [plb.to_device(*_concat(df.get_column(c))) for c in names]
             outs = plb.filter_cmp([d.view() for d in dev], names.index(fcol), fop, fval, location=plb.DEVICE)
             view = {c: outs[i].view() for i, c in enumerate(names)}
-            key, vals = view[key_name], {c: view[c] for c in needed}
+            vals = {c: view[c] for c in needed}
         else:
-            key, vals = cols[key_name], cols
-        (k, kv), outs = plb.group_by_agg(key, [(kind, None if c is None else vals[c]) for kind, c, _ in aggs], maintain_order)
-        res = {key_name: pl.Series(key_name, k).set(pl.Series(~kv), None) if kv is not None else pl.Series(key_name, k)}
+            vals = cols
+        agg_args = [(kind, None if c is None else vals[c]) for kind, c, _ in aggs]
+        if len(key_names) == 1:
+            kout, outs = plb.group_by_agg(vals[key_name], agg_args, maintain_order)
+            kouts = [kout]
+        else:
+            if flt is None and any(len(vals[c]) != 1 for c in key_names):
+                raise plb.B200Error(4, "multi-column keys need single-chunk columns")      # the caller rechunks and retries on CPU
+            kouts, outs = plb.group_by_agg_keys([vals[c][0] if isinstance(vals[c], list) else vals[c] for c in key_names], agg_args, maintain_order)
+        res = {}
+        for name, (k, kv) in zip(key_names, kouts):
+            res[name] = pl.Series(name, k).set(pl.Series(~kv), None) if kv is not None else pl.Series(name, k)
         for (kind, c, out_name), (v, m) in zip(aggs, outs):
             s = pl.Series(out_name, v)
             res[out_name] = s.set(pl.Series(~m), None) if m is not None else s
@@ -147,7 +157,7 @@ def _concat(series):
 
 def _plan_join(plb, nt, root_id, node):
     how = str(node.options[0]).lower() if isinstance(node.options, (tuple, list)) else str(node.options)
-    how = "inner" if "inner" in how else ("left" if "left" in how else None)
+    how = next((h for h in ("inner", "left", "semi", "anti") if h in how), None)
     if how is None or len(node.left_on) != 1 or len(node.right_on) != 1:
         raise _Unsupported("join type / multi-key")
     lkey, rkey = _column_name(nt, node.left_on[0].node), _column_name(nt, node.right_on[0].node)
@@ -158,6 +168,8 @@ def _plan_join(plb, nt, root_id, node):
         import polars as pl
         left, right = left_frame(), right_frame()
         (li, _), (ri, rv) = plb.hash_join(_series_to_column(plb, left.get_column(lkey)), _series_to_column(plb, right.get_column(rkey)), how)
+        if how in ("semi", "anti"):          # only left rows survive (single_keys_semi_anti.rs:41-140)
+            return left[pl.Series(li)]
         ridx = pl.Series(ri) if rv is None else pl.Series(ri).set(pl.Series(~rv), None)
         out_l = left[pl.Series(li)]
         out_r = right.drop(rkey)[ridx] if how == "inner" else right.drop(rkey).select(pl.all().gather(ridx))

@@ -58,13 +58,13 @@ def group_by_plan(agg_name="sum", n_keys=1, with_filter=True, rhs_literal=True, 
 
 
 def test_filter_group_by_is_taken():
-    for with_filter in (True, False):
-        nt = group_by_plan(with_filter=with_filter)
+    for kwargs in (dict(with_filter=True), dict(with_filter=False), dict(n_keys=2)):
+        nt = group_by_plan(**kwargs)
         engine.execute_with_b200(nt)
         assert callable(nt.udf) and nt.cur == 12          # the traverser is left on the replaced root
 
 
-@pytest.mark.parametrize("kwargs", [dict(agg_name="median"), dict(n_keys=2), dict(rhs_literal=False), dict(scan_selection=object())])
+@pytest.mark.parametrize("kwargs", [dict(agg_name="median"), dict(rhs_literal=False), dict(scan_selection=object())])
 def test_unsupported_group_by_shapes_are_left_to_polars(kwargs):
     nt = group_by_plan(**kwargs)
     engine.execute_with_b200(nt)
@@ -82,7 +82,7 @@ def join_plan(how="Inner", n_keys=1):
 
 
 def test_single_key_joins_are_taken_and_others_left():
-    for how in ("Inner", "Left"):
+    for how in ("Inner", "Left", "Semi", "Anti"):
         nt = join_plan(how)
         engine.execute_with_b200(nt)
         assert callable(nt.udf) and nt.cur == 22
