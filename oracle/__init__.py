@@ -55,6 +55,17 @@ def max_threads() -> int:
     return int(lib().or_max_threads())
 
 
+def hw_threads() -> int:
+    """Logical CPUs OpenMP can see (independent of OMP_NUM_THREADS)."""
+    lib().or_hw_threads.restype = C.c_int
+    return int(lib().or_hw_threads())
+
+
+def set_threads(n: int) -> None:
+    """Pool size of the aggregation / probe loops (the reference runs them on its Rayon pool)."""
+    lib().or_set_threads(C.c_int(int(n)))
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 

@@ -318,18 +318,26 @@ int64_t or_group_by(const uint64_t* keys, const uint8_t* key_valid, int64_t n, i
     if (n == 0) { offsets[0] = 0; return 0; }
     int P = n_partitions < 1 ? 1 : n_partitions;
     if (n <= 1000) P = 1;                                /* into_groups.rs:25-28 */
-    idx_t* gid_of_row = (idx_t*)malloc((size_t)n * sizeof(idx_t));
-    /* per-partition: local group count and first idx list */
+    /* per-partition: local group count, first idx / count per local group, and the partition's rows in scan
+     * order with their local group id — the restatement of the per-group IdxVec pushes of hashing.rs:142-153.
+     * Everything a thread writes during the scan is private to it (the reference's threads own their tables
+     * and vectors the same way), so the port scales with threads like the Rayon original. */
     int64_t* part_ngroups = (int64_t*)calloc(P, sizeof(int64_t));
+    int64_t* part_nrows = (int64_t*)calloc(P, sizeof(int64_t));
     idx_t** part_first = (idx_t**)calloc(P, sizeof(idx_t*));
     idx_t** part_count = (idx_t**)calloc(P, sizeof(idx_t*));
+    idx_t** part_rows = (idx_t**)calloc(P, sizeof(idx_t*));
+    idx_t** part_gids = (idx_t**)calloc(P, sizeof(idx_t*));
 
 #pragma omp parallel for schedule(static, 1) num_threads(P > 1 ? P : 1) if (P > 1)
     for (int t = 0; t < P; t++) {
         map_t m; map_init(&m, 512);                      /* _HASHMAP_INIT_SIZE */
         int64_t cap = 1024, ng = 0;
+        int64_t rcap = n / P + n / (8 * P) + 1024, nr = 0;
         idx_t* pf = (idx_t*)malloc(cap * sizeof(idx_t));
         idx_t* pc = (idx_t*)malloc(cap * sizeof(idx_t));
+        idx_t* rows = (idx_t*)malloc((size_t)rcap * sizeof(idx_t));
+        idx_t* gids = (idx_t*)malloc((size_t)rcap * sizeof(idx_t));
         for (int64_t i = 0; i < n; i++) {
             int valid = key_valid == NULL || key_valid[i];
             uint64_t k = keys[i];
@@ -344,15 +352,18 @@ int64_t or_group_by(const uint64_t* keys, const uint8_t* key_valid, int64_t n, i
                 if (ins) { *slot = (uint32_t)ng; g = (idx_t)ng; goto newgroup; }
                 g = *slot;
             }
-            pc[g]++; gid_of_row[i] = g; continue;
+            pc[g]++; goto push;
         newgroup:
             if (ng == cap) { cap *= 2; pf = (idx_t*)realloc(pf, cap * sizeof(idx_t)); pc = (idx_t*)realloc(pc, cap * sizeof(idx_t)); }
-            pf[ng] = (idx_t)i; pc[ng] = 1; gid_of_row[i] = g; ng++;
+            pf[ng] = (idx_t)i; pc[ng] = 1; ng++;
+        push:
+            if (nr == rcap) { rcap += rcap / 2 + 1024; rows = (idx_t*)realloc(rows, (size_t)rcap * sizeof(idx_t)); gids = (idx_t*)realloc(gids, (size_t)rcap * sizeof(idx_t)); }
+            rows[nr] = (idx_t)i; gids[nr] = g; nr++;
         }
         /* Local group ids are in first-occurrence order; the reference iterates the hashbrown
          * table instead (hashing.rs:157-160) — order unpinned when !sorted. */
         map_free(&m);
-        part_ngroups[t] = ng; part_first[t] = pf; part_count[t] = pc;
+        part_ngroups[t] = ng; part_nrows[t] = nr; part_first[t] = pf; part_count[t] = pc; part_rows[t] = rows; part_gids[t] = gids;
     }
     /* global group numbering: partition-major (flatten, hashing.rs:66-71), then optional sort */
     int64_t* part_base = (int64_t*)malloc((P + 1) * sizeof(int64_t));
@@ -361,6 +372,7 @@ int64_t or_group_by(const uint64_t* keys, const uint8_t* key_valid, int64_t n, i
     int64_t G = part_base[P];
     firstgid_t* fg = (firstgid_t*)malloc((size_t)G * sizeof(firstgid_t));
     idx_t* counts = (idx_t*)malloc((size_t)G * sizeof(idx_t));
+#pragma omp parallel for schedule(static, 1) num_threads(P > 1 ? P : 1) if (P > 1)
     for (int t = 0; t < P; t++)
         for (int64_t j = 0; j < part_ngroups[t]; j++) {
             fg[part_base[t] + j].first = part_first[t][j]; fg[part_base[t] + j].gid = (idx_t)(part_base[t] + j);
@@ -372,24 +384,21 @@ int64_t or_group_by(const uint64_t* keys, const uint8_t* key_valid, int64_t n, i
     for (int64_t p = 0; p < G; p++) {
         newpos[fg[p].gid] = (idx_t)p; first[p] = fg[p].first; offsets[p + 1] = offsets[p] + counts[fg[p].gid];
     }
-    /* fill idx lists: every thread scans all rows in order and fills the groups of ITS partition
-     * (the reference pushes into the group's IdxVec during the same T x N scan, hashing.rs:142-153)
-     * => ascending inside each group */
+    /* fill idx lists: every partition replays ITS rows in scan order => ascending inside each group */
     uint64_t* cursor = (uint64_t*)malloc((size_t)G * sizeof(uint64_t));
     memcpy(cursor, offsets, (size_t)G * sizeof(uint64_t));
 #pragma omp parallel for schedule(static, 1) num_threads(P > 1 ? P : 1) if (P > 1)
     for (int t = 0; t < P; t++) {
-        for (int64_t i = 0; i < n; i++) {
-            int valid = key_valid == NULL || key_valid[i];
-            uint64_t h = valid ? dirty_hash_u64(keys[i]) : 0;
-            if (P > 1 && (int)hash_to_partition(h, (uint64_t)P) != t) continue;
-            idx_t p = newpos[part_base[t] + gid_of_row[i]];
-            idx[cursor[p]++] = (idx_t)i;
+        const idx_t* rows = part_rows[t]; const idx_t* gids = part_gids[t];
+        const int64_t base = part_base[t];
+        for (int64_t j = 0; j < part_nrows[t]; j++) {
+            idx_t p = newpos[base + gids[j]];
+            idx[cursor[p]++] = rows[j];
         }
     }
-    for (int t = 0; t < P; t++) { free(part_first[t]); free(part_count[t]); }
-    free(part_first); free(part_count); free(part_ngroups); free(part_base);
-    free(fg); free(counts); free(newpos); free(cursor); free(gid_of_row);
+    for (int t = 0; t < P; t++) { free(part_first[t]); free(part_count[t]); free(part_rows[t]); free(part_gids[t]); }
+    free(part_first); free(part_count); free(part_rows); free(part_gids); free(part_ngroups); free(part_nrows); free(part_base);
+    free(fg); free(counts); free(newpos); free(cursor);
     return G;
 }
 
@@ -703,6 +712,21 @@ void or_stable_sort_pairs(idx_t* left, idx_t* right, int64_t n, int by_right) {
 int or_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+/* Thread count of the aggregation / elementwise loops (the Rayon pool size of the reference: POOL.install). */
+void or_set_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+int or_hw_threads(void) {
+#ifdef _OPENMP
+    return omp_get_num_procs();
 #else
     return 1;
 #endif
