@@ -59,12 +59,27 @@ def _column_name(nt, node: int) -> str:
 
 
 def _parse_agg(nt, expr_ir):
+    """Agg / Len expression view -> (library aggregation, column | None, output name).
+    Agg.options carries the per-aggregation switch (visitor/expr_nodes.rs:953-1032): min/max -> propagate_nans
+    (the library ignores NaNs like the default `min()`/`max()`, so True is left to Polars), count -> include_nulls
+    (`pl.col(x).len()` lowers to count(include_nulls=True) = the group length, dsl/mod.rs:923-929)."""
     e = nt.view_expression(expr_ir.node)
     name = type(e).__name__
     if name == "Len":
         return "len", None, expr_ir.output_name
     if name == "Agg" and str(e.name) in _AGG and len(e.arguments) == 1:
-        return _AGG[str(e.name)], _column_name(nt, e.arguments[0]), expr_ir.output_name
+        kind, opt = _AGG[str(e.name)], getattr(e, "options", None)
+        col = _column_name(nt, e.arguments[0])
+        if kind in ("min", "max") and opt not in (None, False):
+            raise _Unsupported(f"{kind}(propagate_nans=True)")
+        if kind == "count":
+            if opt is True:
+                return "len", None, expr_ir.output_name          # include_nulls: every row of the group counts
+            if opt not in (None, False):
+                raise _Unsupported("count options")
+        elif kind in ("sum", "mean") and opt is not None:
+            raise _Unsupported(f"{kind} options")
+        return kind, col, expr_ir.output_name
     raise _Unsupported(f"aggregation {name}")
 
 
@@ -102,6 +117,10 @@ def _scan_frame(nt, node_id):
 def _plan_group_by(plb, nt, root_id, node):
     if len(node.keys) < 1:
         raise _Unsupported("group_by without keys")
+    # GroupbyOptions (visitor/expr_nodes.rs:757-790): a pushed-down slice, dynamic or rolling windows change the result
+    opts = getattr(node, "options", None)
+    if opts is not None and any(getattr(opts, f, None) is not None for f in ("slice", "dynamic", "rolling")):
+        raise _Unsupported("group_by options (slice / dynamic / rolling)")
     key_names = [_column_name(nt, k.node) for k in node.keys]       # several plain columns -> bl_groupby_agg_keys
     key_name = key_names[0]
     aggs = [_parse_agg(nt, a) for a in node.aggs]
@@ -155,11 +174,35 @@ def _concat(series):
     return (a, None) if series.null_count() == 0 else (np.where(series.is_null().to_numpy(), 0, a), ~series.is_null().to_numpy())
 
 
+_JOIN_HOW = {"Inner": "inner", "Left": "left", "Semi": "semi", "Anti": "anti"}
+_JOIN_ORDER = {"none": "none", "left": "left", "right": "right", "left_right": "left_right", "right_left": "right_left"}
+
+
+def _join_options(options):
+    """Join.options = (how, nulls_equal, slice, suffix, coalesce, maintain_order) (visitor/nodes.rs:590-651).
+    `how` is a plain str for the equi-joins (a tuple for asof / iejoin: never taken).  Returns
+    (how, nulls_equal, suffix, maintain_order) or raises when an option asks for something the UDF does not do."""
+    if not isinstance(options, (tuple, list)) or len(options) != 6:
+        raise _Unsupported("join options")
+    how, nulls_equal, slc, suffix, coalesce, order = options
+    if not isinstance(how, str) or how not in _JOIN_HOW:
+        raise _Unsupported(f"join type {how!r}")
+    if slc is not None:
+        raise _Unsupported("join with a pushed-down slice")
+    if not isinstance(nulls_equal, bool) or not isinstance(suffix, str) or str(order) not in _JOIN_ORDER:
+        raise _Unsupported("join options")
+    how = _JOIN_HOW[how]
+    if how in ("inner", "left") and coalesce is not True:
+        raise _Unsupported("coalesce=False keeps both key columns")          # the UDF drops the right key (general.rs:17-49)
+    if how in ("semi", "anti") and str(order) != "none":
+        raise _Unsupported("maintain_order on a semi/anti join")
+    return how, nulls_equal, suffix, _JOIN_ORDER[str(order)]
+
+
 def _plan_join(plb, nt, root_id, node):
-    how = str(node.options[0]).lower() if isinstance(node.options, (tuple, list)) else str(node.options)
-    how = next((h for h in ("inner", "left", "semi", "anti") if h in how), None)
-    if how is None or len(node.left_on) != 1 or len(node.right_on) != 1:
-        raise _Unsupported("join type / multi-key")
+    how, nulls_equal, suffix, order = _join_options(node.options)
+    if len(node.left_on) != 1 or len(node.right_on) != 1:
+        raise _Unsupported("multi-key join")
     lkey, rkey = _column_name(nt, node.left_on[0].node), _column_name(nt, node.right_on[0].node)
     left_frame, right_frame = _scan_frame(nt, node.input_left), _scan_frame(nt, node.input_right)
     nt.set_node(root_id)
@@ -167,14 +210,15 @@ def _plan_join(plb, nt, root_id, node):
     def run(*_args: Any, **_kwargs: Any):
         import polars as pl
         left, right = left_frame(), right_frame()
-        (li, _), (ri, rv) = plb.hash_join(_series_to_column(plb, left.get_column(lkey)), _series_to_column(plb, right.get_column(rkey)), how)
+        (li, _), (ri, rv) = plb.hash_join(_series_to_column(plb, left.get_column(lkey)), _series_to_column(plb, right.get_column(rkey)), how,
+                                          nulls_equal, order)
         if how in ("semi", "anti"):          # only left rows survive (single_keys_semi_anti.rs:41-140)
             return left[pl.Series(li)]
         ridx = pl.Series(ri) if rv is None else pl.Series(ri).set(pl.Series(~rv), None)
         out_l = left[pl.Series(li)]
         out_r = right.drop(rkey)[ridx] if how == "inner" else right.drop(rkey).select(pl.all().gather(ridx))
         clash = [c for c in out_r.columns if c in out_l.columns]
-        return out_l.hstack(out_r.rename({c: c + "_right" for c in clash}))      # general.rs:17-49
+        return out_l.hstack(out_r.rename({c: c + suffix for c in clash}))      # general.rs:17-49
 
     return run
 

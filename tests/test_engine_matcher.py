@@ -42,8 +42,8 @@ def expr_ir(node, name):
     return types.SimpleNamespace(node=node, output_name=name)
 
 
-def group_by_plan(agg_name="sum", n_keys=1, with_filter=True, rhs_literal=True, scan_selection=None):
-    exprs = {0: make("Column", name="key"), 1: make("Column", name="x"), 2: make("Agg", name=agg_name, arguments=[1]), 3: make("Len"),
+def group_by_plan(agg_name="sum", n_keys=1, with_filter=True, rhs_literal=True, scan_selection=None, agg_options=None, gb_options=None):
+    exprs = {0: make("Column", name="key"), 1: make("Column", name="x"), 2: make("Agg", name=agg_name, arguments=[1], options=agg_options), 3: make("Len"),
              4: make("BinaryExpr", left=1, op="Operator.Gt", right=5), 5: make("Literal", value=0) if rhs_literal else make("Column", name="y"),
              6: make("Column", name="key2")}
     scan = make("DataFrameScan", df=object(), projection=None, selection=scan_selection)
@@ -53,7 +53,8 @@ def group_by_plan(agg_name="sum", n_keys=1, with_filter=True, rhs_literal=True, 
         nodes[11] = make("Filter", input=10, predicate=expr_ir(4, "p"))
         child = 11
     keys = [expr_ir(0, "key")] + ([expr_ir(6, "key2")] if n_keys == 2 else [])
-    nodes[12] = make("GroupBy", input=child, keys=keys, aggs=[expr_ir(2, "x"), expr_ir(3, "len")], maintain_order=True)
+    nodes[12] = make("GroupBy", input=child, keys=keys, aggs=[expr_ir(2, "x"), expr_ir(3, "len")], maintain_order=True,
+                     options=gb_options if gb_options is not None else make("GroupbyOptions", slice=None, dynamic=None, rolling=None))
     return FakeTraverser(nodes, exprs, 12)
 
 
@@ -64,7 +65,11 @@ def test_filter_group_by_is_taken():
         assert callable(nt.udf) and nt.cur == 12          # the traverser is left on the replaced root
 
 
-@pytest.mark.parametrize("kwargs", [dict(agg_name="median"), dict(rhs_literal=False), dict(scan_selection=object())])
+@pytest.mark.parametrize("kwargs", [dict(agg_name="median"), dict(rhs_literal=False), dict(scan_selection=object()),
+                                    dict(agg_name="min", agg_options=True), dict(agg_name="max", agg_options=True),       # propagate_nans
+                                    dict(gb_options=make("GroupbyOptions", slice=(0, 10), dynamic=None, rolling=None)),
+                                    dict(gb_options=make("GroupbyOptions", slice=None, dynamic=object(), rolling=None)),
+                                    dict(gb_options=make("GroupbyOptions", slice=None, dynamic=None, rolling=object()))])
 def test_unsupported_group_by_shapes_are_left_to_polars(kwargs):
     nt = group_by_plan(**kwargs)
     engine.execute_with_b200(nt)
@@ -73,11 +78,22 @@ def test_unsupported_group_by_shapes_are_left_to_polars(kwargs):
         engine.execute_with_b200(group_by_plan(**kwargs), raise_on_fail=True)
 
 
-def join_plan(how="Inner", n_keys=1):
+def test_count_with_include_nulls_is_len():
+    """pl.col(x).len() lowers to Agg count(include_nulls=True) (dsl/mod.rs:923-929): group length, not the non-null count."""
+    nt = group_by_plan(agg_name="count", agg_options=True)
+    assert engine._parse_agg(nt, expr_ir(2, "x")) == ("len", None, "x")
+    nt = group_by_plan(agg_name="count", agg_options=False)
+    assert engine._parse_agg(nt, expr_ir(2, "x")) == ("count", "x", "x")
+    nt = group_by_plan(agg_name="min", agg_options=False)
+    assert engine._parse_agg(nt, expr_ir(2, "x")) == ("min", "x", "x")
+
+
+def join_plan(how="Inner", n_keys=1, nulls_equal=False, slc=None, suffix="_right", coalesce=True, order="none", options=None):
     exprs = {0: make("Column", name="k"), 1: make("Column", name="k"), 2: make("Column", name="k2")}
     nodes = {20: make("DataFrameScan", df=object(), projection=None, selection=None), 21: make("DataFrameScan", df=object(), projection=["k", "r"], selection=None)}
     on = [expr_ir(0, "k")] + ([expr_ir(2, "k2")] if n_keys == 2 else [])
-    nodes[22] = make("Join", input_left=20, input_right=21, left_on=on, right_on=[expr_ir(1, "k")] + on[1:], options=(how, False))
+    nodes[22] = make("Join", input_left=20, input_right=21, left_on=on, right_on=[expr_ir(1, "k")] + on[1:],
+                     options=options if options is not None else (how, nulls_equal, slc, suffix, coalesce, order))
     return FakeTraverser(nodes, exprs, 22)
 
 
@@ -86,9 +102,28 @@ def test_single_key_joins_are_taken_and_others_left():
         nt = join_plan(how)
         engine.execute_with_b200(nt)
         assert callable(nt.udf) and nt.cur == 22
-    for nt in (join_plan("Full"), join_plan("Cross"), join_plan("Inner", n_keys=2)):
+    for nt in (join_plan("Full"), join_plan("Cross"), join_plan("Right"), join_plan("Inner", n_keys=2)):
         engine.execute_with_b200(nt)
         assert nt.udf is None
+
+
+def test_join_options_are_read_not_guessed():
+    """Every option of the Join node (visitor/nodes.rs:590-651) is either implemented by the UDF or the node is left to Polars."""
+    taken = [join_plan("Inner", nulls_equal=True), join_plan("Inner", suffix="_r"), join_plan("Inner", order="left_right"),
+             join_plan("Left", order="right"), join_plan("Semi", coalesce=False)]
+    for nt in taken:
+        engine.execute_with_b200(nt)
+        assert callable(nt.udf)
+    assert engine._join_options(("Inner", True, None, "_r", True, "right_left")) == ("inner", True, "_r", "right_left")
+    left = [join_plan("Inner", slc=(0, 5)), join_plan("Inner", coalesce=False), join_plan("Left", coalesce=False), join_plan("Semi", order="left"),
+            join_plan(options=("Inner", False)),                                                   # wrong arity
+            # an asof join whose `left_by` column happens to be called "left": how is a tuple, never a substring match
+            join_plan(options=(("AsOf", "backward", None, None, ["left"], ["inner"], True, True), False, None, "_right", True, "none"))]
+    for nt in left:
+        engine.execute_with_b200(nt)
+        assert nt.udf is None
+        with pytest.raises(Exception):
+            engine.execute_with_b200(nt, raise_on_fail=True)
 
 
 def test_other_roots_are_untouched():
