@@ -275,6 +275,156 @@ __global__ void __launch_bounds__(THREADS) k_rp_agg(const uint64_t* __restrict__
 __global__ void k_mark(const uint64_t* key, const uint64_t* kid, int64_t n, uint64_t* key_of_id) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) key_of_id[kid[i]] = key[i];
 }
+
+// ---------------------------------------------------------------- pass 2, variant V1: plain coalesced loads, no staging
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+struct AggOut { uint64_t* key; uint64_t* si; double* sf; unsigned* len; unsigned long long* cursor; int* overflow; };
+
+__device__ __forceinline__ void agg_row(uint64_t* tkey, uint64_t* tsi, double* tsf, unsigned* tlen, unsigned S, int logB, unsigned* s_used, int* overflow, uint64_t key, uint64_t a, uint64_t b) {
+    if (key == EMPTY) return;                 // pad row
+    const uint64_t h = key * RANDOM_ODD;
+    unsigned slot = __umulhi((unsigned)((h << logB) >> 32), S);
+    unsigned probes = 0;
+    for (; probes < S; probes++) {
+        const uint64_t cur = *reinterpret_cast<volatile uint64_t*>(tkey + slot);
+        if (cur == key) break;
+        if (cur == EMPTY) {
+            const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(tkey + slot), (unsigned long long)EMPTY, (unsigned long long)key);
+            if (old == EMPTY) { atomicAdd(s_used, 1u); break; }
+            if (old == key) break;
+        }
+        if (++slot == S) slot = 0;
+    }
+    if (probes == S) { *overflow = 2; return; }
+    s_add_u64(tsi + slot, a);
+    atomicAdd(tsf + slot, __longlong_as_double((long long)b));
+    atomicAdd(tlen + slot, 1u);
+}
+__device__ __forceinline__ void agg_flush(const uint64_t* tkey, const uint64_t* tsi, const double* tsf, const unsigned* tlen, unsigned S, unsigned* s_used, unsigned base, const AggOut& o, int tid, int nthr) {
+    for (unsigned i = tid; i < S; i += nthr) {
+        if (tkey[i] == EMPTY) continue;
+        const unsigned at = base + atomicSub(s_used, 1u) - 1u;
+        o.key[at] = tkey[i]; o.si[at] = tsi[i]; o.sf[at] = tsf[i]; o.len[at] = tlen[i];
+    }
+}
+
+template <int ROWW, int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS) k_rp_agg_direct(const uint64_t* __restrict__ recs, int64_t cap_rows, const unsigned* __restrict__ cursor, int logB, unsigned S, AggOut o) {
+    extern __shared__ __align__(16) uint64_t smem[];
+    uint64_t* tkey = smem; uint64_t* tsi = tkey + S; double* tsf = reinterpret_cast<double*>(tsi + S); unsigned* tlen = reinterpret_cast<unsigned*>(tsf + S);
+    __shared__ unsigned s_used, s_base;
+    const int tid = threadIdx.x, B = 1 << logB;
+    for (int p = blockIdx.x; p < B; p += gridDim.x) {
+        for (unsigned i = tid; i < S; i += THREADS) { tkey[i] = EMPTY; tsi[i] = 0; tsf[i] = 0.0; tlen[i] = 0; }
+        if (tid == 0) s_used = 0;
+        __syncthreads();
+        const int64_t rows = min((int64_t)cursor[p], cap_rows);
+        const uint64_t* src = recs + (size_t)p * cap_rows * ROWW;
+        for (int64_t r0 = tid; r0 < rows; r0 += (int64_t)THREADS * UNROLL) {
+            uint64_t k[UNROLL], a[UNROLL], b[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const int64_t r = r0 + (int64_t)u * THREADS;
+                k[u] = EMPTY; a[u] = 0; b[u] = 0;
+                if (r < rows) { k[u] = __ldg(src + r * ROWW); a[u] = __ldg(src + r * ROWW + 1); b[u] = __ldg(src + r * ROWW + 2); }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) agg_row(tkey, tsi, tsf, tlen, S, logB, &s_used, o.overflow, k[u], a[u], b[u]);
+        }
+        __syncthreads();
+        if (tid == 0) s_base = (unsigned)atomicAdd(o.cursor, (unsigned long long)s_used);
+        __syncthreads();
+        agg_flush(tkey, tsi, tsf, tlen, S, &s_used, s_base, o, tid, THREADS);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- pass 2, variant V2: TMA ring, producer warp, warp-granular consumption
+// 1024 threads: warps 0..30 consume (each owns K x 32 rows of every chunk), warp 31 issues the bulk copies.
+// full[s]: TMA complete_tx; empty[s]: one arrival per consumer warp once its rows of the stage sit in registers.
+template <int ROWW, int K, int NST>
+__global__ void __launch_bounds__(1024) k_rp_agg_tma(const uint64_t* __restrict__ recs, int64_t cap_rows, const unsigned* __restrict__ cursor, int logB, unsigned S, AggOut o) {
+    constexpr int NCW = 31, CR = NCW * 32 * K, NCT = NCW * 32;
+    extern __shared__ __align__(128) uint64_t smem[];
+    uint64_t* ring = smem;
+    uint64_t* tkey = ring + (size_t)NST * CR * ROWW; uint64_t* tsi = tkey + S; double* tsf = reinterpret_cast<double*>(tsi + S); unsigned* tlen = reinterpret_cast<unsigned*>(tsf + S);
+    __shared__ uint64_t full[NST], empty[NST];
+    __shared__ unsigned s_used, s_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, B = 1 << logB;
+    if (tid == 0) { for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); } fence_mbar_init(); }
+    __syncthreads();
+    if (warp == NCW) {                      // producer
+        if (lane == 0) {
+            unsigned q = 0;
+            for (int p = blockIdx.x; p < B; p += gridDim.x) {
+                const int64_t rows = min((int64_t)cursor[p], cap_rows);
+                const uint64_t* src = recs + (size_t)p * cap_rows * ROWW;
+                const int nch = (int)((rows + CR - 1) / CR);
+                for (int c = 0; c < nch; c++, q++) {
+                    const int st = q % NST; const unsigned use = q / NST;
+                    if (use > 0) while (!mbar_try_wait(&empty[st], (use - 1) & 1u)) {}
+                    const unsigned bytes = (unsigned)(min((int64_t)CR, rows - (int64_t)c * CR) * ROWW * 8);
+                    mbar_expect_tx(&full[st], bytes);
+                    bulk_g2s(ring + (size_t)st * CR * ROWW, src + (size_t)c * CR * ROWW, bytes, &full[st]);
+                }
+            }
+        }
+        return;
+    }
+    unsigned q = 0;
+    for (int p = blockIdx.x; p < B; p += gridDim.x) {
+        for (unsigned i = tid; i < S; i += NCT) { tkey[i] = EMPTY; tsi[i] = 0; tsf[i] = 0.0; tlen[i] = 0; }
+        if (tid == 0) s_used = 0;
+        named_bar_sync(1, NCT);
+        const int64_t rows = min((int64_t)cursor[p], cap_rows);
+        const int nch = (int)((rows + CR - 1) / CR);
+        for (int c = 0; c < nch; c++, q++) {
+            const int st = q % NST; const unsigned par = (q / NST) & 1u;
+            while (!mbar_try_wait(&full[st], par)) {}
+            const uint64_t* buf = ring + (size_t)st * CR * ROWW;
+            const int crow = (int)min((int64_t)CR, rows - (int64_t)c * CR);
+            uint64_t k[K], a[K], b[K];
+#pragma unroll
+            for (int u = 0; u < K; u++) {
+                const int r = (warp * K + u) * 32 + lane;
+                k[u] = EMPTY; a[u] = 0; b[u] = 0;
+                if (r < crow) { k[u] = buf[r * ROWW]; a[u] = buf[r * ROWW + 1]; b[u] = buf[r * ROWW + 2]; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+#pragma unroll
+            for (int u = 0; u < K; u++) agg_row(tkey, tsi, tsf, tlen, S, logB, &s_used, o.overflow, k[u], a[u], b[u]);
+        }
+        named_bar_sync(1, NCT);
+        if (tid == 0) s_base = (unsigned)atomicAdd(o.cursor, (unsigned long long)s_used);
+        named_bar_sync(1, NCT);
+        agg_flush(tkey, tsi, tsf, tlen, S, &s_used, s_base, o, tid, NCT);
+        named_bar_sync(1, NCT);
+    }
+}
+
+template <typename KFN>
+static float time_agg(KFN kfn, int threads, size_t smem, int B, int sms, int* occ_out, unsigned long long* out_cursor, const uint64_t* recs, int64_t cap_rows, const unsigned* cursor, int logB, unsigned S, AggOut o) {
+    if (smem > 227 * 1024) { *occ_out = 0; return -1.f; }
+    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, threads, smem));
+    *occ_out = occ;
+    if (occ < 1) return -1.f;
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e9f;
+    for (int it = 0; it < 4; it++) {
+        CK(cudaMemset(out_cursor, 0, 8));
+        CK(cudaEventRecord(e0));
+        kfn<<<std::min(B, sms * occ), threads, smem>>>(recs, cap_rows, cursor, logB, S, o);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); best = fminf(best, ms);
+    }
+    CK(cudaGetLastError());
+    return best;
+}
+
 template <int ROWW, int RPT, int THREADS, bool BULK>
 static float run_scatter(const uint64_t* key, const uint64_t* v1, const uint64_t* v2, int64_t n, int logB, uint64_t* out, int64_t cap_rows, unsigned* cursor, int* overflow, int sms, int* ctas_per_sm) {
     const int B = 1 << logB, T = RPT * THREADS;
@@ -371,32 +521,35 @@ int main(int argc, char** argv) {
     };
 
     const uint64_t* k64 = key; const uint64_t* a64 = (const uint64_t*)vi; const uint64_t* b64 = (const uint64_t*)vf;
+    AggOut o{out_key, out_si, out_sf, out_len, out_cursor, overflow};
     for (int logB = 8; logB <= 10; logB++) {
         const int B = 1 << logB;
         int64_t cap_rows = (int64_t)((double)n / B * 1.25) + 64; cap_rows &= ~(int64_t)1;
         if (cap_rows * B > rec_rows) { printf("record buffer too small\n"); return 1; }
-        struct { const char* name; float ms; int occ; } sc[6]; int nsc = 0;
         int occ = 0;
         float t;
-        t = run_scatter<3, 8, 512, false>(k64, a64, b64, n, logB, recs, cap_rows, cursor, overflow, sms, &occ); sc[nsc++] = {"st_T4096", t, occ};
-        t = run_scatter<3, 8, 480, true>(k64, a64, b64, n, logB, recs, cap_rows, cursor, overflow, sms, &occ); sc[nsc++] = {"bulk_T3840", t, occ};
-        t = run_scatter<3, 8, 1024, true>(k64, a64, b64, n, logB, recs, cap_rows, cursor, overflow, sms, &occ); sc[nsc++] = {"bulk_T8192", t, occ};
-        t = run_scatter<3, 8, 1024, false>(k64, a64, b64, n, logB, recs, cap_rows, cursor, overflow, sms, &occ); sc[nsc++] = {"st_T8192", t, occ};
-        t = run_scatter<3, 4, 512, true>(k64, a64, b64, n, logB, recs, cap_rows, cursor, overflow, sms, &occ); sc[nsc++] = {"bulk_T2048", t, occ};
-        // the record stream left in `recs` is the last variant's (bulk_T2048, padded runs): aggregate it
-        float ta; int occa = 0; const char* an;
-        if (logB == 8) { ta = -1.f; an = "none (3906 groups per bucket do not fit a shared-memory table)"; }
-        else if (logB == 9) { ta = run_agg<3, 4096, 1024, 3, 1024>(recs, cap_rows, cursor, logB, out_key, out_si, out_sf, out_len, out_cursor, overflow, sms, &occa); an = "S4096_CR1024x3_1024t"; }
-        else { ta = run_agg<3, 2048, 1024, 2, 512>(recs, cap_rows, cursor, logB, out_key, out_si, out_sf, out_len, out_cursor, overflow, sms, &occa); an = "S2048_CR1024x2_512t"; }
+        printf("{\"buckets\": %d", B);
         const double gb = (double)n * 24 / 1e9;
-        printf("{\"buckets\": %d, \"cap_rows\": %lld", B, (long long)cap_rows);
-        for (int i = 0; i < nsc; i++) printf(", \"%s_ms\": %.3f, \"%s_ctas_per_sm\": %d, \"%s_GBps_rw\": %.0f", sc[i].name, sc[i].ms, sc[i].name, sc[i].occ, sc[i].name, 2 * gb / (sc[i].ms / 1e3));
-        printf(", \"agg\": \"%s\", \"agg_ms\": %.3f, \"agg_ctas_per_sm\": %d, \"agg_GBps\": %.0f}\n", an, ta, occa, gb / (ta / 1e3));
-        if (ta > 0) check(an);
-        if (logB == 9) {     // a second aggregation shape for 512 buckets
-            float tb = run_agg<3, 4096, 512, 4, 512>(recs, cap_rows, cursor, logB, out_key, out_si, out_sf, out_len, out_cursor, overflow, sms, &occa);
-            printf("{\"buckets\": %d, \"agg\": \"S4096_CR512x4_512t\", \"agg_ms\": %.3f, \"agg_ctas_per_sm\": %d}\n", B, tb, occa);
-            check("S4096_CR512x4_512t");
+        t = run_scatter<3, 8, 480, true>(k64, a64, b64, n, logB, recs, cap_rows, cursor, overflow, sms, &occ); printf(", \"scatter_bulk_T3840\": [%.3f, %d, %.0f]", t, occ, 2 * gb / (t / 1e3));
+        t = run_scatter<3, 6, 512, true>(k64, a64, b64, n, logB, recs, cap_rows, cursor, overflow, sms, &occ); printf(", \"scatter_bulk_T3072\": [%.3f, %d, %.0f]", t, occ, 2 * gb / (t / 1e3));
+        t = run_scatter<3, 4, 384, true>(k64, a64, b64, n, logB, recs, cap_rows, cursor, overflow, sms, &occ); printf(", \"scatter_bulk_T1536\": [%.3f, %d, %.0f]", t, occ, 2 * gb / (t / 1e3));
+        t = run_scatter<3, 4, 512, true>(k64, a64, b64, n, logB, recs, cap_rows, cursor, overflow, sms, &occ); printf(", \"scatter_bulk_T2048\": [%.3f, %d, %.0f]", t, occ, 2 * gb / (t / 1e3));
+        printf("}\n");
+        // the record stream left in `recs` is the last variant's (bulk_T2048, padded runs): aggregate it
+        const unsigned S = logB == 8 ? 6144u : (logB == 9 ? 3072u : 1536u);
+        const size_t tab = (size_t)S * 28;
+        float ta;
+        ta = time_agg(k_rp_agg_direct<3, 1024, 2>, 1024, tab, B, sms, &occ, out_cursor, recs, cap_rows, cursor, logB, S, o);
+        printf("{\"buckets\": %d, \"slots\": %u, \"agg\": \"direct_1024t_u2\", \"agg_ms\": %.3f, \"ctas_per_sm\": %d, \"GBps\": %.0f}\n", B, S, ta, occ, gb / (ta / 1e3)); if (ta > 0) check("direct_1024t_u2");
+        ta = time_agg(k_rp_agg_direct<3, 512, 4>, 512, tab, B, sms, &occ, out_cursor, recs, cap_rows, cursor, logB, S, o);
+        printf("{\"buckets\": %d, \"slots\": %u, \"agg\": \"direct_512t_u4\", \"agg_ms\": %.3f, \"ctas_per_sm\": %d, \"GBps\": %.0f}\n", B, S, ta, occ, gb / (ta / 1e3)); if (ta > 0) check("direct_512t_u4");
+        ta = time_agg(k_rp_agg_tma<3, 1, 2>, 1024, tab + (size_t)2 * 992 * 24, B, sms, &occ, out_cursor, recs, cap_rows, cursor, logB, S, o);
+        printf("{\"buckets\": %d, \"slots\": %u, \"agg\": \"tma_K1_x2\", \"agg_ms\": %.3f, \"ctas_per_sm\": %d, \"GBps\": %.0f}\n", B, S, ta, occ, gb / (ta / 1e3)); if (ta > 0) check("tma_K1_x2");
+        if (logB >= 9) {
+            ta = time_agg(k_rp_agg_tma<3, 2, 2>, 1024, tab + (size_t)2 * 1984 * 24, B, sms, &occ, out_cursor, recs, cap_rows, cursor, logB, S, o);
+            printf("{\"buckets\": %d, \"slots\": %u, \"agg\": \"tma_K2_x2\", \"agg_ms\": %.3f, \"ctas_per_sm\": %d, \"GBps\": %.0f}\n", B, S, ta, occ, gb / (ta / 1e3)); if (ta > 0) check("tma_K2_x2");
+            ta = time_agg(k_rp_agg_tma<3, 1, 4>, 1024, tab + (size_t)4 * 992 * 24, B, sms, &occ, out_cursor, recs, cap_rows, cursor, logB, S, o);
+            printf("{\"buckets\": %d, \"slots\": %u, \"agg\": \"tma_K1_x4\", \"agg_ms\": %.3f, \"ctas_per_sm\": %d, \"GBps\": %.0f}\n", B, S, ta, occ, gb / (ta / 1e3)); if (ta > 0) check("tma_K1_x4");
         }
     }
     return 0;
