@@ -1,24 +1,27 @@
 #!/usr/bin/env python
 """bench.py — the hot path on synthetic data, one JSON line (contract: task brief).
 
-Default workload = BASELINE.json configs[1] (C2): hash group_by over 1e8 rows, 1e6 uniform Int64 keys,
-aggregations sum(v_i64), mean(v_f64), len, on ONE B200; inputs (2.4 GB) are larger than L2 (126 MB), so
-no explicit L2 flush is needed between timed iterations.
+BASELINE.json's metric is "rows/sec hash group_by-agg & join", so the default run measures BOTH halves:
+  primary    C2 (configs[1]): hash group_by over 1e8 rows, 1e6 uniform Int64 keys, sum(v_i64)/mean(v_f64)/len
+  secondary  C3 (configs[2]): inner hash join 1e8 x 1e7 Int64 — once with dense surrogate keys (the direct-address
+             table the library picks for them) and once with SPARSE 64-bit keys, where only the hashed table can serve.
+Every workload's result is verified once outside the timed region ("verified" in the line); inputs (>= 0.88 GB) are
+larger than L2 (126 MB), so no explicit L2 flush is needed between timed iterations.
 
-  value     rows/s, whole job, inputs resident in HBM when the timed region starts, through the C ABI
-            with BL_DEVICE columns (estimate + table init + fused build/aggregate + extraction).
-  e2e       same call with BL_HOST columns in pinned memory: H2D of the three columns and D2H of the
-            result inside the timed region.
-  roofline  dominant kernel (k5_groupby_agg): algorithmic bytes (24 B/row) / its CUDA-event duration
-            on the library stream, against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline  the CPU oracle (restatement of the reference's Rayon algorithm, "port") on the host
-            cores over a bounded sample.
+  value     rows/s, whole job, inputs resident in HBM when the timed region starts, through the C ABI with BL_DEVICE
+            columns (sample + table init + fused build/aggregate + extraction; join: build + probe + emit).
+  e2e       the same call with BL_HOST columns in pinned memory: H2D of the inputs and D2H of the result inside the
+            timed region.  N > 1: host columns -> device -> the partitioned multi-GPU plan -> host.
+  roofline  dominant kernel: algorithmic bytes / its CUDA-event duration on the library stream, against
+            MEASURED_PEAKS.json hbm_gbs; kernel_share_of_step for every kernel of the step is in kernels_ms_per_step.
+  cpu_baseline  the CPU oracle (C/OpenMP restatement of the reference's partitioned Rayon algorithm, "port") on the
+            host cores over a bounded sample, with its 1-thread / 16-thread / all-thread points.
 
---workload join: configs[2] (C3) inner hash join 1e8 x 1e7 on Int64 (single GPU here).
---gpus N (torchrun): weak scaling, every rank owns --rows rows; local pre-aggregation, hash partition of
-the partial aggregates, ONE all-to-all (NCCL), final merge.
---impl reference: the oracle on the host cores (the reference itself cannot be installed: Rust, no
-toolchain/wheel — see DESIGN.md), same metric/config, bounded sample per step.
+--gpus N (torchrun): weak scaling, every rank owns --rows rows.  group_by: local pre-aggregation, hash partition of the
+partial aggregates fused with P2P stores into the owners' windows (counts + flags travel through the windows: no
+collective, no host round trip), merge.  join: both relations hash-partitioned (K6) and exchanged with one NCCL
+all-to-all-v per relation, local K7/K8, plus the broadcast-build variant.
+--impl reference: the oracle on ALL host cores at the full configuration (same rows as the B200 arm).
 """
 from __future__ import annotations
 
@@ -35,6 +38,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+SPARSE_MULT = np.uint64(0x9E3779B97F4A7C15)      # odd: id -> id * M mod 2^64 is a bijection, so sparse keys stay unique
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -42,17 +47,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="groupby", choices=["groupby", "join", "q1"])
+    ap.add_argument("--workload", default="all", choices=["all", "groupby", "join", "q1"])
     ap.add_argument("--rows", type=int, default=100_000_000)
     ap.add_argument("--keys", type=int, default=1_000_000)
     ap.add_argument("--build-rows", type=int, default=10_000_000)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample", type=int, default=20_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=20_000_000, help="rows of the in-line cpu_baseline sample (the --impl reference arm runs the full size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--skew", default="uniform", choices=["uniform", "zipf"], help="group_by key distribution (SURVEY.md 8(d) C2 variants)")
     ap.add_argument("--null-frac", type=float, default=0.0, help="group_by: fraction of null rows in each value column")
     ap.add_argument("--hit-frac", type=float, default=1.0, help="join: fraction of probe rows with a match (C3 variant: 0.5)")
     ap.add_argument("--dup", type=int, default=1, help="join: copies of every build key (C3 variant: 4)")
+    ap.add_argument("--join-keys", default="both", choices=["both", "dense", "sparse"], help="join: dense surrogate keys, sparse 64-bit keys, or both")
     ap.add_argument("--acero-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU exchange of the partial aggregates")
     return ap.parse_args()
@@ -97,6 +104,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------- synthetic inputs
 def gen_groupby(rows: int, keys: int, seed: int, skew: str = "uniform"):
     """uniform keys (or the Zipf(1.1) variant folded into [0, keys)), v_i64 in
     [-1000,1000), v_f64 = U(0,100).round(6) (h2oai v3)."""
@@ -110,13 +118,22 @@ def gen_groupby(rows: int, keys: int, seed: int, skew: str = "uniform"):
     return key, vi, vf
 
 
-def gen_join(rows: int, build_rows: int, seed: int, hit_frac: float = 1.0, dup: int = 1):
-    """C3: build = permutation (unique keys, or `dup` copies of each), probe keys uniform over
-    [0, distinct build keys / hit_frac): 100 % hit by default; variants 50 % hit and 4 duplicates per key."""
+def sparsify(ids: np.ndarray) -> np.ndarray:
+    """dense ids -> unique sparse 64-bit keys (value range ~2^64: the direct-address table cannot be used)."""
+    return (ids.astype(np.uint64) * SPARSE_MULT).view(np.int64)
+
+
+def gen_join(rows: int, build_rows: int, seed: int, hit_frac: float = 1.0, dup: int = 1, sparse: bool = False, id_base: int = 0, id_space: int | None = None):
+    """C3: build = a permutation of [id_base, id_base + build_rows) (unique keys, or `dup` copies of each); probe ids uniform
+    over [0, id_space / hit_frac) (id_space = all ranks' build ids under torchrun): 100 % hit by default; variants 50 % hit
+    and 4 duplicates per key.  sparse: ids are mapped to unique 64-bit keys by an odd multiplier."""
     rng = np.random.default_rng(seed)
     distinct = max(1, build_rows // dup)
-    build = rng.permutation(distinct * dup).astype(np.int64) % distinct if dup > 1 else rng.permutation(build_rows).astype(np.int64)
-    probe = rng.integers(0, max(1, int(distinct / hit_frac)), rows, dtype=np.int64)
+    build = (rng.permutation(distinct * dup).astype(np.int64) % distinct if dup > 1 else rng.permutation(build_rows).astype(np.int64)) + id_base
+    space = distinct if id_space is None else id_space
+    probe = rng.integers(0, max(1, int(space / hit_frac)), rows, dtype=np.int64)
+    if sparse:
+        probe, build = sparsify(probe), sparsify(build)
     return probe, build
 
 
@@ -165,272 +182,465 @@ def q1_numpy(h):
     return out
 
 
+# ------------------------------------------------------------------------------------- verification (outside the timed region)
+def verify_groupby(key, vi, vf, val_i, val_f, keys, k, outs) -> str:
+    """numpy restatement: bincount over the key ids (sums of +-1000 integers are exact in f64 below 2^53)."""
+    if val_i is not None or val_f is not None:
+        return "skipped (null variant)"
+    o = np.argsort(k, kind="stable")
+    uk = np.flatnonzero(np.bincount(key, minlength=keys))
+    assert np.array_equal(k[o], uk), "group keys differ from numpy"
+    cnt = np.bincount(key, minlength=keys)[uk]
+    assert np.array_equal(outs[2][o].astype(np.int64), cnt), "group lengths differ from numpy"
+    si = np.bincount(key, weights=vi, minlength=keys)[uk]
+    assert np.array_equal(outs[0][o].astype(np.float64), si), "integer sums differ from numpy"
+    mf = np.bincount(key, weights=vf, minlength=keys)[uk] / cnt
+    assert np.allclose(outs[1][o], mf, rtol=1e-6, atol=0), "means differ from numpy beyond 1e-6 relative"
+    return "numpy bincount: keys, len, sum(i64) exact; mean(f64) rtol 1e-6"
+
+
+def verify_join(probe, build, li, ri, dup) -> str:
+    """Exact tuple sequence: every probe row in order, its matches ascending by build row (hash_join/mod.rs:41-50)."""
+    order = np.argsort(build, kind="stable")
+    sb = build[order]
+    lo = np.searchsorted(sb, probe, "left")
+    hi = np.searchsorted(sb, probe, "right")
+    cnt = hi - lo
+    total = int(cnt.sum())
+    assert li.size == total and ri.size == total, f"join emitted {li.size} tuples, expected {total}"
+    exp_l = np.repeat(np.arange(probe.size, dtype=np.uint32), cnt)
+    assert np.array_equal(li, exp_l), "left indices are not the probe rows in order"
+    if dup == 1:
+        hit = cnt > 0
+        assert np.array_equal(ri, order[lo[hit]].astype(np.uint32)), "right indices differ"
+    else:
+        starts = np.repeat(lo, cnt)
+        within = np.arange(total) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        assert np.array_equal(ri, order[starts + within].astype(np.uint32)), "right indices differ (ascending build rows per probe row)"
+    return "numpy searchsorted: exact (left_idx, right_idx) sequence"
+
+
 # ------------------------------------------------------------------------------------- reference arm
+def _oracle_threads(oracle):
+    hw = oracle.hw_threads()
+    oracle.set_threads(hw)          # torchrun exports OMP_NUM_THREADS=1: the port's pool is sized explicitly
+    return hw
+
+
 def run_reference(a):
     import oracle
     oracle.build()
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = oracle.max_threads()
-    sample = min(a.rows, a.cpu_sample)
-    if a.workload == "groupby":
-        key, vi, vf = gen_groupby(sample, a.keys, 1, a.skew)
+    cores = _oracle_threads(oracle)
+    results = {}
+    if a.workload in ("all", "groupby"):
+        key, vi, vf = gen_groupby(a.rows, a.keys, 1, a.skew)
         aggs = [("sum", vi, None), ("mean", vf, None), ("len", None, None)]
-        fn = lambda: oracle.group_by_agg(key, None, aggs, cores, False)   # noqa: E731
-        unit_rows = sample
-        metric, wl = "group_by_agg_rows_per_sec", f"C2 hash group_by {a.rows} rows, {a.keys} Int64 keys, sum(i64)/mean(f64)/len"
-    else:
-        build_rows = max(1, int(a.build_rows * sample / a.rows))
-        probe, build = gen_join(sample, build_rows, 2, a.hit_frac, a.dup)
-        fn = lambda: oracle.hash_join(probe, build, None, None, "inner", False, "none", cores)   # noqa: E731
-        unit_rows = sample
-        metric, wl = "hash_join_probe_rows_per_sec", f"C3 inner hash join {a.rows} x {a.build_rows} Int64"
-    for _ in range(min(a.warmup, 1)):
-        fn()
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        fn()
-    dt = (time.perf_counter() - t0) / a.steps
-    v = unit_rows / dt
-    line = {"impl": "reference", "metric": metric, "value": v, "unit": "rows/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1),
-            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/float64", "data": "synthetic",
-            "config": {"workload": wl, "sample_rows_per_step": sample},
-            "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} rows/step of the same workload; oracle = C restatement of the reference's partitioned Rayon algorithm (not Polars itself: no Rust toolchain / wheel)"},
-            "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        results["groupby"] = ("group_by_agg_rows_per_sec", lambda: oracle.group_by_agg(key, None, aggs, cores, False), a.rows,
+                              f"C2 hash group_by {a.rows} rows, {a.keys} Int64 keys, sum(i64)/mean(f64)/len")
+    if a.workload in ("all", "join"):
+        probe, build = gen_join(a.rows, a.build_rows, 2, a.hit_frac, a.dup, sparse=a.join_keys == "sparse")
+        results["join"] = ("hash_join_probe_rows_per_sec", lambda: oracle.hash_join(probe, build, None, None, "inner", False, "none", cores), a.rows,
+                           f"C3 inner hash join {a.rows} x {a.build_rows} Int64")
+    lines = {}
+    for name, (metric, fn, unit_rows, wl) in results.items():
+        for _ in range(min(a.warmup, 1)):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            fn()
+        dt = (time.perf_counter() - t0) / a.steps
+        lines[name] = {"metric": metric, "value": unit_rows / dt, "ms_per_step": dt * 1e3, "workload": wl}
+    first = "groupby" if "groupby" in lines else next(iter(lines))
+    p = lines[first]
+    sample = f"{a.rows} rows/step = the full configuration; oracle = C/OpenMP restatement of the reference's partitioned Rayon algorithm (not Polars itself: no Rust toolchain / wheel)"
+    line = {"impl": "reference", "metric": p["metric"], "value": p["value"], "unit": "rows/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1),
+            "ms_per_step": p["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/float64", "data": "synthetic",
+            "config": {"workload": p["workload"], "rows_per_step": a.rows, "same_config": True},
+            "cpu_baseline": {"value": p["value"], "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": p["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if len(lines) > 1:
+        line["secondary"] = [{"metric": v["metric"], "value": v["value"], "unit": "rows/s", "ms_per_step": v["ms_per_step"], "config": {"workload": v["workload"]}}
+                             for k, v in lines.items() if k != first]
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------- B200 arm
+class Harness:
+    """Timing, clocks, max-over-ranks, profiling around one workload's step functions."""
+
+    def __init__(self, a):
+        import torch
+        import torch.distributed as dist
+        import polars_b200 as plb
+        self.a, self.torch, self.dist, self.plb = a, torch, dist, plb
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        plb.init(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.ext = torch.cuda.ExternalStream(plb.stream(), device=torch.device("cuda", self.local))
+        self.peak_gbs, self.peak_src = peaks()
+        self.total_launches = 0
+        self.clock_rows = []
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+        self.plb.sync()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x: int) -> int:
+        if self.world == 1:
+            return int(x)
+        t = self.torch.tensor([int(x)], dtype=self.torch.int64, device="cuda")
+        self.dist.all_reduce(t)
+        return int(t.item())
+
+    def measure(self, step_device, step_e2e, unit_rows, alg_bytes_per_row, dominant_pick, traffic_key):
+        """-> dict(value, ms_per_step, roofline, kernels_ms_per_step, e2e, clocks, n_out)."""
+        a, plb, torch = self.a, self.plb, self.torch
+        for _ in range(max(a.warmup, 3)):
+            n_out = step_device()
+        self.barrier()
+        plb.profile_reset()
+        plb.profile_enable(True)
+        sampler = ClockSampler(self.local)
+        if self.rank == 0:
+            sampler.start()
+        with torch.cuda.stream(self.ext):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.steps):
+                n_out = step_device()
+            e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        prof = plb.profile()
+        self.total_launches += plb.launch_count()
+        plb.profile_enable(False)
+        ms_per_step = self.max_over_ranks(ms) / a.steps
+        value = unit_rows * self.world / (ms_per_step / 1e3)
+        # ---- end to end with pinned host buffers (H2D + compute + D2H per step)
+        e2e_vals, d2h = [], 0
+        for i in range(a.e2e_steps + 1 if (a.e2e_steps > 0 and step_e2e is not None) else 0):
+            self.barrier()
+            t0 = time.perf_counter()
+            _, d2h = step_e2e()
+            dt = time.perf_counter() - t0
+            if i > 0:
+                e2e_vals.append(dt)
+        e2e_s = self.max_over_ranks(float(np.mean(e2e_vals)) if e2e_vals else 0.0)
+        clocks = sampler.stop() if self.rank == 0 else None      # sampled over the timed region and the e2e steps that follow it
+        dominant = dominant_pick(prof)
+        traffic = None      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(traffic_key, {}).get(dominant)
+        except Exception:
+            pass
+        dom = prof.get(dominant, {"launches": 0, "ms": 0.0})
+        dom_ms = dom["ms"] / max(dom["launches"], 1)
+        achieved = (alg_bytes_per_row * unit_rows / 1e9) / (dom_ms / 1e3) if dom_ms > 0 else 0.0
+        total_kernel_ms = sum(v["ms"] for v in prof.values()) / a.steps
+        per_step = {k: v["ms"] / a.steps for k, v in prof.items()}
+        return {"value": value, "ms_per_step": ms_per_step, "n_out": int(n_out),
+                "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": self.peak_gbs, "unit": "GB/s", "frac": achieved / self.peak_gbs if self.peak_gbs else None,
+                             "traffic": traffic, "peak_source": self.peak_src, "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes_per_row * unit_rows,
+                             "kernel_share_of_step": (dom_ms * dom["launches"] / a.steps / total_kernel_ms) if total_kernel_ms else None,
+                             "kernel_shares": {k: v / total_kernel_ms for k, v in per_step.items()} if total_kernel_ms else None},
+                "kernels_ms_per_step": per_step,
+                "e2e": {"value": unit_rows * self.world / e2e_s if e2e_s else None, "unit": "rows/s", "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
+                "clocks": clocks}
+
+
+def bench_groupby(H: Harness):
+    a, plb, world, rank = H.a, H.plb, H.world, H.rank
+    key, vi, vf = gen_groupby(a.rows, a.keys, 1 + rank, a.skew)
+    hkey, hvi, hvf = (plb.to_pinned(key), plb.to_pinned(vi), plb.to_pinned(vf)) if a.e2e_steps > 0 else (None, None, None)
+    val_i = val_f = None
+    if a.null_frac > 0:      # the "+5 % nulls" variant: independent validity bitmaps on both value columns
+        nrng = np.random.default_rng(100 + rank)
+        val_i, val_f = (plb.pack_bits(nrng.random(a.rows) >= a.null_frac) for _ in range(2))      # Arrow LSB bitmaps
+    dkey, dvi, dvf = plb.to_device(key), plb.to_device(vi, val_i), plb.to_device(vf, val_f)
+    spec = [("sum", np.int64), ("mean", np.float64), ("len", None)]
+    nullable = [val_i is not None, val_f is not None, False]
+    peer_ex = None
+    pdist = None
+    if world > 1:
+        from polars_b200 import dist as pdist
+        torch, dist = H.torch, H.dist
+        if a.exchange == "p2p":      # window region per source rank: every group of a rank could go to one peer
+            try:
+                peer_ex = pdist.PeerExchange(plb, rows_per_src=min(a.keys, a.rows) + 1024, row_words=2 + 3 + sum(nullable[:2]))
+                ok_all = torch.tensor([1], device="cuda")
+            except Exception as e:      # CUDA IPC unavailable (container policy): use the NCCL all-to-all instead
+                print(f"[bench] peer windows unavailable ({e}); falling back to --exchange nccl", file=sys.stderr)
+                ok_all = torch.tensor([0], device="cuda")
+            dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+            if int(ok_all.item()) == 0:
+                a.exchange, peer_ex = "nccl", None
+
+    def plan(kc, ic, fc, location):
+        """One step of the multi-GPU plan on device columns -> (key, [sum, mean, len]) at `location`."""
+        vals = [ic, fc, None]
+        if a.exchange == "p2p":
+            return pdist.partitioned_group_by_p2p(plb, peer_ex, kc, vals, spec, nullable=nullable, location=location)
+        return pdist.partitioned_group_by(plb, kc, vals, spec, nullable=nullable, location=location)
+
+    def step_device():
+        if world == 1:
+            ok, outs = plb.group_by_agg(dkey.view(), [("sum", dvi.view()), ("mean", dvf.view()), ("len", None)], False, location=plb.DEVICE)
+        else:
+            ok, outs = plan(dkey.view(), dvi.view(), dvf.view(), plb.DEVICE)
+        return ok.length
+
+    def step_e2e():
+        if world == 1:
+            (k, _), outs = plb.group_by_agg(plb.Column(hkey), [("sum", plb.Column(hvi, val_i)), ("mean", plb.Column(hvf, val_f)), ("len", None)], False, location=plb.HOST)
+            return k.size, k.nbytes + sum(o[0].nbytes for o in outs)
+        # host -> device -> partitioned plan (exchange over NVLink) -> host
+        ck, ci, cf = plb.to_device(hkey), plb.to_device(hvi, val_i), plb.to_device(hvf, val_f)
+        ok, outs = plan(ck.view(), ci.view(), cf.view(), plb.DEVICE)
+        res = [ok.to_numpy()[0]] + [o.to_numpy()[0] for o in outs]
+        return res[0].size, sum(r.nbytes for r in res)
+
+    verified = None
+    if not a.no_verify:
+        if world == 1:
+            (k, _), outs = plb.group_by_agg(dkey.view(), [("sum", dvi.view()), ("mean", dvf.view()), ("len", None)], False, location=plb.HOST)
+            verified = verify_groupby(key, vi, vf, val_i, val_f, a.keys, k, [o[0] for o in outs])
+        else:
+            ok, outs = plan(dkey.view(), dvi.view(), dvf.view(), plb.DEVICE)
+            k = ok.to_numpy()[0]; s = outs[0].to_numpy()[0]; ln = outs[2].to_numpy()[0]
+            # conservation across ranks + ownership: every group exactly once, on the rank its key hashes to
+            h = (k.view(np.uint64) * np.uint64(0x55fbfd6bfc5458e9))
+            # hash_to_partition = (h * P) >> 64, exactly, from 32-bit halves: (hi * P + ((lo * P) >> 32)) >> 32
+            hi, lo = h >> np.uint64(32), h & np.uint64(0xFFFFFFFF)
+            part = ((hi * np.uint64(world) + ((lo * np.uint64(world)) >> np.uint64(32))) >> np.uint64(32)).astype(np.int64)
+            assert (part == rank).all(), "a group sits on the wrong rank"
+            assert H.sum_over_ranks(int(ln.astype(np.int64).sum())) == a.rows * world, "rows lost or duplicated across ranks"
+            assert H.sum_over_ranks(int(s.sum())) == H.sum_over_ranks(int(vi.sum())), "integer sums not conserved across ranks"
+            groups = H.sum_over_ranks(k.size)
+            if a.skew == "uniform" and a.rows * world >= 20 * a.keys:
+                assert groups == a.keys, f"{groups} groups over all ranks, expected {a.keys}"
+            verified = "conservation over all ranks: rows, sum(i64), group count; ownership by hash_to_partition"
+    del key, vi, vf
+
+    def pick(prof):
+        return max((k for k in prof if k.startswith("k5_groupby_agg")), key=lambda k: prof[k]["ms"], default="k5_groupby_agg")
+
+    r = H.measure(step_device, step_e2e if a.e2e_steps > 0 else None, a.rows, 24.0, pick, f"groupby:{a.rows}:{a.keys}")
+    r["e2e"]["h2d_bytes_per_step"] = int(a.rows * 24)
+    r["e2e"]["path"] = ("bl_groupby_agg with BL_HOST columns in pinned memory -> BL_HOST outputs" if world == 1 else
+                        "pinned host columns -> bl_column_to(device) -> partitioned plan (local K5, fused partition + P2P exchange, merge) -> host outputs")
+    r["metric"] = "group_by_agg_rows_per_sec"
+    r["verified"] = verified
+    r["workload"] = (f"C2 hash group_by {a.rows} rows/GPU, {a.keys} {'Zipf(1.1)-skewed' if a.skew == 'zipf' else 'uniform'} Int64 keys, sum(v_i64)/mean(v_f64)/len"
+                     + (f", {a.null_frac:.0%} nulls per value column" if a.null_frac > 0 else "") + "; inputs 2.4 GB > L2 (no flush needed)")
+    r["parallelism"] = ("single GPU" if world == 1 else
+                        (f"hash-partitioned x{world}: local pre-agg + fused partition/P2P-store exchange over NVLink (counts + flags in the peer windows, no host round trip) + merge"
+                         if a.exchange == "p2p" else f"hash-partitioned x{world}: local pre-agg + one NCCL all-to-all of partial aggregates + merge"))
+    if peer_ex is not None:
+        peer_ex.close()
+    return r
+
+
+def bench_join(H: Harness, sparse: bool):
+    a, plb, world, rank = H.a, H.plb, H.world, H.rank
+    probe, build = gen_join(a.rows, a.build_rows, 2 + rank, a.hit_frac, a.dup, sparse=sparse, id_base=rank * a.build_rows, id_space=None if world == 1 else a.build_rows * world)
+    hp, hb = (plb.to_pinned(probe), plb.to_pinned(build)) if a.e2e_steps > 0 else (None, None)
+    dp, db = plb.to_device(probe), plb.to_device(build)
+    pdist = None
+    if world > 1:
+        from polars_b200 import dist as pdist
+
+    def step_device():
+        if world == 1:
+            li, ri = plb.hash_join(dp.view(), db.view(), "inner", False, "none", location=plb.DEVICE)
+            return li.length
+        gl, gr = pdist.partitioned_hash_join(plb, dp.view(), db.view(), rank * a.rows, rank * a.build_rows)
+        return gl.length
+
+    def step_e2e():
+        if world == 1:
+            (li, _), (ri, _) = plb.hash_join(plb.Column(hp), plb.Column(hb), "inner", False, "none", location=plb.HOST)
+            return li.size, li.nbytes + ri.nbytes
+        cp, cb = plb.to_device(hp), plb.to_device(hb)
+        gl, gr = pdist.partitioned_hash_join(plb, cp.view(), cb.view(), rank * a.rows, rank * a.build_rows)
+        l, r_ = gl.to_numpy()[0], gr.to_numpy()[0]
+        return l.size, l.nbytes + r_.nbytes
+
+    verified = None
+    if not a.no_verify:
+        if world == 1:
+            (li, _), (ri, _) = plb.hash_join(dp.view(), db.view(), "inner", False, "none", location=plb.HOST)
+            verified = verify_join(probe, build, li, ri, a.dup)
+        else:
+            gl, gr = pdist.partitioned_hash_join(plb, dp.view(), db.view(), rank * a.rows, rank * a.build_rows)
+            n_pairs = H.sum_over_ranks(gl.length)
+            exp = a.rows * world * a.dup if a.hit_frac >= 1.0 else None
+            assert exp is None or n_pairs == exp, f"{n_pairs} join tuples over all ranks, expected {exp}"
+            # global ids -> every emitted left id is a distinct probe row (unique build keys): checked through the id sum
+            l = gl.to_numpy()[0].astype(np.int64)
+            if a.dup == 1 and a.hit_frac >= 1.0:
+                tot = H.sum_over_ranks(int(l.sum()))
+                nn = a.rows * world
+                assert tot == nn * (nn - 1) // 2, "the emitted probe rows are not each probe row exactly once"
+            verified = "conservation over all ranks: tuple count, every probe row exactly once (id sum)"
+    del probe, build
+
+    def pick(prof):
+        return max((k for k in prof if k.startswith("k8_") and "probe" in k), key=lambda k: prof[k]["ms"], default="k8_join_probe_emit")
+
+    alg = 8.0 + 8.0 * a.hit_frac * a.dup      # probe key + (left_idx, right_idx) u32 per match
+    r = H.measure(step_device, step_e2e if a.e2e_steps > 0 else None, a.rows, alg, pick, f"join:{'sparse' if sparse else 'dense'}:{a.rows}:{a.build_rows}")
+    r["e2e"]["h2d_bytes_per_step"] = int((a.rows + a.build_rows) * 8)
+    r["e2e"]["path"] = ("bl_hash_join with BL_HOST columns in pinned memory -> BL_HOST index columns" if world == 1 else
+                        "pinned host key columns -> device -> partitioned join (K6 both sides, NCCL all-to-all-v, local K7/K8, K4 to global ids) -> host")
+    r["metric"] = "hash_join_probe_rows_per_sec"
+    r["verified"] = verified
+    r["workload"] = (f"C3 inner hash join: probe {a.rows} x build {a.build_rows} Int64 keys per GPU ({'unique' if a.dup == 1 else str(a.dup) + ' copies of each'}; "
+                     f"{'sparse 64-bit values -> hashed table' if sparse else 'dense surrogate ids -> direct-address table'}), {a.hit_frac:.0%} hit; outputs (left_idx,right_idx) u32")
+    r["parallelism"] = "single GPU" if world == 1 else f"radix hash-partitioned x{world}: K6 on both relations + one NCCL all-to-all-v per relation + local build/probe"
+    if world > 1 and not sparse:
+        # the broadcast-build alternative (SURVEY.md 8(e)): all-gather of the small build side, no probe-side exchange
+        def step_bcast():
+            gl, gr = pdist.broadcast_hash_join(plb, dp.view(), db.view(), rank * a.rows)
+            return gl.length
+        try:
+            rb = H.measure(step_bcast, None, a.rows, alg, pick, "join:broadcast")
+            r["broadcast_variant"] = {"value": rb["value"], "unit": "rows/s", "ms_per_step": rb["ms_per_step"], "kernels_ms_per_step": rb["kernels_ms_per_step"],
+                                      "parallelism": f"build side all-gathered ({a.build_rows * world} keys on every GPU), probe rows stay local"}
+        except Exception as e:      # optional evidence: never lose the line
+            r["broadcast_variant"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    return r
+
+
+def bench_q1(H: Harness):
+    a, plb, rank = H.a, H.plb, H.rank
+    rows = a.rows if a.rows != 100_000_000 else 60_000_000      # SF10 lineitem ~ 6e7 rows
+    h = gen_lineitem(rows, 4 + rank)
+    d = {k: plb.to_device(v) for k, v in h.items()}
+    hp = {k: plb.to_pinned(v) for k, v in h.items()}
+    exp = q1_numpy(h)
+    ok, outs = q1_device(plb, d)
+    k, _ = ok.to_numpy(); o = np.argsort(k)
+    assert np.array_equal(k[o], exp["key"]) and np.array_equal(outs[7].to_numpy()[0][o], exp["len"]), "Q1 groups differ"
+    for i, nm in ((0, "qty"), (1, "price"), (2, "dp"), (3, "ch")):
+        assert np.allclose(outs[i].to_numpy()[0][o], exp[nm], rtol=1e-6), "Q1 sums differ: " + nm
+    del h
+
+    def step_device():
+        ok, outs = q1_device(plb, d)
+        return ok.length
+
+    def step_e2e():
+        dd = {k: plb.to_device(v) for k, v in hp.items()}
+        ok, outs = q1_device(plb, dd)
+        res = [ok.to_numpy()[0]] + [o.to_numpy()[0] for o in outs]
+        return res[0].size, sum(r.nbytes for r in res)
+
+    def pick(prof):
+        return max((k for k in prof if k.startswith("k5_groupby_agg")), key=lambda k: prof[k]["ms"], default="k5_groupby_agg_smem")
+
+    r = H.measure(step_device, step_e2e if a.e2e_steps > 0 else None, rows, 8.0 * 6, pick, f"q1:{rows}")
+    r["e2e"]["h2d_bytes_per_step"] = int(rows * 8 * 7)
+    r["e2e"]["path"] = "pinned host lineitem columns -> device -> filter + expressions + group_by -> host"
+    r["metric"] = "pdsh_q1_rows_per_sec"
+    r["verified"] = "numpy: groups, len exact; sums rtol 1e-6"
+    r["workload"] = f"C4 PDS-H Q1 shape on {rows} synthetic lineitem rows (SF10-sized): filter + 4 expressions + group_by(returnflag,linestatus) with 8 aggregates"
+    r["parallelism"] = "single GPU"
+    r["rows"] = rows
+    return r
+
+
 def main():
     a = parse()
-    # NCCL prints its version banner to STDOUT for any NCCL_DEBUG level: keep the JSON line alone on stdout
-    os.environ.pop("NCCL_DEBUG", None)
-    if os.environ.get("BENCH_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
+    # NCCL prints its version banner to STDOUT for any NCCL_DEBUG level: route it to a file so the JSON line stays alone on stdout
+    if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_debug.%h.%p.log")
     if a.acero_child:
         acero_child(a)
         return
     if a.impl == "reference":
         run_reference(a)
         return
-    import torch
-    import torch.distributed as dist
-    import polars_b200 as plb
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    plb.init(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ext = torch.cuda.ExternalStream(plb.stream(), device=torch.device("cuda", local))
-    peak_gbs, peak_src = peaks()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        plb.sync()
-
-    if a.workload == "groupby":
-        key, vi, vf = gen_groupby(a.rows, a.keys, 1 + rank, a.skew)
-        hkey, hvi, hvf = (plb.to_pinned(key), plb.to_pinned(vi), plb.to_pinned(vf)) if a.e2e_steps > 0 else (None, None, None)
-        val_i = val_f = None
-        if a.null_frac > 0:      # the "+5 % nulls" variant: independent validity bitmaps on both value columns
-            nrng = np.random.default_rng(100 + rank)
-            val_i, val_f = (plb.pack_bits(nrng.random(a.rows) >= a.null_frac) for _ in range(2))      # Arrow LSB bitmaps
-        dkey, dvi, dvf = plb.to_device(key), plb.to_device(vi, val_i), plb.to_device(vf, val_f)
-        del key, vi, vf
-        spec = [("sum", np.int64), ("mean", np.float64), ("len", None)]
-        out_bytes = 0
-        peer_ex = None
-        if world > 1:
-            from polars_b200 import dist as pdist
-            if a.exchange == "p2p":      # window region per source rank: every group of a rank could go to one peer
-                try:
-                    peer_ex = pdist.PeerExchange(plb, rows_per_src=min(a.keys, a.rows) + 1024, row_words=2 + 3)
-                    ok_all = torch.tensor([1], device="cuda")
-                except Exception as e:      # CUDA IPC unavailable (container policy): use the NCCL all-to-all instead
-                    print(f"[bench] peer windows unavailable ({e}); falling back to --exchange nccl", file=sys.stderr)
-                    ok_all = torch.tensor([0], device="cuda")
-                dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
-                if int(ok_all.item()) == 0:
-                    a.exchange, peer_ex = "nccl", None
-
-        def step_device():
-            nonlocal out_bytes
-            if world == 1:
-                ok, outs = plb.group_by_agg(dkey.view(), [("sum", dvi.view()), ("mean", dvf.view()), ("len", None)], False, location=plb.DEVICE)
-                out_bytes = ok.length * (8 + 8 + 8 + 4)
-                return ok.length
-            # partitioned plan (polars_b200/dist.py): local pre-aggregation -> hash partition of the partial
-            # aggregates -> exchange (fused P2P stores over NVLink, or one NCCL all-to-all) -> merge
-            vals = [dvi.view(), dvf.view(), None]
-            if a.exchange == "p2p":
-                ok, outs = pdist.partitioned_group_by_p2p(plb, peer_ex, dkey.view(), vals, spec, nullable=[False, False, False])
-            else:
-                ok, outs = pdist.partitioned_group_by(plb, dkey.view(), vals, spec, nullable=[False, False, False])
-            out_bytes = ok.length * 28
-            return ok.length
-
-        def step_e2e():
-            (k, _), outs = plb.group_by_agg(plb.Column(hkey), [("sum", plb.Column(hvi, val_i)), ("mean", plb.Column(hvf, val_f)), ("len", None)], False, location=plb.HOST)
-            return k.size, k.nbytes + sum(o[0].nbytes for o in outs)
-
-        unit_rows = a.rows
-        alg_bytes_per_row = 24.0
-        dominant = "k5_groupby_agg"
-        metric = "group_by_agg_rows_per_sec"
-        wl = (f"C2 hash group_by {a.rows} rows/GPU, {a.keys} {'Zipf(1.1)-skewed' if a.skew == 'zipf' else 'uniform'} Int64 keys, sum(v_i64)/mean(v_f64)/len"
-              + (f", {a.null_frac:.0%} nulls per value column" if a.null_frac > 0 else "") + "; inputs 2.4 GB > L2 (no flush needed)")
-        h2d = a.rows * 24
-    elif a.workload == "q1":
-        rows = a.rows if a.rows != 100_000_000 else 60_000_000      # SF10 lineitem ~ 6e7 rows
-        a.rows = rows
-        h = gen_lineitem(rows, 4 + rank)
-        d = {k: plb.to_device(v) for k, v in h.items()}
-        hp = {k: plb.to_pinned(v) for k, v in h.items()}
-        exp = q1_numpy(h)
-        ok, outs = q1_device(plb, d)
-        k, _ = ok.to_numpy(); o = np.argsort(k)
-        assert np.array_equal(k[o], exp["key"]) and np.array_equal(outs[7].to_numpy()[0][o], exp["len"]), "Q1 groups differ"
-        for i, nm in ((0, "qty"), (1, "price"), (2, "dp"), (3, "ch")):
-            assert np.allclose(outs[i].to_numpy()[0][o], exp[nm], rtol=1e-6), "Q1 sums differ: " + nm
-        del h
-
-        def step_device():
-            ok, outs = q1_device(plb, d)
-            return ok.length
-
-        def step_e2e():
-            dd = {k: plb.to_device(v) for k, v in hp.items()}
-            ok, outs = q1_device(plb, dd)
-            res = [ok.to_numpy()[0]] + [o.to_numpy()[0] for o in outs]
-            return res[0].size, sum(r.nbytes for r in res)
-
-        unit_rows = rows
-        alg_bytes_per_row = 8.0 * 6        # K5 reads key + 5 distinct value columns
-        dominant = "k5_groupby_agg_smem"
-        metric = "pdsh_q1_rows_per_sec"
-        wl = f"C4 PDS-H Q1 shape on {rows} synthetic lineitem rows (SF10-sized): filter + 4 expressions + group_by(returnflag,linestatus) with 8 aggregates"
-        h2d = rows * 8 * 7
-    else:
-        probe, build = gen_join(a.rows, a.build_rows, 2 + rank, a.hit_frac, a.dup)
-        hp, hb = plb.to_pinned(probe), plb.to_pinned(build)
-        dp, db = plb.to_device(probe), plb.to_device(build)
-        del probe, build
-
-        def step_device():
-            li, ri = plb.hash_join(dp.view(), db.view(), "inner", False, "none", location=plb.DEVICE)
-            return li.length
-
-        def step_e2e():
-            (li, _), (ri, _) = plb.hash_join(plb.Column(hp), plb.Column(hb), "inner", False, "none", location=plb.HOST)
-            return li.size, li.nbytes + ri.nbytes
-
-        unit_rows = a.rows
-        alg_bytes_per_row = 8.0 + 8.0 * a.hit_frac * a.dup      # probe key + (left_idx, right_idx) u32 per match
-        dominant = "k8_join_probe"
-        metric = "hash_join_probe_rows_per_sec"
-        wl = (f"C3 inner hash join: probe {a.rows} x build {a.build_rows} Int64 keys ({'unique' if a.dup == 1 else str(a.dup) + ' copies of each'}), "
-              f"{a.hit_frac:.0%} hit; outputs (left_idx,right_idx) u32")
-        h2d = (a.rows + a.build_rows) * 8
-
-    # ---- warm-up, then the timed region (device-resident inputs)
-    for _ in range(max(a.warmup, 3)):
-        n_out = step_device()
-    barrier()
-    plb.profile_reset()
-    plb.profile_enable(True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    with torch.cuda.stream(ext):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(a.steps):
-            n_out = step_device()
-        e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    prof = plb.profile()
-    launches = plb.launch_count()
-    plb.profile_enable(False)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    ms_per_step = ms_max / a.steps
-    value = unit_rows * world / (ms_per_step / 1e3)
-
-    # ---- end to end through the C ABI with pinned host buffers (H2D + compute + D2H per step)
-    e2e_vals, d2h = [], 0
-    for i in range(a.e2e_steps + 1 if a.e2e_steps > 0 else 0):
-        barrier()
-        t0 = time.perf_counter()
-        _, d2h = step_e2e()
-        dt = time.perf_counter() - t0
-        if i > 0:
-            e2e_vals.append(dt)
-    te = torch.tensor([float(np.mean(e2e_vals)) if e2e_vals else 0.0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
-    clocks = sampler.stop() if rank == 0 else None      # sampled over the timed region and the e2e steps that follow it
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+    H = Harness(a)
+    results = []
+    if a.workload in ("all", "groupby"):
+        results.append(bench_groupby(H))
+    if a.workload in ("all", "join"):
+        if a.join_keys in ("both", "dense"):
+            results.append(bench_join(H, sparse=False))
+        if a.join_keys in ("both", "sparse"):
+            results.append(bench_join(H, sparse=True))
+    if a.workload == "q1":
+        results.append(bench_q1(H))
+    if H.rank != 0:
+        if H.world > 1:
+            H.dist.destroy_process_group()
         return
-    if a.workload == "join":      # hashed or dense probe, whichever ran
-        dominant = max((k for k in prof if k.startswith("k8_") and "probe" in k), key=lambda k: prof[k]["ms"], default=dominant)
-    traffic = None      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f).get(f"{a.workload}:{a.rows}:{a.keys if a.workload == 'groupby' else a.build_rows}", {})
-            traffic = t.get(dominant)
-    except Exception:
-        pass
-    dom = prof.get(dominant, {"launches": 0, "ms": 0.0})
-    dom_ms = dom["ms"] / max(dom["launches"], 1)
-    achieved = (alg_bytes_per_row * unit_rows / 1e9) / (dom_ms / 1e3) if dom_ms > 0 else 0.0
-    total_kernel_ms = sum(v["ms"] for v in prof.values()) / a.steps
+    p = results[0]
+
+    def cfg(r):
+        return {"workload": r["workload"], "rows_per_gpu": r.get("rows", a.rows), "rows_out": r["n_out"], "l2_policy": "inputs larger than L2", "parallelism": r["parallelism"]}
+
     line = {
-        "metric": metric, "value": value, "unit": "rows/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step,
+        "metric": p["metric"], "value": p["value"], "unit": "rows/s", "n_gpus": H.world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": p["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/float64", "data": "synthetic",
-        "config": {"workload": wl, "rows_per_gpu": a.rows, "groups_out": int(n_out), "l2_policy": "inputs larger than L2",
-                   "parallelism": "single GPU" if world == 1 else (f"hash-partitioned x{world}: local pre-agg + fused partition/P2P-store exchange over NVLink + merge" if a.exchange == "p2p" else f"hash-partitioned x{world}: local pre-agg + one NCCL all-to-all of partial aggregates + merge")},
-        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs if peak_gbs else None,
-                     "traffic": traffic, "peak_source": peak_src, "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes_per_row * unit_rows,
-                     "kernel_share_of_step": (dom_ms / total_kernel_ms) if total_kernel_ms else None},
-        "kernels_ms_per_step": {k: v["ms"] / a.steps for k, v in prof.items()},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+        "config": cfg(p), "verified": p["verified"], "roofline": p["roofline"], "kernels_ms_per_step": p["kernels_ms_per_step"],
+        "gpu_launches": int(H.total_launches), "clocks": p["clocks"],
         "knobs": {k: v for k, v in os.environ.items() if k.startswith("BL_")},
-        "e2e": {"value": unit_rows * world / e2e_s if e2e_s else None, "unit": "rows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
-                "path": "bl_groupby_agg / bl_hash_join with BL_HOST columns in pinned memory -> BL_HOST outputs"},
+        "e2e": p["e2e"],
     }
-    if world == 1 and not a.no_cpu_baseline and a.workload in ("groupby", "join"):
+    if len(results) > 1:
+        line["secondary"] = [{"metric": r["metric"], "value": r["value"], "unit": "rows/s", "ms_per_step": r["ms_per_step"], "config": cfg(r), "verified": r["verified"],
+                              "roofline": r["roofline"], "kernels_ms_per_step": r["kernels_ms_per_step"], "e2e": r["e2e"], "clocks": r["clocks"],
+                              **({"broadcast_variant": r["broadcast_variant"]} if "broadcast_variant" in r else {})} for r in results[1:]]
+    if H.world == 1 and not a.no_cpu_baseline and a.workload in ("all", "groupby", "join"):
         line["cpu_baseline"] = cpu_baseline(a)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if H.world > 1:
+        H.dist.destroy_process_group()
+        nccl_debug_summary()
 
 
-class _CudaArray:
-    """Zero-copy view of a raw device pointer for torch.as_tensor (CUDA array interface v2)."""
-
-    def __init__(self, ptr: int, n_words: int):
-        self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+def nccl_debug_summary():
+    """NCCL_DEBUG goes to NCCL_DEBUG_FILE (its banner would otherwise land on stdout beside the JSON line); the lines that
+    say how the communicator was built (ranks, NVLS / P2P transport) are repeated on stderr for whoever reads the log."""
+    pat = os.environ.get("NCCL_DEBUG_FILE")
+    if not pat or not os.environ.get("NCCL_DEBUG"):
+        return
+    import glob
+    seen = 0
+    for path in sorted(glob.glob(os.path.join(os.path.dirname(pat), "nccl_debug.*.log"))):
+        try:
+            with open(path) as f:
+                for ln in f:
+                    if any(t in ln for t in ("nranks", "NVLS", "via P2P", "Init COMPLETE")) and seen < 40:
+                        print("[nccl] " + ln.rstrip(), file=sys.stderr)
+                        seen += 1
+        except OSError:
+            pass
 
 
 def acero_child(a):
     """Child process of `acero_baseline`: times the query on pyarrow's Acero engine and prints one JSON object."""
     import pyarrow as pa
-    if a.workload == "groupby":
+    if a.workload in ("all", "groupby"):
         key, vi, vf = gen_groupby(a.rows, a.keys, 1, a.skew)
         t = pa.table({"key": key, "vi": vi, "vf": vf})
         t0 = time.perf_counter()
@@ -446,11 +656,10 @@ def acero_child(a):
     os._exit(0)      # Acero's worker threads occasionally abort the interpreter during static destruction
 
 
-def acero_baseline(a, sample: int, build_rows: int):
+def acero_baseline(a, workload: str, sample: int, build_rows: int):
     """Second, independent CPU reference: the same query on pyarrow's Acero engine with
     its default thread pool, in a child process.  Reported beside the oracle port; neither is the target."""
-    import subprocess
-    cmd = [sys.executable, os.path.abspath(__file__), "--acero-child", "--workload", a.workload, "--rows", str(sample), "--keys", str(a.keys),
+    cmd = [sys.executable, os.path.abspath(__file__), "--acero-child", "--workload", workload, "--rows", str(sample), "--keys", str(a.keys),
            "--build-rows", str(build_rows), "--skew", a.skew, "--hit-frac", str(a.hit_frac), "--dup", str(a.dup)]
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
@@ -460,36 +669,48 @@ def acero_baseline(a, sample: int, build_rows: int):
 
 
 def cpu_baseline(a):
+    """The oracle port on the host cores over a bounded sample (about 10-30 s of CPU work in total), with its thread
+    scaling points.  The full-size number is the --impl reference arm."""
     import oracle
     oracle.build()
-    cores = oracle.max_threads()
+    hw = _oracle_threads(oracle)
     sample = min(a.rows, a.cpu_sample)
-    if a.workload == "groupby":
+    points = sorted({1, min(16, hw), hw})
+    out = {}
+    if a.workload in ("all", "groupby"):
         key, vi, vf = gen_groupby(sample, a.keys, 1, a.skew)
         aggs = [("sum", vi, None), ("mean", vf, None), ("len", None, None)]
-        t0 = time.perf_counter()
-        oracle.group_by_agg(key, None, aggs, cores, False)
-        dt = time.perf_counter() - t0
-        n1 = min(sample, 4_000_000)      # single-thread point of the same port (all cores and 1 core)
-        t1 = time.perf_counter()
-        oracle.group_by_agg(key[:n1], None, [(k, None if v is None else v[:n1], m) for k, v, m in aggs], 1, False)
-        one = n1 / (time.perf_counter() - t1)
-        second = acero_baseline(a, sample, a.build_rows)
-    else:
+        scal = []
+        for t in points:
+            oracle.set_threads(t)
+            n = sample if t > 1 else min(sample, 5_000_000)
+            t0 = time.perf_counter()
+            oracle.group_by_agg(key[:n], None, [(k, None if v is None else v[:n], m) for k, v, m in aggs], t, False)
+            scal.append({"cores": t, "value": n / (time.perf_counter() - t0), "unit": "rows/s", "sample": f"{n} rows"})
+        oracle.set_threads(hw)
+        best = max(scal, key=lambda s: s["value"])
+        out = {"value": best["value"], "unit": "rows/s", "cores": best["cores"], "kind": "port",
+               "sample": f"{sample} rows of the C2 workload, one pass per point; oracle = C/OpenMP restatement of the reference's partitioned algorithm (the Rust reference cannot be built here)",
+               "thread_scaling": scal, "second_reference": acero_baseline(a, "groupby", sample, a.build_rows)}
+    if a.workload in ("all", "join"):
         build_rows = max(1, int(a.build_rows * sample / a.rows))
         probe, build = gen_join(sample, build_rows, 2, a.hit_frac, a.dup)
-        t0 = time.perf_counter()
-        oracle.hash_join(probe, build, None, None, "inner", False, "none", cores)
-        dt = time.perf_counter() - t0
-        n1 = min(sample, 4_000_000)
-        t1 = time.perf_counter()
-        oracle.hash_join(probe[:n1], build, None, None, "inner", False, "none", 1)
-        one = n1 / (time.perf_counter() - t1)
-        second = acero_baseline(a, sample, build_rows)
-    return {"value": sample / dt, "unit": "rows/s", "cores": cores, "kind": "port",
-            "sample": f"{sample} rows of the same workload, one pass; oracle = C/OpenMP restatement of the reference's partitioned algorithm (the Rust reference cannot be built here)",
-            "single_thread": {"value": one, "unit": "rows/s", "cores": 1, "sample": f"{n1} rows"},
-            "second_reference": second}
+        scal = []
+        for t in points:
+            oracle.set_threads(t)
+            n = sample if t > 1 else min(sample, 5_000_000)
+            t0 = time.perf_counter()
+            oracle.hash_join(probe[:n], build, None, None, "inner", False, "none", t)
+            scal.append({"cores": t, "value": n / (time.perf_counter() - t0), "unit": "rows/s", "sample": f"{n} probe rows x {build_rows} build rows"})
+        oracle.set_threads(hw)
+        best = max(scal, key=lambda s: s["value"])
+        j = {"metric": "hash_join_probe_rows_per_sec", "value": best["value"], "unit": "rows/s", "cores": best["cores"], "kind": "port", "thread_scaling": scal,
+             "second_reference": acero_baseline(a, "join", sample, build_rows)}
+        if out:
+            out["join"] = j
+        else:
+            out = {**j, "sample": f"{sample} probe rows of the C3 workload"}
+    return out
 
 
 if __name__ == "__main__":

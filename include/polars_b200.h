@@ -247,6 +247,27 @@ void bl_window_close(void* peer_ptr);
 bl_status bl_groupby_export_partials_p2p(bl_groupby* g, int32_t n_ranks, int32_t my_rank, void* const* windows, int64_t rows_per_src,
                                          int32_t* row_words, int64_t* sent_rows);
 
+/* Exchange without host round trips.  window_halves[p] = base of the half of rank p's window used by this step (as
+ * mapped in THIS process); a half is BL_WINDOW_HEADER_BYTES of header followed by n_ranks regions of rows_per_src
+ * rows.  The export kernel stores the rows AND, from its last thread block, the per-destination row counts plus an
+ * epoch flag into the destination headers (release, system scope); nothing is read back and the call returns as
+ * soon as the kernel is queued.  `epoch` must grow from step to step (flags are never reset); windows must be
+ * zero-initialised (bl_window_create does). */
+#define BL_WINDOW_HEADER_BYTES 1024
+bl_status bl_groupby_export_partials_p2p_async(bl_groupby* g, int32_t n_ranks, int32_t my_rank, void* const* window_halves, int64_t rows_per_src,
+                                               uint64_t epoch, int32_t* row_words);
+/* The owner's side: queues a kernel that waits (acquire, system scope, bounded) until every source rank has published
+ * `epoch` in own_half's header, then merges the n_ranks regions into this state using the published counts.  Errors
+ * (peer region overflow, peer timeout, table overflow) surface at bl_groupby_finish / bl_groupby_status. */
+bl_status bl_groupby_merge_window_async(bl_groupby* g, const void* own_half, int32_t n_ranks, int64_t rows_per_src, uint64_t epoch);
+/* on != 0: bl_groupby_consume no longer synchronises to check for table overflow; the check happens at
+ * bl_groupby_finish (same state) or bl_groupby_status. */
+void bl_groupby_defer_status(bl_groupby* g, int32_t on);
+/* Synchronises and reports the state's device status word: 0 ok, 1 table overflow, 2 peer region overflow, 3 peer timeout. */
+bl_status bl_groupby_status(bl_groupby* g, int32_t* status_out);
+/* Sampled cardinality estimate of the consumed batches (0 before the first consume; no synchronisation). */
+int64_t bl_groupby_estimated_groups(bl_groupby* g);
+
 /* ---- profiling (CUDA events on the library stream) -------------------------------------- */
 /* enable != 0: every kernel launch is bracketed by events; totals accumulate per kernel name. */
 void bl_profile_enable(int32_t enable);

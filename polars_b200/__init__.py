@@ -485,6 +485,30 @@ class GroupBy:
         _check(lib().bl_groupby_export_partials_p2p(self.h, C.c_int32(n), C.c_int32(my_rank), arr, C.c_int64(rows_per_src), C.byref(rw), sent))
         return int(rw.value), np.array(list(sent), dtype=np.int64)
 
+    def export_partials_p2p_async(self, window_halves: Sequence[int], my_rank: int, rows_per_src: int, epoch: int) -> int:
+        """Fused partition + exchange + count publication (no host round trip).  -> row_words"""
+        n = len(window_halves)
+        arr = (C.c_void_p * n)(*[C.c_void_p(w) for w in window_halves])
+        rw = C.c_int32()
+        _check(lib().bl_groupby_export_partials_p2p_async(self.h, C.c_int32(n), C.c_int32(my_rank), arr, C.c_int64(rows_per_src), C.c_uint64(epoch), C.byref(rw)))
+        return int(rw.value)
+
+    def merge_window_async(self, own_half: int, n_ranks: int, rows_per_src: int, epoch: int):
+        _check(lib().bl_groupby_merge_window_async(self.h, C.c_void_p(own_half), C.c_int32(n_ranks), C.c_int64(rows_per_src), C.c_uint64(epoch)))
+
+    def defer_status(self, on: bool = True):
+        lib().bl_groupby_defer_status.restype = None
+        lib().bl_groupby_defer_status(self.h, C.c_int32(int(on)))
+
+    def status(self) -> int:
+        st = C.c_int32()
+        _check(lib().bl_groupby_status(self.h, C.byref(st)))
+        return int(st.value)
+
+    def estimated_groups(self) -> int:
+        lib().bl_groupby_estimated_groups.restype = C.c_int64
+        return int(lib().bl_groupby_estimated_groups(self.h))
+
     def merge_partials(self, rows_dev_ptr: int, n_rows: int):
         _check(lib().bl_groupby_merge_partials(self.h, C.c_void_p(rows_dev_ptr), C.c_int64(n_rows)))
 

@@ -366,6 +366,30 @@ bl_status bl_groupby_export_partials_p2p(bl_groupby* g, int32_t n_ranks, int32_t
     BL_CATCH
 }
 
+bl_status bl_groupby_export_partials_p2p_async(bl_groupby* g, int32_t n_ranks, int32_t my_rank, void* const* window_halves, int64_t rows_per_src, uint64_t epoch, int32_t* row_words) {
+    BL_TRY
+    PLB_REQUIRE(g && window_halves && row_words, BL_ERR_INVALID, "groupby_export_partials_p2p_async: null argument");
+    static_assert(GB_WINDOW_HEADER_WORDS * 8 == BL_WINDOW_HEADER_BYTES, "window header size");
+    int rw = 0;
+    g->st->export_partials_p2p_async(n_ranks, my_rank, window_halves, rows_per_src, epoch, &rw);
+    *row_words = rw;
+    BL_CATCH
+}
+bl_status bl_groupby_merge_window_async(bl_groupby* g, const void* own_half, int32_t n_ranks, int64_t rows_per_src, uint64_t epoch) {
+    BL_TRY
+    PLB_REQUIRE(g && own_half, BL_ERR_INVALID, "groupby_merge_window_async: null argument");
+    g->st->merge_window_async(own_half, n_ranks, rows_per_src, epoch);
+    BL_CATCH
+}
+void bl_groupby_defer_status(bl_groupby* g, int32_t on) { if (g) g->st->defer_status = on != 0; }
+bl_status bl_groupby_status(bl_groupby* g, int32_t* status_out) {
+    BL_TRY
+    PLB_REQUIRE(g && status_out, BL_ERR_INVALID, "groupby_status: null argument");
+    *status_out = g->st->read_status();
+    BL_CATCH
+}
+int64_t bl_groupby_estimated_groups(bl_groupby* g) { return g ? g->st->est_groups : 0; }
+
 // ---- peer windows (CUDA IPC) -------------------------------------------------------------------
 struct bl_window { void* p; size_t bytes; };
 bl_status bl_window_create(size_t bytes, bl_window** out, void* ipc_handle_out) {
@@ -376,6 +400,8 @@ bl_status bl_window_create(size_t bytes, bl_window** out, void* ipc_handle_out) 
     PLB_CUDA(cudaMalloc(&p, bytes));                       // IPC needs a plain cudaMalloc allocation
     cudaIpcMemHandle_t h;
     cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); PLB_CUDA(e); }
+    e = cudaMemset(p, 0, bytes);                           // epoch flags of the async exchange start at 0
     if (e != cudaSuccess) { cudaFree(p); PLB_CUDA(e); }
     memcpy(ipc_handle_out, &h, sizeof h);
     *out = new bl_window{p, bytes};

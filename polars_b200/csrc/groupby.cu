@@ -866,6 +866,101 @@ __global__ void __launch_bounds__(256) k_gb_export_p2p(const uint64_t* __restric
     }
 }
 
+
+// ---------------------------------------------------------------------------- exchange without the host (zero syncs)
+// Round 1 exchanged the per-destination row counts with an NCCL all-to-all and read them back on the host before the
+// merge could be sized and launched (3 host round trips per step).  Here the counts travel through the peer windows
+// themselves: the LAST CTA of the export kernel (every CTA fences its peer stores system-wide, then bumps a done
+// counter) stores count and an epoch flag into the header of every destination's window (st.release.sys), and the
+// owner's merge kernel — already queued on its stream — spins on the P flags with ld.acquire.sys and reads the counts
+// on the device.  Window half: GB_WINDOW_HEADER_WORDS header words, then one region of rows_per_src rows per source.
+__device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p) { uint64_t v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+constexpr unsigned long long GB_WINDOW_OVERFLOW = ~0ull;
+
+__global__ void __launch_bounds__(256) k_gb_export_p2p_async(const uint64_t* __restrict__ entries, int64_t cap, int64_t es, int64_t ws, int n_words, int P, const __grid_constant__ PeerWindows W,
+                                                             int64_t region_words, int my_rank, int64_t rows_per_src, unsigned long long* part_cursor, unsigned* done, uint64_t epoch) {
+    __shared__ unsigned hist[EXP_MAX_PARTS];
+    __shared__ unsigned long long base[EXP_MAX_PARTS];
+    __shared__ unsigned s_last;
+    const int row_words = n_words + 3;
+    const int64_t n_entries = cap + 2;
+    const int64_t ntiles = (n_entries + 255) / 256;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        if (threadIdx.x < EXP_MAX_PARTS) hist[threadIdx.x] = 0;
+        __syncthreads();
+        const int64_t s = t * 256 + threadIdx.x;
+        uint64_t key = GB_EMPTY; int p = 0; unsigned local = 0;
+        if (s < n_entries) key = entries[s * es];
+        if (key != GB_EMPTY) { p = gb_row_partition(key, s, cap, P); local = atomicAdd(&hist[p], 1u); }
+        __syncthreads();
+        if (threadIdx.x < P && hist[threadIdx.x]) base[threadIdx.x] = atomicAdd(&part_cursor[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+        __syncthreads();
+        if (key != GB_EMPTY) {
+            const uint64_t pos = base[p] + local;
+            if ((int64_t)pos < rows_per_src) {
+                const uint64_t* e = entries + s * es;
+                uint64_t* dst = W.base[p] + GB_WINDOW_HEADER_WORDS + (int64_t)my_rank * region_words + pos * row_words;     // peer store
+                dst[0] = s == cap ? 0 : (s == cap + 1 ? GB_EMPTY : key);
+                dst[1] = e[ws];
+                for (int w = 0; w < n_words; w++) dst[2 + w] = e[(2 + w) * ws];
+                dst[2 + n_words] = s == cap ? 1 : (s == cap + 1 ? 2 : 0);
+            }
+        }
+        __syncthreads();
+    }
+    // publish: all peer stores of this CTA are ordered before its done-ticket; the last CTA's flags are ordered after every ticket
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last && threadIdx.x < P) {
+        __threadfence_system();
+        unsigned long long cnt = atomicAdd(&part_cursor[threadIdx.x], 0ull);
+        if ((int64_t)cnt > rows_per_src) cnt = GB_WINDOW_OVERFLOW;
+        uint64_t* hdr = W.base[threadIdx.x] + 2 * my_rank;
+        *reinterpret_cast<volatile uint64_t*>(hdr) = cnt;
+        __threadfence_system();
+        st_release_sys_u64(hdr + 1, epoch);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gb_merge_window(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const uint64_t* __restrict__ half, int P, int64_t rows_per_src,
+                                                         int row_words, uint64_t epoch) {
+    __shared__ long long s_end[EXP_MAX_PARTS];
+    __shared__ int s_fail;
+    if (threadIdx.x == 0) s_fail = 0;
+    __syncthreads();
+    if (threadIdx.x < P) {
+        const long long t0 = clock64();
+        uint64_t f = ld_acquire_sys_u64(half + 2 * threadIdx.x + 1);
+        while (f < epoch) {
+            if (clock64() - t0 > 6000000000ll) break;          // ~3 s: a peer never published (never hang the device)
+            __nanosleep(200);
+            f = ld_acquire_sys_u64(half + 2 * threadIdx.x + 1);
+        }
+        long long c = 0;
+        if (f < epoch) { s_fail = 3; }
+        else {
+            const unsigned long long cnt = *reinterpret_cast<const volatile unsigned long long*>(half + 2 * threadIdx.x);
+            if (cnt == GB_WINDOW_OVERFLOW) s_fail = 2; else c = (long long)cnt;
+        }
+        s_end[threadIdx.x] = c;
+    }
+    __syncthreads();
+    if (s_fail) { if (threadIdx.x == 0) *T.status = s_fail; return; }
+    if (threadIdx.x == 0) { long long acc = 0; for (int r = 0; r < P; r++) { acc += s_end[r]; s_end[r] = acc; } }
+    __syncthreads();
+    const int64_t total = s_end[P - 1];
+    const int64_t region_words = rows_per_src * row_words;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int r = 0; while (i >= s_end[r]) r++;
+        const int64_t local = i - (r ? s_end[r - 1] : 0);
+        const uint64_t* src = half + GB_WINDOW_HEADER_WORDS + (int64_t)r * region_words + local * row_words;
+        gb_merge_row(L, T, src, (int)src[row_words - 1]);
+    }
+}
+
 }  // namespace plb
 
 // =============================================================================================
@@ -1259,7 +1354,7 @@ void GroupByState::consume(const DevCol& key, const std::vector<const DevCol*>& 
         if ((double)g > 0.25 * (double)cap) grow(cap * 4);
     }
     launch_batch(key, values, row_base);
-    if (read_scalar(as<int>(status)) != 0)
+    if (!defer_status && read_scalar(as<int>(status)) != 0)
         fail(BL_ERR_UNSUPPORTED, "group_by: table overflow inside a streamed batch — create the state with expected_groups set");
     rows_seen += key.len;
 }
@@ -1351,6 +1446,30 @@ void GroupByState::export_partials_p2p(int n_ranks, int my_rank, void* const* wi
     for (int p = 0; p < n_ranks; p++) sent_rows[p] = (int64_t)h[p];
 }
 
+void GroupByState::export_partials_p2p_async(int n_ranks, int my_rank, void* const* window_halves, int64_t rows_per_src, uint64_t epoch, int* row_words_out) {
+    PLB_REQUIRE(n_ranks >= 1 && n_ranks <= EXP_MAX_PARTS && my_rank >= 0 && my_rank < n_ranks, BL_ERR_INVALID, "export_partials_p2p_async: bad rank / world size");
+    PLB_REQUIRE(epoch > 0, BL_ERR_INVALID, "export_partials_p2p_async: epoch must be positive");
+    const int row_words = L.n_words + 3;
+    *row_words_out = row_words;
+    PeerWindows W; memset(&W, 0, sizeof W);
+    for (int p = 0; p < n_ranks; p++) { PLB_REQUIRE(window_halves[p] != nullptr, BL_ERR_INVALID, "export_partials_p2p_async: null window"); W.base[p] = reinterpret_cast<uint64_t*>(window_halves[p]); }
+    if (!entries) alloc_table(1024);          // nothing consumed: still publish zero counts so that no peer waits
+    DevPtr ctl = dev_alloc(8 * EXP_MAX_PARTS + 8);
+    dev_memset(ctl->p, 0, 8 * EXP_MAX_PARTS + 8);
+    PLB_LAUNCH("k6_export_p2p", k_gb_export_p2p_async, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, L.n_words, n_ranks, W,
+               rows_per_src * row_words, my_rank, rows_per_src, as<unsigned long long>(ctl), reinterpret_cast<unsigned*>(as<unsigned long long>(ctl) + EXP_MAX_PARTS), epoch);
+}
+
+void GroupByState::merge_window_async(const void* own_half, int n_ranks, int64_t rows_per_src, uint64_t epoch) {
+    PLB_REQUIRE(own_half != nullptr && n_ranks >= 1 && n_ranks <= EXP_MAX_PARTS, BL_ERR_INVALID, "merge_window_async: bad arguments");
+    const int row_words = L.n_words + 3;
+    if (!entries) alloc_table(pow2_at_least((double)std::max<int64_t>(expected_groups, 1024) / 0.6));
+    merged_rows += (int64_t)n_ranks * rows_per_src;          // upper bound (sizes the extraction buffers)
+    PLB_LAUNCH("k5_merge_partials", k_gb_merge_window, ctx().sm_count * 4, 256, 0, L, T, reinterpret_cast<const uint64_t*>(own_half), n_ranks, rows_per_src, row_words, epoch);
+}
+
+int GroupByState::read_status() { return status ? read_scalar(as<int>(status)) : 0; }
+
 void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather, DevCol& out_key, std::vector<DevCol>& out_aggs, DevCol* out_first) {
     out_aggs.clear();
     PLB_REQUIRE(!maintain_order || L.need_first, BL_ERR_INVALID, "group_by: maintain_order needs a state created with track_first");
@@ -1364,12 +1483,17 @@ void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather,
     const long long ctl_init[2] = {0, -1};
     PLB_CUDA(cudaMemcpyAsync(ctl->p, ctl_init, 16, cudaMemcpyHostToDevice, ctx().stream));
     long long ctl_host[2] = {0, -1};
+    int status_host = 0;
     if (entries) {
+        PLB_CUDA(cudaMemcpyAsync(&status_host, status->p, 4, cudaMemcpyDeviceToHost, ctx().stream));
         PLB_LAUNCH("k5_extract", k_gb_extract, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, L.n_words, as<unsigned long long>(ctl),
                    as<uint64_t>(keys), as<uint32_t>(first), as<uint32_t>(len), as<uint64_t>(words), Gb, as<long long>(ctl) + 1);
         PLB_CUDA(cudaMemcpyAsync(ctl_host, ctl->p, 16, cudaMemcpyDeviceToHost, ctx().stream));
     }
     PLB_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (status_host == 2) fail(BL_ERR_INVALID, "group_by: a peer window region was too small for the partial aggregates sent to this rank");
+    if (status_host == 3) fail(BL_ERR_CUDA, "group_by: timed out waiting for a peer rank's partial aggregates");
+    if (status_host != 0) fail(BL_ERR_OOM, "group_by: hash table overflow (deferred check) — create the state with expected_groups set");
     const int64_t G = ctl_host[0];
     const long long null_pos = ctl_host[1];
     // key column

@@ -9,6 +9,7 @@ constexpr uint64_t GB_W1_INIT = 0xFFFFFFFF00000000ULL;  // first = u32::MAX, len
 constexpr int GB_MAX_COLS = 8;
 constexpr int GB_MAX_WORDS = 14;
 constexpr int GB_MAX_PROBE = 1024;
+constexpr int GB_WINDOW_HEADER_WORDS = 128;   // peer-window half: [src * 2] = rows sent by rank src, [src * 2 + 1] = epoch flag; regions follow
 
 enum WordOp { W_ADD_INT = 0, W_ADD_F64 = 1, W_MIN_S64 = 2, W_MAX_S64 = 3, W_MIN_U64 = 4, W_MAX_U64 = 5, W_MIN_F64 = 6, W_MAX_F64 = 7, W_NULLCNT = 8 };
 
@@ -66,6 +67,10 @@ struct GroupByState {
     void merge_partial_regions(const uint64_t* const* ptrs, const int64_t* counts, int n_regions);
     DevPtr export_partials(int n_partitions, int* row_words_out, int64_t* offsets_host);
     void export_partials_p2p(int n_ranks, int my_rank, void* const* windows, int64_t rows_per_src, int* row_words_out, int64_t* sent_rows);
+    void export_partials_p2p_async(int n_ranks, int my_rank, void* const* window_halves, int64_t rows_per_src, uint64_t epoch, int* row_words_out);
+    void merge_window_async(const void* own_half, int n_ranks, int64_t rows_per_src, uint64_t epoch);
+    int read_status();           // host sync: 0 ok, 1 table overflow, 2 peer window overflow, 3 peer timeout
+    bool defer_status = false;   // consume() leaves the overflow check to read_status() / finish()
     void finish(bool maintain_order, const DevCol* key_col_for_gather, DevCol& out_key, std::vector<DevCol>& out_aggs, DevCol* out_first = nullptr);
     void reset();
     int64_t count_groups();

@@ -14,17 +14,19 @@
 // B200 design.  Three table forms, chosen per build relation:
 //   DENSE    build keys are integers whose value range is a few times the row count (surrogate / primary keys):
 //            u32 table[key - min] = build row.  4 B per key value, L2-resident for 1e7 keys.
-//   COMPACT  (default hashed form) u32 table[slot] = fingerprint:8 | build row:24 (plain row ids past 2^24 rows),
+//   WIDE     (default hashed form) 16-byte entries {key, val, cnt}, capacity 2x the build rows: one random sector per probe
+//            step carries everything (key, build row or CSR offset, match count).
+//   COMPACT  (BL_JOIN_TABLE=compact) u32 table[slot] = fingerprint:8 | build row:24 (plain row ids past 2^24 rows),
 //            slot = top bits of key * RANDOM_ODD, capacity = the power of two >= 1.5x the build rows.  The table never
 //            stores the key: a fingerprint match is verified against the build key column itself.  4 B per slot
 //            (1e7 keys: 64 MB, L2-resident) instead of 16 B, so a probe is one L2 hit plus one 8-byte read of the build
-//            column; a miss usually costs the L2 hit only.
-//   WIDE     (BL_JOIN_TABLE=wide, round-1 form) 16-byte entries {key, val, cnt}, capacity 2x the build rows.
+//            column; a miss usually costs the L2 hit only (measured: slower than WIDE when most probes hit,
+//            profiles/r02_proto_radix.md).
 //   build:   claim the key's slot with one CAS; duplicates are detected by the claim that loses.  Unique build keys
 //            (the primary-key case) need nothing else.  With duplicates: per-slot counts -> exclusive scan -> CSR
 //            offsets; the rows of a slot are listed ascending (stable sort of the rows by slot) — the reference's IdxVec.
 //   probe:   unique build keys: ONE fused pass — lookup + decoupled look-back scan over 2048-row tiles + coalesced
-//            tuple stores.  Duplicates: pass 1 stores a 4-byte handle per probe row and per-tile match counts; a scan
+//            tuple stores.  Duplicates: pass 1 stores (list offset, match count) per probe row and per-tile match counts; a scan
 //            gives every tile its output offset; pass 2 expands the handles warp-cooperatively (every 32 consecutive
 //            output tuples are written by the 32 lanes of one warp, whatever the run lengths).
 //   semi / anti: probe-only — one hit bit per left row, then K3 over iota(left): O(left + right), never the
@@ -255,8 +257,8 @@ __global__ void __launch_bounds__(256) k_join_dense_build(uint32_t* __restrict__
 }
 
 // ---------------------------------------------------------------------------- lookup (any table form)
-// Returns the match handle of one probe key — unique mode: the build row; CSR mode: the entry / slot index — or
-// J_NONE; cnt = number of matches.  `kraw` is the raw (not yet canonical) key pattern.
+// Returns the match handle of one probe key — unique mode: the build row; CSR mode: the offset of the key's ascending
+// row list in sorted_rows — or J_NONE; cnt = number of matches.  `kraw` is the raw (not yet canonical) key pattern.
 template <int MODE, int KEY_ELEM, int KEY_CANON>
 __device__ __forceinline__ uint32_t j_lookup(const JoinDev& J, uint64_t kraw, bool valid, uint32_t& cnt) {
     cnt = 0;
@@ -285,7 +287,7 @@ __device__ __forceinline__ uint32_t j_lookup(const JoinDev& J, uint64_t kraw, bo
             }
         }
         cnt = J.csr ? e.w : 1u;
-        return J.csr ? (uint32_t)slot : e.z;
+        return e.z;                                   // unique: the build row; CSR: the list offset (k_join_csr_offsets)
     }
     // COMPACT
     uint32_t slot, row;
@@ -306,14 +308,15 @@ __device__ __forceinline__ uint32_t j_lookup(const JoinDev& J, uint64_t kraw, bo
         }
     }
     cnt = J.csr ? __ldg(J.ccnt + slot) : 1u;
-    return J.csr ? slot : row;
+    return J.csr ? __ldg(J.coff + slot) : row;
 }
 
 // ---------------------------------------------------------------------------- K8 probe, pass 1 (two-pass form)
-// handle[i] = unique mode: build row (J_NONE on miss); CSR mode: entry / slot index (J_NONE on miss).
+// handle[i] = unique mode: build row; CSR mode: offset of the row list, hcnt[i] = its length (J_NONE on miss) — pass 2
+// never goes back to the table (round 1 re-read the entry of every probe row there: a random HBM sector per row).
 template <int MODE, int KEY_ELEM, int KEY_CANON>
 __global__ void __launch_bounds__(256) k_join_probe(const __grid_constant__ JoinDev J, const void* __restrict__ keys, const uint32_t* __restrict__ valid, int64_t n, int left_join,
-                                                    uint32_t* __restrict__ handle, unsigned long long* __restrict__ tile_counts) {
+                                                    uint32_t* __restrict__ handle, uint32_t* __restrict__ hcnt, unsigned long long* __restrict__ tile_counts) {
     const int64_t npairs = (n + 1) >> 1;
     const int64_t rounded = (npairs + 31) / 32 * 32;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < rounded; p += (int64_t)gridDim.x * blockDim.x) {
@@ -323,19 +326,18 @@ __global__ void __launch_bounds__(256) k_join_probe(const __grid_constant__ Join
             if (KEY_ELEM == 8) { ulonglong2 t = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(keys) + r0); kraw[0] = t.x; kraw[1] = t.y; }
             else { uint2 t = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(keys) + r0); kraw[0] = t.x; kraw[1] = t.y; }
         } else if (r0 < n) kraw[0] = KEY_ELEM == 8 ? reinterpret_cast<const uint64_t*>(keys)[r0] : (uint64_t)reinterpret_cast<const uint32_t*>(keys)[r0];
-        uint32_t h[2] = {J_NONE, J_NONE};
+        uint32_t h[2] = {J_NONE, J_NONE}, hc[2] = {0, 0};
         uint32_t cnt = 0;
 #pragma unroll
         for (int j = 0; j < 2; j++) {
             const int64_t row = r0 + j;
             if (row >= n) continue;
             const bool v = valid == nullptr || bit_get(valid, row);
-            uint32_t c;
-            h[j] = j_lookup<MODE, KEY_ELEM, KEY_CANON>(J, kraw[j], v, c);
-            cnt += h[j] != J_NONE ? c : (left_join ? 1u : 0u);
+            h[j] = j_lookup<MODE, KEY_ELEM, KEY_CANON>(J, kraw[j], v, hc[j]);
+            cnt += h[j] != J_NONE ? hc[j] : (left_join ? 1u : 0u);
         }
-        if (r0 + 1 < n) *reinterpret_cast<uint2*>(handle + r0) = make_uint2(h[0], h[1]);
-        else if (r0 < n) handle[r0] = h[0];
+        if (r0 + 1 < n) { *reinterpret_cast<uint2*>(handle + r0) = make_uint2(h[0], h[1]); if (J.csr) *reinterpret_cast<uint2*>(hcnt + r0) = make_uint2(hc[0], hc[1]); }
+        else if (r0 < n) { handle[r0] = h[0]; if (J.csr) hcnt[r0] = hc[0]; }
         // 32 lanes x 2 rows = 64 consecutive rows: always inside one J_TILE
         unsigned long long c = cnt;
         for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(256) k_join_probe(const __grid_constant__ Join
 // whose exclusive prefix is the last one <= q (5-step search over the lanes' prefixes by shuffles), so 32
 // consecutive tuples are always stored by the 32 lanes of the warp — coalesced for any mix of run lengths
 // (round 1 wrote every run with its own thread: 1 TB/s for 4 matches per probe row).
-struct JoinEmitDev { const uint4* wide; const uint32_t* ccnt; const uint32_t* coff; const uint32_t* sorted_rows; int mode, csr; };
+struct JoinEmitDev { const uint32_t* hcnt; const uint32_t* sorted_rows; int csr; };
 __global__ void __launch_bounds__(256) k_join_emit(const __grid_constant__ JoinEmitDev E, const uint32_t* __restrict__ handle, int64_t n, int left_join,
                                                    const uint64_t* __restrict__ tile_off, uint32_t* __restrict__ out_probe, uint32_t* __restrict__ out_build) {
     constexpr int ITERS = J_TILE / 256;           // 8
@@ -362,13 +364,10 @@ __global__ void __launch_bounds__(256) k_join_emit(const __grid_constant__ JoinE
         for (int j = 0; j < ITERS; j++) {
             const int64_t row = t * J_TILE + j * 256 + threadIdx.x;
             h[j] = row < n ? handle[row] : J_NONE;
-            uint32_t ck = 0; off[j] = 0;
+            uint32_t ck = 0; off[j] = h[j];
             if (row < n) {
-                if (h[j] != J_NONE) {
-                    if (!E.csr) ck = 1;
-                    else if (E.mode == JM_WIDE) { const uint4 e = __ldg(&E.wide[h[j]]); ck = e.w; off[j] = e.z; }
-                    else { ck = __ldg(E.ccnt + h[j]); off[j] = __ldg(E.coff + h[j]); }
-                } else if (left_join) ck = 1;
+                if (h[j] != J_NONE) ck = E.csr ? __ldcs(E.hcnt + row) : 1u;
+                else if (left_join) ck = 1;
             }
             c[j] = ck;
             uint32_t x = ck;
@@ -589,7 +588,7 @@ struct JoinBuilt {
 
 static int join_table_pref() {
     const char* e = getenv("BL_JOIN_TABLE");
-    return (e && (e[0] == 'w' || e[0] == 'W')) ? JM_WIDE : JM_COMPACT;
+    return (e && (e[0] == 'c' || e[0] == 'C')) ? JM_COMPACT : JM_WIDE;      // measured (profiles/r02_proto_radix.md): WIDE wins when most probes hit
 }
 
 // K7.  need_lists = false (semi / anti): duplicates need no row lists, only membership.
@@ -765,12 +764,12 @@ static JoinResult hash_join_inner_left(const DevCol& left, const DevCol& right, 
     trace_point("join:probe");
     if (!done) {
         // ---- probe pass 1
-        DevPtr handle = dev_alloc((size_t)std::max<int64_t>(np, 1) * 4 + 16), tc = dev_alloc((size_t)std::max<int64_t>(ntiles, 1) * 8), toff = dev_alloc((size_t)std::max<int64_t>(ntiles, 1) * 8), total = dev_alloc(8);
+        DevPtr handle = dev_alloc((size_t)std::max<int64_t>(np, 1) * 4 + 16), hcnt = dev_alloc(B.csr ? (size_t)std::max<int64_t>(np, 1) * 4 + 16 : 16), tc = dev_alloc((size_t)std::max<int64_t>(ntiles, 1) * 8), toff = dev_alloc((size_t)std::max<int64_t>(ntiles, 1) * 8), total = dev_alloc(8);
         dev_memset(tc->p, 0, (size_t)std::max<int64_t>(ntiles, 1) * 8); dev_memset(total->p, 0, 8);
         if (np > 0) {
             const int grid = grid_for((np + 1) / 2, 256);
             uint32_t* hp = as<uint32_t>(handle); unsigned long long* tcp = as<unsigned long long>(tc);
-#define PR_CALL(M_, E, CN) PLB_LAUNCH("k8_join_probe", (k_join_probe<M_, E, CN>), grid, 256, 0, B.J, probe.v(), probe.vm(), np, left_join, hp, tcp)
+#define PR_CALL(M_, E, CN) PLB_LAUNCH("k8_join_probe", (k_join_probe<M_, E, CN>), grid, 256, 0, B.J, probe.v(), probe.vm(), np, left_join, hp, as<uint32_t>(hcnt), tcp)
             J_DISPATCH(PR_CALL);
 #undef PR_CALL
             exclusive_scan_u64(as<uint64_t>(tc), as<uint64_t>(toff), ntiles, as<uint64_t>(total));
@@ -781,7 +780,7 @@ static JoinResult hash_join_inner_left(const DevCol& left, const DevCol& right, 
         out_probe = dev_alloc((size_t)std::max<uint64_t>(M, 1) * 4 + 16); out_build = dev_alloc((size_t)std::max<uint64_t>(M, 1) * 4 + 16);
         if (M > 0) {
             JoinEmitDev E; memset(&E, 0, sizeof E);
-            E.wide = B.J.W.entries; E.ccnt = B.J.ccnt; E.coff = B.J.coff; E.sorted_rows = as<uint32_t>(B.sorted_rows); E.mode = B.mode; E.csr = B.csr ? 1 : 0;
+            E.hcnt = as<uint32_t>(hcnt); E.sorted_rows = as<uint32_t>(B.sorted_rows); E.csr = B.csr ? 1 : 0;
             PLB_LAUNCH("k8_join_emit", k_join_emit, (int)std::min<int64_t>(ntiles, (int64_t)c.sm_count * 8), 256, 0, E, as<uint32_t>(handle), np, left_join,
                        as<uint64_t>(toff), as<uint32_t>(out_probe), as<uint32_t>(out_build));
         }

@@ -86,18 +86,25 @@ def partitioned_group_by(plb, key_col, value_cols, spec, location=None, nullable
         plb.dev_free(ptr)
 
 
+WINDOW_HEADER_BYTES = 1024      # BL_WINDOW_HEADER_BYTES: per source rank (rows sent, epoch flag)
+
+
 class PeerExchange:
     """Peer windows for the fused partition + exchange (K6 stores straight into the destination GPU's
-    memory over NVLink; the only collective left on the step is a tiny count exchange).
-    Two window halves alternate between steps, so a fast rank that already runs step k+1 writes into the
-    other half than the one a slow rank is still merging from step k; the count exchange of step k+1
-    cannot complete before every rank has finished merging step k, so two halves are enough and no
-    barrier is needed."""
+    memory over NVLink; the row counts and a ready flag travel through the window headers, so the data
+    path has no collective and no host round trip at all).
+    Two window halves alternate between steps: a rank that already runs step k+1 writes into the other
+    half than the one a slow rank is still merging from step k; it can only reach step k+2 (same half
+    again) after its own merge of step k+1, which waits for the slow rank's step-k+1 flags — and those are
+    published by the slow rank's export kernel, stream-ordered after its merge of step k.  So two halves
+    are enough and no barrier is needed."""
 
     def __init__(self, plb, rows_per_src: int, row_words: int):
         self.plb, self.rows_per_src, self.row_words = plb, int(rows_per_src), int(row_words)
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
-        self.half_bytes = self.world * self.rows_per_src * self.row_words * 8
+        self.half_bytes = WINDOW_HEADER_BYTES + self.world * self.rows_per_src * self.row_words * 8
+        self.half_bytes = (self.half_bytes + 255) // 256 * 256
+        self.epoch = 0
         # every collective below is reached by every rank even if a local step fails (no rank may hang)
         try:
             self.win, err = plb.Window(2 * self.half_bytes), None
@@ -121,14 +128,17 @@ class PeerExchange:
             raise RuntimeError("peer windows unavailable: " + "; ".join(str(f) for f in flags if f))
         self.half = 0
 
-    def flip(self):
+    def next_step(self) -> int:
+        """Flips the window half and returns the step's epoch (strictly increasing; flags are never reset)."""
         self.half ^= 1
+        self.epoch += 1
+        return self.epoch
 
-    def peer_ptrs(self):
+    def peer_halves(self):
         return [p + self.half * self.half_bytes for p in self.peers]
 
-    def region_ptr(self, src: int) -> int:
-        return self.win.ptr + self.half * self.half_bytes + src * self.rows_per_src * self.row_words * 8
+    def own_half(self) -> int:
+        return self.win.ptr + self.half * self.half_bytes
 
     def close(self):
         dist.barrier()
@@ -138,18 +148,29 @@ class PeerExchange:
         self.win.destroy()
 
 
-def partitioned_group_by_p2p(plb, ex: PeerExchange, key_col, value_cols, spec, location=None, nullable=None):
-    """Same plan as partitioned_group_by, but the partial aggregates reach their owner by P2P stores from
-    inside the partition kernel (bl_groupby_export_partials_p2p) instead of an NCCL all-to-all."""
-    g = plb.GroupBy(plb.NP_OF[key_col.dtype], spec, nullable=nullable)
+def partitioned_group_by_p2p(plb, ex: PeerExchange, key_col, value_cols, spec, location=None, nullable=None, expected_groups: int = 0):
+    """Same plan as partitioned_group_by, but the partial aggregates reach their owner by P2P stores from inside
+    the partition kernel and the owner's merge kernel picks the row counts up from its window header on the
+    device: local K5 -> export (stores + publish) -> merge (wait + merge) -> finish are queued back to back;
+    the only host synchronisations of the step are the cardinality sample of the local K5 and the final read-back
+    of the group count.  Errors of the deferred checks (local table overflow, peer region overflow, peer timeout)
+    are raised at the end of the step."""
+    g = plb.GroupBy(plb.NP_OF[key_col.dtype], spec, nullable=nullable, expected_groups=expected_groups)
+    g.defer_status(True)
     g.consume(key_col, value_cols, row_base=0)
-    ex.flip()
-    rw, sent = g.export_partials_p2p(ex.peer_ptrs(), ex.rank, ex.rows_per_src)
+    epoch = ex.next_step()
+    rw = g.export_partials_p2p_async(ex.peer_halves(), ex.rank, ex.rows_per_src, epoch)
     assert rw == ex.row_words
-    recv = exchange_counts(sent, "cuda")          # also orders the peer stores before the merge
-    f = plb.GroupBy(plb.NP_OF[key_col.dtype], spec, expected_groups=max(int(recv.sum()), 1), nullable=nullable)
-    f.merge_partial_regions([ex.region_ptr(src) for src in range(ex.world)], [int(c) for c in recv])
-    return f.finish(False, location=plb.DEVICE if location is None else location)
+    # the owner's table: at most the groups of one rank's worth of rows land here when the ranks share a key domain,
+    # up to the local group count when they do not
+    est = max(g.estimated_groups(), expected_groups, 1024)
+    f = plb.GroupBy(plb.NP_OF[key_col.dtype], spec, expected_groups=int(est * 1.3) + 1024, nullable=nullable)
+    f.merge_window_async(ex.own_half(), ex.world, ex.rows_per_src, epoch)
+    out = f.finish(False, location=plb.DEVICE if location is None else location)
+    st = g.status()
+    if st != 0:
+        raise plb.B200Error(3, f"partitioned group_by: local pre-aggregation table overflowed (status {st}); pass expected_groups")
+    return out
 
 
 class _CudaArr:

@@ -14,7 +14,7 @@ KEYS = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_
 
 
 def run_bench(*args):
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-sample", "200000", *args],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--rows", "200000", "--keys", "1000", "--build-rows", "20000", *args],
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
@@ -22,7 +22,7 @@ def run_bench(*args):
     return json.loads(lines[0])
 
 
-@pytest.mark.parametrize("args,metric", [((), "group_by_agg_rows_per_sec"), (("--skew", "zipf"), "group_by_agg_rows_per_sec"),
+@pytest.mark.parametrize("args,metric", [((), "group_by_agg_rows_per_sec"), (("--workload", "groupby", "--skew", "zipf"), "group_by_agg_rows_per_sec"),
                                          (("--workload", "join", "--hit-frac", "0.5", "--dup", "4"), "hash_join_probe_rows_per_sec")])
 def test_reference_arm_line(args, metric):
     d = run_bench(*args)
@@ -31,11 +31,13 @@ def test_reference_arm_line(args, metric):
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["config"]["same_config"] is True and d["config"]["rows_per_step"] == 200000
+    if not args:      # the default run covers both halves of BASELINE.json's metric: group_by primary, join secondary
+        assert [x["metric"] for x in d["secondary"]] == ["hash_join_probe_rows_per_sec"] and d["secondary"][0]["value"] > 0
 
 
 def test_reference_arm_other_ranks_stay_silent():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--cpu-sample", "100000"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--rows", "100000", "--keys", "1000", "--build-rows", "10000"],
                        capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
