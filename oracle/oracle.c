@@ -24,6 +24,17 @@
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
+#include <malloc.h>
+
+/* Keep freed blocks in the heap instead of returning them to the kernel: the per-thread vectors of the group_by / join
+ * restatements are re-allocated on every call, and with 64+ threads the mmap / page-fault traffic of glibc's default
+ * policy (every block > 128 KB is its own mapping) serialises on the process' address-space lock — the Rayon original
+ * keeps its thread-local buffers in jemalloc arenas and does not pay this. */
+__attribute__((constructor)) static void or_malloc_policy(void) {
+    mallopt(M_MMAP_THRESHOLD, 32 * 1024 * 1024);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    mallopt(M_TOP_PAD, 16 * 1024 * 1024);
+}
 #endif
 
 typedef uint32_t idx_t;                 /* IdxSize = u32: polars-utils/src/index.rs:9 */
@@ -682,11 +693,16 @@ int64_t or_hash_join(const uint64_t* lk, const uint8_t* lvalid, int64_t nl, cons
     int64_t total = 0; for (int t = 0; t < T; t++) total += res[t].len;
     idx_t* L = (idx_t*)malloc((size_t)(total ? total : 1) * sizeof(idx_t));
     idx_t* R = (idx_t*)malloc((size_t)(total ? total : 1) * sizeof(idx_t));
-    int64_t o = 0;
+    int64_t* starts = (int64_t*)malloc((size_t)(T + 1) * sizeof(int64_t));
+    starts[0] = 0;
+    for (int t = 0; t < T; t++) starts[t + 1] = starts[t] + res[t].len;
+    /* flatten (single_keys_inner.rs:118-148 flattens the per-thread vectors in parallel too) */
+#pragma omp parallel for schedule(static, 1) num_threads(T) if (T > 1)
     for (int t = 0; t < T; t++) {
-        if (res[t].len) { memcpy(L + o, res[t].a, (size_t)res[t].len * sizeof(idx_t)); memcpy(R + o, res[t].b, (size_t)res[t].len * sizeof(idx_t)); }
-        o += res[t].len; free(res[t].a); free(res[t].b);
+        if (res[t].len) { memcpy(L + starts[t], res[t].a, (size_t)res[t].len * sizeof(idx_t)); memcpy(R + starts[t], res[t].b, (size_t)res[t].len * sizeof(idx_t)); }
+        free(res[t].a); free(res[t].b);
     }
+    free(starts);
     free(res); free_tables(&jt);
     *out_left = L; *out_right = R;
     return total;

@@ -160,8 +160,9 @@ DevPtr bitmap_and(const uint32_t* a, const uint32_t* b, const uint32_t* c, int64
 int64_t bitmap_popcount(const uint32_t* bm, int64_t bits);
 void exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out, int64_t n, uint64_t* total_dev);
 void exclusive_scan_u64(const uint64_t* in, uint64_t* out, int64_t n, uint64_t* total_dev);
-void sort_pairs_u32(uint32_t* keys, uint32_t* vals, int64_t n);   // stable, ascending (device)
+void sort_pairs_u32(uint32_t* keys, uint32_t* vals, int64_t n, int key_bits = 32);   // stable LSD radix sort on the low key_bits, ascending (device)
 void iota_u32(uint32_t* p, int64_t n, uint32_t base);
+inline int bits_for(uint64_t max_value) { int b = 1; while (b < 32 && (max_value >> b)) b++; return b; }   // digits the radix sort has to look at
 
 struct JoinResult { DevCol left, right; };
 JoinResult op_hash_join(const DevCol& left, const DevCol& right, int how, bool nulls_equal, int maintain_order);

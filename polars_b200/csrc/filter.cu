@@ -10,8 +10,6 @@
 // before it.  Kept rows of a warp are contiguous in the output, so stores coalesce; unselected
 // rows are never loaded (predicated loads skip whole sectors at low selectivity).
 // Algorithmic bytes: 8*c + 8*c*s per row (+1/8 for the mask); bound: HBM.
-#include <cub/device/device_radix_sort.cuh>
-
 #include "common.cuh"
 #include "dev_utils.cuh"
 
@@ -186,20 +184,97 @@ void op_filter(const std::vector<DevCol>& cols, const DevCol& mask, std::vector<
 }
 
 // ---------------------------------------------------------------------------- sort helper
-// Stable ascending sort of (key u32, value u32) pairs — used only for the ordering modes
-// (maintain_order, duplicate build keys), never on the headline path.  CUB radix sort (library).
-void sort_pairs_u32(uint32_t* keys, uint32_t* vals, int64_t n) {
+// Stable ascending LSD radix sort of (key u32, value u32) pairs, 8-bit digits — the ordering modes only
+// (maintain_order, ascending row lists of duplicate build keys, GroupsIdx), never the headline path.
+// Hand-written (round 1 called cub::DeviceRadixSort here).  Per pass:
+//   k_rs_hist     every CTA owns one contiguous chunk of the input; 256-bin shared-memory histogram -> hist[digit][cta]
+//   k_scan_u64    one exclusive scan over the digit-major matrix = global start of every (digit, cta) run
+//   k_rs_scatter  the CTA walks its chunk tile by tile, in order.  Inside a tile warp w owns a contiguous segment and
+//                 ranks its items 32 at a time with __match_any_sync (lanes holding the same digit): rank = the warp's
+//                 running count of the digit + the number of equal-digit lanes below — original order is kept at every
+//                 level (tile, warp segment, round, lane), which is what makes the pass stable.
+// Only the digits below `key_bits` are processed (slot / row-index keys rarely need all 32 bits).
+constexpr int RS_THREADS = 256, RS_ITEMS = 16, RS_TILE = RS_THREADS * RS_ITEMS, RS_WARPS = RS_THREADS / 32;
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint32_t* __restrict__ keys, int64_t n, int64_t chunk, int shift, uint32_t* __restrict__ hist, int n_ctas) {
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(n, lo + chunk);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += RS_THREADS) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    hist[(int64_t)threadIdx.x * n_ctas + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                           int64_t n, int64_t chunk, int shift, const uint64_t* __restrict__ starts, int n_ctas) {
+    __shared__ unsigned warp_cnt[RS_WARPS][256];
+    __shared__ unsigned long long gbase[256];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    gbase[threadIdx.x] = starts[(int64_t)threadIdx.x * n_ctas + blockIdx.x];
+    const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(n, lo + chunk);
+    for (int64_t tile = lo; tile < hi; tile += RS_TILE) {
+        for (int w = 0; w < RS_WARPS; w++) warp_cnt[w][threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t k[RS_ITEMS], v[RS_ITEMS]; unsigned rank[RS_ITEMS];
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; r++) {
+            const int64_t i = tile + ((int64_t)warp * RS_ITEMS + r) * 32 + lane;
+            const bool in = i < hi;
+            k[r] = in ? keys_in[i] : 0u; v[r] = in ? vals_in[i] : 0u;
+            const unsigned d = in ? ((k[r] >> shift) & 255u) : 256u;          // 256 = "no item": its own match class
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const unsigned leader = __ffs(peers) - 1;
+            unsigned old = 0;
+            if (in && lane == leader) { old = warp_cnt[warp][d]; warp_cnt[warp][d] = old + __popc(peers); }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            rank[r] = old + __popc(peers & lanemask_lt());
+            __syncwarp();
+        }
+        __syncthreads();
+        // digit = threadIdx.x: exclusive scan of the warps' counts on top of the CTA's running global offset
+        {
+            unsigned long long run = gbase[threadIdx.x];
+            for (int w = 0; w < RS_WARPS; w++) { const unsigned c = warp_cnt[w][threadIdx.x]; warp_cnt[w][threadIdx.x] = (unsigned)(run - gbase[threadIdx.x]); run += c; }
+            __syncthreads();
+            // warp_cnt now holds offsets relative to the OLD gbase; publish the new base after everyone has read the old one below
+#pragma unroll
+            for (int r = 0; r < RS_ITEMS; r++) {
+                const int64_t i = tile + ((int64_t)warp * RS_ITEMS + r) * 32 + lane;
+                if (i < hi) {
+                    const unsigned d = (k[r] >> shift) & 255u;
+                    const unsigned long long pos = gbase[d] + warp_cnt[warp][d] + rank[r];
+                    keys_out[pos] = k[r]; vals_out[pos] = v[r];
+                }
+            }
+            __syncthreads();
+            gbase[threadIdx.x] = run;
+        }
+        __syncthreads();
+    }
+}
+
+void sort_pairs_u32(uint32_t* keys, uint32_t* vals, int64_t n, int key_bits) {
     if (n <= 1) return;
-    PLB_REQUIRE(n <= 0x7FFFFFFFll, BL_ERR_UNSUPPORTED, "ordered output with more than 2^31-1 rows (radix sort item count)");
+    if (key_bits < 1 || key_bits > 32) key_bits = 32;
     Context& c = ctx();
+    const int passes = (key_bits + 7) / 8;
+    const int64_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    const int n_ctas = (int)std::min<int64_t>(tiles, (int64_t)c.sm_count * 4);
+    const int64_t chunk = (tiles + n_ctas - 1) / n_ctas * RS_TILE;
     DevPtr k2 = dev_alloc((size_t)n * 4), v2 = dev_alloc((size_t)n * 4);
-    size_t tmp_bytes = 0;
-    PLB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, as<uint32_t>(k2), vals, as<uint32_t>(v2), (int)n, 0, 32, c.stream));
-    DevPtr tmp = dev_alloc(tmp_bytes);
-    c.launch_count++;
-    PLB_CUDA(cub::DeviceRadixSort::SortPairs(tmp->p, tmp_bytes, keys, as<uint32_t>(k2), vals, as<uint32_t>(v2), (int)n, 0, 32, c.stream));
-    PLB_CUDA(cudaMemcpyAsync(keys, k2->p, (size_t)n * 4, cudaMemcpyDeviceToDevice, c.stream));
-    PLB_CUDA(cudaMemcpyAsync(vals, v2->p, (size_t)n * 4, cudaMemcpyDeviceToDevice, c.stream));
+    DevPtr hist = dev_alloc((size_t)256 * n_ctas * 4), starts = dev_alloc((size_t)256 * n_ctas * 8);
+    uint32_t *ki = keys, *vi = vals, *ko = as<uint32_t>(k2), *vo = as<uint32_t>(v2);
+    for (int p = 0; p < passes; p++) {
+        PLB_LAUNCH("sort_hist", k_rs_hist, n_ctas, RS_THREADS, 0, ki, n, chunk, 8 * p, as<uint32_t>(hist), n_ctas);
+        exclusive_scan_u32_to_u64(as<uint32_t>(hist), as<uint64_t>(starts), (int64_t)256 * n_ctas, nullptr);
+        PLB_LAUNCH("sort_scatter", k_rs_scatter, n_ctas, RS_THREADS, 0, ki, vi, ko, vo, n, chunk, 8 * p, as<uint64_t>(starts), n_ctas);
+        std::swap(ki, ko); std::swap(vi, vo);
+    }
+    if (ki != keys) {
+        PLB_CUDA(cudaMemcpyAsync(keys, ki, (size_t)n * 4, cudaMemcpyDeviceToDevice, c.stream));
+        PLB_CUDA(cudaMemcpyAsync(vals, vi, (size_t)n * 4, cudaMemcpyDeviceToDevice, c.stream));
+    }
 }
 
 }  // namespace plb

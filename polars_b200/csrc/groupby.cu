@@ -1530,7 +1530,7 @@ void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather,
         DevPtr perm = dev_alloc((size_t)G * 4), fkeys = dev_alloc((size_t)G * 4);
         PLB_CUDA(cudaMemcpyAsync(fkeys->p, first->p, (size_t)G * 4, cudaMemcpyDeviceToDevice, ctx().stream));
         iota_u32(as<uint32_t>(perm), G, 0);
-        sort_pairs_u32(as<uint32_t>(fkeys), as<uint32_t>(perm), G);
+        sort_pairs_u32(as<uint32_t>(fkeys), as<uint32_t>(perm), G);      // first-row ids carry the caller's row_base: all 32 bits
         DevCol pidx; pidx.dtype = BL_UINT32; pidx.len = G; pidx.values = perm; pidx.null_count = 0;
         std::vector<DevCol> in{out_key}, outv;
         for (auto& a : out_aggs) in.push_back(a);
@@ -1655,7 +1655,7 @@ void op_group_tuples(const DevCol& key, DevCol& out_first, DevCol& out_offsets, 
     DevCol ids = op_group_first_ids(key);
     DevPtr gid = ids.values;
     iota_u32(as<uint32_t>(out_all.values), n, 0);
-    sort_pairs_u32(as<uint32_t>(gid), as<uint32_t>(out_all.values), n);
+    sort_pairs_u32(as<uint32_t>(gid), as<uint32_t>(out_all.values), n, bits_for((uint64_t)n));
     DevCol starts = make_col(BL_BOOL, n, false);
     const int64_t n_round = (n + 31) / 32 * 32;
     PLB_LAUNCH("k5_run_starts", k_run_starts, grid_for(n_round, 256, 16), 256, 0, as<uint32_t>(gid), n, n_round, as<uint32_t>(starts.values));

@@ -14,8 +14,9 @@
 // B200 design.  Three table forms, chosen per build relation:
 //   DENSE    build keys are integers whose value range is a few times the row count (surrogate / primary keys):
 //            u32 table[key - min] = build row.  4 B per key value, L2-resident for 1e7 keys.
-//   WIDE     (default hashed form) 16-byte entries {key, val, cnt}, capacity 2x the build rows: one random sector per probe
-//            step carries everything (key, build row or CSR offset, match count).
+//   WIDE     (default hashed form) 32-byte buckets of two {key, val, cnt} entries (<= 0.7 full), bucket = mulhi(key *
+//            RANDOM_ODD, buckets) — the reference's own hash_to_partition.  One 256-bit load = one sector per probe step
+//            carries everything (both keys, build row or CSR offset, match count).
 //   COMPACT  (BL_JOIN_TABLE=compact) u32 table[slot] = fingerprint:8 | build row:24 (plain row ids past 2^24 rows),
 //            slot = top bits of key * RANDOM_ODD, capacity = the power of two >= 1.5x the build rows.  The table never
 //            stores the key: a fingerprint match is verified against the build key column itself.  4 B per slot
@@ -46,7 +47,14 @@ constexpr uint32_t J_NONE = 0xFFFFFFFFu;
 constexpr int J_TILE = 2048;
 enum { JM_WIDE = 0, JM_DENSE = 1, JM_COMPACT = 2 };
 
-struct JoinTableDev { uint4* entries; uint64_t cap; };   // WIDE: entries[cap] = null-key entry, [cap+1] = J_EMPTY-key entry
+// WIDE: 32-byte buckets of two entries — one sector, one 256-bit load per probe step.  Logical slot id = 2 * bucket + j.
+// buckets[nb] is the special bucket: entry 0 = null-key group, entry 1 = J_EMPTY-key group (their key word is only a "used" marker).
+struct JoinBucket { unsigned long long key[2]; uint32_t val[2]; uint32_t cnt[2]; };
+static_assert(sizeof(JoinBucket) == 32, "bucket = one 32-byte sector");
+struct JoinTableDev { JoinBucket* buckets; uint64_t nb; };
+__device__ __forceinline__ void j_load_bucket(const JoinBucket* b, unsigned long long& k0, unsigned long long& k1, unsigned long long& v, unsigned long long& c) {
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k0), "=l"(k1), "=l"(v), "=l"(c) : "l"(b));      // LDG.E.256: the whole bucket
+}
 
 // Everything a probe needs, for any table form (unused members stay zero).
 struct JoinDev {
@@ -81,52 +89,65 @@ __device__ __forceinline__ uint64_t j_ordered(uint64_t raw, int sign_bits) {
     return raw;
 }
 
-__global__ void k_join_init(uint4* entries, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        entries[i] = make_uint4((uint32_t)J_EMPTY, (uint32_t)(J_EMPTY >> 32), J_NONE, 0u);
+__global__ void k_join_init(JoinBucket* buckets, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4* q = reinterpret_cast<uint4*>(buckets + i);
+        q[0] = make_uint4((uint32_t)J_EMPTY, (uint32_t)(J_EMPTY >> 32), (uint32_t)J_EMPTY, (uint32_t)(J_EMPTY >> 32));
+        q[1] = make_uint4(J_NONE, J_NONE, 0u, 0u);
+    }
 }
 __global__ void k_fill_u32j(uint32_t* p, uint32_t v, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
 // ---------------------------------------------------------------------------- K7 build: WIDE
+// A key lives in the first bucket of its probe sequence that had a free entry when it arrived (entries are never
+// removed), so a lookup may stop at the first bucket that still has a free entry.
 __global__ void __launch_bounds__(256) k_join_build(JoinTableDev T, const void* __restrict__ keys, const uint32_t* __restrict__ valid, int key_dtype, int64_t n,
                                                     int nulls_equal, uint32_t* __restrict__ slot_of_row, int* __restrict__ has_dups) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
         const bool v = valid == nullptr || bit_get(valid, r);
-        uint64_t slot;
+        uint64_t b; int j;
         if (!v) {
             if (!nulls_equal) { slot_of_row[r] = J_NONE; continue; }     // null keys are not inserted (single_keys.rs:41,148)
-            slot = T.cap;
-            atomicCAS(reinterpret_cast<unsigned long long*>(&T.entries[slot]), (unsigned long long)J_EMPTY, 0ull);
+            b = T.nb; j = 0;
+            atomicCAS(&T.buckets[b].key[0], (unsigned long long)J_EMPTY, 0ull);
         } else {
             const uint64_t key = j_load_key(keys, key_dtype, r);
-            if (key == J_EMPTY) { slot = T.cap + 1; atomicCAS(reinterpret_cast<unsigned long long*>(&T.entries[slot]), (unsigned long long)J_EMPTY, 1ull); }
+            if (key == J_EMPTY) { b = T.nb; j = 1; atomicCAS(&T.buckets[b].key[1], (unsigned long long)J_EMPTY, 1ull); }
             else {
-                slot = __umul64hi(dirty_hash(key), T.cap);
+                b = __umul64hi(dirty_hash(key), T.nb);
+                j = 0;
                 while (true) {
-                    unsigned long long* kp = reinterpret_cast<unsigned long long*>(&T.entries[slot]);
-                    unsigned long long k = __ldcg(kp);
-                    if (k == key) break;
-                    if (k == J_EMPTY) { unsigned long long old = atomicCAS(kp, (unsigned long long)J_EMPTY, (unsigned long long)key); if (old == J_EMPTY || old == key) break; }
-                    if (++slot == T.cap) slot = 0;
+                    bool found = false;
+#pragma unroll
+                    for (int jj = 0; jj < 2; jj++) {
+                        if (found) continue;
+                        unsigned long long* kp = &T.buckets[b].key[jj];
+                        unsigned long long k = __ldcg(kp);
+                        if (k == J_EMPTY) k = atomicCAS(kp, (unsigned long long)J_EMPTY, (unsigned long long)key);
+                        if (k == key || k == J_EMPTY) { found = true; j = jj; }
+                    }
+                    if (found) break;
+                    if (++b == T.nb) b = 0;
                 }
             }
         }
-        uint32_t* w = reinterpret_cast<uint32_t*>(&T.entries[slot]);
-        const uint32_t old = atomicAdd(w + 3, 1u);
-        atomicMin(w + 2, (uint32_t)r);
+        const uint32_t old = atomicAdd(&T.buckets[b].cnt[j], 1u);
+        atomicMin(&T.buckets[b].val[j], (uint32_t)r);
         if (old != 0) *has_dups = 1;
-        slot_of_row[r] = (uint32_t)slot;
+        slot_of_row[r] = (uint32_t)(2 * b + j);
     }
 }
-// WIDE duplicates: val <- CSR offset (exclusive scan of cnt over the entries, in entry order)
-__global__ void __launch_bounds__(256) k_join_tile_sums(const uint4* __restrict__ entries, int64_t n, uint32_t* __restrict__ sums) {
+// WIDE duplicates: val <- CSR offset (exclusive scan of cnt over the logical slots, in slot order).  The table is walked as
+// an array of u32 words: slot s -> cnt at word (s >> 1) * 8 + 6 + (s & 1), val at word (s >> 1) * 8 + 4 + (s & 1).
+__device__ __forceinline__ int64_t j_cnt_word(int64_t s) { return (s >> 1) * 8 + 6 + (s & 1); }
+__global__ void __launch_bounds__(256) k_join_tile_sums(const uint32_t* __restrict__ words, int64_t n, uint32_t* __restrict__ sums) {
     __shared__ uint32_t ws[8];
     const int64_t ntiles = (n + J_TILE - 1) / J_TILE;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         uint32_t c = 0;
-        for (int k = 0; k < J_TILE / 256; k++) { int64_t i = t * J_TILE + k * 256 + threadIdx.x; if (i < n) c += entries[i].w; }
+        for (int k = 0; k < J_TILE / 256; k++) { int64_t i = t * J_TILE + k * 256 + threadIdx.x; if (i < n) c += words[j_cnt_word(i)]; }
         for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if (lane_id() == 0) ws[threadIdx.x >> 5] = c;
         __syncthreads();
@@ -134,7 +155,7 @@ __global__ void __launch_bounds__(256) k_join_tile_sums(const uint4* __restrict_
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(256) k_join_csr_offsets(uint4* __restrict__ entries, int64_t n, const uint64_t* __restrict__ tile_off) {
+__global__ void __launch_bounds__(256) k_join_csr_offsets(uint32_t* __restrict__ words, int64_t n, const uint64_t* __restrict__ tile_off) {
     __shared__ uint32_t ws[8];
     __shared__ uint32_t carry;
     const int64_t ntiles = (n + J_TILE - 1) / J_TILE;
@@ -143,14 +164,14 @@ __global__ void __launch_bounds__(256) k_join_csr_offsets(uint4* __restrict__ en
         __syncthreads();
         for (int k = 0; k < J_TILE / 256; k++) {
             const int64_t i = t * J_TILE + k * 256 + threadIdx.x;
-            const uint32_t c = i < n ? entries[i].w : 0;
+            const uint32_t c = i < n ? words[j_cnt_word(i)] : 0;
             uint32_t x = c;
             for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane_id() >= (unsigned)o) x += y; }
             if (lane_id() == 31) ws[threadIdx.x >> 5] = x;
             __syncthreads();
             uint32_t wbase = 0;
             for (unsigned w = 0; w < (threadIdx.x >> 5); w++) wbase += ws[w];
-            if (i < n) entries[i].z = carry + wbase + x - c;
+            if (i < n) words[j_cnt_word(i) - 2] = carry + wbase + x - c;      // the slot's val word
             __syncthreads();
             if (threadIdx.x == 255) carry += wbase + x;
             __syncthreads();
@@ -271,23 +292,25 @@ __device__ __forceinline__ uint32_t j_lookup(const JoinDev& J, uint64_t kraw, bo
     }
     const uint64_t key = j_canon<KEY_CANON>(kraw);
     if (MODE == JM_WIDE) {
-        uint64_t slot;
-        if (!valid) { if (!J.nulls_equal) return J_NONE; slot = J.W.cap; }
-        else if (key == J_EMPTY) slot = J.W.cap + 1;
-        else slot = __umul64hi(dirty_hash(key), J.W.cap);
-        uint4 e = __ldg(&J.W.entries[slot]);
-        if (!valid || key == J_EMPTY) { if (e.w == 0) return J_NONE; }
-        else {
+        unsigned long long k0, k1, vv, cc;
+        int j;
+        if (!valid || key == J_EMPTY) {
+            if (!valid && !J.nulls_equal) return J_NONE;
+            j_load_bucket(J.W.buckets + J.W.nb, k0, k1, vv, cc);
+            j = valid ? 1 : 0;
+            if (((uint32_t)(cc >> (32 * j))) == 0) return J_NONE;
+        } else {
+            uint64_t b = __umul64hi(dirty_hash(key), J.W.nb);
             while (true) {
-                const uint64_t k = ((uint64_t)e.y << 32) | e.x;
-                if (k == key) break;
-                if (k == J_EMPTY) return J_NONE;
-                if (++slot == J.W.cap) slot = 0;
-                e = __ldg(&J.W.entries[slot]);
+                j_load_bucket(J.W.buckets + b, k0, k1, vv, cc);
+                if (k0 == key) { j = 0; break; }
+                if (k1 == key) { j = 1; break; }
+                if (k0 == J_EMPTY || k1 == J_EMPTY) return J_NONE;
+                if (++b == J.W.nb) b = 0;
             }
         }
-        cnt = J.csr ? e.w : 1u;
-        return e.z;                                   // unique: the build row; CSR: the list offset (k_join_csr_offsets)
+        cnt = J.csr ? (uint32_t)(cc >> (32 * j)) : 1u;
+        return (uint32_t)(vv >> (32 * j));            // unique: the build row; CSR: the list offset (k_join_csr_offsets)
     }
     // COMPACT
     uint32_t slot, row;
@@ -628,20 +651,22 @@ static JoinBuilt join_build(const DevCol& build, bool nulls_equal, bool need_lis
     DevPtr has_dups = dev_alloc(4);
     dev_memset(has_dups->p, 0, 4);
     if (B.mode == JM_WIDE) {
-        JoinTableDev T; T.cap = (uint64_t)std::max<int64_t>(2 * nb, 16);
-        B.entries = dev_alloc((size_t)(T.cap + 2) * 16);
-        T.entries = as<uint4>(B.entries);
-        PLB_LAUNCH("k7_join_init", k_join_init, grid_for((int64_t)T.cap + 2, 256), 256, 0, T.entries, (int64_t)T.cap + 2);
+        // two-entry buckets, <= 0.7 entries used per entry slot: C3 (1e7 keys) = 7.1 M buckets = 229 MB (round 1: 320 MB of 16-byte entries)
+        JoinTableDev T; T.nb = (uint64_t)std::max<int64_t>((int64_t)((double)nb / 1.4) + 1, 8);
+        PLB_REQUIRE(2 * (T.nb + 1) < 0xFFFFFFFFull, BL_ERR_UNSUPPORTED, "join: build side too large for 32-bit slots");
+        B.entries = dev_alloc((size_t)(T.nb + 1) * sizeof(JoinBucket));
+        T.buckets = as<JoinBucket>(B.entries);
+        PLB_LAUNCH("k7_join_init", k_join_init, grid_for((int64_t)T.nb + 1, 256), 256, 0, T.buckets, (int64_t)T.nb + 1);
         if (nb > 0)
             PLB_LAUNCH("k7_join_build", k_join_build, grid_for(nb, 256), 256, 0, T, build.v(), build.vm(), dt, nb, nulls_equal ? 1 : 0, as<uint32_t>(B.slot_of_row), as<int>(has_dups));
         B.J.W = T;
         B.csr = need_lists && nb > 0 && read_scalar(as<int>(has_dups)) != 0;
         if (B.csr) {
-            const int64_t ne = (int64_t)T.cap + 2, ntiles_e = (ne + J_TILE - 1) / J_TILE;
+            const int64_t ne = 2 * ((int64_t)T.nb + 1), ntiles_e = (ne + J_TILE - 1) / J_TILE;
             DevPtr sums = dev_alloc((size_t)ntiles_e * 4), offs = dev_alloc((size_t)ntiles_e * 8);
-            PLB_LAUNCH("k7_tile_sums", k_join_tile_sums, grid_for(ntiles_e * 256, 256), 256, 0, T.entries, ne, as<uint32_t>(sums));
+            PLB_LAUNCH("k7_tile_sums", k_join_tile_sums, grid_for(ntiles_e * 256, 256), 256, 0, as<uint32_t>(B.entries), ne, as<uint32_t>(sums));
             exclusive_scan_u32_to_u64(as<uint32_t>(sums), as<uint64_t>(offs), ntiles_e, nullptr);
-            PLB_LAUNCH("k7_csr_offsets", k_join_csr_offsets, grid_for(ntiles_e * 256, 256), 256, 0, T.entries, ne, as<uint64_t>(offs));
+            PLB_LAUNCH("k7_csr_offsets", k_join_csr_offsets, grid_for(ntiles_e * 256, 256), 256, 0, as<uint32_t>(B.entries), ne, as<uint64_t>(offs));
         }
     } else {
         uint64_t cap = 1024; while (cap < (uint64_t)nb + (uint64_t)nb / 2) cap <<= 1;
@@ -794,8 +819,8 @@ static JoinResult hash_join_inner_left(const DevCol& left, const DevCol& right, 
     if (how == BL_JOIN_INNER && maintain_order != BL_ORDER_NONE && M > 1) {
         const bool by_left = maintain_order == BL_ORDER_LEFT || maintain_order == BL_ORDER_LEFT_RIGHT;
         const bool left_sorted = !swapped;
-        if (by_left && !left_sorted) sort_pairs_u32(as<uint32_t>(r.left.values), as<uint32_t>(r.right.values), (int64_t)M);
-        else if (!by_left && !swapped) sort_pairs_u32(as<uint32_t>(r.right.values), as<uint32_t>(r.left.values), (int64_t)M);
+        if (by_left && !left_sorted) sort_pairs_u32(as<uint32_t>(r.left.values), as<uint32_t>(r.right.values), (int64_t)M, bits_for((uint64_t)left.len));
+        else if (!by_left && !swapped) sort_pairs_u32(as<uint32_t>(r.right.values), as<uint32_t>(r.left.values), (int64_t)M, bits_for((uint64_t)right.len));
     }
     // left join: only Right / RightLeft reorder (stable sort on the right idx, unmatched rows = u32::MAX last;
     // dispatch_left_right.rs:142-170); the probe order already is the left order
