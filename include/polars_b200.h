@@ -170,16 +170,27 @@ bl_status bl_group_tuples(const bl_column* key_chunks, int32_t n_key_chunks, int
 /* ---- K7/K8: hash join on one numeric key ----------------------------------------------- */
 /* (build_tables single_keys.rs:16-167, probe_inner single_keys_inner.rs:11-149,
  *  hash_join_tuples_left single_keys_left.rs:106-195) */
-enum { BL_JOIN_INNER = 0, BL_JOIN_LEFT = 1, BL_JOIN_SEMI = 2, BL_JOIN_ANTI = 3 };
+enum { BL_JOIN_INNER = 0, BL_JOIN_LEFT = 1, BL_JOIN_SEMI = 2, BL_JOIN_ANTI = 3, BL_JOIN_FULL = 4 };
 enum { BL_ORDER_NONE = 0, BL_ORDER_LEFT = 1, BL_ORDER_LEFT_RIGHT = 2, BL_ORDER_RIGHT = 3, BL_ORDER_RIGHT_LEFT = 4 };
 /* Returns the join tuples as two UINT32 columns.  BL_ORDER_NONE reproduces the in-memory engine's
  * order (probe = longer relation, tie -> right probes; probe-row order; matches ascending build
  * idx — hash_join/mod.rs:41-50).  Null keys match only if nulls_equal.  Left join: unmatched
  * right idx = BL_IDX_NULL (and a null slot).  BL_JOIN_SEMI / BL_JOIN_ANTI (single_keys_semi_anti.rs:41-140):
- * out_left_idx = the left rows, in row order, with / without a match; out_right_idx is an empty column. */
+ * out_left_idx = the left rows, in row order, with / without a match; out_right_idx is an empty column.
+ * BL_JOIN_FULL (hash_join_tuples_outer, single_keys_outer.rs:100-260): the longer relation probes; first its left-join
+ * tuples in probe order, then the build rows no probe key matched with a null on the probe side (ascending build row;
+ * the reference drains its hash tables there, order unspecified).  Both outputs are nullable; BL_ORDER_NONE only. */
 bl_status bl_hash_join(const bl_column* left_key, int32_t n_left_chunks, const bl_column* right_key, int32_t n_right_chunks,
                        int32_t how, int32_t nulls_equal, int32_t maintain_order, int32_t out_location,
                        bl_column* out_left_idx, bl_column* out_right_idx);
+
+/* Several key columns per side (prepare_keys_multiple, polars-ops/src/frame/join/mod.rs:658-678: the reference row-encodes
+ * the key columns of each side and runs the single-key machinery on the encoded rows).  left_keys[i] pairs with
+ * right_keys[i] (same dtype; any numeric dtype incl. 8/16-bit; one chunk each).  nulls_equal == 0: a null in ANY key
+ * column makes the row's key null (it matches nothing); != 0: nulls are part of the key and match each other per column.
+ * Everything else as bl_hash_join. */
+bl_status bl_hash_join_keys(const bl_column* left_keys, const bl_column* right_keys, int32_t n_keys, int32_t how, int32_t nulls_equal,
+                            int32_t maintain_order, int32_t out_location, bl_column* out_left_idx, bl_column* out_right_idx);
 
 /* Join + materialisation (_finish_join, polars-ops/src/frame/join/general.rs:17-49; JoinExec,
  * polars-mem-engine/src/executors/join.rs:39-120): bl_hash_join on the key columns followed by one K4

@@ -320,6 +320,21 @@ def hash_join(left_keys, right_keys, left_valid=None, right_valid=None, how: str
         idx = np.nonzero(match if how == "semi" else ~match)[0].astype(np.uint32)
         return idx, np.zeros(0, np.uint32)
     T = n_threads if n_threads is not None else max_threads()
+    if how == "full":
+        # polars-ops/src/frame/join/hash_join/single_keys_outer.rs:100-260 + single_keys_dispatch.rs:653-694: the longer
+        # relation probes (det_hash_prone_order!, tie -> right probes); the probe phase emits exactly the left-join tuples
+        # of the probe side (a null probe key is unmatched unless nulls_equal, :144-150), then the build rows no probe key
+        # reached are drained from the hash tables as (None, idx_b) — in hashbrown iteration order (UNPINNED); this
+        # restatement drains them in ascending build-row order.
+        swapped = not (lk.size > rk.size)
+        pk, pv, bk, bv = (rk, right_valid, lk, left_valid) if swapped else (lk, left_valid, rk, right_valid)
+        pi, bi = hash_join(pk, bk, pv, bv, "left", nulls_equal, "none", T)
+        matched = np.zeros(bk.size, np.bool_)
+        matched[bi[bi != IDX_NULL]] = True
+        drained = np.nonzero(~matched)[0].astype(np.uint32)
+        pi = np.concatenate([pi, np.full(drained.size, IDX_NULL, np.uint32)])
+        bi = np.concatenate([bi, drained])
+        return (bi, pi) if swapped else (pi, bi)
     pl, pr = C.c_void_p(), C.c_void_p()
     m = lib().or_hash_join(_p(lk), _p(_valid(left_valid, lk.size)), C.c_int64(lk.size), _p(rk),
                            _p(_valid(right_valid, rk.size)), C.c_int64(rk.size), C.c_int({"inner": 0, "left": 1}[how]),

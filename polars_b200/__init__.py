@@ -27,7 +27,7 @@ BOOL = 10
 OPS = {"add": 0, "sub": 1, "mul": 2, "floordiv": 3, "mod": 4, "truediv": 5}
 CMPS = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5}
 AGGS = {"sum": 0, "mean": 1, "min": 2, "max": 3, "count": 4, "len": 5}
-JOINS = {"inner": 0, "left": 1, "semi": 2, "anti": 3}
+JOINS = {"inner": 0, "left": 1, "semi": 2, "anti": 3, "full": 4}
 ORDERS = {"none": 0, "left": 1, "left_right": 2, "right": 3, "right_left": 4}
 STATUS = {1: "INVALID", 2: "CUDA", 3: "OOM", 4: "UNSUPPORTED", 5: "DTYPE", 6: "BOUNDS"}
 
@@ -417,6 +417,18 @@ def hash_join(left_key, right_key, how: str = "inner", nulls_equal: bool = False
     ol, orr = BlColumn(), BlColumn()
     _check(lib().bl_hash_join(la, C.c_int32(len(lch)), ra, C.c_int32(len(rch)), C.c_int32(JOINS[how]), C.c_int32(int(nulls_equal)),
                               C.c_int32(ORDERS[maintain_order]), C.c_int32(location), C.byref(ol), C.byref(orr)))
+    res = _finish([ol, orr], location)
+    return res[0], res[1]
+
+
+def hash_join_keys(left_keys: Sequence, right_keys: Sequence, how: str = "inner", nulls_equal: bool = False, maintain_order: str = "none", location: int = HOST):
+    """Join on several key columns per side (bl_hash_join_keys)."""
+    lc, rc = [_as_col(c) for c in left_keys], [_as_col(c) for c in right_keys]
+    assert len(lc) == len(rc) and lc
+    la, ra = _col_array(lc), _col_array(rc)
+    ol, orr = BlColumn(), BlColumn()
+    _check(lib().bl_hash_join_keys(la, ra, C.c_int32(len(lc)), C.c_int32(JOINS[how]), C.c_int32(int(nulls_equal)), C.c_int32(ORDERS[maintain_order]), C.c_int32(location),
+                                   C.byref(ol), C.byref(orr)))
     res = _finish([ol, orr], location)
     return res[0], res[1]
 

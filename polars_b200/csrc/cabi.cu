@@ -249,6 +249,42 @@ bl_status bl_hash_join(const bl_column* left_key, int32_t n_left_chunks, const b
     BL_CATCH
 }
 
+bl_status bl_hash_join_keys(const bl_column* left_keys, const bl_column* right_keys, int32_t n_keys, int32_t how, int32_t nulls_equal, int32_t maintain_order,
+                            int32_t out_location, bl_column* out_left_idx, bl_column* out_right_idx) {
+    BL_TRY
+    PLB_REQUIRE(left_keys && right_keys && out_left_idx && out_right_idx && n_keys >= 1, BL_ERR_INVALID, "hash_join_keys: null argument");
+    PLB_REQUIRE(maintain_order >= BL_ORDER_NONE && maintain_order <= BL_ORDER_RIGHT_LEFT, BL_ERR_INVALID, "hash_join_keys: unknown maintain_order");
+    const int64_t nl = left_keys[0].length, nr = right_keys[0].length;
+    // Both relations are packed TOGETHER (left rows followed by right rows) so that the id compression of wide columns
+    // (op_pack_keys) assigns the same id to equal values on either side; nulls become part of the packed value.
+    std::vector<DevCol> cats;
+    DevPtr lvalid, rvalid;          // AND of the key columns' validities per side (nulls_equal == 0)
+    bool l_nullable = false, r_nullable = false;
+    for (int i = 0; i < n_keys; i++) {
+        PLB_REQUIRE(left_keys[i].dtype == right_keys[i].dtype, BL_ERR_DTYPE, "hash_join_keys: key dtypes differ");      // join/mod.rs:231-241
+        PLB_REQUIRE(left_keys[i].length == nl && right_keys[i].length == nr, BL_ERR_INVALID, "hash_join_keys: key columns of one side differ in length");
+        const bl_column pair[2] = {left_keys[i], right_keys[i]};
+        cats.push_back(import_column(pair, 2));
+        if (!nulls_equal) {
+            DevCol l = import_column(&left_keys[i], 1), r = import_column(&right_keys[i], 1);
+            if (l.validity) { lvalid = l_nullable ? bitmap_and(as<uint32_t>(lvalid), l.vm(), nullptr, nl) : l.validity; l_nullable = true; }
+            if (r.validity) { rvalid = r_nullable ? bitmap_and(as<uint32_t>(rvalid), r.vm(), nullptr, nr) : r.validity; r_nullable = true; }
+        }
+    }
+    DevCol packed = n_keys == 1 && !dtype_is_small_int(cats[0].dtype) && cats[0].dtype != BL_BOOL ? cats[0] : op_pack_keys(cats);
+    if (n_keys == 1 && packed.validity && nulls_equal) packed = op_pack_keys(cats);      // fold the nulls into the value
+    const int es = dtype_size(packed.dtype);
+    DevCol lk, rk;
+    lk.dtype = rk.dtype = packed.dtype; lk.len = nl; rk.len = nr;
+    lk.values = dev_alloc((size_t)std::max<int64_t>(nl, 1) * es + 16); rk.values = dev_alloc((size_t)std::max<int64_t>(nr, 1) * es + 16);
+    if (nl) PLB_CUDA(cudaMemcpyAsync(lk.values->p, packed.v(), (size_t)nl * es, cudaMemcpyDeviceToDevice, ctx().stream));
+    if (nr) PLB_CUDA(cudaMemcpyAsync(rk.values->p, (const char*)packed.v() + (size_t)nl * es, (size_t)nr * es, cudaMemcpyDeviceToDevice, ctx().stream));
+    if (!nulls_equal) { lk.validity = lvalid; rk.validity = rvalid; lk.null_count = l_nullable ? -1 : 0; rk.null_count = r_nullable ? -1 : 0; }
+    JoinResult jr = op_hash_join(lk, rk, how, nulls_equal != 0, maintain_order);
+    { std::vector<DevCol> both{jr.left, jr.right}; bl_column t[2]; export_many(both, out_location, t); *out_left_idx = t[0]; *out_right_idx = t[1]; }
+    BL_CATCH
+}
+
 bl_status bl_join(const bl_column* left_key, const bl_column* right_key, const bl_column* left_cols, int32_t n_left_cols, const bl_column* right_cols, int32_t n_right_cols,
                   int32_t how, int32_t nulls_equal, int32_t maintain_order, int32_t out_location, bl_column* out_left_cols, bl_column* out_right_cols) {
     BL_TRY

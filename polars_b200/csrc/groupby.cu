@@ -30,33 +30,11 @@
 #include "common.cuh"
 #include "dev_utils.cuh"
 #include "groupby.h"
+#include "groupby_dev.cuh"
 
 namespace plb {
 
-__host__ __device__ inline uint64_t word_identity(int op) {
-    switch (op) {
-        case W_MIN_S64: return 0x7FFFFFFFFFFFFFFFULL;
-        case W_MAX_S64: return 0x8000000000000000ULL;
-        case W_MIN_U64: case W_MIN_F64: return 0xFFFFFFFFFFFFFFFFULL;
-        default: return 0;   // adds, MAX_U64, MAX_F64
-    }
-}
-
 // ---------------------------------------------------------------------------- device pieces
-template <int KEY_CANON> __device__ __forceinline__ uint64_t canon_key(uint64_t raw) {
-    if (KEY_CANON == 1) return canonical_f64_bits(__longlong_as_double((long long)raw));
-    if (KEY_CANON == 2) return canonical_f32_bits(__uint_as_float((uint32_t)raw));
-    return raw;
-}
-__device__ __forceinline__ uint64_t load_key_rt(const void* keys, int dtype, int64_t row) {
-    switch (dtype) {
-        case BL_INT64: case BL_UINT64: return reinterpret_cast<const uint64_t*>(keys)[row];
-        case BL_FLOAT64: return canonical_f64_bits(reinterpret_cast<const double*>(keys)[row]);
-        case BL_FLOAT32: return canonical_f32_bits(reinterpret_cast<const float*>(keys)[row]);
-        default: return (uint64_t)reinterpret_cast<const uint32_t*>(keys)[row];   // i32/u32 bit pattern, zero-extended
-    }
-}
-
 // ---- L2 cache-policy hints (sm_80+ createpolicy): the hash table is the only data with reuse, the
 //      scanned columns are read once.  hint != 0: table loads / CAS / REDs carry an evict_last policy.
 __device__ __forceinline__ uint64_t make_policy_evict_last() {
@@ -112,20 +90,6 @@ __device__ __forceinline__ uint64_t* gb_special(const GbTableDev& T, int which) 
     if (__ldcg(reinterpret_cast<const unsigned long long*>(e)) == GB_EMPTY)
         atomicCAS(reinterpret_cast<unsigned long long*>(e), (unsigned long long)GB_EMPTY, (unsigned long long)which);
     return e;
-}
-
-__device__ __forceinline__ double raw_to_f64(int dtype, uint64_t raw) {
-    switch (dtype) {
-        case BL_INT64: return (double)(long long)raw;
-        case BL_UINT64: return (double)(unsigned long long)raw;
-        case BL_INT32: return (double)(int)(uint32_t)raw;
-        case BL_UINT32: return (double)(uint32_t)raw;
-        case BL_FLOAT64: return __longlong_as_double((long long)raw);
-        default: return (double)__uint_as_float((uint32_t)raw);
-    }
-}
-__device__ __forceinline__ uint64_t raw_to_int(int dtype, uint64_t raw) {
-    return dtype == BL_INT32 ? (uint64_t)(long long)(int)(uint32_t)raw : raw;   // sign-extend i32; u32 already zero-extended
 }
 
 __device__ __forceinline__ void gb_apply(int op, uint64_t* addr, int dtype, uint64_t raw, bool valid, uint64_t pol = 0, bool hint = false) {
@@ -535,31 +499,6 @@ __global__ void __launch_bounds__(256) k_gb_merge(const __grid_constant__ GbLayo
 // 32-bit adds with carry (exact, order-free); f64 add and 64-bit min/max as CAS loops.
 // Rows whose key cannot be placed (table 3/4 full) fall through to the global table, so the
 // result is exact for any input; a wrong estimate only costs speed.
-__device__ __forceinline__ void s_add_u64(uint64_t* a, uint64_t v) {
-    uint32_t* w = reinterpret_cast<uint32_t*>(a);
-    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
-    const uint32_t old = atomicAdd(w, lo);
-    const uint32_t up = hi + (((uint32_t)(old + lo) < old) ? 1u : 0u);
-    if (up) atomicAdd(w + 1, up);
-}
-// FAST: every value column is 8 bytes wide and has no validity bitmap (the common analytic case): the
-// dtype dispatch collapses to one select and the null checks disappear (this kernel is issue-bound).
-template <bool FAST>
-__device__ __forceinline__ void gb_apply_smem(int op, uint64_t* addr, int dtype, uint64_t raw, bool valid) {
-    switch (op) {
-        case W_ADD_INT: { uint64_t v = FAST ? raw : raw_to_int(dtype, raw); if (valid && v) s_add_u64(addr, v); break; }
-        case W_ADD_F64: { double f = FAST ? (dtype == BL_FLOAT64 ? __longlong_as_double((long long)raw) : (dtype == BL_INT64 ? (double)(long long)raw : (double)(unsigned long long)raw)) : raw_to_f64(dtype, raw);
-                          if (valid && f != 0.0) atomicAdd(reinterpret_cast<double*>(addr), f); break; }
-        case W_MIN_S64: if (valid) atomicMin(reinterpret_cast<long long*>(addr), (long long)raw_to_int(dtype, raw)); break;
-        case W_MAX_S64: if (valid) atomicMax(reinterpret_cast<long long*>(addr), (long long)raw_to_int(dtype, raw)); break;
-        case W_MIN_U64: if (valid) atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)raw); break;
-        case W_MAX_U64: if (valid) atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)raw); break;
-        case W_MIN_F64: { double f = raw_to_f64(dtype, raw); if (valid && f == f) atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)f64_to_ordered(f)); break; }
-        case W_MAX_F64: { double f = raw_to_f64(dtype, raw); if (valid && f == f) atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)f64_to_ordered(f)); break; }
-        default: if (!valid) atomicAdd(reinterpret_cast<unsigned*>(addr), 1u); break;   // W_NULLCNT (< 2^32 per CTA)
-    }
-}
-
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC, bool FAST>
 __global__ void __launch_bounds__(512) k_gb_consume_smem(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const __grid_constant__ GbBatch B, int scap, int sshift, int copies) {
     // `copies` replicas of the table (tiny cardinalities): lane l works on replica l % copies, so the
@@ -1333,6 +1272,7 @@ void GroupByState::consume_all(const DevCol& key, const std::vector<const DevCol
     PLB_REQUIRE(key.dtype == key_dtype, BL_ERR_DTYPE, "group_by: key dtype differs from the plan");
     PLB_REQUIRE(key.len <= 0xFFFFFFFEll, BL_ERR_UNSUPPORTED, "group_by: more than 2^32-2 rows (IdxSize = u32)");
     uint64_t c = choose_cap(key, key.len);
+    if (consume_radix(key, values)) return;      // tables beyond L2: partition the rows instead (groupby_radix.cu)
     for (int attempt = 0; attempt < 8; attempt++) {
         alloc_table(c);
         launch_batch(key, values, 0);
@@ -1476,15 +1416,21 @@ void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather,
     // Extract into buffers sized by an upper bound of the group count, then read the real count and
     // the null-group position back with ONE 16-byte copy (one host sync for the whole finish).
     const int kelem = dtype_size(key_dtype);
-    const int64_t Gb = entries ? std::max<int64_t>(1, std::min<int64_t>((int64_t)cap + 2, rows_seen + merged_rows + 2)) : 1;
-    DevPtr keys = dev_alloc((size_t)Gb * 8), first = dev_alloc((size_t)Gb * 4), len = dev_alloc((size_t)Gb * 4);
-    DevPtr words = dev_alloc((size_t)Gb * 8 * std::max(L.n_words, 1));
-    DevPtr ctl = dev_alloc(16);                       // [0] cursor (#groups), [1] null-group position
-    const long long ctl_init[2] = {0, -1};
-    PLB_CUDA(cudaMemcpyAsync(ctl->p, ctl_init, 16, cudaMemcpyHostToDevice, ctx().stream));
+    const int64_t Gb = dense.ready ? dense.Gb : (entries ? std::max<int64_t>(1, std::min<int64_t>((int64_t)cap + 2, rows_seen + merged_rows + 2)) : 1);
+    DevPtr keys, first, len, words, ctl;
     long long ctl_host[2] = {0, -1};
     int status_host = 0;
-    if (entries) {
+    if (dense.ready) {      // the partitioned plan wrote the dense arrays itself
+        keys = dense.keys; first = dense.first; len = dense.len; words = dense.words; ctl = dense.ctl;
+        PLB_CUDA(cudaMemcpyAsync(ctl_host, ctl->p, 16, cudaMemcpyDeviceToHost, ctx().stream));
+    } else {
+        keys = dev_alloc((size_t)Gb * 8); first = dev_alloc((size_t)Gb * 4); len = dev_alloc((size_t)Gb * 4);
+        words = dev_alloc((size_t)Gb * 8 * std::max(L.n_words, 1));
+        ctl = dev_alloc(16);                       // [0] cursor (#groups), [1] null-group position
+        const long long ctl_init[2] = {0, -1};
+        PLB_CUDA(cudaMemcpyAsync(ctl->p, ctl_init, 16, cudaMemcpyHostToDevice, ctx().stream));
+    }
+    if (entries && !dense.ready) {
         PLB_CUDA(cudaMemcpyAsync(&status_host, status->p, 4, cudaMemcpyDeviceToHost, ctx().stream));
         PLB_LAUNCH("k5_extract", k_gb_extract, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, L.n_words, as<unsigned long long>(ctl),
                    as<uint64_t>(keys), as<uint32_t>(first), as<uint32_t>(len), as<uint64_t>(words), Gb, as<long long>(ctl) + 1);

@@ -38,6 +38,9 @@ constexpr int GB_HOT_BITS = 8;
 constexpr int GB_HOT_SLOTS = 1 << GB_HOT_BITS;   // lookup table slots (open addressing, <= 25 % full)
 struct GbHotDev { const uint64_t* keys; const uint8_t* idx; int32_t n_hot, null_hot, empty_hot, rows; };
 
+// dense per-group arrays (the layout k_gb_extract produces): filled directly by the partitioned plan (groupby_radix.cu)
+struct GbDense { DevPtr keys, first, len, words, ctl; int64_t Gb = 0; bool ready = false; };
+
 struct AggPlan { int kind, in_dtype, out_dtype; int main, nullcnt; bool nullable; };
 
 // Host mirror of group_by_helper (crates/polars-mem-engine/src/executors/group_by.rs:60-98): owns
@@ -61,6 +64,8 @@ struct GroupByState {
 
     GroupByState(int key_dt, const std::vector<int>& kinds, const std::vector<int>& dtypes, const std::vector<int>& nullable, int64_t expected, bool track_first);
     void consume_all(const DevCol& key, const std::vector<const DevCol*>& values);
+    bool consume_radix(const DevCol& key, const std::vector<const DevCol*>& values);   // partitioned plan (tables beyond L2); false = not applicable
+    GbDense dense;               // set by consume_radix: finish() takes the groups from here, there is no table
     void consume_pipelined(const DevCol& key, const std::vector<const DevCol*>& values, int64_t chunk_rows, const std::vector<cudaEvent_t>& ready);
     void consume(const DevCol& key, const std::vector<const DevCol*>& values, int64_t row_base);
     void merge_partials(const uint64_t* rows, int64_t n_rows);

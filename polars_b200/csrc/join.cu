@@ -749,14 +749,11 @@ static JoinResult hash_join_semi_anti(const DevCol& left, const DevCol& right, i
     return r;
 }
 
-static JoinResult hash_join_inner_left(const DevCol& left, const DevCol& right, int how, bool nulls_equal, int maintain_order) {
-    PLB_REQUIRE(how == BL_JOIN_INNER || how == BL_JOIN_LEFT, BL_ERR_UNSUPPORTED, "join: only inner, left, semi and anti joins are on the hot path");
-    check_join_keys(left, right);
-    const int dt = left.dtype;
-    // hash_join/mod.rs:41-50: probe the longer relation; on a tie the right side probes (swapped)
-    const bool swapped = how == BL_JOIN_INNER && !(left.len > right.len);
-    const DevCol& probe = swapped ? right : left;
-    const DevCol& build = swapped ? left : right;
+// Probe `probe` against a table built over `build`: tuples (probe row, build row) in probe-row order, matches ascending
+// by build row; left_join != 0 also emits (probe row, J_NONE) for probe rows without a match.
+struct ProbeTuples { DevPtr out_probe, out_build; uint64_t M = 0; };
+static ProbeTuples probe_tuples(const DevCol& probe, const DevCol& build, bool nulls_equal, int left_join) {
+    const int dt = probe.dtype;
     const int64_t np = probe.len;
     const int elem = dtype_size(dt);
     Context& c = ctx();
@@ -764,7 +761,6 @@ static JoinResult hash_join_inner_left(const DevCol& left, const DevCol& right, 
     trace_point("join:start");
     JoinBuilt B = join_build(build, nulls_equal, true);
     trace_point("join:build");
-    const int left_join = how == BL_JOIN_LEFT ? 1 : 0;
     // ---- unique build keys: fused single-pass probe + emit
     static const int fused_on = [] { const char* e = getenv("BL_JOIN_FUSED"); return e ? atoi(e) : 1; }();
     const int64_t ntiles = (np + J_TILE - 1) / J_TILE;
@@ -812,6 +808,86 @@ static JoinResult hash_join_inner_left(const DevCol& left, const DevCol& right, 
     }
     if (!out_probe) { out_probe = dev_alloc(16); out_build = dev_alloc(16); }
     trace_point("join:emit");
+    ProbeTuples t; t.out_probe = out_probe; t.out_build = out_build; t.M = M;
+    return t;
+}
+
+// nullable index column: validity bit = (idx != BL_IDX_NULL)
+static void set_idx_validity(DevCol& col) {
+    if (col.len == 0) return;
+    DevCol none = make_col(BL_UINT32, 1, false);
+    const uint32_t nv = J_NONE;
+    PLB_CUDA(cudaMemcpyAsync(none.values->p, &nv, 4, cudaMemcpyHostToDevice, ctx().stream));
+    PLB_CUDA(cudaStreamSynchronize(ctx().stream));
+    DevCol m = op_compare(BL_CMP_NE, col, none, false);
+    col.validity = m.values;
+    col.null_count = -1;
+}
+
+__global__ void __launch_bounds__(256) k_join_mark_rows(const uint32_t* __restrict__ rows, int64_t m, uint32_t* __restrict__ bits) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = __ldcs(rows + i);
+        if (r != J_NONE) atomicOr(&bits[r >> 5], 1u << (r & 31));
+    }
+}
+__global__ void __launch_bounds__(256) k_join_invert_bits(uint32_t* __restrict__ bits, int64_t words) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x) bits[i] = ~bits[i];
+}
+
+// hash_join_tuples_outer (single_keys_outer.rs:100-260): left-join tuples of the probing (longer) side, then the build rows
+// nobody matched — found from the emitted build indices themselves (one bit per build row), compacted in ascending order.
+static JoinResult hash_join_full(const DevCol& left, const DevCol& right, bool nulls_equal, int maintain_order) {
+    PLB_REQUIRE(maintain_order == BL_ORDER_NONE, BL_ERR_UNSUPPORTED, "join: maintain_order on a full join is outside the hot path");
+    check_join_keys(left, right);
+    const bool swapped = !(left.len > right.len);
+    const DevCol& probe = swapped ? right : left;
+    const DevCol& build = swapped ? left : right;
+    ProbeTuples t = probe_tuples(probe, build, nulls_equal, 1);
+    PLB_REQUIRE(t.M + (uint64_t)build.len < 0xFFFFFFFFull, BL_ERR_UNSUPPORTED, "join: result has more than 2^32-2 rows (IdxSize = u32)");
+    const int64_t nb = build.len;
+    DevCol unmatched; unmatched.dtype = BL_UINT32; unmatched.len = 0;
+    if (nb > 0) {
+        DevCol mask = make_col(BL_BOOL, nb, false);
+        const int64_t words = (nb + 31) / 32;
+        dev_memset(mask.values->p, 0, (size_t)words * 4);
+        if (t.M > 0) PLB_LAUNCH("k8_join_mark_rows", k_join_mark_rows, grid_for((int64_t)t.M, 256, 16), 256, 0, as<uint32_t>(t.out_build), (int64_t)t.M, as<uint32_t>(mask.values));
+        PLB_LAUNCH("k8_join_invert", k_join_invert_bits, grid_for(words, 256), 256, 0, as<uint32_t>(mask.values), words);
+        DevCol rows = make_col(BL_UINT32, nb, false);
+        iota_u32(as<uint32_t>(rows.values), nb, 0);
+        std::vector<DevCol> in{rows}, out;
+        op_filter(in, mask, out);
+        unmatched = out[0];
+    }
+    const int64_t D = unmatched.len, M = (int64_t)t.M;
+    DevPtr fp = dev_alloc((size_t)std::max<int64_t>(M + D, 1) * 4 + 16), fb = dev_alloc((size_t)std::max<int64_t>(M + D, 1) * 4 + 16);
+    if (M > 0) {
+        PLB_CUDA(cudaMemcpyAsync(fp->p, t.out_probe->p, (size_t)M * 4, cudaMemcpyDeviceToDevice, ctx().stream));
+        PLB_CUDA(cudaMemcpyAsync(fb->p, t.out_build->p, (size_t)M * 4, cudaMemcpyDeviceToDevice, ctx().stream));
+    }
+    if (D > 0) {
+        PLB_LAUNCH("k7_dense_init", k_fill_u32j, grid_for(D, 256), 256, 0, as<uint32_t>(fp) + M, J_NONE, D);
+        PLB_CUDA(cudaMemcpyAsync(as<uint32_t>(fb) + M, unmatched.values->p, (size_t)D * 4, cudaMemcpyDeviceToDevice, ctx().stream));
+    }
+    JoinResult r;
+    r.left = idx_col(swapped ? fb : fp, M + D, -1);
+    r.right = idx_col(swapped ? fp : fb, M + D, -1);
+    set_idx_validity(r.left);
+    set_idx_validity(r.right);
+    return r;
+}
+
+static JoinResult hash_join_inner_left(const DevCol& left, const DevCol& right, int how, bool nulls_equal, int maintain_order) {
+    PLB_REQUIRE(how == BL_JOIN_INNER || how == BL_JOIN_LEFT, BL_ERR_UNSUPPORTED, "join: only inner, left, full, semi and anti joins are on the hot path");
+    check_join_keys(left, right);
+    // hash_join/mod.rs:41-50: probe the longer relation; on a tie the right side probes (swapped)
+    const bool swapped = how == BL_JOIN_INNER && !(left.len > right.len);
+    const DevCol& probe = swapped ? right : left;
+    const DevCol& build = swapped ? left : right;
+    Context& c = ctx();
+    ProbeTuples t = probe_tuples(probe, build, nulls_equal, how == BL_JOIN_LEFT ? 1 : 0);
+    DevPtr out_probe = t.out_probe, out_build = t.out_build;
+    const uint64_t M = t.M;
+
     JoinResult r;
     r.left = idx_col(swapped ? out_build : out_probe, (int64_t)M, 0);
     r.right = idx_col(swapped ? out_probe : out_build, (int64_t)M, how == BL_JOIN_LEFT ? -1 : 0);
@@ -826,22 +902,15 @@ static JoinResult hash_join_inner_left(const DevCol& left, const DevCol& right, 
     // dispatch_left_right.rs:142-170); the probe order already is the left order
     if (how == BL_JOIN_LEFT && (maintain_order == BL_ORDER_RIGHT || maintain_order == BL_ORDER_RIGHT_LEFT) && M > 1)
         sort_pairs_u32(as<uint32_t>(r.right.values), as<uint32_t>(r.left.values), (int64_t)M);
-    if (how == BL_JOIN_LEFT && M > 0) {
-        // Arrow-proper validity for the nullable right index: bit = (idx != BL_IDX_NULL)
-        DevCol none = make_col(BL_UINT32, 1, false);
-        const uint32_t nv = J_NONE;
-        PLB_CUDA(cudaMemcpyAsync(none.values->p, &nv, 4, cudaMemcpyHostToDevice, c.stream));
-        PLB_CUDA(cudaStreamSynchronize(c.stream));
-        DevCol m = op_compare(BL_CMP_NE, r.right, none, false);
-        r.right.validity = m.values;
-        r.right.null_count = -1;
-    }
+    if (how == BL_JOIN_LEFT && M > 0) set_idx_validity(r.right);      // Arrow-proper validity for the nullable right index
+    (void)c;
     trace_point("join:done");
     return r;
 }
 
 JoinResult op_hash_join(const DevCol& left, const DevCol& right, int how, bool nulls_equal, int maintain_order) {
     if (how == BL_JOIN_SEMI || how == BL_JOIN_ANTI) return hash_join_semi_anti(left, right, how, nulls_equal);
+    if (how == BL_JOIN_FULL) return hash_join_full(left, right, nulls_equal, maintain_order);
     return hash_join_inner_left(left, right, how, nulls_equal, maintain_order);
 }
 

@@ -212,6 +212,13 @@ __global__ void k_bitmap_copy(uint32_t* __restrict__ dst, int64_t dpos, const ui
     }
 }
 
+DevPtr bitmap_slice(const uint32_t* bm, int64_t pos, int64_t len) {
+    DevPtr out = dev_alloc(bitmap_bytes(len) + 16);
+    dev_memset(out->p, 0, bitmap_bytes(len) + 16);
+    if (len > 0) PLB_LAUNCH("bitmap_copy", k_bitmap_copy, grid_for((len + 31) / 32 + 1, 256), 256, 0, as<uint32_t>(out), (int64_t)0, reinterpret_cast<const uint8_t*>(bm), pos, len);
+    return out;
+}
+
 // ---------------------------------------------------------------------------- import / export
 DevCol import_column(const bl_column* chunks, int n_chunks) {
     PLB_REQUIRE(chunks != nullptr && n_chunks >= 1, BL_ERR_INVALID, "column: no chunks");

@@ -130,6 +130,13 @@ KATS = {
     ],
     "join": [
         {
+            "cite": "crates/polars/tests/it/core/joins.rs:128-148 (test_full_outer_join) with create_frames :40-50",
+            "note": "temp.days [0,1,2] FULL rain.days [1,2,3,1]: height 5, coalesced days sum 7 -> tuples {(0,-), (1,0), (1,3), (2,1), (-,2)}; "
+                    "the drain order of unmatched build rows is unpinned (hashbrown iteration), so the tuples are compared as a sorted set",
+            "left_key": [0, 1, 2], "right_key": [1, 2, 3, 1], "key_dtype": "int32", "how": "full", "maintain_order": "none", "exact_order": False,
+            "expect_pairs_sorted": [[0, 4294967295], [1, 0], [1, 3], [2, 1], [4294967295, 2]],
+        },
+        {
             "cite": "crates/polars/tests/it/core/joins.rs:40-78 (test_inner_join, POLARS_MAX_THREADS 1..7)",
             "note": "exact row order pinned: probe = longer side (tie -> right), build matches ascending",
             "left_key": [0, 1, 2], "right_key": [1, 2, 3, 1], "key_dtype": "int32", "how": "inner", "maintain_order": "none",

@@ -774,3 +774,116 @@ def test_group_by_multipass_beyond_l2(plb):
     assert_close(k, ek, kv, ekv, "keys")
     for name, (v, m), (ev, em) in zip(("sum", "mean", "len"), outs, eouts):
         assert_close(v, ev, m, em, name)
+
+
+@pytest.mark.parametrize("shape", ["i64_c2", "i32_keys_u32_vals", "one_col_minmax", "high_card", "many_buckets"])
+def test_group_by_radix_plan(plb, monkeypatch, shape):
+    """K5r (groupby_radix.cu): histogram -> TMA tile scatter -> TMA-staged shared-memory aggregation.  Forced with
+    BL_K5_RADIX=2 at sizes the oracle finishes quickly; the profile proves the partitioned kernels ran.  The sentinel key
+    (i64::MIN = the pad marker of the record streams) and negative keys must survive."""
+    monkeypatch.setenv("BL_K5_RADIX", "2")
+    rng = np.random.default_rng(len(shape))
+    n = 1_300_001
+    if shape == "i64_c2":
+        key = (rng.integers(0, 200_000, n) * 104729 - 10**10).astype(np.int64); key[::5000] = -2**63
+        vi = rng.integers(-1000, 1000, n).astype(np.int64); vf = rng.uniform(0, 100, n).round(6)
+        aggs = [("sum", vi, None), ("mean", vf, None), ("len", None, None)]
+    elif shape == "i32_keys_u32_vals":
+        key = rng.integers(-50_000, 50_000, n).astype(np.int32)
+        vu = rng.integers(0, 2**32 - 1, n, dtype=np.uint64).astype(np.uint32); vf = rng.normal(size=n).astype(np.float32)
+        aggs = [("sum", vu, None), ("max", vu, None), ("mean", vf, None), ("min", vf, None)]
+    elif shape == "one_col_minmax":
+        key = rng.integers(0, 30_000, n).astype(np.uint64)
+        vi = rng.integers(-2**62, 2**62, n).astype(np.int64)
+        aggs = [("min", vi, None), ("max", vi, None), ("sum", vi, None), ("count", vi, None)]
+    elif shape == "high_card":
+        n = 2_500_000
+        key = rng.integers(0, 2_000_000, n).astype(np.int64)
+        vi = rng.integers(-1000, 1000, n).astype(np.int64); vf = rng.uniform(0, 100, n).round(6)
+        aggs = [("sum", vi, None), ("mean", vf, None), ("len", None, None)]
+    else:      # > 512 buckets: the unpadded store path of pass 1
+        n = 3_000_000
+        key = rng.integers(0, 1_500_000, n).astype(np.int64) * 3 + 1
+        vi = rng.integers(-1000, 1000, n).astype(np.int64)
+        aggs = [("sum", vi, None), ("len", None, None)]
+    dk = plb.to_device(key)
+    dv = {id(v): plb.to_device(v) for _, v, _ in aggs if v is not None}
+    plb.profile_reset(); plb.profile_enable(True)
+    ok, outs = plb.group_by_agg(dk.view(), [(kind, None if v is None else dv[id(v)].view()) for kind, v, _ in aggs], False, location=plb.DEVICE)
+    prof = plb.profile(); plb.profile_enable(False)
+    assert "k5r_scatter" in prof and "k5r_aggregate" in prof, sorted(prof)
+    k, kv = ok.to_numpy()
+    res = [o.to_numpy() for o in outs]
+    ek, ekv, eouts, _ = oracle.group_by_agg(key, None, aggs, 8, False)
+    k, kv, res = sort_groups(k, kv, res)
+    ek, ekv, eouts = sort_groups(ek, ekv, eouts)
+    assert_close(k, ek, kv, ekv, "keys")
+    for (kind, _, _), (v, m), (ev, em) in zip(aggs, res, eouts):
+        assert v.dtype == ev.dtype, (kind, v.dtype, ev.dtype)
+        assert_close(v, ev, m, em, kind)
+
+
+@pytest.mark.parametrize("nl,nr,krange,dups", [(0, 0, 10, 1), (5, 0, 10, 1), (0, 5, 10, 1), (300, 100, 150, 1), (3000, 2000, 500, 3), (40_000, 100_000, 20_000, 2), (300_000, 50_000, 90_000, 1)])
+@pytest.mark.parametrize("key_dtype", ["int64", "float64"])
+def test_full_join_vs_oracle(plb, nl, nr, krange, dups, key_dtype):
+    """BL_JOIN_FULL vs the oracle's hash_join_tuples_outer restatement: the probe-phase tuples are compared as an exact
+    sequence, the drained build rows (order unpinned in the reference, ascending here and in the oracle) too."""
+    rng = np.random.default_rng(nl * 11 + nr)
+    lk = rng.integers(0, krange, nl).astype(key_dtype)
+    rk = np.repeat(rng.permutation(max(krange, nr))[: max(nr // dups, 0)], dups)[:nr].astype(key_dtype)
+    rng.shuffle(rk)
+    lv = rng.random(nl) > 0.1
+    rv = rng.random(nr) > 0.1
+    for nulls_equal in ((False, True) if nl <= 3000 else (False,)):
+        (li, lvv), (ri, rvv) = plb.hash_join(plb.Column(lk, lv), plb.Column(rk, rv), "full", nulls_equal, "none")
+        eli, eri = oracle.hash_join(lk, rk, lv, rv, "full", nulls_equal, "none", 4)
+        assert np.array_equal(li, eli) and np.array_equal(ri, eri), (nulls_equal, li[:10], eli[:10], ri[:10], eri[:10])
+        if li.size:
+            assert np.array_equal(np.ones(li.size, bool) if lvv is None else lvv, eli != 0xFFFFFFFF)
+            assert np.array_equal(np.ones(ri.size, bool) if rvv is None else rvv, eri != 0xFFFFFFFF)
+    # materialised: unmatched sides come back as nulls
+    if nl and nr:
+        lp, rp = rng.normal(size=nl), rng.integers(0, 100, nr).astype(np.int64)
+        louts, routs = plb.join(plb.Column(lk, lv), plb.Column(rk, rv), [lp], [rp], "full")
+        eli, eri = oracle.hash_join(lk, rk, lv, rv, "full", False, "none", 4)
+        lh, rh = eli != 0xFFFFFFFF, eri != 0xFFFFFFFF
+        assert np.array_equal(louts[0][0][lh], lp[eli[lh]]) and np.array_equal(routs[0][0][rh], rp[eri[rh]])
+        assert (louts[0][1] is None and lh.all()) or np.array_equal(louts[0][1], lh)
+        assert (routs[0][1] is None and rh.all()) or np.array_equal(routs[0][1], rh)
+
+
+def test_join_multi_kats_gpu(plb, kats):
+    """Multi-column join keys (joins.rs:602-684 known answers) through bl_hash_join_keys."""
+    from helpers import col
+    for case in kats["join_multi"]:
+        lk = [plb.Column(*col(k, case["key_dtype"])) for k in case["left_keys"]]
+        rk = [plb.Column(*col(k, case["key_dtype"])) for k in case["right_keys"]]
+        (li, _), (ri, _) = plb.hash_join_keys(lk, rk, case["how"], case["nulls_equal"], "none")
+        assert li.tolist() == case["expect_left_idx"], case["cite"]
+        assert ri.tolist() == [0xFFFFFFFF if x is None else x for x in case["expect_right_idx"]], case["cite"]
+
+
+@pytest.mark.parametrize("shape", ["two_i32", "i64_f64", "u8_i16_i64", "three_i64_wide"])
+@pytest.mark.parametrize("how", ["inner", "left", "semi", "anti", "full"])
+def test_join_multi_vs_oracle(plb, shape, how):
+    """prepare_keys_multiple semantics (join/mod.rs:658-678): nulls_equal = false -> a null in any key column nulls the row
+    key; true -> nulls are part of the key.  Exact tuple sequence vs the oracle (hash_join_multi)."""
+    rng = np.random.default_rng(len(shape) * 7 + len(how))
+    nl, nr = 5000, 1200
+    dts = {"two_i32": ["int32", "int32"], "i64_f64": ["int64", "float64"], "u8_i16_i64": ["uint8", "int16", "int64"], "three_i64_wide": ["int64", "int64", "int64"]}[shape]
+    def gen(n, dt, wide):
+        if np.dtype(dt).kind == "f":
+            v = rng.integers(0, 6, n).astype(dt); v[rng.random(n) < 0.05] = np.nan; v[rng.random(n) < 0.05] = -0.0
+            return v
+        span = 6 if not wide else 3
+        base = rng.integers(0, span, n)
+        return (base * (2**40 + 12345) - 7 if wide and np.dtype(dt).itemsize == 8 else base).astype(dt)
+    wide = shape == "three_i64_wide"
+    L = [gen(nl, dt, wide) for dt in dts]; R = [gen(nr, dt, wide) for dt in dts]
+    LV = [rng.random(nl) > 0.08 if i != 1 else None for i in range(len(dts))]
+    RV = [rng.random(nr) > 0.08 if i != 0 else None for i in range(len(dts))]
+    for nulls_equal in (False, True):
+        (li, _), (ri, _) = plb.hash_join_keys([plb.Column(k, v) for k, v in zip(L, LV)], [plb.Column(k, v) for k, v in zip(R, RV)], how, nulls_equal, "none")
+        eli, eri = oracle.hash_join_multi(L, R, LV, RV, how, nulls_equal, "none", 4)
+        assert np.array_equal(li, eli), (shape, how, nulls_equal, li[:8], eli[:8])
+        assert np.array_equal(ri, eri), (shape, how, nulls_equal, ri[:8], eri[:8])

@@ -338,3 +338,29 @@ def test_join_multi_matches_acero():
     j = lt.join(rt, keys=["a", "b"], join_type="inner")
     exp = sorted(zip(j.column("i").to_pylist(), j.column("j").to_pylist()))
     assert sorted(zip(li.tolist(), ri.tolist())) == exp
+
+
+@pytest.mark.parametrize("nl,nr,krange", [(0, 0, 5), (7, 0, 5), (0, 7, 5), (50, 80, 30), (400, 300, 200), (2000, 2500, 50)])
+@pytest.mark.parametrize("nulls_equal", [False, True])
+def test_full_join_vs_bruteforce(nl, nr, krange, nulls_equal):
+    """hash_join_tuples_outer (single_keys_outer.rs:100-260): the matched pairs are the inner-join pairs, every left and
+    every right row appears at least once, unmatched rows carry a null on the other side; the probe-phase tuples come
+    first in probe order (longer side probes, tie -> right)."""
+    rng = np.random.default_rng(nl * 3 + nr + int(nulls_equal))
+    lk = rng.integers(0, krange, nl).astype(np.int64); rk = rng.integers(0, krange, nr).astype(np.int64)
+    lv = rng.random(nl) > 0.15; rv = rng.random(nr) > 0.15
+    li, ri = oracle.hash_join(lk, rk, lv, rv, "full", nulls_equal, "none", 3)
+    NUL = oracle.IDX_NULL
+    exp = set()
+    lm, rm = np.zeros(nl, bool), np.zeros(nr, bool)
+    for i in range(nl):
+        for j in range(nr):
+            if (lv[i] and rv[j] and lk[i] == rk[j]) or (nulls_equal and not lv[i] and not rv[j]):
+                exp.add((i, j)); lm[i] = True; rm[j] = True
+    exp |= {(i, int(NUL)) for i in range(nl) if not lm[i]} | {(int(NUL), j) for j in range(nr) if not rm[j]}
+    got = list(zip(li.tolist(), ri.tolist()))
+    assert len(got) == len(set(got)) == len(exp) and set(got) == exp
+    # probe phase first, in probe order; drained build rows last
+    probe_side = ri if not (nl > nr) else li
+    k = int((probe_side != NUL).sum())
+    assert (probe_side[:k] != NUL).all() and np.all(np.diff(probe_side[:k].astype(np.int64)) >= 0) and (probe_side[k:] == NUL).all()
