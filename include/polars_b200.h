@@ -89,6 +89,12 @@ const char* bl_last_error(void);
 /* device facts for the host side: writes sm count, L2 bytes, total/free HBM bytes */
 bl_status bl_device_info(int32_t* sm_count, int64_t* l2_bytes, int64_t* hbm_total, int64_t* hbm_free);
 
+/* Deterministic aggregation: on != 0 makes bl_groupby_agg / bl_groupby_agg_keys build the reference's
+ * GroupsIdx and fold every group sequentially in row order with the reference's reducers (sequential Kahan float sums,
+ * aggregations/mod.rs:854-977): results are bit-identical from run to run and to the reference's in-memory engine, floats
+ * included, at a fraction of the fused path's speed.  Also enabled by the environment variable BL_DETERMINISTIC=1. */
+void bl_set_deterministic(int32_t on);
+
 /* ---- memory ---------------------------------------------------------------------------- */
 /* Pinned host buffers (the SharedStorage::ForeignOwner seam, crates/polars-buffer/src/storage.rs:37-53). */
 bl_status bl_alloc_pinned(size_t bytes, void** out);

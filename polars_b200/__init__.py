@@ -60,8 +60,9 @@ _lib = None
 
 def lib() -> C.CDLL:
     """Loads libpolars_b200.so.  Fails loudly when it has not been built (python -m polars_b200.build)."""
-    global _lib
+    global _lib, _SO
     if _lib is None:
+        _SO = os.environ.get("POLARS_B200_LIB", _SO)      # a freshly built copy (see __graft_entry__.smoke)
         if not os.path.exists(_SO):
             raise ImportError(f"{_SO} is missing: build it with `python -m polars_b200.build` (nvcc, sm_100a). "
                               "polars_b200 has no CPU fallback.")
@@ -95,6 +96,18 @@ def device_info() -> dict:
     sm, l2, tot, free = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int64()
     _check(lib().bl_device_info(C.byref(sm), C.byref(l2), C.byref(tot), C.byref(free)))
     return {"sm_count": sm.value, "l2_bytes": l2.value, "hbm_total": tot.value, "hbm_free": free.value}
+
+
+def set_deterministic(on: bool = True):
+    """Bit-stable group_by aggregation in the reference's own order (bl_set_deterministic)."""
+    lib().bl_set_deterministic.restype = None
+    lib().bl_set_deterministic(C.c_int32(int(on)))
+
+
+def loaded_library() -> str:
+    """Path of the shared library this process has loaded (after the first call into it)."""
+    lib()
+    return _SO
 
 
 def sync():

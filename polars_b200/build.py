@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 SO = os.path.join(OUT_DIR, "libpolars_b200.so")
-SOURCES = ["runtime.cu", "elementwise.cu", "filter.cu", "gather.cu", "groupby.cu", "groupby_radix.cu", "join.cu", "partition.cu", "cabi.cu", "plugin.cu"]
+SOURCES = ["runtime.cu", "elementwise.cu", "filter.cu", "gather.cu", "groupby.cu", "groupby_radix.cu", "groupby_exact.cu", "join.cu", "partition.cu", "cabi.cu", "plugin.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -34,7 +34,12 @@ def _deps_mtime() -> float:
     return m
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, out_dir: str | None = None) -> str:
+    """Compiles every source with nvcc for sm_100a and links libpolars_b200.so.  out_dir: build somewhere else than
+    polars_b200/_lib (smoke() builds a fresh copy on the GPU box and loads THAT one, so a stale prebuilt binary cannot
+    hide a source tree that no longer compiles)."""
+    OUT_DIR = out_dir or globals()["OUT_DIR"]
+    SO = os.path.join(OUT_DIR, "libpolars_b200.so")
     os.makedirs(OUT_DIR, exist_ok=True)
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     if not force and os.path.exists(SO) and os.path.getmtime(SO) >= _deps_mtime():

@@ -67,6 +67,7 @@ struct Context {
     int sm_count = 148;
     int64_t l2_bytes = 0;
     bool profiling = false;
+    bool deterministic = false;      // bl_set_deterministic / BL_DETERMINISTIC: group_by folds every group sequentially in row order
     int64_t launch_count = 0;
     std::vector<KernelStat> stats;
     struct Pending { int stat; cudaEvent_t a, b; };
@@ -156,6 +157,8 @@ DevCol op_cast_small_int(const DevCol& in, int to_dtype, bool bits);
 DevCol op_group_first_ids(const DevCol& key);
 DevCol op_pack_keys(const std::vector<DevCol>& keys);
 void op_group_tuples(const DevCol& key, DevCol& out_first, DevCol& out_offsets, DevCol& out_all);
+// deterministic mode: GroupsIdx + one sequential fold per group in the reference's order (groupby_exact.cu)
+void op_group_by_exact(const DevCol& key, const std::vector<int>& kinds, const std::vector<const DevCol*>& values, DevCol& out_first, std::vector<DevCol>& outs);
 DevPtr bitmap_and(const uint32_t* a, const uint32_t* b, const uint32_t* c, int64_t bits);
 int64_t bitmap_popcount(const uint32_t* bm, int64_t bits);
 DevPtr bitmap_slice(const uint32_t* bm, int64_t pos, int64_t len);      // bits [pos, pos + len) as a fresh word-aligned bitmap

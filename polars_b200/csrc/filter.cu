@@ -260,7 +260,7 @@ void sort_pairs_u32(uint32_t* keys, uint32_t* vals, int64_t n, int key_bits) {
     Context& c = ctx();
     const int passes = (key_bits + 7) / 8;
     const int64_t tiles = (n + RS_TILE - 1) / RS_TILE;
-    const int n_ctas = (int)std::min<int64_t>(tiles, (int64_t)c.sm_count * 4);
+    const int n_ctas = (int)std::min<int64_t>(tiles, (int64_t)c.sm_count * 2);      // the (digit x cta) matrix is scanned by one CTA: keep it small
     const int64_t chunk = (tiles + n_ctas - 1) / n_ctas * RS_TILE;
     DevPtr k2 = dev_alloc((size_t)n * 4), v2 = dev_alloc((size_t)n * 4);
     DevPtr hist = dev_alloc((size_t)256 * n_ctas * 4), starts = dev_alloc((size_t)256 * n_ctas * 8);

@@ -952,9 +952,9 @@ void GroupByState::alloc_table(uint64_t new_cap) {
     cap = new_cap;
     entries = dev_alloc((size_t)(cap + 2) * L.stride * 8);
     int shift = 64; for (uint64_t c = cap; c > 1; c >>= 1) shift--;
-    static const int hint = [] { const char* e = getenv("BL_K5_HINT"); return e ? atoi(e) : 0; }();
+    const int hint = [] { const char* e = getenv("BL_K5_HINT"); return e ? atoi(e) : 0; }();
     // word-major planes by default: the REDs of one row then hit different sectors / L2 slices (ubench: 54 vs 38 G rows/s)
-    static const int soa = [] { const char* e = getenv("BL_K5_SOA"); return e ? atoi(e) : 1; }();
+    const int soa = [] { const char* e = getenv("BL_K5_SOA"); return e ? atoi(e) : 1; }();
     T.entries = as<uint64_t>(entries); T.cap = cap; T.shift = shift; T.status = as<int>(status); T.hint = hint;
     T.es = soa ? 1 : L.stride; T.ws = soa ? (int64_t)(cap + 2) : 1; T.soa = soa; T.pass_bits = 0; T.pass_id = 0;
     PLB_LAUNCH("k5_table_init", k_gb_init, grid_for((int64_t)(cap + 2) * L.stride, 256), 256, 0, T.entries, (int64_t)(cap + 2), L.stride, soa, L);
@@ -1031,6 +1031,10 @@ uint64_t GroupByState::choose_cap(const DevCol& key, int64_t n_total) {
         if (m < n && st.f1 > 0) {
             const double chao = (double)st.distinct + (double)st.f1 * ((double)st.f1 - 1.0) / (2.0 * ((double)st.f2 + 1.0));
             if (chao > G_raw) G_raw = chao;
+            // (almost) every sampled key distinct: the inversion above gives up and answers "up to one group per row" (1e7 keys
+            // in 1e8 rows were sized for 1e8 groups: an 8 GB table, 19 ms).  With a handful of keys seen twice Chao's estimator
+            // is already tight (f2 = 215 for that case -> 9.9e6); keep a 2x margin, an under-estimate only costs a restart.
+            if ((double)st.distinct >= (double)m * 0.995 && st.f2 >= 16) G_raw = std::min(G_raw, 2.0 * chao);
         }
         // sorted / clustered keys: every group is at least one run of equal neighbours, so groups <= runs
         // = rows * (1 - P[next row has the same key]) — a strided sample of such data looks all-distinct
@@ -1050,7 +1054,7 @@ uint64_t GroupByState::choose_cap(const DevCol& key, int64_t n_total) {
         build_hot_list(cand, (int)std::min<unsigned>(st.n_cand, GB_CAND_MAX), st.nulls >= hot_thr, st.empties >= hot_thr, (double)m);
     }
     est_groups = (int64_t)(G_raw * 1.25) + 2;      // for the shared-memory plan (overflow falls through to the global table)
-    static const double lf = [] { const char* e = getenv("BL_K5_LF"); double v = e ? atof(e) / 100.0 : 0.6; return (v > 0.05 && v < 0.95) ? v : 0.6; }();
+    const double lf = [] { const char* e = getenv("BL_K5_LF"); double v = e ? atof(e) / 100.0 : 0.6; return (v > 0.05 && v < 0.95) ? v : 0.6; }();
     uint64_t c = pow2_at_least(G / lf);       // load factor <= 0.6 by default
     // keep the table inside L2 when a load factor <= 0.85 allows it: past ~55 % of L2 the REDs miss and the
     // kernel slows down ~3x (measured: 67 MB table 1.95 ms, 134 MB table 5.8 ms), while linear probing over
@@ -1075,7 +1079,7 @@ static void launch_consume_p(const GbLayout& L, const GbTableDev& T, const GbBat
 }
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS>
 static void launch_consume(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int grid) {
-    static const int pairs = [] { const char* e = getenv("BL_K5_PAIRS"); int v = e ? atoi(e) : 1; return v == 2 ? 2 : 1; }();
+    const int pairs = [] { const char* e = getenv("BL_K5_PAIRS"); int v = e ? atoi(e) : 1; return v == 2 ? 2 : 1; }();
     if (pairs == 2) launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 2>(L, T, B, grid);
     else launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 1>(L, T, B, grid);
 }
@@ -1157,14 +1161,14 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
     for (int c = Lb.n_cols; c <= GB_MAX_COLS; c++) Lb.col_kbegin[c] = k;
     const int64_t n = key.len;
     if (n == 0) return;
-    static const int bps = [] { const char* e = getenv("BL_K5_BPS"); int v = e ? atoi(e) : 8; return v > 0 ? v : 8; }();
+    const int bps = [] { const char* e = getenv("BL_K5_BPS"); int v = e ? atoi(e) : 8; return v > 0 ? v : 8; }();
     const int grid = grid_for((n / 2 + 1), 256, bps);
     const bool kn = key.validity != nullptr;
     const int elem = dtype_size(key.dtype);
     const int canon = key.dtype == BL_FLOAT64 ? 1 : (key.dtype == BL_FLOAT32 ? 2 : 0);
     // keys must be 16-byte aligned for the 128-bit path (device columns always are)
     // low-cardinality plan: CTA-private shared-memory tables (largest table that leaves >= 1 CTA per SM)
-    static const int smem_on = [] { const char* e = getenv("BL_K5_SMEM"); return e ? atoi(e) : 1; }();
+    const int smem_on = [] { const char* e = getenv("BL_K5_SMEM"); return e ? atoi(e) : 1; }();
     int scap = 0;
     if (smem_on && est_groups > 0) {
         // load factor <= 2/3 (probing a shared-memory table is cheap; occupancy is not)
@@ -1189,7 +1193,7 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
     // slot sub-range h of every plane (slot = top hash bits), so each pass works on an L2-sized slice
     int pass_bits = 0;
     if (!scap) {
-        static const int mp = [] { const char* e = getenv("BL_K5_MULTIPASS"); return e ? atoi(e) : 1; }();
+        const int mp = [] { const char* e = getenv("BL_K5_MULTIPASS"); return e ? atoi(e) : 1; }();
         const double tbl = (double)(cap + 2) * L.stride * 8, budget = 0.55 * (double)ctx().l2_bytes;
         while (mp && pass_bits < 3 && tbl / (double)(1 << pass_bits) > budget) pass_bits++;
         // every pass re-reads the batch: beyond 4 passes (or when even a quarter does not fit) the extra scans cost
@@ -1290,8 +1294,12 @@ void GroupByState::consume(const DevCol& key, const std::vector<const DevCol*>& 
     PLB_REQUIRE(row_base + key.len <= 0xFFFFFFFEll, BL_ERR_UNSUPPORTED, "group_by: more than 2^32-2 rows (IdxSize = u32)");
     if (!entries) alloc_table(choose_cap(key, key.len));
     else if (expected_groups <= 0) {
-        int64_t g = count_groups();
-        if ((double)g > 0.25 * (double)cap) grow(cap * 4);
+        // a later batch can bring more NEW keys than the spare capacity (sorted / time-clustered streams): sample every
+        // batch and grow (a rehash keeps the accumulators) until groups so far + the batch's estimate fit at load <= 0.6
+        const int64_t g = count_groups();
+        (void)choose_cap(key, key.len);                         // refreshes est_groups / the heavy-hitter list for this batch
+        const double need = ((double)g + (double)est_groups) / 0.6;
+        if ((double)g > 0.25 * (double)cap || need > (double)cap) grow(std::max<uint64_t>(cap * 4, pow2_at_least(need)));
     }
     launch_batch(key, values, row_base);
     if (!defer_status && read_scalar(as<int>(status)) != 0)

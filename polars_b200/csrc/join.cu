@@ -416,27 +416,35 @@ __global__ void __launch_bounds__(256) k_join_emit(const __grid_constant__ JoinE
             if (total == 0) continue;
             const uint64_t sbase = base + seg[j * 8 + warp];
             const uint32_t pi = (uint32_t)(t * J_TILE + j * 256 + threadIdx.x);
-            for (uint32_t q0 = 0; q0 < total; q0 += 32) {
-                const uint32_t q = q0 + lane;
-                // owner lane = last lane whose exclusive prefix is <= q (lanes without tuples share their successor's prefix and lose the tie)
-                int lo = 0;
+            // 4 independent 32-tuple groups per round: the owner search (shuffles) of all four runs first, then their four
+            // sorted_rows loads together, then the stores — one dependent L2 access per round instead of per group
+            for (uint32_t q0 = 0; q0 < total; q0 += 128) {
+                uint32_t s_h[4], s_pi[4], s_at[4]; bool live[4];
 #pragma unroll
-                for (int step = 16; step; step >>= 1) {
-                    const int cand = lo + step;
-                    const uint32_t pe = __shfl_sync(0xffffffffu, lane_excl[j], cand & 31);
-                    if (cand < 32 && pe <= q) lo = cand;
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t q = q0 + 32 * u + lane;
+                    int lo = 0;
+#pragma unroll
+                    for (int step = 16; step; step >>= 1) {
+                        const int cand = lo + step;
+                        const uint32_t pe = __shfl_sync(0xffffffffu, lane_excl[j], cand & 31);
+                        if (cand < 32 && pe <= q) lo = cand;      // owner = last lane whose exclusive prefix is <= q (empty lanes lose the tie)
+                    }
+                    const uint32_t s_excl = __shfl_sync(0xffffffffu, lane_excl[j], lo);
+                    s_h[u] = __shfl_sync(0xffffffffu, h[j], lo);
+                    s_pi[u] = __shfl_sync(0xffffffffu, pi, lo);
+                    s_at[u] = __shfl_sync(0xffffffffu, off[j], lo) + (q - s_excl);
+                    live[u] = q < total;
                 }
-                const uint32_t s_excl = __shfl_sync(0xffffffffu, lane_excl[j], lo);
-                const uint32_t s_h = __shfl_sync(0xffffffffu, h[j], lo);
-                const uint32_t s_off = __shfl_sync(0xffffffffu, off[j], lo);
-                const uint32_t s_pi = __shfl_sync(0xffffffffu, pi, lo);
-                if (q < total) {
-                    uint32_t b;
-                    if (s_h == J_NONE) b = J_NONE;
-                    else if (!E.csr) b = s_h;
-                    else b = __ldg(E.sorted_rows + s_off + (q - s_excl));
-                    out_probe[sbase + q] = s_pi; out_build[sbase + q] = b;
+                uint32_t b[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    b[u] = s_h[u];
+                    if (live[u] && E.csr && s_h[u] != J_NONE) b[u] = __ldg(E.sorted_rows + s_at[u]);
                 }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (live[u]) { const uint64_t at = sbase + q0 + 32 * u + lane; __stcs(out_probe + at, s_pi[u]); __stcs(out_build + at, b[u]); }
             }
         }
         __syncthreads();
@@ -652,7 +660,8 @@ static JoinBuilt join_build(const DevCol& build, bool nulls_equal, bool need_lis
     dev_memset(has_dups->p, 0, 4);
     if (B.mode == JM_WIDE) {
         // two-entry buckets, <= 0.7 entries used per entry slot: C3 (1e7 keys) = 7.1 M buckets = 229 MB (round 1: 320 MB of 16-byte entries)
-        JoinTableDev T; T.nb = (uint64_t)std::max<int64_t>((int64_t)((double)nb / 1.4) + 1, 8);
+        const double per_bucket = [] { const char* e = getenv("BL_JOIN_BUCKET_FILL"); double v = e ? atof(e) : 1.4; return (v >= 0.5 && v <= 1.9) ? v : 1.4; }();      // build rows per 2-entry bucket
+        JoinTableDev T; T.nb = (uint64_t)std::max<int64_t>((int64_t)((double)nb / per_bucket) + 1, 8);
         PLB_REQUIRE(2 * (T.nb + 1) < 0xFFFFFFFFull, BL_ERR_UNSUPPORTED, "join: build side too large for 32-bit slots");
         B.entries = dev_alloc((size_t)(T.nb + 1) * sizeof(JoinBucket));
         T.buckets = as<JoinBucket>(B.entries);
@@ -700,7 +709,9 @@ static JoinBuilt join_build(const DevCol& build, bool nulls_equal, bool need_lis
         // ascending row lists: stable sort of the build rows by slot (skipped null rows sort last)
         B.sorted_rows = dev_alloc((size_t)nb * 4);
         iota_u32(as<uint32_t>(B.sorted_rows), nb, 0);
-        sort_pairs_u32(as<uint32_t>(B.slot_of_row), as<uint32_t>(B.sorted_rows), nb);
+        // J_NONE (skipped null rows) has every bit set and sorts last with any digit count that covers the real slots + 1 bit
+        const uint64_t max_slot = B.mode == JM_WIDE ? 2 * (B.J.W.nb + 1) : (uint64_t)B.J.ccap + 1;
+        sort_pairs_u32(as<uint32_t>(B.slot_of_row), as<uint32_t>(B.sorted_rows), nb, std::min(32, bits_for(max_slot) + 1));
     }
     B.J.csr = B.csr ? 1 : 0;
     return B;
@@ -762,7 +773,7 @@ static ProbeTuples probe_tuples(const DevCol& probe, const DevCol& build, bool n
     JoinBuilt B = join_build(build, nulls_equal, true);
     trace_point("join:build");
     // ---- unique build keys: fused single-pass probe + emit
-    static const int fused_on = [] { const char* e = getenv("BL_JOIN_FUSED"); return e ? atoi(e) : 1; }();
+    const int fused_on = [] { const char* e = getenv("BL_JOIN_FUSED"); return e ? atoi(e) : 1; }();
     const int64_t ntiles = (np + J_TILE - 1) / J_TILE;
     uint64_t M = 0;
     DevPtr out_probe, out_build;

@@ -48,6 +48,7 @@ void ensure_init(int device) {
     PLB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;
     PLB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    { const char* d = getenv("BL_DETERMINISTIC"); c->deterministic = d != nullptr && d[0] != '\0' && d[0] != '0'; }
     g_ctx = c;
 }
 
@@ -244,7 +245,16 @@ DevCol import_column(const bl_column* chunks, int n_chunks) {
         if (any_validity) { ok &= (chunks[0].offset % 8) == 0; mp = chunks[0].validity + chunks[0].offset / 8; ok &= ((uintptr_t)mp % 4) == 0; }
         if (ok) {
             out.values = dev_borrow(vp, (size_t)total * es);
-            if (any_validity) out.validity = dev_borrow(mp, bitmap_bytes(total));
+            if (any_validity) {
+                // the kernels read validity as 32-bit words: an Arrow bitmap only guarantees ceil(n / 8) bytes, so the last
+                // word may only be borrowed when it lies wholly inside them; otherwise the bitmap (1/64 of the column) is copied
+                if (total % 32 == 0) out.validity = dev_borrow(mp, bitmap_bytes(total));
+                else {
+                    out.validity = dev_alloc(bitmap_bytes(total) + 16);
+                    dev_memset(out.validity->p, 0, bitmap_bytes(total) + 16);
+                    PLB_LAUNCH("bitmap_copy", k_bitmap_copy, grid_for((total + 31) / 32 + 1, 256), 256, 0, as<uint32_t>(out.validity), (int64_t)0, mp, (int64_t)0, total);
+                }
+            }
             out.null_count = any_validity ? chunks[0].null_count : 0;
             return out;
         }
@@ -353,6 +363,7 @@ bl_status bl_init(int32_t device) {
     catch (const plb::Error& e) { t_last_error = e.what(); return e.code; }
     catch (...) { t_last_error = "bl_init failed"; return BL_ERR_CUDA; }
 }
+void bl_set_deterministic(int32_t on) { try { ctx().deterministic = on != 0; } catch (...) {} }
 void bl_shutdown(void) {
     if (!g_ctx) return;
     cudaStreamSynchronize(g_ctx->stream);

@@ -887,3 +887,76 @@ def test_join_multi_vs_oracle(plb, shape, how):
         eli, eri = oracle.hash_join_multi(L, R, LV, RV, how, nulls_equal, "none", 4)
         assert np.array_equal(li, eli), (shape, how, nulls_equal, li[:8], eli[:8])
         assert np.array_equal(ri, eri), (shape, how, nulls_equal, ri[:8], eri[:8])
+
+
+def test_group_by_deterministic_mode_is_bit_exact(plb):
+    """bl_set_deterministic(1): GroupsIdx + one sequential fold per group in row order with the reference's reducers
+    (sequential Kahan, kahan_sum.rs:36-47) -> float sums and means are BIT-identical to the oracle (no tolerance), and
+    identical from run to run.  Values span 12 orders of magnitude so that the addition order matters."""
+    rng = np.random.default_rng(99)
+    n = 400_000
+    key = rng.integers(-500, 500, n).astype(np.int64)
+    kvalid = rng.random(n) > 0.02
+    vf = (rng.normal(size=n) * 10.0 ** rng.integers(-6, 7, n)); fvalid = rng.random(n) > 0.1
+    vs = (rng.normal(size=n) * 10.0 ** rng.integers(-3, 4, n)).astype(np.float32)
+    vi = rng.integers(-2**62, 2**62, n).astype(np.int64)
+    aggs = [("sum", vf, fvalid), ("mean", vf, fvalid), ("sum", vs, None), ("mean", vs, None), ("min", vf, fvalid), ("max", vs, None), ("sum", vi, None), ("mean", vi, None),
+            ("count", vf, fvalid), ("len", None, None)]
+    plb.set_deterministic(True)
+    try:
+        runs = []
+        for _ in range(2):
+            keys, kv, outs = GpuImpl(plb).group_by_agg(key, kvalid, aggs, True)
+            runs.append((keys, kv, outs))
+        ek, ekv, eouts, _ = oracle.group_by_agg(key, kvalid, aggs, 4, True)
+        keys, kv, outs = runs[0]
+        assert np.array_equal(keys[kv] if kv is not None else keys, ek[ekv] if ekv is not None else ek)
+        for (kind, vals, _), (v, m), (ev, em), (v2, m2) in zip(aggs, outs, eouts, runs[1][2]):
+            assert v.dtype == ev.dtype, (kind, v.dtype, ev.dtype)
+            gv = np.ones(v.shape, bool) if m is None else m
+            xv = np.ones(ev.shape, bool) if em is None else em
+            assert np.array_equal(gv, xv), kind
+            assert np.array_equal(v[gv].view(np.uint8), ev[xv].view(np.uint8)), (kind, "not bit-identical to the oracle")
+            assert np.array_equal(v[gv].view(np.uint8), v2[gv].view(np.uint8)), (kind, "differs between runs")
+        # several key columns take the same path
+        (kouts, outs2) = plb.group_by_agg_keys([plb.Column(key, kvalid), plb.Column((key % 7).astype(np.int32))], [("sum", plb.Column(vf, fvalid)), ("len", None)], True)
+        ekk, eo, _ = oracle.group_by_agg_multi([key, (key % 7).astype(np.int32)], [kvalid, None], [("sum", vf, fvalid), ("len", None, None)], True)
+        assert np.array_equal(outs2[0][0].view(np.uint8), eo[0][0].view(np.uint8)) and np.array_equal(outs2[1][0], eo[1][0])
+    finally:
+        plb.set_deterministic(False)
+
+
+@pytest.mark.parametrize("knob,value", [("BL_K5_SOA", "0"), ("BL_K5_PAIRS", "2"), ("BL_K5_HINT", "1"), ("BL_K5_HINT", "3"), ("BL_K5_MULTIPASS", "0"), ("BL_K5_SMEM", "0"),
+                                        ("BL_K5_RADIX", "0"), ("BL_K5_LF", "30")])
+def test_group_by_knob_variants(plb, monkeypatch, knob, value):
+    """Every documented BL_K5_* fallback (entry-major table, 4 rows per thread, L2 policy hints, single pass beyond L2, no
+    CTA-private tables, ...) is read per call and has to give the reference's answer."""
+    monkeypatch.setenv(knob, value)
+    rng = np.random.default_rng(5)
+    for n, k in ((200_001, 50_000), (2_000_001, 1_400_000)) if knob in ("BL_K5_MULTIPASS", "BL_K5_RADIX") else ((200_001, 50_000), (60_000, 300)):
+        key = (rng.integers(0, k, n) * 7919 - 10**9).astype(np.int64); key[::997] = -2**63
+        kvalid = rng.random(n) > 0.01
+        vi = rng.integers(-1000, 1000, n).astype(np.int64); ivalid = rng.random(n) > 0.05
+        vf = rng.uniform(0, 100, n).round(6)
+        aggs = [("sum", vi, ivalid), ("mean", vf, None), ("len", None, None), ("max", vi, ivalid)]
+        keys, kv, outs = GpuImpl(plb).group_by_agg(key, kvalid, aggs, False)
+        ek, ekv, eouts, _ = oracle.group_by_agg(key, kvalid, aggs, 8, False)
+        keys, kv, outs = sort_groups(keys, kv, outs)
+        ek, ekv, eouts = sort_groups(ek, ekv, eouts)
+        assert_close(keys, ek, kv, ekv, "keys")
+        for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
+            assert_close(v, ev, m, em, f"{knob}={value} {kind}")
+
+
+@pytest.mark.parametrize("knob,value", [("BL_JOIN_FUSED", "0"), ("BL_JOIN_TABLE", "compact"), ("BL_JOIN_DENSE", "0")])
+def test_join_knob_variants(plb, monkeypatch, knob, value):
+    monkeypatch.setenv(knob, value)
+    rng = np.random.default_rng(6)
+    for nl, nr, dups in ((50_000, 20_000, 1), (30_000, 9_000, 3)):
+        lk = rng.integers(0, 25_000, nl).astype(np.int64)
+        rk = np.repeat(rng.permutation(25_000)[: nr // dups], dups).astype(np.int64); rng.shuffle(rk)
+        lv = rng.random(nl) > 0.05; rv = rng.random(rk.size) > 0.05
+        for how in ("inner", "left", "semi", "anti", "full"):
+            (li, _), (ri, _) = plb.hash_join(plb.Column(lk, lv), plb.Column(rk, rv), how, False, "none")
+            eli, eri = oracle.hash_join(lk, rk, lv, rv, how, False, "none", 4)
+            assert np.array_equal(li, eli) and np.array_equal(ri, eri), (knob, value, how, dups)
