@@ -143,7 +143,12 @@ bl_status bl_gather(const bl_column* cols, int32_t n_cols, const bl_column* idx,
 /* ---- K5: hash group_by + aggregation --------------------------------------------------- */
 /* (group_by_threaded_slice hashing.rs:116-167 + agg_sum/mean/min/max aggregations/mod.rs:486-1018,
  *  fused: index lists are never materialised) */
-enum { BL_AGG_SUM = 0, BL_AGG_MEAN = 1, BL_AGG_MIN = 2, BL_AGG_MAX = 3, BL_AGG_COUNT = 4, BL_AGG_LEN = 5 };
+enum { BL_AGG_SUM = 0, BL_AGG_MEAN = 1, BL_AGG_MIN = 2, BL_AGG_MAX = 3, BL_AGG_COUNT = 4, BL_AGG_LEN = 5,
+       /* evaluated per group over the reference's GroupsIdx (row lists in row order), not by the fused atomics path: */
+       BL_AGG_FIRST = 6, BL_AGG_LAST = 7,   /* value at the group's first / last row, nulls included (dispatch.rs:57-120) */
+       BL_AGG_VAR = 8, BL_AGG_STD = 9 };    /* Welford in row order, f64; null when count <= ddof (aggregations/mod.rs:1020-1178, take_agg/var.rs:11-41) */
+/* delta degrees of freedom of VAR / STD travel in bits 16..23 of `kind` (Polars' default is 1) */
+#define BL_AGG_WITH_DDOF(kind, ddof) ((kind) | ((ddof) << 16))
 typedef struct bl_agg {
     int32_t kind;           /* BL_AGG_* */
     int32_t n_chunks;       /* chunks of the value column (ignored for BL_AGG_LEN) */
@@ -154,7 +159,9 @@ typedef struct bl_agg {
  * maintain_order != 0: groups ordered by first occurrence (hashing.rs:41-63); else unspecified.
  * out_key = key taken at each group's first row (group_by/mod.rs:258-266).
  * Output dtypes: SUM keeps the dtype (Int8/16,UInt8/16 -> Int64), ints wrap; MEAN -> FLOAT64
- * (FLOAT32 stays); MIN/MAX keep dtype; COUNT/LEN -> UINT32.  All-null group: SUM 0, MEAN/MIN/MAX null. */
+ * (FLOAT32 stays); MIN/MAX keep dtype; COUNT/LEN -> UINT32.  All-null group: SUM 0, MEAN/MIN/MAX null.
+ * FIRST/LAST keep dtype; VAR/STD -> FLOAT64 (FLOAT32 stays).  A call that asks for any of FIRST/LAST/VAR/STD is evaluated
+ * whole over GroupsIdx (groups then come in first-occurrence order), like bl_set_deterministic. */
 bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, const bl_agg* aggs, int32_t n_aggs,
                          int32_t maintain_order, int32_t out_location, bl_column* out_key, bl_column* out_aggs);
 
@@ -212,7 +219,8 @@ bl_status bl_join(const bl_column* left_key, const bl_column* right_key,
 /* partition id = hash_to_partition(dirty_hash(key), n_partitions)
  *              = ((key * 0x55fbfd6bfc5458e9 mod 2^64) * n_partitions) >> 64   (hashing.rs:62-69,132-142),
  * null keys -> partition 0 (hashing.rs:113-115,183-187).  Rows are scattered so that partition p
- * occupies [offsets[p], offsets[p+1]) of every output column, in stable row order.
+ * occupies [offsets[p], offsets[p+1]) of every output column (the same permutation for every column; the row order
+ * inside a partition is unspecified).
  * offsets: caller array of n_partitions+1 int64 (host). */
 bl_status bl_hash_partition(const bl_column* key, const bl_column* payload, int32_t n_payload, int32_t n_partitions,
                             int32_t out_location, bl_column* out_key, bl_column* out_payload, int64_t* offsets);

@@ -260,7 +260,7 @@ def agg(kind: str, values, valid, groups: Groups):
         # 8/16-bit integers aggregate after a cast to Int64 (polars-core/src/series/implementations/mod.rs:145-154);
         # sum stays Int64, mean is Float64 (aggregations/mod.rs:1227-1296), min/max return the input dtype
         out, ov = agg(kind, values.astype(np.int64), valid, groups)
-        return (out.astype(values.dtype) if kind in ("min", "max") else out), ov
+        return (out.astype(values.dtype) if kind in ("min", "max", "first", "last") else out), ov
     sfx = _SUFFIX[values.dtype]
     if kind == "sum":
         out = np.empty(G, values.dtype)
@@ -270,6 +270,20 @@ def agg(kind: str, values, valid, groups: Groups):
     if kind == "mean":
         out = np.empty(G, np.float64)
         getattr(L, f"or_agg_mean_{sfx}")(_p(values), _p(v), _p(off), _p(idx), C.c_int64(G), _p(out), _p(ov))
+        if values.dtype == np.float32:
+            out = out.astype(np.float32)
+        return out, (None if ov.all() else ov)
+    if kind in ("first", "last"):
+        # agg_first / agg_last (aggregations/agg_list.rs / dispatch.rs:57-120): the value at the group's first / last row, nulls included
+        rows = groups.first if kind == "first" else idx[(off[1:] - np.uint64(1)).astype(np.int64)] if G else np.zeros(0, np.uint32)
+        out = values[rows]
+        ov = None if v is None else v[rows]
+        return out, (None if ov is None or ov.all() else ov)
+    if kind in ("var", "std") or kind.startswith(("var:", "std:")):
+        name, _, dd = kind.partition(":")
+        ddof = int(dd) if dd else 1
+        out = np.empty(G, np.float64)
+        getattr(L, f"or_agg_var_{sfx}")(_p(values), _p(v), _p(off), _p(idx), C.c_int64(G), C.c_int(ddof), C.c_int(int(name == "std")), _p(out), _p(ov))
         if values.dtype == np.float32:
             out = out.astype(np.float32)
         return out, (None if ov.all() else ov)

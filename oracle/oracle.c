@@ -525,6 +525,35 @@ DEF_AGG_MEAN(or_agg_mean_u32, uint32_t)
 DEF_AGG_MEAN(or_agg_mean_f64, double)
 DEF_AGG_MEAN(or_agg_mean_f32, float)   /* caller casts the f64 result back to f32 (:976) */
 
+/* var / std: polars-core/src/frame/group_by/aggregations/mod.rs:1020-1178 -> take_var_*_primitive_iter_unchecked
+ * (polars-arrow/src/legacy/kernels/take_agg/var.rs:11-41): Welford's online update in row order over the group's
+ * non-null values converted to f64; None when count <= ddof; std = sqrt(var).  Output f64 (Float32 input: caller casts). */
+#define DEF_AGG_VAR(NAME, T)                                                                \
+    void NAME(const T* v, const uint8_t* valid, const uint64_t* offsets, const idx_t* idx,  \
+              int64_t G, int ddof, int is_std, double* out, uint8_t* out_valid) {           \
+        _Pragma("omp parallel for schedule(static)")                                        \
+        for (int64_t g = 0; g < G; g++) {                                                   \
+            double m2 = 0.0, mean = 0.0; uint64_t count = 0;                                \
+            for (uint64_t j = offsets[g]; j < offsets[g + 1]; j++) {                        \
+                if (valid != NULL && !valid[idx[j]]) continue;                              \
+                double value = (double)v[idx[j]];                                           \
+                uint64_t new_count = count + 1;                                             \
+                double delta_1 = value - mean;                                              \
+                double new_mean = delta_1 / (double)new_count + mean;                       \
+                double delta_2 = value - new_mean;                                          \
+                m2 = m2 + delta_1 * delta_2; count = new_count; mean = new_mean;            \
+            }                                                                               \
+            if (count <= (uint64_t)ddof) { out[g] = 0; out_valid[g] = 0; }                  \
+            else { double r = m2 / ((double)count - (double)ddof); out[g] = is_std ? sqrt(r) : r; out_valid[g] = 1; } \
+        }                                                                                   \
+    }
+DEF_AGG_VAR(or_agg_var_i64, int64_t)
+DEF_AGG_VAR(or_agg_var_i32, int32_t)
+DEF_AGG_VAR(or_agg_var_u64, uint64_t)
+DEF_AGG_VAR(or_agg_var_u32, uint32_t)
+DEF_AGG_VAR(or_agg_var_f64, double)
+DEF_AGG_VAR(or_agg_var_f32, float)
+
 #define MIN_INT(a, b) ((a) < (b) ? (a) : (b))
 #define MAX_INT(a, b) ((a) < (b) ? (b) : (a))
 #define DEF_AGG_MINMAX(NAME, T, RED)                                                        \

@@ -26,7 +26,13 @@ NP_OF = {v: k for k, v in DTYPES.items()}
 BOOL = 10
 OPS = {"add": 0, "sub": 1, "mul": 2, "floordiv": 3, "mod": 4, "truediv": 5}
 CMPS = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5}
-AGGS = {"sum": 0, "mean": 1, "min": 2, "max": 3, "count": 4, "len": 5}
+AGGS = {"sum": 0, "mean": 1, "min": 2, "max": 3, "count": 4, "len": 5, "first": 6, "last": 7, "var": 8 | (1 << 16), "std": 9 | (1 << 16)}
+
+
+def _agg_kind(kind: str) -> int:
+    """"var" / "std" default to ddof = 1 (Polars); "var:0", "std:2" ... carry an explicit ddof (BL_AGG_WITH_DDOF)."""
+    name, _, dd = kind.partition(":")
+    return (AGGS[name] & 0xFFFF) | (int(dd) << 16) if dd else AGGS[name]
 JOINS = {"inner": 0, "left": 1, "semi": 2, "anti": 3, "full": 4}
 ORDERS = {"none": 0, "left": 1, "left_right": 2, "right": 3, "right_left": 4}
 STATUS = {1: "INVALID", 2: "CUDA", 3: "OOM", 4: "UNSUPPORTED", 5: "DTYPE", 6: "BOUNDS"}
@@ -102,6 +108,15 @@ def set_deterministic(on: bool = True):
     """Bit-stable group_by aggregation in the reference's own order (bl_set_deterministic)."""
     lib().bl_set_deterministic.restype = None
     lib().bl_set_deterministic(C.c_int32(int(on)))
+
+
+def use_library(path: str) -> None:
+    """Bind this module to another build of libpolars_b200.so (a fresh build made by __graft_entry__.smoke()).  A copy that
+    is already loaded keeps running for whoever still holds its objects; everything created afterwards uses `path`."""
+    global _lib, _SO
+    _SO, _lib = path, None
+    os.environ["POLARS_B200_LIB"] = path
+    lib()
 
 
 def loaded_library() -> str:
@@ -369,7 +384,7 @@ def group_by_agg(key, aggs: Sequence, maintain_order: bool = False, location: in
     cache = {}
     for kind, vals in aggs:
         if kind == "len" or vals is None:
-            agg_structs.append(BlAgg(AGGS[kind], 0, None))
+            agg_structs.append(BlAgg(_agg_kind(kind), 0, None))
             continue
         ident = id(vals)
         if ident not in cache:
@@ -377,7 +392,7 @@ def group_by_agg(key, aggs: Sequence, maintain_order: bool = False, location: in
             cache[ident] = (chunks, _col_array(chunks))
         chunks, arr = cache[ident]
         keep.append((chunks, arr))
-        agg_structs.append(BlAgg(AGGS[kind], len(chunks), C.cast(arr, C.POINTER(BlColumn))))
+        agg_structs.append(BlAgg(_agg_kind(kind), len(chunks), C.cast(arr, C.POINTER(BlColumn))))
     aarr = (BlAgg * max(len(agg_structs), 1))(*agg_structs)
     out_key, out_aggs = BlColumn(), (BlColumn * max(len(agg_structs), 1))()
     _check(lib().bl_groupby_agg(karr, C.c_int32(len(kchunks)), aarr, C.c_int32(len(agg_structs)), C.c_int32(int(maintain_order)), C.c_int32(location),
@@ -394,7 +409,7 @@ def group_by_agg_keys(keys: Sequence, aggs: Sequence, maintain_order: bool = Fal
     cache = {}
     for kind, vals in aggs:
         if kind == "len" or vals is None:
-            agg_structs.append(BlAgg(AGGS[kind], 0, None))
+            agg_structs.append(BlAgg(_agg_kind(kind), 0, None))
             continue
         ident = id(vals)
         if ident not in cache:
@@ -402,7 +417,7 @@ def group_by_agg_keys(keys: Sequence, aggs: Sequence, maintain_order: bool = Fal
             cache[ident] = (chunks, _col_array(chunks))
         chunks, arr = cache[ident]
         keep.append((chunks, arr))
-        agg_structs.append(BlAgg(AGGS[kind], len(chunks), C.cast(arr, C.POINTER(BlColumn))))
+        agg_structs.append(BlAgg(_agg_kind(kind), len(chunks), C.cast(arr, C.POINTER(BlColumn))))
     aarr = (BlAgg * max(len(agg_structs), 1))(*agg_structs)
     out_keys, out_aggs = (BlColumn * len(kcols))(), (BlColumn * max(len(agg_structs), 1))()
     _check(lib().bl_groupby_agg_keys(karr, C.c_int32(len(kcols)), aarr, C.c_int32(len(agg_structs)), C.c_int32(int(maintain_order)), C.c_int32(location),

@@ -84,7 +84,9 @@ bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, cons
                                                                     a.values[0].offset == b.values[0].offset && a.values[0].length == b.values[0].length && a.values[0].dtype == b.values[0].dtype));
     };
     // Host inputs without nulls: chunked H2D on the copy stream overlapped with K5 on the compute stream.
-    bool pipelined = !ctx().deterministic && n_key_chunks == 1 && key_chunks[0].location == BL_HOST && (key_chunks[0].validity == nullptr || key_chunks[0].null_count == 0) &&
+    bool needs_groups_idx = ctx().deterministic;      // FIRST / LAST / VAR / STD fold per group over GroupsIdx (groupby_exact.cu)
+    for (int i = 0; i < n_aggs; i++) needs_groups_idx |= (aggs[i].kind & 0xFFFF) >= BL_AGG_FIRST;
+    bool pipelined = !needs_groups_idx && n_key_chunks == 1 && key_chunks[0].location == BL_HOST && (key_chunks[0].validity == nullptr || key_chunks[0].null_count == 0) &&
                      key_chunks[0].length >= (int64_t)1 << 22 && dtype_size(key_chunks[0].dtype) >= 4 && key_chunks[0].dtype != BL_BOOL;
     for (int i = 0; i < n_aggs && pipelined; i++)
         if (aggs[i].kind != BL_AGG_LEN)
@@ -158,7 +160,7 @@ bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, cons
     }
     for (int i = 0; i < n_aggs; i++) nullable[i] = vptr[i] != nullptr && vptr[i]->validity != nullptr;
     DevCol ok; std::vector<DevCol> oa;
-    if (ctx().deterministic) {      // the reference's own order: GroupsIdx + sequential folds (groupby_exact.cu); groups in first-occurrence order
+    if (needs_groups_idx) {      // the reference's own order: GroupsIdx + sequential folds (groupby_exact.cu); groups in first-occurrence order
         DevCol first;
         op_group_by_exact(key, kinds, vptr, first, oa);
         std::vector<DevCol> in{key}, o;
@@ -171,7 +173,8 @@ bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, cons
     }
     if (dtype_is_small_int(key_in_dtype)) ok = op_cast_small_int(ok, key_in_dtype, true);
     for (int i = 0; i < n_aggs; i++)
-        if ((aggs[i].kind == BL_AGG_MIN || aggs[i].kind == BL_AGG_MAX) && dtype_is_small_int(val_in_dtype[i])) oa[i] = op_cast_small_int(oa[i], val_in_dtype[i], false);
+        if ((aggs[i].kind == BL_AGG_MIN || aggs[i].kind == BL_AGG_MAX || aggs[i].kind == BL_AGG_FIRST || aggs[i].kind == BL_AGG_LAST) && dtype_is_small_int(val_in_dtype[i]))
+            oa[i] = op_cast_small_int(oa[i], val_in_dtype[i], false);
     { std::vector<DevCol> all{ok}; all.insert(all.end(), oa.begin(), oa.end());
       std::vector<bl_column> t(all.size()); export_many(all, out_location, t.data());
       *out_key = t[0]; for (int i = 0; i < n_aggs; i++) out_aggs[i] = t[i + 1]; }
@@ -210,14 +213,17 @@ bl_status bl_groupby_agg_keys(const bl_column* keys, int32_t n_keys, const bl_ag
         nullable[i] = vals[i].validity != nullptr;
     }
     DevCol ok, first; std::vector<DevCol> oa;
-    if (ctx().deterministic) op_group_by_exact(packed, kinds, vptr, first, oa);
+    bool needs_groups_idx = ctx().deterministic;
+    for (int i = 0; i < n_aggs; i++) needs_groups_idx |= (aggs[i].kind & 0xFFFF) >= BL_AGG_FIRST;
+    if (needs_groups_idx) op_group_by_exact(packed, kinds, vptr, first, oa);
     else {
         GroupByState st(BL_UINT64, kinds, dts, nullable, 0, true);
         st.consume_all(packed, vptr);
         st.finish(maintain_order != 0, nullptr, ok, oa, &first);
     }
     for (int i = 0; i < n_aggs; i++)
-        if ((aggs[i].kind == BL_AGG_MIN || aggs[i].kind == BL_AGG_MAX) && dtype_is_small_int(val_in_dtype[i])) oa[i] = op_cast_small_int(oa[i], val_in_dtype[i], false);
+        if ((aggs[i].kind == BL_AGG_MIN || aggs[i].kind == BL_AGG_MAX || aggs[i].kind == BL_AGG_FIRST || aggs[i].kind == BL_AGG_LAST) && dtype_is_small_int(val_in_dtype[i]))
+            oa[i] = op_cast_small_int(oa[i], val_in_dtype[i], false);
     // key output = every key column taken at the group's first row (group_by/mod.rs:258-266)
     std::vector<DevCol> all;
     for (int i = 0; i < n_keys; i++) {

@@ -22,7 +22,7 @@ namespace plb {
 
 struct SegArgs {
     const void* values; const uint32_t* validity; const uint32_t* offsets; const uint32_t* all; int64_t G;
-    void* out; uint32_t* out_valid; int kind;
+    void* out; uint32_t* out_valid; int kind, ddof;
 };
 
 struct KahanD { double sum, err; };
@@ -87,6 +87,31 @@ __global__ void __launch_bounds__(128) k_seg_agg(const __grid_constant__ SegArgs
                     if constexpr (sizeof(T) == 4 && is_fp<T>::v) reinterpret_cast<float*>(a.out)[g] = (float)m; else reinterpret_cast<double*>(a.out)[g] = m;
                     break;
                 }
+                case BL_AGG_FIRST: case BL_AGG_LAST: {
+                    if (hi == lo) { ok = false; reinterpret_cast<T*>(a.out)[g] = (T)0; break; }
+                    const uint32_t r = a.all[a.kind == BL_AGG_FIRST ? lo : hi - 1];
+                    ok = a.validity == nullptr || bit_get(a.validity, r);
+                    reinterpret_cast<T*>(a.out)[g] = ok ? v[r] : (T)0;
+                    break;
+                }
+                case BL_AGG_VAR: case BL_AGG_STD: {      // Welford, row order (take_agg/var.rs:11-41)
+                    double m2 = 0.0, mean = 0.0; uint32_t count = 0;
+                    for (uint32_t j = lo; j < hi; j++) {
+                        const uint32_t r = a.all[j];
+                        if (a.validity != nullptr && !bit_get(a.validity, r)) continue;
+                        const double value = (double)v[r];
+                        const uint32_t new_count = count + 1;
+                        const double delta_1 = value - mean;
+                        const double new_mean = delta_1 / (double)new_count + mean;
+                        const double delta_2 = value - new_mean;
+                        m2 = m2 + delta_1 * delta_2; count = new_count; mean = new_mean;
+                    }
+                    ok = count > (uint32_t)a.ddof;
+                    double res = ok ? m2 / ((double)count - (double)a.ddof) : 0.0;
+                    if (a.kind == BL_AGG_STD) res = sqrt(res);
+                    if constexpr (sizeof(T) == 4 && is_fp<T>::v) reinterpret_cast<float*>(a.out)[g] = (float)res; else reinterpret_cast<double*>(a.out)[g] = res;
+                    break;
+                }
                 default: {      // MIN / MAX
                     bool have = false; T acc = (T)0;
                     for (uint32_t j = lo; j < hi; j++) {
@@ -108,7 +133,8 @@ static int exact_out_dtype(int kind, int in_dtype) {
     switch (kind) {
         case BL_AGG_SUM: return in_dtype;                                   // 8/16-bit columns arrive widened to Int64 (cabi.cu)
         case BL_AGG_MEAN: return in_dtype == BL_FLOAT32 ? BL_FLOAT32 : BL_FLOAT64;
-        case BL_AGG_MIN: case BL_AGG_MAX: return in_dtype;
+        case BL_AGG_MIN: case BL_AGG_MAX: case BL_AGG_FIRST: case BL_AGG_LAST: return in_dtype;
+        case BL_AGG_VAR: case BL_AGG_STD: return in_dtype == BL_FLOAT32 ? BL_FLOAT32 : BL_FLOAT64;
         default: return BL_UINT32;
     }
 }
@@ -120,18 +146,19 @@ void op_group_by_exact(const DevCol& key, const std::vector<int>& kinds, const s
     const int64_t G = out_first.len;
     outs.clear();
     for (size_t i = 0; i < kinds.size(); i++) {
-        const int kind = kinds[i];
+        const int kind = kinds[i] & 0xFFFF, ddof = (kinds[i] >> 16) & 0xFF;
         const DevCol* v = values[i];
         PLB_REQUIRE(kind == BL_AGG_LEN || v != nullptr, BL_ERR_INVALID, "group_by: aggregation without a value column");
         const int in_dt = v ? v->dtype : BL_INT64;
         PLB_REQUIRE(kind == BL_AGG_LEN || in_dt == BL_INT64 || in_dt == BL_UINT64 || in_dt == BL_INT32 || in_dt == BL_UINT32 || in_dt == BL_FLOAT64 || in_dt == BL_FLOAT32, BL_ERR_UNSUPPORTED,
                     std::string("group_by: value dtype ") + dtype_name(in_dt) + " is outside the hot path");
-        const bool nullable = kind == BL_AGG_MEAN || kind == BL_AGG_MIN || kind == BL_AGG_MAX;
+        PLB_REQUIRE(kind >= BL_AGG_SUM && kind <= BL_AGG_STD, BL_ERR_INVALID, "group_by: unknown aggregation kind");
+        const bool nullable = kind == BL_AGG_MEAN || kind == BL_AGG_MIN || kind == BL_AGG_MAX || kind >= BL_AGG_FIRST;
         DevCol o = make_col(exact_out_dtype(kind, in_dt), G, nullable);
         if (G > 0) {
             SegArgs a; memset(&a, 0, sizeof a);
             a.values = v ? v->v() : nullptr; a.validity = v ? v->vm() : nullptr; a.offsets = as<uint32_t>(offsets.values); a.all = as<uint32_t>(all.values);
-            a.G = G; a.out = o.values->p; a.out_valid = as<uint32_t>(o.validity); a.kind = kind;
+            a.G = G; a.out = o.values->p; a.out_valid = as<uint32_t>(o.validity); a.kind = kind; a.ddof = ddof;
             const int grid = grid_for(G, 128, 16);
             switch (in_dt) {
                 case BL_INT64: PLB_LAUNCH("k5x_fold_groups", k_seg_agg<int64_t>, grid, 128, 0, a); break;

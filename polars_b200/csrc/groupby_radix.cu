@@ -33,7 +33,7 @@
 
 namespace plb {
 
-constexpr int GBR_THREADS = 512, GBR_RPT = 4, GBR_TILE = GBR_THREADS * GBR_RPT;      // pass 1: 2048-row tiles
+constexpr int GBR_THREADS = 512;      // pass 1: 2048-row tiles (bulk stores) / 4096-row tiles (many buckets: longer runs per bucket)
 constexpr int GBR_MAX_LOGB = 13;
 constexpr int GBR_NCW = 31, GBR_NCT = GBR_NCW * 32;                                    // pass 2: 31 consumer warps + 1 producer warp
 
@@ -130,9 +130,9 @@ __device__ __forceinline__ void gbr_apply_special(const GbLayout& L, const GbBat
         }
 }
 
-template <int ROWW, int KEY_ELEM, int KEY_CANON, bool BULK>
+template <int ROWW, int KEY_ELEM, int KEY_CANON, bool BULK, int RPT>
 __global__ void __launch_bounds__(GBR_THREADS) k_gbr_scatter(const __grid_constant__ GbLayout L, const __grid_constant__ GbBatch Bt, const __grid_constant__ GbRadixDev R) {
-    constexpr int T = GBR_TILE, THREADS = GBR_THREADS, RPT = GBR_RPT, NC = ROWW - 1;
+    constexpr int T = GBR_THREADS * RPT, THREADS = GBR_THREADS, NC = ROWW - 1;
     const int logB = R.logB, B = 1 << logB;
     extern __shared__ __align__(16) uint64_t gbr_smem[];
     uint64_t* stage = gbr_smem;                                        // (T + (BULK ? B : 0)) records
@@ -359,18 +359,21 @@ __global__ void k_gbr_append_special(const uint64_t* __restrict__ special, int n
 // =============================================================================================
 // Host side
 // =============================================================================================
+constexpr int GBR_RPT_BULK = 4, GBR_RPT_PLAIN = 8;
+static int64_t gbr_tile_rows(bool bulk) { return (int64_t)GBR_THREADS * (bulk ? GBR_RPT_BULK : GBR_RPT_PLAIN); }
 template <int ROWW, int KEY_ELEM, int KEY_CANON>
 static void launch_scatter(const GbLayout& L, const GbBatch& Bt, const GbRadixDev& R, bool bulk) {
     const int B = 1 << R.logB;
-    const size_t smem = (size_t)(GBR_TILE + (bulk ? B : 0)) * ROWW * 8 + (size_t)3 * B * 4 + (bulk ? 0 : (size_t)GBR_TILE * 2);
+    const size_t tile = (size_t)gbr_tile_rows(bulk);
+    const size_t smem = (tile + (bulk ? B : 0)) * ROWW * 8 + (size_t)3 * B * 4 + (bulk ? 0 : tile * 2);
     int occ = 0;
     if (bulk) {
-        auto kfn = k_gbr_scatter<ROWW, KEY_ELEM, KEY_CANON, true>;
+        auto kfn = k_gbr_scatter<ROWW, KEY_ELEM, KEY_CANON, true, GBR_RPT_BULK>;
         PLB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, GBR_THREADS, smem));
         PLB_LAUNCH("k5r_scatter", kfn, ctx().sm_count * std::max(occ, 1), GBR_THREADS, smem, L, Bt, R);
     } else {
-        auto kfn = k_gbr_scatter<ROWW, KEY_ELEM, KEY_CANON, false>;
+        auto kfn = k_gbr_scatter<ROWW, KEY_ELEM, KEY_CANON, false, GBR_RPT_PLAIN>;
         PLB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, GBR_THREADS, smem));
         PLB_LAUNCH("k5r_scatter", kfn, ctx().sm_count * std::max(occ, 1), GBR_THREADS, smem, L, Bt, R);
@@ -425,24 +428,31 @@ bool GroupByState::consume_radix(const DevCol& key, const std::vector<const DevC
     for (int c = Lb.n_cols; c <= GB_MAX_COLS; c++) Lb.col_kbegin[c] = kk;
     const int roww = 1 + Lb.n_cols;
     const int64_t n = key.len;
-    // shared-memory table per bucket: what is left of ~110 KB (2 CTAs / SM) after a 2-stage ring
+    // shared-memory table per bucket: what is left of ~110 KB (2 CTAs / SM: measured best, profiles/r02_proto_radix.md) after a
+    // 2-stage ring; when even 8192 buckets of that size cannot take the estimated groups, one CTA / SM with a ~200 KB table
     const size_t entry = 8 + 4 + 8 * (size_t)L.n_words;
     const size_t ring2 = (size_t)2 * GBR_NCW * 32 * roww * 8;
-    const size_t budget = (size_t)110 * 1024 - ring2 - 1024;
-    if (budget < 512 * entry) return false;
-    unsigned S = (unsigned)(budget / entry) & ~31u;
-    const double per_bucket = 0.55 * (double)S;                       // groups per bucket the table takes comfortably
-    int logB = 6;
-    while (logB < GBR_MAX_LOGB && (double)est_groups / (double)(1 << logB) > per_bucket) logB++;
-    if ((double)est_groups / (double)(1 << logB) > 0.7 * (double)S) return false;      // too many groups even for 8192 buckets
+    unsigned S = 0; int logB = 6;
+    for (const size_t total_kb : {(size_t)110, (size_t)222}) {
+        if (total_kb * 1024 < ring2 + 1024 + 512 * entry) continue;
+        S = (unsigned)((total_kb * 1024 - ring2 - 1024) / entry) & ~31u;
+        const double per_bucket = 0.55 * (double)S;                   // groups per bucket the table takes comfortably
+        logB = 6;
+        while (logB < GBR_MAX_LOGB && (double)est_groups / (double)(1 << logB) > per_bucket) logB++;
+        if ((double)est_groups / (double)(1 << logB) <= 0.7 * (double)S) break;
+        S = 0;
+    }
+    if (S == 0) return false;                                         // too many groups even for 8192 buckets of the large table
     if (mode == 1) {
+        // the L2 plan keeps a table of up to ~3x its L2 budget competitive by filling it in slot-range passes (launch_batch:
+        // pass_bits); measured cross-over on C2-shaped rows: 3e6 keys 3.2 ms (L2 plan) / 4e6 keys 6.5 vs 4.2 ms (this plan)
         const double l2_budget = 0.55 * (double)ctx().l2_bytes;
         double c = 1024; while (c < (double)est_groups / 0.6) c *= 2;
-        if (c * L.stride * 8 <= l2_budget) return false;             // the L2 plan keeps its table resident: it is the faster one
+        if (c * L.stride * 8 <= 3.0 * l2_budget) return false;
     }
     const int B = 1 << logB;
     const bool bulk = logB <= 9;
-    const int64_t ntiles = (n + GBR_TILE - 1) / GBR_TILE;
+    const int64_t ntiles = (n + gbr_tile_rows(bulk) - 1) / gbr_tile_rows(bulk);
     const int64_t rec_rows = n + (bulk ? std::min<int64_t>(n, (int64_t)B * ntiles) : 0) + 2 * B + 16;
     const int elem = dtype_size(key.dtype);
     const int canon = key.dtype == BL_FLOAT64 ? 1 : (key.dtype == BL_FLOAT32 ? 2 : 0);

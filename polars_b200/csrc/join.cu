@@ -14,7 +14,7 @@
 // B200 design.  Three table forms, chosen per build relation:
 //   DENSE    build keys are integers whose value range is a few times the row count (surrogate / primary keys):
 //            u32 table[key - min] = build row.  4 B per key value, L2-resident for 1e7 keys.
-//   WIDE     (default hashed form) 32-byte buckets of two {key, val, cnt} entries (<= 0.7 full), bucket = mulhi(key *
+//   WIDE     (default hashed form) 32-byte buckets of two {key, val, cnt} entries (half full), bucket = mulhi(key *
 //            RANDOM_ODD, buckets) — the reference's own hash_to_partition.  One 256-bit load = one sector per probe step
 //            carries everything (both keys, build row or CSR offset, match count).
 //   COMPACT  (BL_JOIN_TABLE=compact) u32 table[slot] = fingerprint:8 | build row:24 (plain row ids past 2^24 rows),
@@ -659,8 +659,8 @@ static JoinBuilt join_build(const DevCol& build, bool nulls_equal, bool need_lis
     DevPtr has_dups = dev_alloc(4);
     dev_memset(has_dups->p, 0, 4);
     if (B.mode == JM_WIDE) {
-        // two-entry buckets, <= 0.7 entries used per entry slot: C3 (1e7 keys) = 7.1 M buckets = 229 MB (round 1: 320 MB of 16-byte entries)
-        const double per_bucket = [] { const char* e = getenv("BL_JOIN_BUCKET_FILL"); double v = e ? atof(e) : 1.4; return (v >= 0.5 && v <= 1.9) ? v : 1.4; }();      // build rows per 2-entry bucket
+        // two-entry buckets, half full by default: C3 (1e7 keys) = 1e7 buckets = 320 MB
+        const double per_bucket = [] { const char* e = getenv("BL_JOIN_BUCKET_FILL"); double v = e ? atof(e) : 1.0; return (v >= 0.5 && v <= 1.9) ? v : 1.0; }();      // build rows per 2-entry bucket (measured: 1.0 -> probe 1.71 ms / build 0.62 ms, 1.4 -> 1.90 / 0.43 ms on C3 sparse)
         JoinTableDev T; T.nb = (uint64_t)std::max<int64_t>((int64_t)((double)nb / per_bucket) + 1, 8);
         PLB_REQUIRE(2 * (T.nb + 1) < 0xFFFFFFFFull, BL_ERR_UNSUPPORTED, "join: build side too large for 32-bit slots");
         B.entries = dev_alloc((size_t)(T.nb + 1) * sizeof(JoinBucket));

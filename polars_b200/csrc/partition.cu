@@ -10,8 +10,9 @@
 // B200 design: two streaming passes.  Pass 1: per-CTA shared-memory histogram (32-bit smem atomics),
 // one global add per (CTA, partition).  Pass 2: each CTA re-reads its tile, reserves one contiguous
 // range per partition with a single global atomicAdd, and its threads take slots inside the range
-// from shared-memory cursors — so global atomics are O(CTAs * P), not O(rows).  Row order inside a
-// partition is unspecified.  Algorithmic bytes: 2 * row_bytes per row (+8 for the key re-read).
+// from shared-memory cursors — so global atomics are O(CTAs * P), not O(rows) — and stages every column through
+// shared memory in partition order so that the stores are coalesced runs.  Row order inside a partition is
+// unspecified.  Algorithmic bytes: 2 * row_bytes per row (+8 for the key re-read).
 #include "common.cuh"
 #include "dev_utils.cuh"
 
@@ -45,36 +46,58 @@ __global__ void __launch_bounds__(256) k_part_count(const void* __restrict__ key
     if (threadIdx.x < P && hist[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
 }
 
+// Tile sort in shared memory, then coalesced run stores: the 2048 rows of a tile are ranked per partition (shared-memory
+// atomics), every column is staged into shared memory in partition order and written out so that consecutive threads
+// store consecutive elements of a run (round 1 stored every row straight to its slot: 8-byte scattered stores, 0.40 of
+// the copy peak).  One global atomic per (tile, partition).
 __global__ void __launch_bounds__(256) k_part_scatter(PartArgs a, const uint32_t* __restrict__ valid, uint32_t* __restrict__ out_valid, int dtype, int64_t n, int P,
                                                       const unsigned long long* __restrict__ part_off, unsigned long long* __restrict__ cursor) {
-    __shared__ unsigned hist[P_MAX];
+    __shared__ unsigned hist[P_MAX], start[P_MAX];
     __shared__ unsigned long long base[P_MAX];
+    __shared__ uint64_t stage[P_TILE];
+    __shared__ uint8_t sp[P_TILE];                 // partition of every sorted slot
+    __shared__ uint8_t sv[P_TILE];                 // key validity of every sorted slot (nullable keys)
+    constexpr int RPT = P_TILE / 256;
     const int64_t ntiles = (n + P_TILE - 1) / P_TILE;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         if (threadIdx.x < P_MAX) hist[threadIdx.x] = 0;
         __syncthreads();
-        int p[P_TILE / 256]; unsigned local[P_TILE / 256];
+        int p[RPT]; unsigned local[RPT];
 #pragma unroll
-        for (int k = 0; k < P_TILE / 256; k++) {
+        for (int k = 0; k < RPT; k++) {
             const int64_t r = t * P_TILE + k * 256 + threadIdx.x;
-            p[k] = -1;
+            p[k] = -1; local[k] = 0;
             if (r < n) { p[k] = part_of(a.c[0].in, valid, dtype, r, P); local[k] = atomicAdd(&hist[p[k]], 1u); }
         }
         __syncthreads();
+        if (threadIdx.x == 0) { unsigned run = 0; for (int q = 0; q < P; q++) { start[q] = run; run += hist[q]; } }
         if (threadIdx.x < P && hist[threadIdx.x]) base[threadIdx.x] = part_off[threadIdx.x] + atomicAdd(&cursor[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
         __syncthreads();
+        const int rows = (int)min((int64_t)P_TILE, n - t * P_TILE);
 #pragma unroll
-        for (int k = 0; k < P_TILE / 256; k++) {
+        for (int k = 0; k < RPT; k++) {
             if (p[k] < 0) continue;
-            const int64_t r = t * P_TILE + k * 256 + threadIdx.x;
-            const uint64_t dst = base[p[k]] + local[k];
-            for (int c = 0; c < a.ncols; c++) {
-                if (a.c[c].elem == 8) reinterpret_cast<uint64_t*>(a.c[c].out)[dst] = reinterpret_cast<const uint64_t*>(a.c[c].in)[r];
-                else reinterpret_cast<uint32_t*>(a.c[c].out)[dst] = reinterpret_cast<const uint32_t*>(a.c[c].in)[r];
-            }
-            if (out_valid != nullptr && bit_get(valid, r)) atomicOr(&out_valid[dst >> 5], 1u << (dst & 31));
+            const unsigned pos = start[p[k]] + local[k];
+            sp[pos] = (uint8_t)p[k];
+            if (out_valid != nullptr) sv[pos] = bit_get(valid, t * P_TILE + k * 256 + threadIdx.x) ? 1 : 0;
         }
-        __syncthreads();
+        for (int c = 0; c < a.ncols; c++) {
+#pragma unroll
+            for (int k = 0; k < RPT; k++) {
+                if (p[k] < 0) continue;
+                const int64_t r = t * P_TILE + k * 256 + threadIdx.x;
+                stage[start[p[k]] + local[k]] = a.c[c].elem == 8 ? __ldcs(reinterpret_cast<const unsigned long long*>(a.c[c].in) + r) : (uint64_t)__ldcs(reinterpret_cast<const unsigned int*>(a.c[c].in) + r);
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < rows; i += 256) {
+                const unsigned q = sp[i];
+                const uint64_t dst = base[q] + (i - start[q]);
+                if (a.c[c].elem == 8) reinterpret_cast<uint64_t*>(a.c[c].out)[dst] = stage[i];
+                else reinterpret_cast<uint32_t*>(a.c[c].out)[dst] = (uint32_t)stage[i];
+                if (c == 0 && out_valid != nullptr && sv[i]) atomicOr(&out_valid[dst >> 5], 1u << (dst & 31));
+            }
+            __syncthreads();
+        }
     }
 }
 

@@ -633,7 +633,7 @@ def test_join_dtype_mismatch_is_compute_error(plb):
 
 
 def test_join_then_gather_materialises(plb, kats):
-    case = kats["join"][0]
+    case = next(c for c in kats["join"] if "payload_left" in c)
     lk = np.array(case["left_key"], np.int32)
     rk = np.array(case["right_key"], np.int32)
     (li, _), (ri, _) = plb.hash_join(lk, rk)
@@ -832,6 +832,7 @@ def test_full_join_vs_oracle(plb, nl, nr, krange, dups, key_dtype):
     lk = rng.integers(0, krange, nl).astype(key_dtype)
     rk = np.repeat(rng.permutation(max(krange, nr))[: max(nr // dups, 0)], dups)[:nr].astype(key_dtype)
     rng.shuffle(rk)
+    nr = rk.size
     lv = rng.random(nl) > 0.1
     rv = rng.random(nr) > 0.1
     for nulls_equal in ((False, True) if nl <= 3000 else (False,)):
@@ -960,3 +961,29 @@ def test_join_knob_variants(plb, monkeypatch, knob, value):
             (li, _), (ri, _) = plb.hash_join(plb.Column(lk, lv), plb.Column(rk, rv), how, False, "none")
             eli, eri = oracle.hash_join(lk, rk, lv, rv, how, False, "none", 4)
             assert np.array_equal(li, eli) and np.array_equal(ri, eri), (knob, value, how, dups)
+
+
+@pytest.mark.parametrize("val_dtype", ["float64", "float32", "int64", "int32", "int16"])
+def test_group_by_first_last_var_std(plb, val_dtype):
+    """Aggregations outside the fused set fold per group over GroupsIdx in row order (groupby_exact.cu): first / last incl.
+    nulls, Welford var / std with ddof (take_agg/var.rs:11-41) — bit-identical to the oracle's restatement."""
+    rng = np.random.default_rng(17)
+    n = 120_000
+    key = rng.integers(-300, 300, n).astype(np.int64)
+    kvalid = rng.random(n) > 0.02
+    if np.dtype(val_dtype).kind == "f":
+        x = (rng.normal(1e6, 3.0, n)).astype(val_dtype)       # large mean, small spread: the naive sum-of-squares formula would lose everything
+    else:
+        x = rng.integers(-30000, 30000, n).astype(val_dtype)
+    xvalid = rng.random(n) > 0.15
+    key[-5:] = 9999; xvalid[-5:] = False                      # an all-null group
+    aggs = [("first", x, xvalid), ("last", x, xvalid), ("var", x, xvalid), ("std:0", x, xvalid), ("var:2", x, None), ("mean", x, xvalid), ("len", None, None)]
+    keys, kv, outs = GpuImpl(plb).group_by_agg(key, kvalid, aggs, True)
+    ek, ekv, eouts, _ = oracle.group_by_agg(key, kvalid, aggs, 4, True)
+    assert_close(keys, ek, kv, ekv, "keys")
+    for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
+        assert v.dtype == ev.dtype, (kind, v.dtype, ev.dtype)
+        gv = np.ones(v.shape, bool) if m is None else m
+        xv = np.ones(ev.shape, bool) if em is None else em
+        assert np.array_equal(gv, xv), kind
+        assert np.array_equal(v[gv].view(np.uint8), ev[xv].view(np.uint8)), (kind, "not bit-identical")

@@ -364,3 +364,25 @@ def test_full_join_vs_bruteforce(nl, nr, krange, nulls_equal):
     probe_side = ri if not (nl > nr) else li
     k = int((probe_side != NUL).sum())
     assert (probe_side[:k] != NUL).all() and np.all(np.diff(probe_side[:k].astype(np.int64)) >= 0) and (probe_side[k:] == NUL).all()
+
+
+def test_first_last_var_std_vs_numpy():
+    """agg_first / agg_last / agg_var / agg_std restatements against numpy on every group (ddof 0, 1, 2; nulls; count <= ddof -> null)."""
+    rng = np.random.default_rng(8)
+    n = 30_000
+    key = rng.integers(0, 400, n).astype(np.int64)
+    x = rng.normal(1e5, 2.0, n); valid = rng.random(n) > 0.2
+    key[:3] = 10_000; valid[:3] = [True, False, False]          # a group with one valid value: var(ddof=1) is null, var(ddof=0) is 0
+    g = oracle.group_by(key, None, 4, True)
+    rows = [np.nonzero(key == k)[0] for k in key[g.first]]
+    f, fv = oracle.agg("first", x, valid, g); l, lv = oracle.agg("last", x, valid, g)
+    fv = np.ones(len(g), bool) if fv is None else fv; lv = np.ones(len(g), bool) if lv is None else lv
+    assert np.array_equal(fv, [valid[r[0]] for r in rows]) and np.array_equal(lv, [valid[r[-1]] for r in rows])
+    assert np.array_equal(f[fv], np.array([x[r[0]] for r in rows])[fv]) and np.array_equal(l[lv], np.array([x[r[-1]] for r in rows])[lv])
+    for ddof in (0, 1, 2):
+        var, vv = oracle.agg(f"var:{ddof}", x, valid, g); std, sv = oracle.agg(f"std:{ddof}", x, valid, g)
+        vv = np.ones(len(g), bool) if vv is None else vv
+        cnt = np.array([valid[r].sum() for r in rows])
+        assert np.array_equal(vv, cnt > ddof)
+        exp = np.array([np.var(x[r][valid[r]], ddof=ddof) if c > ddof else 0.0 for r, c in zip(rows, cnt)])
+        assert np.allclose(var[vv], exp[vv], rtol=1e-9, atol=0) and np.allclose(std[vv], np.sqrt(exp[vv]), rtol=1e-9, atol=0)
