@@ -11,6 +11,12 @@ namespace plb {
 #define PLB_RANDOM_ODD 0x55fbfd6bfc5458e9ULL
 __host__ __device__ __forceinline__ uint64_t dirty_hash(uint64_t k) { return k * PLB_RANDOM_ODD; }
 __device__ __forceinline__ uint32_t hash_to_partition(uint64_t h, uint32_t n) { return (uint32_t)__umul64hi(h, (uint64_t)n); }
+// Slot hash of every hash TABLE (group_by tables and buckets, join tables).  It must not be the partition hash: rows that
+// reach a GPU through hash_to_partition(dirty_hash(key), P) all carry the same top bits of key * RANDOM_ODD, so a table
+// slotted on those bits would use 1/P of its slots (measured: the 2-GPU partitioned join on sparse keys ran 1000x slower
+// on exactly full buckets).  The reference has the same separation: hash_to_partition(dirty_hash) picks the thread,
+// hashbrown + foldhash place the key inside the thread's table.
+__host__ __device__ __forceinline__ uint64_t table_hash(uint64_t k) { return (k ^ (k >> 31)) * 0x9E3779B97F4A7C15ULL; }
 
 // ---- float canonicalisation for keys: polars-utils/src/total_ord.rs:37-47 (-0 -> +0, one NaN)
 __device__ __forceinline__ uint64_t canonical_f64_bits(double x) {

@@ -82,7 +82,7 @@ __device__ __forceinline__ uint64_t* gb_resolve(const GbTableDev& T, uint64_t ke
     return nullptr;
 }
 __device__ __forceinline__ uint64_t* gb_find_or_insert(const GbTableDev& T, uint64_t key) {
-    const uint64_t slot = dirty_hash(key) >> T.shift;
+    const uint64_t slot = table_hash(key) >> T.shift;
     return gb_resolve(T, key, slot, __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + slot * T.es)), 0, 0);
 }
 __device__ __forceinline__ uint64_t* gb_special(const GbTableDev& T, int which) {
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
                 if (KEY_NULLS) kvalid = bit_get(B.key_validity, row);
                 key[r] = canon_key<KEY_CANON>(kraw[r]);
                 kind[r] = !kvalid ? 1 : (key[r] == GB_EMPTY ? 2 : 0);
-                const uint64_t hsh = dirty_hash(key[r]);
+                const uint64_t hsh = table_hash(key[r]);
                 // multi-pass mode (tables larger than L2): this launch only owns the slot sub-range `pass_id`
                 if (T.pass_bits && (kind[r] == 0 ? (int)(hsh >> (64 - T.pass_bits)) != T.pass_id : T.pass_id != 0)) kind[r] = -1;
                 if (kind[r] == 0) { slot[r] = hsh >> T.shift; k0[r] = tbl_load(T.entries + slot[r] * T.es, pol, khint); }
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
         bool kvalid = B.key_validity == nullptr || bit_get(B.key_validity, row);
         uint64_t key = load_key_rt(B.keys, B.key_dtype, row);
         const bool regular = kvalid && key != GB_EMPTY;
-        const bool mine = !T.pass_bits || (regular ? (int)(dirty_hash(key) >> (64 - T.pass_bits)) == T.pass_id : T.pass_id == 0);
+        const bool mine = !T.pass_bits || (regular ? (int)(table_hash(key) >> (64 - T.pass_bits)) == T.pass_id : T.pass_id == 0);
         uint64_t* e = !mine ? nullptr : (!kvalid ? gb_special(T, 0) : (key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key)));
         if (e) {
             if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + T.ws), 1u);
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) k_gb_consume_hot(const __grid_constant__ 
                 if (KEY_NULLS) kvalid = bit_get(B.key_validity, row);
                 key[r] = canon_key<KEY_CANON>(kraw[r]);
                 kind[r] = !kvalid ? 1 : (key[r] == GB_EMPTY ? 2 : 0);
-                const uint64_t hsh = dirty_hash(key[r]);
+                const uint64_t hsh = table_hash(key[r]);
                 if (T.pass_bits && (kind[r] == 0 ? (int)(hsh >> (64 - T.pass_bits)) != T.pass_id : T.pass_id != 0)) kind[r] = -1;
                 if (kind[r] == 0) {
                     unsigned hs = (unsigned)(hsh >> (64 - GB_HOT_BITS));
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(256) k_gb_consume_hot(const __grid_constant__ 
         bool kvalid = B.key_validity == nullptr || bit_get(B.key_validity, row);
         uint64_t key = load_key_rt(B.keys, B.key_dtype, row);
         const bool regular = kvalid && key != GB_EMPTY;
-        const bool mine = !T.pass_bits || (regular ? (int)(dirty_hash(key) >> (64 - T.pass_bits)) == T.pass_id : T.pass_id == 0);
+        const bool mine = !T.pass_bits || (regular ? (int)(table_hash(key) >> (64 - T.pass_bits)) == T.pass_id : T.pass_id == 0);
         uint64_t* e = !mine ? nullptr : (!kvalid ? gb_special(T, 0) : (key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key)));
         if (e) {
             if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + T.ws), 1u);
@@ -413,7 +413,7 @@ __global__ void k_gb_estimate(const void* keys, const uint32_t* key_validity, in
             uint64_t key = load_key_rt(keys, key_dtype, row);
             adj = row + 1 < n && load_key_rt(keys, key_dtype, row + 1) == key && (key_validity == nullptr || bit_get(key_validity, row + 1));
             if (key != GB_EMPTY) {
-                uint64_t slot = dirty_hash(key) >> shift;
+                uint64_t slot = table_hash(key) >> shift;
                 for (int pr = 0; pr < (int)cap; pr++) {
                     uint64_t k = __ldcg(reinterpret_cast<const unsigned long long*>(scratch + slot));
                     if (k == GB_EMPTY) {
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(512) k_gb_consume_smem(const __grid_constant__
                 se = stab + (scap + (kvalid ? 1 : 0)) * stride;
                 if (*reinterpret_cast<volatile uint64_t*>(se) == GB_EMPTY) atomicCAS(reinterpret_cast<unsigned long long*>(se), (unsigned long long)GB_EMPTY, kvalid ? 1ull : 0ull);
             } else {
-                uint32_t slot = (uint32_t)(dirty_hash(key) >> sshift);
+                uint32_t slot = (uint32_t)(table_hash(key) >> sshift);
                 for (int probes = 0; probes < 32; probes++) {
                     uint64_t* e = stab + slot * stride;
                     const uint64_t k = *reinterpret_cast<volatile uint64_t*>(e);
@@ -989,7 +989,7 @@ void GroupByState::build_hot_list(const void* cand_v, int n_cand, bool null_hot,
     unsigned char* hi = h.data() + GB_HOT_SLOTS * 8;
     for (int i = 0; i < GB_HOT_SLOTS; i++) hk[i] = GB_EMPTY;
     for (int i = 0; i < n_hot; i++) {
-        unsigned sl = (unsigned)(dirty_hash(c[i].key) >> (64 - GB_HOT_BITS));
+        unsigned sl = (unsigned)(table_hash(c[i].key) >> (64 - GB_HOT_BITS));
         while (hk[sl] != GB_EMPTY) sl = (sl + 1) & (GB_HOT_SLOTS - 1);
         hk[sl] = c[i].key; hi[sl] = (unsigned char)i;
     }
@@ -1276,7 +1276,7 @@ void GroupByState::consume_all(const DevCol& key, const std::vector<const DevCol
     PLB_REQUIRE(key.dtype == key_dtype, BL_ERR_DTYPE, "group_by: key dtype differs from the plan");
     PLB_REQUIRE(key.len <= 0xFFFFFFFEll, BL_ERR_UNSUPPORTED, "group_by: more than 2^32-2 rows (IdxSize = u32)");
     uint64_t c = choose_cap(key, key.len);
-    if (consume_radix(key, values)) return;      // tables beyond L2: partition the rows instead (groupby_radix.cu)
+    if (consume_radix(key, values, c)) return;      // tables beyond L2: partition the rows instead (groupby_radix.cu)
     for (int attempt = 0; attempt < 8; attempt++) {
         alloc_table(c);
         launch_batch(key, values, 0);
@@ -1515,7 +1515,7 @@ __global__ void __launch_bounds__(256) k_gb_lookup_first(const __grid_constant__
         if (!kvalid) slot = T.cap;
         else if (key == GB_EMPTY) slot = T.cap + 1;
         else {
-            slot = dirty_hash(key) >> T.shift;
+            slot = table_hash(key) >> T.shift;
             for (int probes = 0; probes < GB_MAX_PROBE; ++probes) {
                 if (__ldcg(reinterpret_cast<const unsigned long long*>(T.entries + slot * T.es)) == key) break;
                 slot = (slot + 1) & mask;

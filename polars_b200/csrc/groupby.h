@@ -64,7 +64,7 @@ struct GroupByState {
 
     GroupByState(int key_dt, const std::vector<int>& kinds, const std::vector<int>& dtypes, const std::vector<int>& nullable, int64_t expected, bool track_first);
     void consume_all(const DevCol& key, const std::vector<const DevCol*>& values);
-    bool consume_radix(const DevCol& key, const std::vector<const DevCol*>& values);   // partitioned plan (tables beyond L2); false = not applicable
+    bool consume_radix(const DevCol& key, const std::vector<const DevCol*>& values, uint64_t planned_cap);   // partitioned plan (tables beyond L2); false = not applicable
     GbDense dense;               // set by consume_radix: finish() takes the groups from here, there is no table
     void consume_pipelined(const DevCol& key, const std::vector<const DevCol*>& values, int64_t chunk_rows, const std::vector<cudaEvent_t>& ready);
     void consume(const DevCol& key, const std::vector<const DevCol*>& values, int64_t row_base);

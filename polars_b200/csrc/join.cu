@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) k_join_build(JoinTableDev T, const void* 
             const uint64_t key = j_load_key(keys, key_dtype, r);
             if (key == J_EMPTY) { b = T.nb; j = 1; atomicCAS(&T.buckets[b].key[1], (unsigned long long)J_EMPTY, 1ull); }
             else {
-                b = __umul64hi(dirty_hash(key), T.nb);
+                b = __umul64hi(table_hash(key), T.nb);
                 j = 0;
                 while (true) {
                     bool found = false;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) k_jc_build(uint32_t* __restrict__ tab, ui
             continue;
         }
         const uint64_t key = j_bkey<KEY_ELEM, KEY_CANON>(keys, (uint32_t)r);
-        const uint64_t h = dirty_hash(key);
+        const uint64_t h = table_hash(key);
         uint32_t slot = (uint32_t)(h >> shift);
         const uint32_t fp = (uint32_t)(h >> (shift - 8)) & 0xFFu;
         const uint32_t mine = fp_mode ? ((fp << 24) | (uint32_t)r) : (uint32_t)r;
@@ -300,7 +300,7 @@ __device__ __forceinline__ uint32_t j_lookup(const JoinDev& J, uint64_t kraw, bo
             j = valid ? 1 : 0;
             if (((uint32_t)(cc >> (32 * j))) == 0) return J_NONE;
         } else {
-            uint64_t b = __umul64hi(dirty_hash(key), J.W.nb);
+            uint64_t b = __umul64hi(table_hash(key), J.W.nb);
             while (true) {
                 j_load_bucket(J.W.buckets + b, k0, k1, vv, cc);
                 if (k0 == key) { j = 0; break; }
@@ -319,7 +319,7 @@ __device__ __forceinline__ uint32_t j_lookup(const JoinDev& J, uint64_t kraw, bo
         slot = J.ccap; row = __ldg(J.tab + slot);
         if (row == J_NONE) return J_NONE;
     } else {
-        const uint64_t h = dirty_hash(key);
+        const uint64_t h = table_hash(key);
         slot = (uint32_t)(h >> J.cshift);
         const uint32_t fp = (uint32_t)(h >> (J.cshift - 8)) & 0xFFu;
         while (true) {
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(256) k_join_probe_emit(const __grid_constant__
                     const bool v = valid == nullptr || bit_get(valid, row);
                     if (!v) { if (J.nulls_equal) h[j] = __ldg(J.tab + J.ccap); continue; }
                     key[u] = j_canon<KEY_CANON>(kraw[j]);
-                    const uint64_t hs = dirty_hash(key[u]);
+                    const uint64_t hs = table_hash(key[u]);
                     slot[u] = (uint32_t)(hs >> J.cshift); fp[u] = (uint32_t)(hs >> (J.cshift - 8)) & 0xFFu;
                     e[u] = __ldg(J.tab + slot[u]);
                     st[u] = 2;

@@ -192,25 +192,24 @@ def all_to_all_1d(send: torch.Tensor, send_counts: np.ndarray):
 
 def partitioned_hash_join(plb, left_key, right_key, left_base: int, right_base: int, how: str = "inner"):
     """Partitioned inner/left hash join on P GPUs: both sides are hash-partitioned on the key
-    (K6, the reference's partition function), exchanged with one all-to-all-v per relation, joined locally
-    (K7/K8) and mapped back to GLOBAL row ids (K4).  left_key/right_key: device Columns of this rank's rows;
-    *_base: global index of this rank's first row.  Returns (left_global_idx, right_global_idx) as torch
-    uint32-valued int32 tensors; the output is partitioned by key."""
+    (K6, the reference's partition function), exchanged with ONE count exchange + one all-to-all-v per column and
+    relation, joined locally (K7/K8) and mapped back to GLOBAL row ids (K4).  left_key/right_key: device Columns of this
+    rank's rows; *_base: global index of this rank's first row.  Returns (left_global_idx, right_global_idx) device
+    columns; the output is partitioned by key."""
     world = dist.get_world_size()
     sides = []
     for key, base in ((left_key, left_base), (right_key, right_base)):
         n = key.length
-        gid = (torch.arange(n, dtype=torch.int64, device="cuda") + base).to(torch.int32)   # u32 bit pattern
-        torch.cuda.synchronize()
+        gid = torch.arange(base, base + n, dtype=torch.int32, device="cuda") if base + n < 2**31 else (torch.arange(n, dtype=torch.int64, device="cuda") + base).to(torch.int32)
+        torch.cuda.current_stream().synchronize()
         gcol = plb.Column(gid.data_ptr(), dtype=np.uint32, length=n, location=plb.DEVICE)
         kp, [gp], offs = plb.hash_partition(key, [gcol], world, location=plb.DEVICE)
         counts = np.diff(offs)
         kt = _as_torch(kp, n, "<i8", torch.int64)
         gt = _as_torch(gp, n, "<i4", torch.int32)
-        rk, _ = all_to_all_1d(kt, counts)
-        rg, _ = all_to_all_1d(gt, counts)
-        torch.cuda.synchronize()
+        (rk, rg), _ = exchange_columns([kt, gt], counts)
         sides.append((rk, rg, kp, gp))
+    torch.cuda.synchronize()
     (lk, lg, *_), (rk, rg, *_) = sides
     lcol = plb.Column(lk.data_ptr(), dtype=np.int64, length=lk.numel(), location=plb.DEVICE)
     rcol = plb.Column(rk.data_ptr(), dtype=np.int64, length=rk.numel(), location=plb.DEVICE)

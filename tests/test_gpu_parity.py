@@ -1,6 +1,8 @@
 """GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on
 the same seeded inputs, the reference's golden vectors, and size-independent properties.
 Integer / index results must be bit-exact; float aggregates within 1e-6 relative."""
+import os
+
 import numpy as np
 import pytest
 
@@ -987,3 +989,42 @@ def test_group_by_first_last_var_std(plb, val_dtype):
         xv = np.ones(ev.shape, bool) if em is None else em
         assert np.array_equal(gv, xv), kind
         assert np.array_equal(v[gv].view(np.uint8), ev[xv].view(np.uint8)), (kind, "not bit-identical")
+
+
+def test_pdsh_q1_from_the_reference_schema(plb):
+    """PDS-H Q1 on the reference's own lineitem sample (examples/datasets/pds_heads/lineitem.feather -> tests/golden/
+    pdsh_lineitem_head.json): string flags enter as dictionary codes (the physical representation Polars groups
+    Categorical / Enum keys on), the timestamp[us] ship date as Int64, quantity as Int64 — filter (K2+K3), expressions (K1),
+    two-column group_by (K5) — against a direct numpy evaluation of the query."""
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "pdsh_lineitem_head.json")) as f:
+        li = json.load(f)["columns"]
+    qty = np.array(li["l_quantity"], np.int64); price = np.array(li["l_extendedprice"]); disc = np.array(li["l_discount"]); tax = np.array(li["l_tax"])
+    ship = np.array(li["l_shipdate"], np.int64)
+    rf_dict, rf = np.unique(np.array(li["l_returnflag"]), return_inverse=True)      # dictionary encoding on the host
+    ls_dict, ls = np.unique(np.array(li["l_linestatus"]), return_inverse=True)
+    rf, ls = rf.astype(np.uint32), ls.astype(np.uint32)
+    cutoff = np.int64((np.datetime64("1998-09-02") - np.datetime64("1970-01-01")) // np.timedelta64(1, "us"))
+    D = plb.DEVICE
+    f_ = plb.filter_cmp([ship, qty, price, disc, tax, rf, ls], 0, "le", cutoff, location=D)
+    _, fq, fp, fd, ft, frf, fls = f_
+    one_minus = plb.elementwise("sub", np.array([1.0]), fd.view(), location=D)
+    disc_price = plb.elementwise("mul", fp.view(), one_minus.view(), location=D)
+    charge = plb.elementwise("mul", disc_price.view(), plb.elementwise("add", ft.view(), np.array([1.0]), location=D).view(), location=D)
+    kouts, outs = plb.group_by_agg_keys([frf.view(), fls.view()], [("sum", fq.view()), ("sum", fp.view()), ("sum", disc_price.view()), ("sum", charge.view()),
+                                                                     ("mean", fq.view()), ("mean", fp.view()), ("mean", fd.view()), ("len", None)], True)
+    m = ship <= cutoff
+    seen, exp = [], {}
+    for i in np.nonzero(m)[0]:
+        k = (int(rf[i]), int(ls[i]))
+        if k not in exp:
+            seen.append(k); exp[k] = []
+        exp[k].append(i)
+    assert [(int(a), int(b)) for a, b in zip(kouts[0][0], kouts[1][0])] == seen
+    dp = price * (1.0 - disc); ch = dp * (tax + 1.0)
+    for g, k in enumerate(seen):
+        r = np.array(exp[k])
+        assert outs[0][0][g] == qty[r].sum() and outs[7][0][g] == r.size
+        for o, ref in ((1, price[r].sum()), (2, dp[r].sum()), (3, ch[r].sum()), (4, qty[r].mean()), (5, price[r].mean()), (6, disc[r].mean())):
+            assert abs(outs[o][0][g] - ref) <= 1e-9 * abs(ref), (o, k)
+    assert [str(rf_dict[a]) + str(ls_dict[b]) for a, b in seen] == ["NO", "RF", "AF"]      # the groups of the sample, first-occurrence order
