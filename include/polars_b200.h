@@ -293,6 +293,14 @@ bl_status bl_groupby_status(bl_groupby* g, int32_t* status_out);
 /* Sampled cardinality estimate of the consumed batches (0 before the first consume; no synchronisation). */
 int64_t bl_groupby_estimated_groups(bl_groupby* g);
 
+/* One rank's whole step of the partitioned group_by in ONE call (what polars_b200/dist.py composes from the pieces above):
+ * local pre-aggregation of (key, aggs) -> bl_groupby_export_partials_p2p_async into the peers' window halves -> merge of this
+ * rank's own half -> finish.  The outputs are the groups this rank owns (hash_to_partition(dirty_hash(key), n_ranks) ==
+ * my_rank).  peer_halves[p] / own_half / rows_per_src / epoch as for the two calls it fuses; value columns one chunk each. */
+bl_status bl_groupby_agg_partitioned(const bl_column* key, const bl_agg* aggs, int32_t n_aggs, int32_t n_ranks, int32_t my_rank,
+                                     void* const* peer_halves, const void* own_half, int64_t rows_per_src, uint64_t epoch,
+                                     int64_t expected_groups, int32_t out_location, bl_column* out_key, bl_column* out_aggs);
+
 /* ---- profiling (CUDA events on the library stream) -------------------------------------- */
 /* enable != 0: every kernel launch is bracketed by events; totals accumulate per kernel name. */
 void bl_profile_enable(int32_t enable);

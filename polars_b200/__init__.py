@@ -401,6 +401,34 @@ def group_by_agg(key, aggs: Sequence, maintain_order: bool = False, location: in
     return res[0], res[1:]
 
 
+def group_by_agg_partitioned(key, aggs: Sequence, my_rank: int, peer_halves: Sequence[int], own_half: int, rows_per_src: int, epoch: int,
+                             expected_groups: int = 0, location: int = HOST):
+    """One rank's step of the multi-GPU group_by in one C call (bl_groupby_agg_partitioned): local pre-aggregation, fused
+    partition + P2P exchange, merge of the rows this rank owns, finish.  aggs as in group_by_agg (one chunk per column)."""
+    k = _as_col(key)
+    ks = k.struct()
+    keep, agg_structs, cache = [], [], {}
+    for kind, vals in aggs:
+        if kind == "len" or vals is None:
+            agg_structs.append(BlAgg(_agg_kind(kind), 0, None))
+            continue
+        ident = id(vals)
+        if ident not in cache:
+            chunks = [_as_col(vals)]
+            cache[ident] = (chunks, _col_array(chunks))
+        chunks, arr = cache[ident]
+        keep.append((chunks, arr))
+        agg_structs.append(BlAgg(_agg_kind(kind), 1, C.cast(arr, C.POINTER(BlColumn))))
+    aarr = (BlAgg * max(len(agg_structs), 1))(*agg_structs)
+    n = len(peer_halves)
+    parr = (C.c_void_p * n)(*[C.c_void_p(w) for w in peer_halves])
+    out_key, out_aggs = BlColumn(), (BlColumn * max(len(agg_structs), 1))()
+    _check(lib().bl_groupby_agg_partitioned(C.byref(ks), aarr, C.c_int32(len(agg_structs)), C.c_int32(n), C.c_int32(my_rank), parr, C.c_void_p(own_half),
+                                            C.c_int64(rows_per_src), C.c_uint64(epoch), C.c_int64(expected_groups), C.c_int32(location), C.byref(out_key), out_aggs))
+    res = _finish([out_key] + list(out_aggs)[: len(agg_structs)], location)
+    return res[0], res[1:]
+
+
 def group_by_agg_keys(keys: Sequence, aggs: Sequence, maintain_order: bool = False, location: int = HOST):
     """Several key columns (one chunk each); aggs as in group_by_agg.  Returns ([key_outs], [agg_outs])."""
     kcols = [_as_col(c) for c in keys]

@@ -443,6 +443,44 @@ bl_status bl_groupby_status(bl_groupby* g, int32_t* status_out) {
 }
 int64_t bl_groupby_estimated_groups(bl_groupby* g) { return g ? g->st->est_groups : 0; }
 
+bl_status bl_groupby_agg_partitioned(const bl_column* key, const bl_agg* aggs, int32_t n_aggs, int32_t n_ranks, int32_t my_rank, void* const* peer_halves, const void* own_half,
+                                     int64_t rows_per_src, uint64_t epoch, int64_t expected_groups, int32_t out_location, bl_column* out_key, bl_column* out_aggs) {
+    BL_TRY
+    PLB_REQUIRE(key && out_key && peer_halves && own_half && (n_aggs == 0 || (aggs && out_aggs)), BL_ERR_INVALID, "groupby_agg_partitioned: null argument");
+    DevCol k = import_column(key, 1);
+    std::vector<int> kinds, dts, nullable(n_aggs, 0);
+    std::vector<DevCol> vals(n_aggs);
+    std::vector<const DevCol*> vptr(n_aggs, nullptr);
+    for (int i = 0; i < n_aggs; i++) {
+        kinds.push_back(aggs[i].kind);
+        if (aggs[i].kind == BL_AGG_LEN) { dts.push_back(BL_INT64); continue; }
+        PLB_REQUIRE(aggs[i].values && aggs[i].n_chunks >= 1, BL_ERR_INVALID, "groupby_agg_partitioned: aggregation without a value column");
+        int dup = -1;
+        for (int j = 0; j < i; j++) if (aggs[j].kind != BL_AGG_LEN && aggs[j].values == aggs[i].values) { dup = j; break; }
+        if (dup >= 0) vals[i] = vals[dup]; else vals[i] = import_column(aggs[i].values, aggs[i].n_chunks);
+        vptr[i] = &vals[i];
+        dts.push_back(vals[i].dtype);
+        nullable[i] = vals[i].validity != nullptr;
+    }
+    // local pre-aggregation (overflow check deferred to the end of the step: no host round trip before the exchange)
+    GroupByState local(k.dtype, kinds, dts, nullable, expected_groups, false);
+    local.defer_status = true;
+    local.consume(k, vptr, 0);
+    int rw = 0;
+    local.export_partials_p2p_async(n_ranks, my_rank, peer_halves, rows_per_src, epoch, &rw);
+    // the owner's table: the groups of one rank's worth of rows when the ranks share a key domain, up to the local group count when they do not
+    const int64_t est = std::max<int64_t>(std::max<int64_t>(local.est_groups, expected_groups), 1024);
+    GroupByState owner(k.dtype, kinds, dts, nullable, est + est / 4 + 1024, false);
+    owner.merge_window_async(own_half, n_ranks, rows_per_src, epoch);
+    DevCol ok; std::vector<DevCol> oa;
+    owner.finish(false, nullptr, ok, oa);
+    PLB_REQUIRE(local.read_status() == 0, BL_ERR_OOM, "groupby_agg_partitioned: the local pre-aggregation table overflowed — pass expected_groups");
+    { std::vector<DevCol> all{ok}; all.insert(all.end(), oa.begin(), oa.end());
+      std::vector<bl_column> t(all.size()); export_many(all, out_location, t.data());
+      *out_key = t[0]; for (int i = 0; i < n_aggs; i++) out_aggs[i] = t[i + 1]; }
+    BL_CATCH
+}
+
 // ---- peer windows (CUDA IPC) -------------------------------------------------------------------
 struct bl_window { void* p; size_t bytes; };
 bl_status bl_window_create(size_t bytes, bl_window** out, void* ipc_handle_out) {

@@ -822,25 +822,37 @@ __global__ void __launch_bounds__(256) k_gb_export_p2p_async(const uint64_t* __r
     __shared__ unsigned hist[EXP_MAX_PARTS];
     __shared__ unsigned long long base[EXP_MAX_PARTS];
     __shared__ unsigned s_last;
+    constexpr int SPT = 4, TILE = 256 * SPT;          // 1024 slots per reservation round (one global atomic per (round, partition))
     const int row_words = n_words + 3;
     const int64_t n_entries = cap + 2;
-    const int64_t ntiles = (n_entries + 255) / 256;
+    const int64_t ntiles = (n_entries + TILE - 1) / TILE;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         if (threadIdx.x < EXP_MAX_PARTS) hist[threadIdx.x] = 0;
         __syncthreads();
-        const int64_t s = t * 256 + threadIdx.x;
-        uint64_t key = GB_EMPTY; int p = 0; unsigned local = 0;
-        if (s < n_entries) key = entries[s * es];
-        if (key != GB_EMPTY) { p = gb_row_partition(key, s, cap, P); local = atomicAdd(&hist[p], 1u); }
+        uint64_t key[SPT]; int p[SPT]; unsigned local[SPT];
+#pragma unroll
+        for (int u = 0; u < SPT; u++) {
+            const int64_t s = t * TILE + u * 256 + threadIdx.x;
+            key[u] = s < n_entries ? entries[s * es] : GB_EMPTY;
+        }
+#pragma unroll
+        for (int u = 0; u < SPT; u++) {
+            const int64_t s = t * TILE + u * 256 + threadIdx.x;
+            p[u] = 0; local[u] = 0;
+            if (key[u] != GB_EMPTY) { p[u] = gb_row_partition(key[u], s, cap, P); local[u] = atomicAdd(&hist[p[u]], 1u); }
+        }
         __syncthreads();
         if (threadIdx.x < P && hist[threadIdx.x]) base[threadIdx.x] = atomicAdd(&part_cursor[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
         __syncthreads();
-        if (key != GB_EMPTY) {
-            const uint64_t pos = base[p] + local;
+#pragma unroll
+        for (int u = 0; u < SPT; u++) {
+            if (key[u] == GB_EMPTY) continue;
+            const int64_t s = t * TILE + u * 256 + threadIdx.x;
+            const uint64_t pos = base[p[u]] + local[u];
             if ((int64_t)pos < rows_per_src) {
                 const uint64_t* e = entries + s * es;
-                uint64_t* dst = W.base[p] + GB_WINDOW_HEADER_WORDS + (int64_t)my_rank * region_words + pos * row_words;     // peer store
-                dst[0] = s == cap ? 0 : (s == cap + 1 ? GB_EMPTY : key);
+                uint64_t* dst = W.base[p[u]] + GB_WINDOW_HEADER_WORDS + (int64_t)my_rank * region_words + pos * row_words;     // peer store
+                dst[0] = s == cap ? 0 : (s == cap + 1 ? GB_EMPTY : key[u]);
                 dst[1] = e[ws];
                 for (int w = 0; w < n_words; w++) dst[2 + w] = e[(2 + w) * ws];
                 dst[2 + n_words] = s == cap ? 1 : (s == cap + 1 ? 2 : 0);
@@ -1404,7 +1416,7 @@ void GroupByState::export_partials_p2p_async(int n_ranks, int my_rank, void* con
     if (!entries) alloc_table(1024);          // nothing consumed: still publish zero counts so that no peer waits
     DevPtr ctl = dev_alloc(8 * EXP_MAX_PARTS + 8);
     dev_memset(ctl->p, 0, 8 * EXP_MAX_PARTS + 8);
-    PLB_LAUNCH("k6_export_p2p", k_gb_export_p2p_async, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, L.n_words, n_ranks, W,
+    PLB_LAUNCH("k6_export_p2p", k_gb_export_p2p_async, grid_for(((int64_t)cap + 2 + 3) / 4, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, L.n_words, n_ranks, W,
                rows_per_src * row_words, my_rank, rows_per_src, as<unsigned long long>(ctl), reinterpret_cast<unsigned*>(as<unsigned long long>(ctl) + EXP_MAX_PARTS), epoch);
 }
 

@@ -151,26 +151,14 @@ class PeerExchange:
 def partitioned_group_by_p2p(plb, ex: PeerExchange, key_col, value_cols, spec, location=None, nullable=None, expected_groups: int = 0):
     """Same plan as partitioned_group_by, but the partial aggregates reach their owner by P2P stores from inside
     the partition kernel and the owner's merge kernel picks the row counts up from its window header on the
-    device: local K5 -> export (stores + publish) -> merge (wait + merge) -> finish are queued back to back;
-    the only host synchronisations of the step are the cardinality sample of the local K5 and the final read-back
-    of the group count.  Errors of the deferred checks (local table overflow, peer region overflow, peer timeout)
-    are raised at the end of the step."""
-    g = plb.GroupBy(plb.NP_OF[key_col.dtype], spec, nullable=nullable, expected_groups=expected_groups)
-    g.defer_status(True)
-    g.consume(key_col, value_cols, row_base=0)
+    device: local K5 -> export (stores + publish) -> merge (wait + merge) -> finish are queued back to back by ONE
+    library call (bl_groupby_agg_partitioned); the only host synchronisations of the step are the cardinality sample of
+    the local K5 and the final read-back of the group count.  Errors of the deferred checks (local table overflow, peer
+    region overflow, peer timeout) are raised at the end of the step.  spec: [(kind, dtype | None)], value_cols aligned."""
     epoch = ex.next_step()
-    rw = g.export_partials_p2p_async(ex.peer_halves(), ex.rank, ex.rows_per_src, epoch)
-    assert rw == ex.row_words
-    # the owner's table: at most the groups of one rank's worth of rows land here when the ranks share a key domain,
-    # up to the local group count when they do not
-    est = max(g.estimated_groups(), expected_groups, 1024)
-    f = plb.GroupBy(plb.NP_OF[key_col.dtype], spec, expected_groups=int(est * 1.3) + 1024, nullable=nullable)
-    f.merge_window_async(ex.own_half(), ex.world, ex.rows_per_src, epoch)
-    out = f.finish(False, location=plb.DEVICE if location is None else location)
-    st = g.status()
-    if st != 0:
-        raise plb.B200Error(3, f"partitioned group_by: local pre-aggregation table overflowed (status {st}); pass expected_groups")
-    return out
+    aggs = [(kind, v) for (kind, _), v in zip(spec, value_cols)]
+    return plb.group_by_agg_partitioned(key_col, aggs, ex.rank, ex.peer_halves(), ex.own_half(), ex.rows_per_src, epoch, expected_groups,
+                                        location=plb.DEVICE if location is None else location)
 
 
 class _CudaArr:
