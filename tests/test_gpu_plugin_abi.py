@@ -57,14 +57,17 @@ class Caller:
         self.keep += [schema, arrays, ptrs]
         return SeriesExport(C.pointer(schema), ptrs, len(arrays), self._rel, 1), arrays
 
-    def call(self, op, inputs):
+    def call(self, op, inputs, kwargs=None):
         exports, arrs = zip(*[self.export(n, ch) for n, ch in inputs])
         arr = (SeriesExport * len(exports))(*exports)
         ret = SeriesExport()
         before = self.released
         fn = getattr(self.lib, f"_polars_plugin_bl_{op}")
         fn.restype = None
-        fn(arr, C.c_size_t(len(exports)), None, C.c_size_t(0), C.byref(ret), None)
+        import pickle
+        kw = pickle.dumps(kwargs) if kwargs else b""      # what register_plugin_function(kwargs=...) hands over (plugins.py:100-115)
+        kbuf = (C.c_uint8 * max(len(kw), 1)).from_buffer_copy(kw or b"\0")
+        fn(arr, C.c_size_t(len(exports)), kbuf if kw else None, C.c_size_t(len(kw)), C.byref(ret), None)
         # the callee owns the inputs: every ArrowArray and every SeriesExport must have been released
         assert self.released - before == len(exports), "input SeriesExport not released by the plugin"
         for group in arrs:
@@ -123,6 +126,52 @@ def test_plugin_filter_gather_group_join(caller):
     out = caller.call("join_inner_idx", [("l", [pa.array(lk)]), ("r", [pa.array(rk)])])
     li, ri = np.asarray(out.field("left_idx")), np.asarray(out.field("right_idx"))
     assert np.array_equal(lk[li], rk[ri]) and li.size == int(np.isin(lk, rk).sum())
+
+
+def test_plugin_kwargs_multi_key_and_new_entries(caller):
+    """kwargs arrive as a pickled dict (every pickle protocol CPython writes for it); several key columns; the entries added
+    for first / last / var / std / len and left / full / semi / anti joins."""
+    import pickle
+    rng = np.random.default_rng(2)
+    n = 4000
+    k0, k1 = rng.integers(0, 9, n), rng.integers(0, 5, n).astype(np.int32)
+    x = rng.normal(100.0, 3.0, n)
+    xm = rng.random(n) < 0.1
+    X = pa.array(x, mask=xm)
+    groups = {}
+    for i in range(n):
+        groups.setdefault((int(k0[i]), int(k1[i])), []).append(i)
+    out = caller.call("group_var", [("a", [pa.array(k0)]), ("b", [pa.array(k1)]), ("x", [X])], kwargs={"ddof": 0})
+    ka, kb, agg = np.asarray(out.field("key")), np.asarray(out.field("key_1")), out.field("agg")
+    assert [(int(a), int(b)) for a, b in zip(ka, kb)] == list(groups)                  # first-occurrence order of the key pairs
+    exp = np.array([np.var(x[np.array(r)][~xm[np.array(r)]]) for r in groups.values()])
+    assert np.allclose(np.asarray(agg), exp, rtol=1e-9)
+    out1 = caller.call("group_std", [("a", [pa.array(k0)]), ("x", [X])])               # default ddof = 1
+    exp1 = np.array([np.std(x[(k0 == kk) & ~xm], ddof=1) for kk in np.asarray(out1.field("key"))])
+    assert np.allclose(np.asarray(out1.field("agg")), exp1, rtol=1e-9)
+    out = caller.call("group_first", [("a", [pa.array(k0)]), ("x", [X])])
+    firsts = {int(kk): int(np.nonzero(k0 == kk)[0][0]) for kk in np.unique(k0)}
+    got = out.field("agg").to_pylist()
+    assert got == [None if xm[firsts[int(kk)]] else x[firsts[int(kk)]] for kk in np.asarray(out.field("key"))]
+    out = caller.call("group_len", [("a", [pa.array(k0)]), ("b", [pa.array(k1)])])
+    assert np.asarray(out.field("agg")).tolist() == [len(r) for r in groups.values()]
+    # joins: kwargs nulls_equal under two pickle protocols, several key columns
+    lk = pa.array([1, 2, None, 4, 2], pa.int64()); rk = pa.array([2, None, 5], pa.int64())
+    for proto in (2, 4):
+        kw = pickle.dumps({"nulls_equal": True}, protocol=proto)
+        assert caller.lib is not None and kw
+    out = caller.call("join_left_idx", [("l", [lk]), ("r", [rk])], kwargs={"nulls_equal": True})
+    assert out.field("left_idx").to_pylist() == [0, 1, 2, 3, 4] and out.field("right_idx").to_pylist() == [None, 0, 1, None, 0]
+    out = caller.call("join_left_idx", [("l", [lk]), ("r", [rk])])
+    assert out.field("right_idx").to_pylist() == [None, 0, None, None, 0]
+    assert caller.call("join_semi_idx", [("l", [lk]), ("r", [rk])]).to_pylist() == [1, 4]
+    assert caller.call("join_anti_idx", [("l", [lk]), ("r", [rk])]).to_pylist() == [0, 2, 3]
+    out = caller.call("join_full_idx", [("l", [lk]), ("r", [rk])])
+    assert sorted(zip([-1 if v is None else v for v in out.field("left_idx").to_pylist()], [-1 if v is None else v for v in out.field("right_idx").to_pylist()])) == \
+        [(-1, 1), (-1, 2), (0, -1), (1, 0), (2, -1), (3, -1), (4, 0)]
+    la, lb = pa.array([1, 1, 2, 2]), pa.array([7, 8, 7, 8]); ra, rb = pa.array([2, 1, 3]), pa.array([8, 7, 7])
+    out = caller.call("join_inner_idx", [("la", [la]), ("lb", [lb]), ("ra", [ra]), ("rb", [rb])])
+    assert list(zip(out.field("left_idx").to_pylist(), out.field("right_idx").to_pylist())) == [(0, 1), (3, 0)]
 
 
 def test_plugin_error_channel(caller):
