@@ -498,11 +498,19 @@ def bench_join(H: Harness, sparse: bool):
     if world > 1:
         from polars_b200 import dist as pdist
 
+    plan = "single GPU" if world == 1 else pdist.choose_join_plan(a.rows, a.build_rows, world)
+
+    def run_plan(which, pc, bc):
+        """One step of a multi-GPU join plan on device key columns -> (left, right) global row-id columns."""
+        if which == "broadcast":
+            return pdist.broadcast_hash_join(plb, pc, bc, rank * a.rows)
+        return pdist.partitioned_hash_join(plb, pc, bc, rank * a.rows, rank * a.build_rows)
+
     def step_device():
         if world == 1:
             li, ri = plb.hash_join(dp.view(), db.view(), "inner", False, "none", location=plb.DEVICE)
             return li.length
-        gl, gr = pdist.partitioned_hash_join(plb, dp.view(), db.view(), rank * a.rows, rank * a.build_rows)
+        gl, gr = run_plan(plan, dp.view(), db.view())
         return gl.length
 
     def step_e2e():
@@ -510,7 +518,7 @@ def bench_join(H: Harness, sparse: bool):
             (li, _), (ri, _) = plb.hash_join(plb.Column(hp), plb.Column(hb), "inner", False, "none", location=plb.HOST)
             return li.size, li.nbytes + ri.nbytes
         cp, cb = plb.to_device(hp), plb.to_device(hb)
-        gl, gr = pdist.partitioned_hash_join(plb, cp.view(), cb.view(), rank * a.rows, rank * a.build_rows)
+        gl, gr = run_plan(plan, cp.view(), cb.view())
         l, r_ = gl.to_numpy()[0], gr.to_numpy()[0]
         return l.size, l.nbytes + r_.nbytes
 
@@ -520,7 +528,7 @@ def bench_join(H: Harness, sparse: bool):
             (li, _), (ri, _) = plb.hash_join(dp.view(), db.view(), "inner", False, "none", location=plb.HOST)
             verified = verify_join(probe, build, li, ri, a.dup)
         else:
-            gl, gr = pdist.partitioned_hash_join(plb, dp.view(), db.view(), rank * a.rows, rank * a.build_rows)
+            gl, gr = run_plan(plan, dp.view(), db.view())
             n_pairs = H.sum_over_ranks(gl.length)
             exp = a.rows * world * a.dup if a.hit_frac >= 1.0 else None
             assert exp is None or n_pairs == exp, f"{n_pairs} join tuples over all ranks, expected {exp}"
@@ -540,23 +548,26 @@ def bench_join(H: Harness, sparse: bool):
     r = H.measure(step_device, step_e2e if a.e2e_steps > 0 else None, a.rows, alg, pick, f"join:{'sparse' if sparse else 'dense'}:{a.rows}:{a.build_rows}")
     r["e2e"]["h2d_bytes_per_step"] = int((a.rows + a.build_rows) * 8)
     r["e2e"]["path"] = ("bl_hash_join with BL_HOST columns in pinned memory -> BL_HOST index columns" if world == 1 else
-                        "pinned host key columns -> device -> partitioned join (K6 both sides, NCCL all-to-all-v, local K7/K8, K4 to global ids) -> host")
+                        f"pinned host key columns -> device -> {plan} join plan -> global (left, right) row ids on the host")
     r["metric"] = "hash_join_probe_rows_per_sec"
     r["verified"] = verified
     r["workload"] = (f"C3 inner hash join: probe {a.rows} x build {a.build_rows} Int64 keys per GPU ({'unique' if a.dup == 1 else str(a.dup) + ' copies of each'}; "
                      f"{'sparse 64-bit values -> hashed table' if sparse else 'dense surrogate ids -> direct-address table'}), {a.hit_frac:.0%} hit; outputs (left_idx,right_idx) u32")
-    r["parallelism"] = "single GPU" if world == 1 else f"radix hash-partitioned x{world}: K6 on both relations + one NCCL all-to-all-v per relation + local build/probe"
-    if world > 1 and not sparse:
-        # the broadcast-build alternative: all-gather of the small build side, no probe-side exchange
-        def step_bcast():
-            gl, gr = pdist.broadcast_hash_join(plb, dp.view(), db.view(), rank * a.rows)
+    names = {"partitioned": f"radix hash-partitioned x{world}: K6 on both relations + one NCCL all-to-all-v per relation + local build/probe + K4 to global ids",
+             "broadcast": f"broadcast build side x{world}: all-gather of the {a.build_rows * world} build keys (NCCL), probe rows stay local, local build/probe"}
+    r["parallelism"] = "single GPU" if world == 1 else names[plan] + " (chosen by the exchange-volume rule, dist.choose_join_plan)"
+    if world > 1:
+        # the other plan, measured beside the chosen one (BASELINE configs[2] names the radix-partitioned exchange)
+        other = "partitioned" if plan == "broadcast" else "broadcast"
+
+        def step_other():
+            gl, gr = run_plan(other, dp.view(), db.view())
             return gl.length
         try:
-            rb = H.measure(step_bcast, None, a.rows, alg, pick, "join:broadcast")
-            r["broadcast_variant"] = {"value": rb["value"], "unit": "rows/s", "ms_per_step": rb["ms_per_step"], "kernels_ms_per_step": rb["kernels_ms_per_step"],
-                                      "parallelism": f"build side all-gathered ({a.build_rows * world} keys on every GPU), probe rows stay local"}
+            rb = H.measure(step_other, None, a.rows, alg, pick, "join:" + other)
+            r["alternative_plan"] = {"value": rb["value"], "unit": "rows/s", "ms_per_step": rb["ms_per_step"], "kernels_ms_per_step": rb["kernels_ms_per_step"], "parallelism": names[other]}
         except Exception as e:      # optional evidence: never lose the line
-            r["broadcast_variant"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+            r["alternative_plan"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     return r
 
 
@@ -641,7 +652,7 @@ def main():
     if len(results) > 1:
         line["secondary"] = [{"metric": r["metric"], "value": r["value"], "unit": "rows/s", "ms_per_step": r["ms_per_step"], "config": cfg(r), "verified": r["verified"],
                               "roofline": r["roofline"], "kernels_ms_per_step": r["kernels_ms_per_step"], "e2e": r["e2e"], "clocks": r["clocks"],
-                              **({"broadcast_variant": r["broadcast_variant"]} if "broadcast_variant" in r else {})} for r in results[1:]]
+                              **({"alternative_plan": r["alternative_plan"]} if "alternative_plan" in r else {})} for r in results[1:]]
     if H.world == 1 and not a.no_cpu_baseline and a.workload in ("all", "groupby", "join"):
         line["cpu_baseline"] = cpu_baseline(a)
     print(json.dumps(line), flush=True)

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import polars_b200 as plb  # noqa: E402
 import bench  # noqa: E402
 
-N = int(os.environ.get("NCU_ROWS", 100_000_000))
+N = int(os.environ.get("NCU_ROWS", 100_000_000))      # headline kernels at the benchmarked size
 D = plb.DEVICE
 plb.init(0)
 rng = np.random.default_rng(0)
