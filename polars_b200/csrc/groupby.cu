@@ -669,9 +669,8 @@ struct FinalizeArgs {
     const uint32_t* len;           // per-group len
     void* out; uint32_t* out_valid; int64_t G;
 };
-__global__ void __launch_bounds__(256) k_gb_finalize(const __grid_constant__ FinalizeArgs a) {
-    const int64_t rounded = (a.G + 31) / 32 * 32;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < rounded; g += (int64_t)gridDim.x * blockDim.x) {
+__device__ __forceinline__ void gb_finalize_one(const FinalizeArgs& a, int64_t g) {
+    {
         bool valid = false;
         if (g < a.G) {
             const uint64_t len = a.len ? a.len[g] : 0;
@@ -708,6 +707,18 @@ __global__ void __launch_bounds__(256) k_gb_finalize(const __grid_constant__ Fin
             }
         }
         if (a.out_valid) { unsigned b = __ballot_sync(0xffffffffu, valid); if (lane_id() == 0) a.out_valid[g >> 5] = b; }
+    }
+}
+
+// all outputs of finish() in ONE launch: the typed key column and every aggregate (round 1: one launch each)
+constexpr int GB_FIN_MAX = 16;
+struct FinalizeAll { FinalizeArgs agg[GB_FIN_MAX]; int n_aggs; const uint64_t* key_bits; int key_elem; void* key_out; uint32_t* key_valid; long long null_pos; int64_t G; };
+__global__ void __launch_bounds__(256) k_gb_finalize_all(const __grid_constant__ FinalizeAll f) {
+    const int64_t rounded = (f.G + 31) / 32 * 32;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < rounded; g += (int64_t)gridDim.x * blockDim.x) {
+        if (f.key_out != nullptr && g < f.G) { if (f.key_elem == 8) reinterpret_cast<uint64_t*>(f.key_out)[g] = f.key_bits[g]; else reinterpret_cast<uint32_t*>(f.key_out)[g] = (uint32_t)f.key_bits[g]; }
+        if (f.key_valid) { const unsigned b = __ballot_sync(0xffffffffu, g < f.G && g != f.null_pos); if (lane_id() == 0) f.key_valid[g >> 5] = b; }
+        for (int i = 0; i < f.n_aggs; i++) gb_finalize_one(f.agg[i], g);
     }
 }
 
@@ -1289,13 +1300,12 @@ void GroupByState::consume_all(const DevCol& key, const std::vector<const DevCol
     PLB_REQUIRE(key.len <= 0xFFFFFFFEll, BL_ERR_UNSUPPORTED, "group_by: more than 2^32-2 rows (IdxSize = u32)");
     uint64_t c = choose_cap(key, key.len);
     if (consume_radix(key, values, c)) return;      // tables beyond L2: partition the rows instead (groupby_radix.cu)
-    for (int attempt = 0; attempt < 8; attempt++) {
-        alloc_table(c);
-        launch_batch(key, values, 0);
-        if (read_scalar(as<int>(status)) == 0) { rows_seen = key.len; return; }
-        c *= 8;
-    }
-    fail(BL_ERR_OOM, "group_by: hash table kept overflowing");
+    // optimistic: no host round trip here — finish() reads the status word together with the group count and, if the sampled
+    // estimate was too small, redoes the batch into a table 8x larger (the inputs outlive the state in every caller)
+    alloc_table(c);
+    launch_batch(key, values, 0);
+    rows_seen = key.len;
+    redo_key = &key; redo_values = values; redo_cap = c;
 }
 
 // Streaming consume (chunked H2D overlap, multi-GPU): the table is grown between batches so that it
@@ -1428,6 +1438,17 @@ void GroupByState::merge_window_async(const void* own_half, int n_ranks, int64_t
     PLB_LAUNCH("k5_merge_partials", k_gb_merge_window, ctx().sm_count * 4, 256, 0, L, T, reinterpret_cast<const uint64_t*>(own_half), n_ranks, rows_per_src, row_words, epoch);
 }
 
+void GroupByState::settle() {
+    if (redo_key == nullptr || dense.ready) return;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        if (read_scalar(as<int>(status)) == 0) { redo_key = nullptr; return; }
+        redo_cap *= 8;
+        alloc_table(redo_cap);
+        launch_batch(*redo_key, redo_values, 0);
+    }
+    fail(BL_ERR_OOM, "group_by: hash table kept overflowing");
+}
+
 int GroupByState::read_status() { return status ? read_scalar(as<int>(status)) : 0; }
 
 void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather, DevCol& out_key, std::vector<DevCol>& out_aggs, DevCol* out_first) {
@@ -1436,10 +1457,13 @@ void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather,
     // Extract into buffers sized by an upper bound of the group count, then read the real count and
     // the null-group position back with ONE 16-byte copy (one host sync for the whole finish).
     const int kelem = dtype_size(key_dtype);
-    const int64_t Gb = dense.ready ? dense.Gb : (entries ? std::max<int64_t>(1, std::min<int64_t>((int64_t)cap + 2, rows_seen + merged_rows + 2)) : 1);
+    int64_t Gb = 1;
     DevPtr keys, first, len, words, ctl;
     long long ctl_host[2] = {0, -1};
     int status_host = 0;
+  for (int attempt = 0;; attempt++) {
+    Gb = dense.ready ? dense.Gb : (entries ? std::max<int64_t>(1, std::min<int64_t>((int64_t)cap + 2, rows_seen + merged_rows + 2)) : 1);
+    ctl_host[0] = 0; ctl_host[1] = -1; status_host = 0;
     if (dense.ready) {      // the partitioned plan wrote the dense arrays itself
         keys = dense.keys; first = dense.first; len = dense.len; words = dense.words; ctl = dense.ctl;
         PLB_CUDA(cudaMemcpyAsync(ctl_host, ctl->p, 16, cudaMemcpyDeviceToHost, ctx().stream));
@@ -1457,30 +1481,45 @@ void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather,
         PLB_CUDA(cudaMemcpyAsync(ctl_host, ctl->p, 16, cudaMemcpyDeviceToHost, ctx().stream));
     }
     PLB_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (status_host == 1 && redo_key != nullptr && attempt < 8) {      // one-shot batch, table too small: redo into a larger one
+        redo_cap *= 8;
+        alloc_table(redo_cap);
+        launch_batch(*redo_key, redo_values, 0);
+        continue;
+    }
+    break;
+  }
     if (status_host == 2) fail(BL_ERR_INVALID, "group_by: a peer window region was too small for the partial aggregates sent to this rank");
     if (status_host == 3) fail(BL_ERR_CUDA, "group_by: timed out waiting for a peer rank's partial aggregates");
     if (status_host != 0) fail(BL_ERR_OOM, "group_by: hash table overflow (deferred check) — create the state with expected_groups set");
     const int64_t G = ctl_host[0];
     const long long null_pos = ctl_host[1];
-    // key column
+    // key column + aggregates: one launch (k_gb_finalize_all); more than 16 aggregates take further launches
     out_key = make_col(key_dtype, G, null_pos >= 0);
-    if (G > 0)
-        PLB_LAUNCH("k5_keys_out", k_gb_keys_out, grid_for(G, 256), 256, 0, as<uint64_t>(keys), G, kelem, out_key.values->p, as<uint32_t>(out_key.validity), null_pos);
     out_key.null_count = null_pos >= 0 ? 1 : 0;
-    // aggregates
+    FinalizeAll fall; memset(&fall, 0, sizeof fall);
+    fall.key_bits = as<uint64_t>(keys); fall.key_elem = kelem; fall.key_out = out_key.values->p; fall.key_valid = as<uint32_t>(out_key.validity); fall.null_pos = null_pos; fall.G = G;
+    bool keys_pending = true;
+    auto flush = [&]() {
+        if (G > 0 && (fall.n_aggs > 0 || keys_pending)) {
+            if (!keys_pending) { fall.key_out = nullptr; fall.key_valid = nullptr; fall.key_elem = 0; }
+            PLB_LAUNCH("k5_finalize", k_gb_finalize_all, grid_for(G, 256), 256, 0, fall);
+        }
+        keys_pending = false; fall.n_aggs = 0;
+    };
     for (auto& ap : plans) {
         const bool nullable = ap.kind == BL_AGG_MEAN || ap.kind == BL_AGG_MIN || ap.kind == BL_AGG_MAX;
         DevCol o = make_col(ap.out_dtype, G, nullable);
-        if (G > 0) {
-            FinalizeArgs fa; memset(&fa, 0, sizeof fa);
-            fa.kind = ap.kind; fa.in_dtype = ap.in_dtype; fa.out_dtype = ap.out_dtype; fa.G = G;
-            fa.main_word = ap.main >= 0 ? as<uint64_t>(words) + (int64_t)ap.main * Gb : nullptr;
-            fa.nullcnt_word = ap.nullcnt >= 0 ? as<uint64_t>(words) + (int64_t)ap.nullcnt * Gb : nullptr;
-            fa.len = as<uint32_t>(len); fa.out = o.values->p; fa.out_valid = as<uint32_t>(o.validity);
-            PLB_LAUNCH("k5_finalize", k_gb_finalize, grid_for(G, 256), 256, 0, fa);
-        }
+        FinalizeArgs& fa = fall.agg[fall.n_aggs++];
+        memset(&fa, 0, sizeof fa);
+        fa.kind = ap.kind; fa.in_dtype = ap.in_dtype; fa.out_dtype = ap.out_dtype; fa.G = G;
+        fa.main_word = ap.main >= 0 ? as<uint64_t>(words) + (int64_t)ap.main * Gb : nullptr;
+        fa.nullcnt_word = ap.nullcnt >= 0 ? as<uint64_t>(words) + (int64_t)ap.nullcnt * Gb : nullptr;
+        fa.len = as<uint32_t>(len); fa.out = o.values->p; fa.out_valid = as<uint32_t>(o.validity);
         out_aggs.push_back(o);
+        if (fall.n_aggs == GB_FIN_MAX) flush();
     }
+    flush();
     // float keys (and any key when the column is at hand): output = key at the group's first row
     // (group_by/mod.rs:258-266) so that -0.0 / NaN payloads of the first occurrence survive
     const bool gather_keys = key_col_for_gather != nullptr && dtype_is_float(key_dtype) && G > 0 && L.need_first;
@@ -1553,6 +1592,7 @@ DevCol op_group_first_ids(const DevCol& key) {
     if (n == 0) return ids;
     GroupByState st(key.dtype, {}, {}, {}, 0, true);
     st.consume_all(key, {});
+    st.settle();
     PLB_LAUNCH("k5_lookup_first", k_gb_lookup_first, grid_for(n, 256, 16), 256, 0, st.T, key.v(), key.vm(), key.dtype, n, as<uint32_t>(ids.values));
     return ids;
 }

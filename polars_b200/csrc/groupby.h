@@ -74,8 +74,11 @@ struct GroupByState {
     void export_partials_p2p(int n_ranks, int my_rank, void* const* windows, int64_t rows_per_src, int* row_words_out, int64_t* sent_rows);
     void export_partials_p2p_async(int n_ranks, int my_rank, void* const* window_halves, int64_t rows_per_src, uint64_t epoch, int* row_words_out);
     void merge_window_async(const void* own_half, int n_ranks, int64_t rows_per_src, uint64_t epoch);
+    void settle();               // resolves a deferred one-shot overflow check now (host sync); for users of the table that skip finish()
     int read_status();           // host sync: 0 ok, 1 table overflow, 2 peer window overflow, 3 peer timeout
     bool defer_status = false;   // consume() leaves the overflow check to read_status() / finish()
+    // one-shot consume_all: the overflow check rides on finish()'s synchronisation; on overflow finish() redoes the batch
+    const DevCol* redo_key = nullptr; std::vector<const DevCol*> redo_values; uint64_t redo_cap = 0;
     void finish(bool maintain_order, const DevCol* key_col_for_gather, DevCol& out_key, std::vector<DevCol>& out_aggs, DevCol* out_first = nullptr);
     void reset();
     int64_t count_groups();
