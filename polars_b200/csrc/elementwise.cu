@@ -236,9 +236,57 @@ __global__ void __launch_bounds__(256) k_compare(const T* __restrict__ lhs, cons
     }
 }
 
+// 8-byte types, second form: lane l of a warp-step owns rows l and l + 32 of a 64-row group (two coalesced 256-byte
+// loads), so the two ballots ARE the two mask words in row order — no bit interleave at all.  The 128-bit form above spends
+// ~40 integer instructions per 16 bytes on ballot + spread_bits, which is what capped the scalar compare (8 B/row in,
+// 1 bit/row out) at 0.65 of the copy peak; array-vs-array (16 B/row) was already memory-bound.
+template <typename T, int OP, bool SCALAR>
+__global__ void __launch_bounds__(256) k_compare64(const T* __restrict__ lhs, const T* __restrict__ rhs, uint32_t* __restrict__ out, int64_t n, T scalar) {
+    static_assert(sizeof(T) == 8, "8-byte elements");
+    const int64_t nsteps = n / 64;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const unsigned lane = lane_id();
+    constexpr int UNROLL = 4;
+    int64_t s = warp;
+    for (; s + (UNROLL - 1) * nwarps < nsteps; s += UNROLL * nwarps) {
+        T a0[UNROLL], a1[UNROLL], b0[UNROLL], b1[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const int64_t r = (s + u * nwarps) * 64 + lane;
+            a0[u] = __ldcs(lhs + r); a1[u] = __ldcs(lhs + r + 32);
+            if (!SCALAR) { b0[u] = __ldcs(rhs + r); b1[u] = __ldcs(rhs + r + 32); }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const uint32_t m0 = __ballot_sync(0xffffffffu, cmp_op<T, OP>(a0[u], SCALAR ? scalar : b0[u]));
+            const uint32_t m1 = __ballot_sync(0xffffffffu, cmp_op<T, OP>(a1[u], SCALAR ? scalar : b1[u]));
+            if (lane == 0) *reinterpret_cast<uint2*>(out + (s + u * nwarps) * 2) = make_uint2(m0, m1);
+        }
+    }
+    for (; s < nsteps; s += nwarps) {
+        const int64_t r = s * 64 + lane;
+        const uint32_t m0 = __ballot_sync(0xffffffffu, cmp_op<T, OP>(lhs[r], SCALAR ? scalar : rhs[r]));
+        const uint32_t m1 = __ballot_sync(0xffffffffu, cmp_op<T, OP>(lhs[r + 32], SCALAR ? scalar : rhs[r + 32]));
+        if (lane == 0) *reinterpret_cast<uint2*>(out + s * 2) = make_uint2(m0, m1);
+    }
+    if (warp == 0) {
+        for (int64_t base = nsteps * 64; base < n; base += 32) {
+            const int64_t i = base + lane;
+            bool p = false;
+            if (i < n) p = cmp_op<T, OP>(lhs[i], SCALAR ? scalar : rhs[i]);
+            const uint32_t w = __ballot_sync(0xffffffffu, p);
+            if (lane == 0) out[base >> 5] = w;
+        }
+    }
+}
+
 template <typename T, int OP>
 static void launch_cmp_s(bool scalar_rhs, const T* l, const T* r, uint32_t* o, int64_t n, T scalar) {
     int grid = grid_for(n / (16 / sizeof(T)) + 1, 256);
+    if constexpr (sizeof(T) == 8) {
+        if (scalar_rhs) { PLB_LAUNCH("k2_compare", (k_compare64<T, OP, true>), grid, 256, 0, l, r, o, n, scalar); return; }      // instruction-bound in the 128-bit form
+    }
     if (scalar_rhs) PLB_LAUNCH("k2_compare", (k_compare<T, OP, true>), grid, 256, 0, l, r, o, n, scalar);
     else PLB_LAUNCH("k2_compare", (k_compare<T, OP, false>), grid, 256, 0, l, r, o, n, scalar);
 }

@@ -108,21 +108,44 @@ __global__ void __launch_bounds__(F_THREADS) k_compact(FilterArgs args, const ui
         }
         __syncthreads();
         const uint64_t out_base = tile_off[t];
-        // rows: iteration j covers rows row_base + j*256 + tid; word index = j*8 + warp
+        // values: lane l of a warp-step owns the row PAIR (2l, 2l+1) of a 64-row group — one 128-bit (8-byte elements) or 64-bit
+        // load per kept pair, skipped when neither row is kept; unselected rows cost their sector anyway, so the wide load is free
+        // (round 1 issued one 8-byte load and one store per thread-step and sat at 0.57-0.72 of the copy peak)
 #pragma unroll 4
-        for (int j = 0; j < F_TILE / F_THREADS; j++) {
-            const int widx = j * (F_THREADS / 32) + warp;
-            const uint32_t m = wmask[widx];
-            if (m == 0) continue;                                  // warp-uniform
-            const bool keep = (m >> lane) & 1u;
-            const uint32_t rank = gsum[widx >> 5] + wpre[widx] + __popc(m & lanemask_lt());
-            const int64_t row = row_base + (int64_t)widx * 32 + lane;
-            const uint64_t dst = out_base + rank;
-            if (keep) {
-                if (col.elem == 8) reinterpret_cast<uint64_t*>(col.out)[dst] = __ldcs(reinterpret_cast<const uint64_t*>(col.in) + row);
-                else reinterpret_cast<uint32_t*>(col.out)[dst] = __ldcs(reinterpret_cast<const uint32_t*>(col.in) + row);
+        for (int j = 0; j < F_TILE / (2 * F_THREADS); j++) {
+            const int wa = (j * (F_THREADS / 32) + warp) * 2;
+            if ((wmask[wa] | wmask[wa + 1]) == 0) continue;          // warp-uniform
+            const int w = wa + (lane >> 4);
+            const unsigned b0 = (lane & 15) * 2;
+            const uint32_t m = wmask[w];
+            const bool k0 = (m >> b0) & 1u, k1 = (m >> (b0 + 1)) & 1u;
+            if (!(k0 | k1)) continue;
+            const uint64_t dst = out_base + gsum[w >> 5] + wpre[w] + __popc(m & ((1u << b0) - 1u));
+            const int64_t row = row_base + (int64_t)w * 32 + b0;
+            if (col.elem == 8) {
+                uint64_t v0, v1 = 0;
+                if (row + 1 < n) { const ulonglong2 v = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(col.in) + row); v0 = v.x; v1 = v.y; }
+                else v0 = reinterpret_cast<const uint64_t*>(col.in)[row];
+                uint64_t* o = reinterpret_cast<uint64_t*>(col.out);
+                if (k0) o[dst] = v0;
+                if (k1) o[dst + (k0 ? 1 : 0)] = v1;
+            } else {
+                uint32_t v0, v1 = 0;
+                if (row + 1 < n) { const uint2 v = ld_stream_u32x2(reinterpret_cast<const uint32_t*>(col.in) + row); v0 = v.x; v1 = v.y; }
+                else v0 = reinterpret_cast<const uint32_t*>(col.in)[row];
+                uint32_t* o = reinterpret_cast<uint32_t*>(col.out);
+                if (k0) o[dst] = v0;
+                if (k1) o[dst + (k0 ? 1 : 0)] = v1;
             }
-            if (col.vin != nullptr) {
+        }
+        // validity: one 32-row mask word per warp-step (rows row_base + j*256 + tid; word index = j*8 + warp)
+        if (col.vin != nullptr) {
+#pragma unroll 4
+            for (int j = 0; j < F_TILE / F_THREADS; j++) {
+                const int widx = j * (F_THREADS / 32) + warp;
+                const uint32_t m = wmask[widx];
+                if (m == 0) continue;                                  // warp-uniform
+                const bool keep = (m >> lane) & 1u;
                 // compact the validity bits of this 32-row word: kept rows occupy output bits
                 // [first, first + cnt) — build them with a warp OR-reduce, then <= 2 atomicOr
                 const uint32_t vw = col.vin[row_base / 32 + widx];
