@@ -135,3 +135,12 @@ def test_raw_row_exchange_world2():
     assert np.array_equal(np.concatenate([res[r][1] for r in range(world)])[o], outs[0][0][eo])
     assert np.allclose(np.concatenate([res[r][2] for r in range(world)])[o], outs[1][0][eo], rtol=1e-9)
     assert np.array_equal(np.concatenate([res[r][3] for r in range(world)])[o], outs[2][0][eo])
+
+
+def test_join_plan_rule():
+    """Exchange-volume rule (dist.choose_join_plan): C3's small build side is broadcast, relations of similar size are partitioned."""
+    from polars_b200 import dist as pdist
+    assert pdist.choose_join_plan(100_000_000, 10_000_000, 2) == "broadcast"
+    assert pdist.choose_join_plan(100_000_000, 10_000_000, 8) == "broadcast"
+    assert pdist.choose_join_plan(100_000_000, 100_000_000, 8) == "partitioned"
+    assert pdist.choose_join_plan(100_000_000, 70_000_000, 4) == "partitioned"
