@@ -92,6 +92,19 @@ __device__ __forceinline__ uint64_t* gb_special(const GbTableDev& T, int which) 
     return e;
 }
 
+// address of word w of the entry whose key word is at `e` (the layouts are described at GbTableDev)
+__device__ __forceinline__ uint64_t* gb_wp(const GbTableDev& T, uint64_t* e, int w) {
+    return e + gb_woff(T.pw ? (int64_t)(e - T.entries) : 0, w, T.ws, T.pw);
+}
+// ---- bulk reduce (TMA): one cp.reduce.async.bulk adds the 16-byte shared-memory cell {1, v} to the table cell {len | first, sum}.
+//      Measured on B200 (profiles/r02_ubench2_bulkred.jsonl): key load + this + 1 RED.F64 retires 73 G rows/s against 54-60 G rows/s
+//      for key load + 3 REDs — the L2 / LSU RED rate (~195 G/s) is the ceiling of the table update and the TMA unit is a second,
+//      otherwise idle, path into the same L2 atomic units.  SASS: UBLKRED.G.S.ADD.U64 (uniform datapath: ptxas serialises the lanes).
+__device__ __forceinline__ void bulk_add_u64x2(uint64_t* dst, const uint64_t* src_smem) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(src_smem);
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], 16;" :: "l"(dst), "r"(sa) : "memory");
+}
+
 __device__ __forceinline__ void gb_apply(int op, uint64_t* addr, int dtype, uint64_t raw, bool valid, uint64_t pol = 0, bool hint = false) {
     switch (op) {
         case W_ADD_INT: { uint64_t v = raw_to_int(dtype, raw); if (valid && v) red_add_u64(addr, v, pol, hint); break; }
@@ -112,9 +125,13 @@ __device__ __forceinline__ void gb_apply(int op, uint64_t* addr, int dtype, uint
 // value-column pair (64-bit loads for 4-byte types), then the first table probe of ALL its rows is
 // issued before any of them is resolved (memory-level parallelism: the kernel is bound by L2
 // latency, not by any throughput unit), then one RED per accumulator.
-template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC, int PAIRS>
+// BULK (pair layout only): len and the paired integer sum of a row travel as ONE 16-byte bulk reduce issued from a per-thread
+// staging cell in shared memory (R x 256 cells); lanes >= T.bulk_lanes keep the plain REDs (knob: balance of the two paths).
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC, int PAIRS, bool BULK>
 __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const __grid_constant__ GbBatch B) {
     constexpr int R = 2 * PAIRS;
+    extern __shared__ __align__(16) uint64_t gb_stage[];
+    const bool bulk_lane = BULK && (int)(threadIdx.x & 31) < T.bulk_lanes;
     const int64_t npairs = B.n >> 1;
     const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
     const int khint = T.hint;                 // key-load flavour (bit 0: evict_last policy, bit 1: L1-cached)
@@ -122,7 +139,7 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
     const uint64_t pol = hint ? make_policy_evict_last() : 0;
     int iter = 0;
     for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p0 < npairs; p0 += gstride * PAIRS) {
-        if (((iter++) & 15) == 0 && *reinterpret_cast<volatile int*>(T.status)) return;
+        if (((iter++) & 15) == 0 && *reinterpret_cast<volatile int*>(T.status)) break;
         uint64_t kraw[R];
         uint64_t raw[MAXC][R];
 #pragma unroll
@@ -159,24 +176,55 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
                 if (kind[r] == 0) { slot[r] = hsh >> T.shift; k0[r] = tbl_load(T.entries + slot[r] * T.es, pol, khint); }
             }
         }
+        uint64_t* ent[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) ent[r] = kind[r] < 0 ? nullptr : (kind[r] == 0 ? gb_resolve(T, key[r], slot[r], k0[r], pol, khint) : gb_special(T, kind[r] - 1));
+        if (BULK) {
+            // Bulk reduces FIRST: the proxy fence below is a MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in SASS and would wait for every RED this
+            // thread has in flight (measured with the REDs ahead of it: 2.28 ms against 2.00 ms for the plain 3-RED kernel).
+            // The staging cells are reused every iteration: the previous iteration's bulk reduces must have read them.
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (bulk_lane) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if (ent[r] == nullptr) continue;
+                    const int64_t row = 2 * (p0 + (r >> 1) * gstride) + (r & 1);
+                    uint64_t pv = 0;
+#pragma unroll
+                    for (int c = 0; c < MAXC; c++)
+                        if (c == L.pair_c) pv = (B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row)) ? raw_to_int(B.cols[c].dtype, raw[c][r]) : 0ull;
+                    uint64_t* cell = gb_stage + 2 * (r * 256 + (int)threadIdx.x);
+                    asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"((uint32_t)__cvta_generic_to_shared(cell)), "l"((uint64_t)(L.need_len ? 1 : 0)), "l"(pv) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores above -> visible to the TMA unit
+#pragma unroll
+                for (int r = 0; r < R; r++) if (ent[r]) bulk_add_u64x2(gb_wp(T, ent[r], 1), gb_stage + 2 * (r * 256 + (int)threadIdx.x));
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            if (kind[r] < 0) continue;
-            uint64_t* e = kind[r] == 0 ? gb_resolve(T, key[r], slot[r], k0[r], pol, khint) : gb_special(T, kind[r] - 1);
+            uint64_t* e = ent[r];
             if (e == nullptr) continue;
             const int64_t row = 2 * (p0 + (r >> 1) * gstride) + (r & 1);
-            if (L.need_len) red_add_u32(reinterpret_cast<uint32_t*>(e + T.ws), 1u, pol, hint);
-            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + T.ws) + 1, B.row_base + (uint32_t)row);
+            uint64_t* const w1 = gb_wp(T, e, 1);
+            if (L.need_len && !bulk_lane) red_add_u32(reinterpret_cast<uint32_t*>(w1), 1u, pol, hint);
+            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(w1) + 1, B.row_base + (uint32_t)row);
 #pragma unroll
             for (int c = 0; c < MAXC; c++) {
                 if (c < L.n_cols) {
                     const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
                     const int dt = B.cols[c].dtype;
-                    for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + (2 + L.wslot[k]) * T.ws, dt, raw[c][r], valid, pol, hint);
+                    for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) {
+                        if (bulk_lane && k == L.pair_k) continue;      // already on its way as half of the bulk reduce
+                        gb_apply(L.wop[k], gb_wp(T, e, 2 + L.wslot[k]), dt, raw[c][r], valid, pol, hint);
+                    }
                 }
             }
         }
     }
+    // all bulk reduces of this thread have been performed (not just read) before the CTA may retire
+    if (BULK) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     // odd tail row
     if ((B.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const int64_t row = B.n - 1;
@@ -186,18 +234,18 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
         const bool mine = !T.pass_bits || (regular ? (int)(table_hash(key) >> (64 - T.pass_bits)) == T.pass_id : T.pass_id == 0);
         uint64_t* e = !mine ? nullptr : (!kvalid ? gb_special(T, 0) : (key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key)));
         if (e) {
-            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + T.ws), 1u);
-            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + T.ws) + 1, B.row_base + (uint32_t)row);
+            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(gb_wp(T, e, 1)), 1u);
+            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(gb_wp(T, e, 1)) + 1, B.row_base + (uint32_t)row);
             for (int c = 0; c < L.n_cols; c++) {
                 const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
                 uint64_t raw = B.cols[c].elem == 8 ? reinterpret_cast<const uint64_t*>(B.cols[c].values)[row] : (uint64_t)reinterpret_cast<const uint32_t*>(B.cols[c].values)[row];
-                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + (2 + L.wslot[k]) * T.ws, B.cols[c].dtype, raw, valid);
+                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], gb_wp(T, e, 2 + L.wslot[k]), B.cols[c].dtype, raw, valid);
             }
         }
     }
 }
 
-__device__ __forceinline__ void gb_merge_row(const GbLayout& L, const GbTableDev& T, const uint64_t* src, int meta, int64_t sws = 1);
+__device__ __forceinline__ void gb_merge_row(const GbLayout& L, const GbTableDev& T, const uint64_t* src, int meta, int64_t sws = 1, int64_t sslot = 0, int spw = 0);
 
 // ---------------------------------------------------------------------------- K5, heavy-hitter variant
 // Skewed keys: all rows of a hot key hit ONE entry, and same-address L2 atomics retire serially
@@ -348,14 +396,14 @@ __global__ void __launch_bounds__(256) k_gb_consume_hot(const __grid_constant__ 
             uint64_t* e = kind[r] == 0 ? gb_resolve(T, key[r], slot[r], k0[r], 0, khint) : gb_special(T, kind[r] - 1);
             if (e == nullptr) continue;
             const int64_t row = 2 * p + r;
-            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + T.ws), 1u);
-            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + T.ws) + 1, B.row_base + (uint32_t)row);
+            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(gb_wp(T, e, 1)), 1u);
+            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(gb_wp(T, e, 1)) + 1, B.row_base + (uint32_t)row);
 #pragma unroll
             for (int c = 0; c < MAXC; c++) {
                 if (c < L.n_cols) {
                     const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
                     const int dt = B.cols[c].dtype;
-                    for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + (2 + L.wslot[k]) * T.ws, dt, raw[c][r], valid);
+                    for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], gb_wp(T, e, 2 + L.wslot[k]), dt, raw[c][r], valid);
                 }
             }
         }
@@ -369,12 +417,12 @@ __global__ void __launch_bounds__(256) k_gb_consume_hot(const __grid_constant__ 
         const bool mine = !T.pass_bits || (regular ? (int)(table_hash(key) >> (64 - T.pass_bits)) == T.pass_id : T.pass_id == 0);
         uint64_t* e = !mine ? nullptr : (!kvalid ? gb_special(T, 0) : (key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key)));
         if (e) {
-            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + T.ws), 1u);
-            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + T.ws) + 1, B.row_base + (uint32_t)row);
+            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(gb_wp(T, e, 1)), 1u);
+            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(gb_wp(T, e, 1)) + 1, B.row_base + (uint32_t)row);
             for (int c = 0; c < L.n_cols; c++) {
                 const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
                 uint64_t raw = B.cols[c].elem == 8 ? reinterpret_cast<const uint64_t*>(B.cols[c].values)[row] : (uint64_t)reinterpret_cast<const uint32_t*>(B.cols[c].values)[row];
-                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + (2 + L.wslot[k]) * T.ws, B.cols[c].dtype, raw, valid);
+                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], gb_wp(T, e, 2 + L.wslot[k]), B.cols[c].dtype, raw, valid);
             }
         }
     }
@@ -388,10 +436,14 @@ __global__ void __launch_bounds__(256) k_gb_consume_hot(const __grid_constant__ 
 }
 
 // word w of entry s lives at entries[s * es + w * ws]: AoS (es = stride, ws = 1) or word-major planes (es = 1, ws = n_entries)
-__global__ void k_gb_init(uint64_t* entries, int64_t n_entries, int stride, int soa, const __grid_constant__ GbLayout L) {
+__global__ void k_gb_init(uint64_t* entries, int64_t n_entries, int stride, int soa, int pw, const __grid_constant__ GbLayout L) {
     const int64_t total = n_entries * stride;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int w = soa ? (int)(i / n_entries) : (int)(i % stride);
+        if (pw) {   // pair layout: planes 1 and 2 hold the cells {word 1, word pw}; plane pw holds word 2
+            if (w == 1 || w == 2) w = ((i - n_entries) & 1) ? pw : 1;
+            else if (w == pw) w = 2;
+        }
         uint64_t v = 0;
         if (w == 0) v = GB_EMPTY; else if (w == 1) v = GB_W1_INIT; else if (w - 2 < L.n_words) v = L.init[w - 2];
         entries[i] = v;
@@ -460,16 +512,17 @@ __global__ void k_fill_u64(uint64_t* p, uint64_t v, int64_t n) {
 // rows: n_rows x row_words.  table_mode: rows are the slots of another table (stride = row_words,
 // special slots at src_cap, src_cap+1); else exported partial rows whose last word is meta
 // (0 normal, 1 null-key group, 2 GB_EMPTY-key group).
-__device__ __forceinline__ void gb_merge_row(const GbLayout& L, const GbTableDev& T, const uint64_t* src, int meta, int64_t sws) {
+// (sslot, spw): the source is slot sslot of a table in the pair layout (rehash); spw == 0 for rows and word-major / AoS tables.
+__device__ __forceinline__ void gb_merge_row(const GbLayout& L, const GbTableDev& T, const uint64_t* src, int meta, int64_t sws, int64_t sslot, int spw) {
     uint64_t* e = meta == 1 ? gb_special(T, 0) : (meta == 2 ? gb_special(T, 1) : gb_find_or_insert(T, src[0]));
     if (!e) return;
-    const uint64_t lf = src[sws];
-    if ((uint32_t)lf) atomicAdd(reinterpret_cast<unsigned*>(e + T.ws), (uint32_t)lf);
-    if ((uint32_t)(lf >> 32) != 0xFFFFFFFFu) atomicMin(reinterpret_cast<unsigned*>(e + T.ws) + 1, (uint32_t)(lf >> 32));
+    const uint64_t lf = src[gb_woff(sslot, 1, sws, spw)];
+    if ((uint32_t)lf) atomicAdd(reinterpret_cast<unsigned*>(gb_wp(T, e, 1)), (uint32_t)lf);
+    if ((uint32_t)(lf >> 32) != 0xFFFFFFFFu) atomicMin(reinterpret_cast<unsigned*>(gb_wp(T, e, 1)) + 1, (uint32_t)(lf >> 32));
     for (int w = 0; w < L.n_words; w++) {
-        const uint64_t v = src[(2 + w) * sws];
+        const uint64_t v = src[gb_woff(sslot, 2 + w, sws, spw)];
         if (v == L.init[w]) continue;
-        uint64_t* a = e + (2 + w) * T.ws;
+        uint64_t* a = gb_wp(T, e, 2 + w);
         switch (L.slot_op[w]) {
             case W_ADD_F64: atomicAdd(reinterpret_cast<double*>(a), __longlong_as_double((long long)v)); break;
             case W_MIN_S64: atomicMin(reinterpret_cast<long long*>(a), (long long)v); break;
@@ -480,13 +533,13 @@ __device__ __forceinline__ void gb_merge_row(const GbLayout& L, const GbTableDev
         }
     }
 }
-__global__ void __launch_bounds__(256) k_gb_merge(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const uint64_t* __restrict__ rows, int64_t n_rows, int64_t src_es, int64_t src_ws, int table_mode, int64_t src_cap) {
+__global__ void __launch_bounds__(256) k_gb_merge(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const uint64_t* __restrict__ rows, int64_t n_rows, int64_t src_es, int64_t src_ws, int table_mode, int64_t src_cap, int src_pw) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t* src = rows + r * src_es;
         int meta;
         if (table_mode) { if (src[0] == GB_EMPTY) continue; meta = r == src_cap ? 1 : (r == src_cap + 1 ? 2 : 0); }
         else meta = (int)src[(L.n_words + 2) * src_ws];
-        gb_merge_row(L, T, src, meta, src_ws);
+        gb_merge_row(L, T, src, meta, src_ws, r, table_mode ? src_pw : 0);
     }
 }
 
@@ -572,14 +625,14 @@ __global__ void __launch_bounds__(512) k_gb_consume_smem(const __grid_constant__
             } else {
                 uint64_t* e = gb_find_or_insert(T, key);
                 if (e != nullptr) {
-                    if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + T.ws), 1u);
-                    if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + T.ws) + 1, B.row_base + (uint32_t)row);
+                    if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(gb_wp(T, e, 1)), 1u);
+                    if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(gb_wp(T, e, 1)) + 1, B.row_base + (uint32_t)row);
 #pragma unroll
                     for (int c = 0; c < MAXC; c++) {
                         if (c < L.n_cols) {
                             const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
                             const int dt = B.cols[c].dtype;
-                            for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + (2 + L.wslot[k]) * T.ws, dt, raw[c][j], valid);
+                            for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], gb_wp(T, e, 2 + L.wslot[k]), dt, raw[c][j], valid);
                         }
                     }
                 }
@@ -593,12 +646,12 @@ __global__ void __launch_bounds__(512) k_gb_consume_smem(const __grid_constant__
         uint64_t key = load_key_rt(B.keys, B.key_dtype, row);
         uint64_t* e = !kvalid ? gb_special(T, 0) : (key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key));
         if (e) {
-            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(e + T.ws), 1u);
-            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(e + T.ws) + 1, B.row_base + (uint32_t)row);
+            if (L.need_len) atomicAdd(reinterpret_cast<unsigned*>(gb_wp(T, e, 1)), 1u);
+            if (L.need_first) atomicMin(reinterpret_cast<unsigned*>(gb_wp(T, e, 1)) + 1, B.row_base + (uint32_t)row);
             for (int c = 0; c < L.n_cols; c++) {
                 const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
                 uint64_t raw = B.cols[c].elem == 8 ? reinterpret_cast<const uint64_t*>(B.cols[c].values)[row] : (uint64_t)reinterpret_cast<const uint32_t*>(B.cols[c].values)[row];
-                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], e + (2 + L.wslot[k]) * T.ws, B.cols[c].dtype, raw, valid);
+                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], gb_wp(T, e, 2 + L.wslot[k]), B.cols[c].dtype, raw, valid);
             }
         }
     }
@@ -624,7 +677,7 @@ __global__ void k_gb_count_used(const uint64_t* entries, int64_t n_entries, int6
 // Dense SoA extraction.  Group order = slot order within 256-slot tiles, tiles in atomic-arrival
 // order (unspecified, like the reference's hashbrown iteration order).
 // out_words: n_words arrays of G u64.  null_pos: position of the null-key group or -1.
-__global__ void __launch_bounds__(256) k_gb_extract(const uint64_t* __restrict__ entries, int64_t cap, int64_t es, int64_t ws, int n_words, unsigned long long* cursor,
+__global__ void __launch_bounds__(256) k_gb_extract(const uint64_t* __restrict__ entries, int64_t cap, int64_t es, int64_t ws, int pw, int n_words, unsigned long long* cursor,
                                                     uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_first, uint32_t* __restrict__ out_len,
                                                     uint64_t* __restrict__ out_words, int64_t G, long long* null_pos) {
     const int64_t n_entries = cap + 2;
@@ -652,10 +705,10 @@ __global__ void __launch_bounds__(256) k_gb_extract(const uint64_t* __restrict__
             if (s == cap) { kout = 0; *null_pos = pos; }
             else if (s == cap + 1) kout = GB_EMPTY;
             out_keys[pos] = kout;
-            const uint64_t lf = e[ws];
+            const uint64_t lf = e[gb_woff(s, 1, ws, pw)];
             out_len[pos] = (uint32_t)lf;
             out_first[pos] = (uint32_t)(lf >> 32);
-            for (int w = 0; w < n_words; w++) out_words[(int64_t)w * G + pos] = e[(2 + w) * ws];
+            for (int w = 0; w < n_words; w++) out_words[(int64_t)w * G + pos] = e[gb_woff(s, 2 + w, ws, pw)];
         }
         __syncthreads();
     }
@@ -750,7 +803,7 @@ __global__ void __launch_bounds__(256) k_gb_export_count(const uint64_t* __restr
     __syncthreads();
     if (threadIdx.x < P && hist[threadIdx.x]) atomicAdd(&part_counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
 }
-__global__ void __launch_bounds__(256) k_gb_export_scatter(const uint64_t* __restrict__ entries, int64_t cap, int64_t es, int64_t ws, int n_words, int P,
+__global__ void __launch_bounds__(256) k_gb_export_scatter(const uint64_t* __restrict__ entries, int64_t cap, int64_t es, int64_t ws, int pw, int n_words, int P,
                                                            const unsigned long long* __restrict__ part_off, unsigned long long* part_cursor, uint64_t* __restrict__ rows) {
     __shared__ unsigned hist[EXP_MAX_PARTS];
     __shared__ unsigned long long base[EXP_MAX_PARTS];
@@ -771,8 +824,8 @@ __global__ void __launch_bounds__(256) k_gb_export_scatter(const uint64_t* __res
             const uint64_t* e = entries + s * es;
             uint64_t* dst = rows + (base[p] + local) * row_words;
             dst[0] = s == cap ? 0 : (s == cap + 1 ? GB_EMPTY : key);
-            dst[1] = e[ws];
-            for (int w = 0; w < n_words; w++) dst[2 + w] = e[(2 + w) * ws];
+            dst[1] = e[gb_woff(s, 1, ws, pw)];
+            for (int w = 0; w < n_words; w++) dst[2 + w] = e[gb_woff(s, 2 + w, ws, pw)];
             dst[2 + n_words] = s == cap ? 1 : (s == cap + 1 ? 2 : 0);
         }
         __syncthreads();
@@ -783,7 +836,7 @@ __global__ void __launch_bounds__(256) k_gb_export_scatter(const uint64_t* __res
 // stored straight into the destination rank's window (peer memory over NVLink): partition p's rows
 // land in region `my_rank` of windows[p] at [cursor .. cursor + n).  No staging copy, no collective.
 struct PeerWindows { uint64_t* base[EXP_MAX_PARTS]; };
-__global__ void __launch_bounds__(256) k_gb_export_p2p(const uint64_t* __restrict__ entries, int64_t cap, int64_t es, int64_t ws, int n_words, int P, const __grid_constant__ PeerWindows W,
+__global__ void __launch_bounds__(256) k_gb_export_p2p(const uint64_t* __restrict__ entries, int64_t cap, int64_t es, int64_t ws, int pw, int n_words, int P, const __grid_constant__ PeerWindows W,
                                                        int64_t region_words, int my_rank, int64_t rows_per_src, unsigned long long* part_cursor, int* overflow) {
     __shared__ unsigned hist[EXP_MAX_PARTS];
     __shared__ unsigned long long base[EXP_MAX_PARTS];
@@ -807,8 +860,8 @@ __global__ void __launch_bounds__(256) k_gb_export_p2p(const uint64_t* __restric
                 const uint64_t* e = entries + s * es;
                 uint64_t* dst = W.base[p] + (int64_t)my_rank * region_words + pos * row_words;     // peer store
                 dst[0] = s == cap ? 0 : (s == cap + 1 ? GB_EMPTY : key);
-                dst[1] = e[ws];
-                for (int w = 0; w < n_words; w++) dst[2 + w] = e[(2 + w) * ws];
+                dst[1] = e[gb_woff(s, 1, ws, pw)];
+                for (int w = 0; w < n_words; w++) dst[2 + w] = e[gb_woff(s, 2 + w, ws, pw)];
                 dst[2 + n_words] = s == cap ? 1 : (s == cap + 1 ? 2 : 0);
             }
         }
@@ -828,7 +881,7 @@ __device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v) { as
 __device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p) { uint64_t v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 constexpr unsigned long long GB_WINDOW_OVERFLOW = ~0ull;
 
-__global__ void __launch_bounds__(256) k_gb_export_p2p_async(const uint64_t* __restrict__ entries, int64_t cap, int64_t es, int64_t ws, int n_words, int P, const __grid_constant__ PeerWindows W,
+__global__ void __launch_bounds__(256) k_gb_export_p2p_async(const uint64_t* __restrict__ entries, int64_t cap, int64_t es, int64_t ws, int pw, int n_words, int P, const __grid_constant__ PeerWindows W,
                                                              int64_t region_words, int my_rank, int64_t rows_per_src, unsigned long long* part_cursor, unsigned* done, uint64_t epoch) {
     __shared__ unsigned hist[EXP_MAX_PARTS];
     __shared__ unsigned long long base[EXP_MAX_PARTS];
@@ -864,8 +917,8 @@ __global__ void __launch_bounds__(256) k_gb_export_p2p_async(const uint64_t* __r
                 const uint64_t* e = entries + s * es;
                 uint64_t* dst = W.base[p[u]] + GB_WINDOW_HEADER_WORDS + (int64_t)my_rank * region_words + pos * row_words;     // peer store
                 dst[0] = s == cap ? 0 : (s == cap + 1 ? GB_EMPTY : key[u]);
-                dst[1] = e[ws];
-                for (int w = 0; w < n_words; w++) dst[2 + w] = e[(2 + w) * ws];
+                dst[1] = e[gb_woff(s, 1, ws, pw)];
+                for (int w = 0; w < n_words; w++) dst[2 + w] = e[gb_woff(s, 2 + w, ws, pw)];
                 dst[2 + n_words] = s == cap ? 1 : (s == cap + 1 ? 2 : 0);
             }
         }
@@ -931,6 +984,8 @@ __global__ void __launch_bounds__(256) k_gb_merge_window(const __grid_constant__
 // =============================================================================================
 namespace plb {
 
+static int knob_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }   // read per call (tests flip them)
+
 static int sum_out_dtype(int dt) {
     // series/implementations/mod.rs:145-154: Int8/16, UInt8/16 sums are computed as Int64
     if (dt == BL_INT8 || dt == BL_INT16 || dt == BL_UINT8 || dt == BL_UINT16) return BL_INT64;
@@ -966,6 +1021,8 @@ GroupByState::GroupByState(int key_dt, const std::vector<int>& kinds, const std:
         plans.push_back(ap);
     }
     L.n_words = nw;
+    L.pair_k = -1; L.pair_c = -1;
+    if (L.need_len) for (int w = 0; w < nw && !pair_word; w++) if (L.slot_op[w] == W_ADD_INT) pair_word = 2 + w;
     L.stride = ((2 + nw + 3) / 4) * 4;      // whole 32-byte sectors per entry
     L.need_first = track_first ? 1 : 0;      // maintain_order / first-occurrence key output; costs one 32-bit RED per row
     status = dev_alloc(4);
@@ -980,7 +1037,14 @@ void GroupByState::alloc_table(uint64_t new_cap) {
     const int soa = [] { const char* e = getenv("BL_K5_SOA"); return e ? atoi(e) : 1; }();
     T.entries = as<uint64_t>(entries); T.cap = cap; T.shift = shift; T.status = as<int>(status); T.hint = hint;
     T.es = soa ? 1 : L.stride; T.ws = soa ? (int64_t)(cap + 2) : 1; T.soa = soa; T.pass_bits = 0; T.pass_id = 0;
-    PLB_LAUNCH("k5_table_init", k_gb_init, grid_for((int64_t)(cap + 2) * L.stride, 256), 256, 0, T.entries, (int64_t)(cap + 2), L.stride, soa, L);
+    // pair layout + bulk reduce (k_gb_consume<BULK>): only where the plain-RED kernels do not run on this table — the shared-memory plan
+    // (few groups) and the heavy-hitter kernel keep word-major planes (their cold-path REDs on len and the paired sum would share a sector)
+    const int bulk = knob_int("BL_K5_BULK", 1);
+    bool smem_plan = false;     // same rule as launch_batch
+    if (est_groups > 0 && knob_int("BL_K5_SMEM", 1)) { int64_t want = 16; while (2 * want < 3 * est_groups && want < (1 << 20)) want <<= 1; smem_plan = (size_t)(want + 2) * L.stride * 8 <= (size_t)72 * 1024; }
+    T.pw = (soa && bulk > 0 && pair_word >= 2 && hot.rows == 0 && !smem_plan) ? pair_word : 0;
+    T.bulk_lanes = T.pw ? std::min(32, std::max(0, knob_int("BL_K5_BULK_LANES", 32))) : 0;
+    PLB_LAUNCH("k5_table_init", k_gb_init, grid_for((int64_t)(cap + 2) * L.stride, 256), 256, 0, T.entries, (int64_t)(cap + 2), L.stride, soa, T.pw, L);
     dev_memset(status->p, 0, 4);
 }
 
@@ -1093,18 +1157,20 @@ uint64_t GroupByState::choose_cap(const DevCol& key, int64_t n_total) {
     return c;
 }
 
-template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int PAIRS>
+template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int PAIRS, bool BULK>
 static void launch_consume_p(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int grid) {
-    if (L.n_cols <= 1) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 1, PAIRS>), grid, 256, 0, L, T, B);
-    else if (L.n_cols <= 2) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 2, PAIRS>), grid, 256, 0, L, T, B);
-    else if (L.n_cols <= 4) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 4, PAIRS>), grid, 256, 0, L, T, B);
-    else PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 8, 1>), grid, 256, 0, L, T, B);
+    const size_t smem = BULK ? (size_t)2 * PAIRS * 256 * 16 : 0;     // staging cells of the bulk reduces
+    if (L.n_cols <= 1) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 1, PAIRS, BULK>), grid, 256, smem, L, T, B);
+    else if (L.n_cols <= 2) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 2, PAIRS, BULK>), grid, 256, smem, L, T, B);
+    else if (L.n_cols <= 4) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 4, PAIRS, BULK>), grid, 256, smem, L, T, B);
+    else PLB_LAUNCH("k5_groupby_agg", (k_gb_consume<KEY_ELEM, KEY_CANON, KEY_NULLS, 8, 1, BULK>), grid, 256, BULK ? (size_t)2 * 256 * 16 : 0, L, T, B);
 }
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS>
 static void launch_consume(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int grid) {
-    const int pairs = [] { const char* e = getenv("BL_K5_PAIRS"); int v = e ? atoi(e) : 1; return v == 2 ? 2 : 1; }();
-    if (pairs == 2) launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 2>(L, T, B, grid);
-    else launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 1>(L, T, B, grid);
+    const int pairs = knob_int("BL_K5_PAIRS", 1) == 2 ? 2 : 1;
+    if (T.pw && T.bulk_lanes > 0 && L.pair_k >= 0) launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 1, true>(L, T, B, grid);
+    else if (pairs == 2) launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 2, false>(L, T, B, grid);
+    else launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 1, false>(L, T, B, grid);
 }
 
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS, int MAXC>
@@ -1182,6 +1248,8 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
         }
     }
     for (int c = Lb.n_cols; c <= GB_MAX_COLS; c++) Lb.col_kbegin[c] = k;
+    Lb.pair_k = -1; Lb.pair_c = -1;
+    if (T.pw) for (int c = 0; c < Lb.n_cols; c++) for (int j = Lb.col_kbegin[c]; j < Lb.col_kbegin[c + 1]; j++) if (2 + Lb.wslot[j] == T.pw && Lb.wop[j] == W_ADD_INT) { Lb.pair_k = j; Lb.pair_c = c; }
     const int64_t n = key.len;
     if (n == 0) return;
     const int bps = [] { const char* e = getenv("BL_K5_BPS"); int v = e ? atoi(e) : 8; return v > 0 ? v : 8; }();
@@ -1239,9 +1307,9 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
 
 void GroupByState::grow(uint64_t new_cap) {
     // rehash: merge the old table's entries into a bigger one
-    DevPtr old = entries; const uint64_t old_cap = cap; const int64_t old_es = T.es, old_ws = T.ws;
+    DevPtr old = entries; const uint64_t old_cap = cap; const int64_t old_es = T.es, old_ws = T.ws; const int old_pw = T.pw;
     alloc_table(new_cap);
-    if (old) PLB_LAUNCH("k5_rehash", k_gb_merge, grid_for((int64_t)old_cap + 2, 256), 256, 0, L, T, as<uint64_t>(old), (int64_t)old_cap + 2, old_es, old_ws, 1, (int64_t)old_cap);
+    if (old) PLB_LAUNCH("k5_rehash", k_gb_merge, grid_for((int64_t)old_cap + 2, 256), 256, 0, L, T, as<uint64_t>(old), (int64_t)old_cap + 2, old_es, old_ws, 1, (int64_t)old_cap, old_pw);
 }
 
 int64_t GroupByState::count_groups() {
@@ -1331,7 +1399,7 @@ void GroupByState::consume(const DevCol& key, const std::vector<const DevCol*>& 
 
 void GroupByState::reset() {
     if (entries) {
-        PLB_LAUNCH("k5_table_init", k_gb_init, grid_for((int64_t)(cap + 2) * L.stride, 256), 256, 0, T.entries, (int64_t)(cap + 2), L.stride, T.soa, L);
+        PLB_LAUNCH("k5_table_init", k_gb_init, grid_for((int64_t)(cap + 2) * L.stride, 256), 256, 0, T.entries, (int64_t)(cap + 2), L.stride, T.soa, T.pw, L);
         dev_memset(status->p, 0, 4);
     }
     rows_seen = 0; merged_rows = 0;
@@ -1391,7 +1459,7 @@ DevPtr GroupByState::export_partials(int n_partitions, int* row_words_out, int64
     const int64_t G = (int64_t)ho[n_partitions];
     DevPtr rows = dev_alloc((size_t)std::max<int64_t>(G, 1) * row_words * 8);
     if (G > 0)
-        PLB_LAUNCH("k6_export_scatter", k_gb_export_scatter, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, L.n_words, n_partitions,
+        PLB_LAUNCH("k6_export_scatter", k_gb_export_scatter, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, T.pw, L.n_words, n_partitions,
                    as<unsigned long long>(off), as<unsigned long long>(cursor), as<uint64_t>(rows));
     PLB_CUDA(cudaStreamSynchronize(ctx().stream));   // ho[] is on this stack frame
     return rows;
@@ -1407,7 +1475,7 @@ void GroupByState::export_partials_p2p(int n_ranks, int my_rank, void* const* wi
     for (int p = 0; p < n_ranks; p++) { PLB_REQUIRE(windows[p] != nullptr, BL_ERR_INVALID, "export_partials_p2p: null window"); W.base[p] = reinterpret_cast<uint64_t*>(windows[p]); }
     DevPtr cursor = dev_alloc(8 * EXP_MAX_PARTS), ovf = dev_alloc(4);
     dev_memset(cursor->p, 0, 8 * EXP_MAX_PARTS); dev_memset(ovf->p, 0, 4);
-    PLB_LAUNCH("k6_export_p2p", k_gb_export_p2p, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, L.n_words, n_ranks, W,
+    PLB_LAUNCH("k6_export_p2p", k_gb_export_p2p, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, T.pw, L.n_words, n_ranks, W,
                rows_per_src * row_words, my_rank, rows_per_src, as<unsigned long long>(cursor), as<int>(ovf));
     unsigned long long h[EXP_MAX_PARTS];
     PLB_CUDA(cudaMemcpyAsync(h, cursor->p, 8 * n_ranks, cudaMemcpyDeviceToHost, ctx().stream));
@@ -1426,7 +1494,7 @@ void GroupByState::export_partials_p2p_async(int n_ranks, int my_rank, void* con
     if (!entries) alloc_table(1024);          // nothing consumed: still publish zero counts so that no peer waits
     DevPtr ctl = dev_alloc(8 * EXP_MAX_PARTS + 8);
     dev_memset(ctl->p, 0, 8 * EXP_MAX_PARTS + 8);
-    PLB_LAUNCH("k6_export_p2p", k_gb_export_p2p_async, grid_for(((int64_t)cap + 2 + 3) / 4, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, L.n_words, n_ranks, W,
+    PLB_LAUNCH("k6_export_p2p", k_gb_export_p2p_async, grid_for(((int64_t)cap + 2 + 3) / 4, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, T.pw, L.n_words, n_ranks, W,
                rows_per_src * row_words, my_rank, rows_per_src, as<unsigned long long>(ctl), reinterpret_cast<unsigned*>(as<unsigned long long>(ctl) + EXP_MAX_PARTS), epoch);
 }
 
@@ -1476,7 +1544,7 @@ void GroupByState::finish(bool maintain_order, const DevCol* key_col_for_gather,
     }
     if (entries && !dense.ready) {
         PLB_CUDA(cudaMemcpyAsync(&status_host, status->p, 4, cudaMemcpyDeviceToHost, ctx().stream));
-        PLB_LAUNCH("k5_extract", k_gb_extract, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, L.n_words, as<unsigned long long>(ctl),
+        PLB_LAUNCH("k5_extract", k_gb_extract, grid_for((int64_t)cap + 2, 256), 256, 0, T.entries, (int64_t)cap, T.es, T.ws, T.pw, L.n_words, as<unsigned long long>(ctl),
                    as<uint64_t>(keys), as<uint32_t>(first), as<uint32_t>(len), as<uint64_t>(words), Gb, as<long long>(ctl) + 1);
         PLB_CUDA(cudaMemcpyAsync(ctl_host, ctl->p, 16, cudaMemcpyDeviceToHost, ctx().stream));
     }
@@ -1572,7 +1640,7 @@ __global__ void __launch_bounds__(256) k_gb_lookup_first(const __grid_constant__
                 slot = (slot + 1) & mask;
             }
         }
-        const uint64_t w1 = __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + slot * T.es + T.ws));
+        const uint64_t w1 = __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + slot * T.es + gb_woff((int64_t)slot, 1, T.ws, T.pw)));
         out[row] = (uint32_t)(w1 >> 32);
     }
 }

@@ -16,14 +16,27 @@ enum WordOp { W_ADD_INT = 0, W_ADD_F64 = 1, W_MIN_S64 = 2, W_MAX_S64 = 3, W_MIN_
 struct GbColDev { const void* values; const uint32_t* validity; int32_t dtype; int32_t elem; };
 struct GbLayout {
     int32_t stride, n_words, n_cols, need_len, need_first;
+    int32_t pair_k, pair_c;           // per batch: iteration index k (and its column) of the accumulator that shares a 16-byte cell with word 1 (-1: none)
     int32_t wslot[GB_MAX_WORDS];      // iteration order k -> accumulator word index (table word = 2 + slot)
     int32_t wop[GB_MAX_WORDS];        // iteration order k -> WordOp
     int32_t col_kbegin[GB_MAX_COLS + 1];
     int32_t slot_op[GB_MAX_WORDS];    // word index -> WordOp (merge / init)
     uint64_t init[GB_MAX_WORDS];      // word index -> identity
 };
-// word w of entry s: entries[s * es + w * ws]  (AoS: es = stride, ws = 1;  word-major planes: es = 1, ws = cap + 2)
-struct GbTableDev { uint64_t* entries; uint64_t cap; int64_t es, ws; int32_t shift; int32_t soa; int32_t* status; int32_t hint; int32_t pass_bits; int32_t pass_id; int32_t pad; };
+// word w of entry s: entries[s * es + w * ws]  (AoS: es = stride, ws = 1;  word-major planes: es = 1, ws = cap + 2).
+// Pair layout (pw != 0, word-major only): word 1 (len | first) and accumulator word pw (a 64-bit integer sum) of slot s share the
+// 16-byte cell entries[ws + 2 s .. ws + 2 s + 1] (planes 1 and 2 of the word-major form), so that ONE bulk reduce
+// (cp.reduce.async.bulk .add.u64, 16 bytes) updates both; word 2, if it is not pw itself, moves to plane pw.  gb_woff() is the
+// only place that knows this.
+struct GbTableDev { uint64_t* entries; uint64_t cap; int64_t es, ws; int32_t shift; int32_t soa; int32_t* status; int32_t hint; int32_t pass_bits; int32_t pass_id; int32_t pw; int32_t bulk_lanes; int32_t pad; };
+// offset of word w of slot s, in words from (entries + s * es)
+__host__ __device__ __forceinline__ int64_t gb_woff(int64_t s, int w, int64_t ws, int pw) {
+    if (pw) {
+        if (w == 1 || w == pw) return ws + s + (w != 1);
+        if (w == 2) w = pw;
+    }
+    return (int64_t)w * ws;
+}
 struct GbBatch {
     const void* keys; const uint32_t* key_validity; int64_t n; uint32_t row_base; int32_t key_dtype;
     GbColDev cols[GB_MAX_COLS];
@@ -51,6 +64,7 @@ struct GroupByState {
     int64_t expected_groups;
     std::vector<AggPlan> plans;
     GbLayout L;
+    int pair_word = 0;           // table word (>= 2) of the first 64-bit integer sum when len is tracked too: candidates for the pair layout
     GbTableDev T{};
     DevPtr entries, status;
     uint64_t cap = 0;

@@ -930,7 +930,7 @@ def test_group_by_deterministic_mode_is_bit_exact(plb):
 
 
 @pytest.mark.parametrize("knob,value", [("BL_K5_SOA", "0"), ("BL_K5_PAIRS", "2"), ("BL_K5_HINT", "1"), ("BL_K5_HINT", "3"), ("BL_K5_MULTIPASS", "0"), ("BL_K5_SMEM", "0"),
-                                        ("BL_K5_RADIX", "0"), ("BL_K5_LF", "30")])
+                                        ("BL_K5_RADIX", "0"), ("BL_K5_LF", "30"), ("BL_K5_BULK", "0"), ("BL_K5_BULK_LANES", "12")])
 def test_group_by_knob_variants(plb, monkeypatch, knob, value):
     """Every documented BL_K5_* fallback (entry-major table, 4 rows per thread, L2 policy hints, single pass beyond L2, no
     CTA-private tables, ...) is read per call and has to give the reference's answer."""
@@ -949,6 +949,30 @@ def test_group_by_knob_variants(plb, monkeypatch, knob, value):
         assert_close(keys, ek, kv, ekv, "keys")
         for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
             assert_close(v, ev, m, em, f"{knob}={value} {kind}")
+
+
+@pytest.mark.parametrize("val_dtype,order", [("int64", False), ("int64", True), ("int32", False), ("uint64", True)])
+def test_group_by_bulk_reduce_pair_layout(plb, val_dtype, order):
+    """Pair layout + TMA bulk reduce (len and the first integer sum share a 16-byte table cell): the integer sum is NOT the first
+    accumulator here (the displaced word moves to the sum's plane), values wrap, columns carry nulls, maintain_order tracks
+    `first` in the high half of the cell's first word, and an odd row count exercises the scalar tail."""
+    rng = np.random.default_rng(11)
+    n, k = 400_001, 120_000
+    key = (rng.integers(0, k, n) * 104729 - 5 * 10**8).astype(np.int64); key[::1009] = -2**63
+    kvalid = rng.random(n) > 0.02
+    info = np.iinfo(val_dtype)
+    vi = rng.integers(info.min // 2, info.max // 2, n, dtype=val_dtype); ivalid = rng.random(n) > 0.1
+    vf = rng.uniform(-50, 50, n).round(6); fvalid = rng.random(n) > 0.2
+    aggs = [("mean", vf, fvalid), ("max", vf, fvalid), ("sum", vi, ivalid), ("len", None, None), ("count", vi, ivalid), ("min", vi, None)]
+    keys, kv, outs = GpuImpl(plb).group_by_agg(key, kvalid, aggs, order)
+    ek, ekv, eouts, _ = oracle.group_by_agg(key, kvalid, aggs, 8, order)
+    if not order:
+        keys, kv, outs = sort_groups(keys, kv, outs)
+        ek, ekv, eouts = sort_groups(ek, ekv, eouts)
+    assert_close(keys, ek, kv, ekv, "keys")
+    for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
+        assert v.dtype == ev.dtype, (kind, v.dtype, ev.dtype)
+        assert_close(v, ev, m, em, f"pair layout {kind}")
 
 
 @pytest.mark.parametrize("knob,value", [("BL_JOIN_FUSED", "0"), ("BL_JOIN_TABLE", "compact"), ("BL_JOIN_DENSE", "0")])

@@ -89,6 +89,44 @@ __global__ void k_bulk_b4(uint64_t* entries, uint64_t mask, int64_t nops) {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// closer to K5: 2 rows per thread per iteration from streamed 128-bit loads of three 8-byte columns, single staging ring
+// (wait_group.read 0), grid-stride with `g` CTAs per SM.  MODE 0: 3 REDs; 1: bulk {len,sum} + RED f64; 2: bulk only; 3: bulk, RED issued before the fence
+template <int MODE>
+__global__ void __launch_bounds__(256) k_real(const ulonglong2* __restrict__ kcol, const ulonglong2* __restrict__ icol, const ulonglong2* __restrict__ fcol, const uint64_t* keys, uint64_t* pair, unsigned* len, uint64_t* si, double* sf, uint64_t mask, int64_t npairs) {
+    extern __shared__ __align__(128) uint64_t sm[];
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * blockDim.x) {
+        const ulonglong2 k2 = __ldcs(kcol + p), i2 = __ldcs(icol + p), f2 = __ldcs(fcol + p);
+        const uint64_t kk[2] = {k2.x, k2.y}, iv[2] = {i2.x, i2.y}; const double fv[2] = {__longlong_as_double((long long)f2.x), __longlong_as_double((long long)f2.y)};
+        uint64_t slot[2], k0[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++) { slot[r] = mix(kk[r]) & mask; k0[r] = __ldcg(keys + slot[r]); }
+        if (MODE >= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (MODE == 3) {
+#pragma unroll
+            for (int r = 0; r < 2; r++) if (k0[r] != 0xdeadbeefULL) red_f64(sf + slot[r], fv[r]);
+        }
+        if (MODE >= 1) {
+#pragma unroll
+            for (int r = 0; r < 2; r++) { uint64_t* c = sm + 2 * (r * 256 + threadIdx.x); c[0] = 1; c[1] = iv[r]; }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                if (k0[r] == 0xdeadbeefULL) continue;
+                uint32_t sa = (uint32_t)__cvta_generic_to_shared(sm + 2 * (r * 256 + threadIdx.x));
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], 16;" :: "l"(pair + 2 * slot[r]), "r"(sa) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            if (k0[r] == 0xdeadbeefULL) continue;
+            if (MODE == 0) { red_u32(len + slot[r], 1u); red_u64(si + slot[r], iv[r]); }
+            if (MODE <= 1) red_f64(sf + slot[r], fv[r]);
+        }
+    }
+    if (MODE >= 1) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <typename F> float timeit(F f, int reps = 4) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     f(); CK(cudaDeviceSynchronize());
@@ -145,6 +183,21 @@ int main(int argc, char** argv) {
         auto kern16 = k_bulk_b4<16>; const int smem16 = 256 * 16 * 4;
         ms = timeit([&] { kern16<<<sms * 8, 256, smem16>>>(ent, mask, nops); });
         printf("{\"test\": \"bulk_reduce_batched4\", \"bytes\": 16, \"Grows\": %.2f, \"ms\": %.3f}\n", nops / ms / 1e6, ms);
+    }
+    {
+        const int64_t npairs = nops / 2;
+        ulonglong2 *kc, *ic, *fc; CK(cudaMalloc(&kc, npairs * 16)); CK(cudaMalloc(&ic, npairs * 16)); CK(cudaMalloc(&fc, npairs * 16));
+        CK(cudaMemset(ic, 1, npairs * 16)); CK(cudaMemset(fc, 0x3f, npairs * 16));
+        {   // keys = row index (mix() makes the slots random)
+            uint64_t* h = (uint64_t*)malloc(nops * 8); for (int64_t i = 0; i < nops; i++) h[i] = (uint64_t)i * 0x9E3779B97F4A7C15ull; CK(cudaMemcpy(kc, h, nops * 8, cudaMemcpyHostToDevice)); free(h);
+        }
+        for (int g : {4, 8}) {
+            float m0 = timeit([&] { k_real<0><<<sms * g, 256, 8192>>>(kc, ic, fc, keys, ent, len, si, sf, mask, npairs); });
+            float m1 = timeit([&] { k_real<1><<<sms * g, 256, 8192>>>(kc, ic, fc, keys, ent, len, si, sf, mask, npairs); });
+            float m2 = timeit([&] { k_real<2><<<sms * g, 256, 8192>>>(kc, ic, fc, keys, ent, len, si, sf, mask, npairs); });
+            float m3 = timeit([&] { k_real<3><<<sms * g, 256, 8192>>>(kc, ic, fc, keys, ent, len, si, sf, mask, npairs); });
+            printf("{\"test\": \"k5_like\", \"ctas_per_sm\": %d, \"three_red_ms\": %.3f, \"bulk_plus_red_ms\": %.3f, \"bulk_only_ms\": %.3f, \"red_before_fence_ms\": %.3f}\n", g, m0, m1, m2, m3);
+        }
     }
     return 0;
 }
