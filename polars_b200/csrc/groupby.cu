@@ -100,9 +100,10 @@ __device__ __forceinline__ uint64_t* gb_wp(const GbTableDev& T, uint64_t* e, int
 //      Measured on B200 (profiles/r02_ubench2_bulkred.jsonl): key load + this + 1 RED.F64 retires 73 G rows/s against 54-60 G rows/s
 //      for key load + 3 REDs — the L2 / LSU RED rate (~195 G/s) is the ceiling of the table update and the TMA unit is a second,
 //      otherwise idle, path into the same L2 atomic units.  SASS: UBLKRED.G.S.ADD.U64 (uniform datapath: ptxas serialises the lanes).
-__device__ __forceinline__ void bulk_add_u64x2(uint64_t* dst, const uint64_t* src_smem) {
+__device__ __forceinline__ void bulk_add_u64x2(uint64_t* dst, const uint64_t* src_smem, uint64_t pol, bool hint) {
     const uint32_t sa = (uint32_t)__cvta_generic_to_shared(src_smem);
-    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], 16;" :: "l"(dst), "r"(sa) : "memory");
+    if (hint) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.L2::cache_hint.add.u64 [%0], [%1], 16, %2;" :: "l"(dst), "r"(sa), "l"(pol) : "memory");
+    else asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], 16;" :: "l"(dst), "r"(sa) : "memory");
 }
 
 __device__ __forceinline__ void gb_apply(int op, uint64_t* addr, int dtype, uint64_t raw, bool valid, uint64_t pol = 0, bool hint = false) {
@@ -189,16 +190,15 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
                 for (int r = 0; r < R; r++) {
                     if (ent[r] == nullptr) continue;
                     const int64_t row = 2 * (p0 + (r >> 1) * gstride) + (r & 1);
-                    uint64_t pv = 0;
-#pragma unroll
-                    for (int c = 0; c < MAXC; c++)
-                        if (c == L.pair_c) pv = (B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row)) ? raw_to_int(B.cols[c].dtype, raw[c][r]) : 0ull;
+                    // the paired sum's column is bound to column 0 of the batch (launch_batch): a runtime column index here made
+                    // ptxas spill raw[][] to local memory (STL.128 per row: 1.6 GB of local stores, 1.1 GB of DRAM writes in ncu)
+                    const uint64_t pv = (B.cols[0].validity == nullptr || bit_get(B.cols[0].validity, row)) ? raw_to_int(B.cols[0].dtype, raw[0][r]) : 0ull;
                     uint64_t* cell = gb_stage + 2 * (r * 256 + (int)threadIdx.x);
                     asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"((uint32_t)__cvta_generic_to_shared(cell)), "l"((uint64_t)(L.need_len ? 1 : 0)), "l"(pv) : "memory");
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores above -> visible to the TMA unit
 #pragma unroll
-                for (int r = 0; r < R; r++) if (ent[r]) bulk_add_u64x2(gb_wp(T, ent[r], 1), gb_stage + 2 * (r * 256 + (int)threadIdx.x));
+                for (int r = 0; r < R; r++) if (ent[r]) bulk_add_u64x2(gb_wp(T, ent[r], 1), gb_stage + 2 * (r * 256 + (int)threadIdx.x), pol, hint);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
@@ -243,6 +243,77 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------- K5, lean bulk-reduce kernel
+// The general k_gb_consume<BULK> executes ~570 warp instructions per row pair (dtype / validity / layout dispatch + two 32-lane
+// UBLKRED issue loops) and is issue-bound (ncu: 65 % issue slots busy, L2 at 54 %).  This kernel is the same algorithm for the
+// common analytic shape — 8-byte integer key without nulls, every value column 8 bytes wide without a validity bitmap, at most
+// two accumulators per column, single pass, pair layout — with everything that is uniform per launch hoisted out of the row
+// loop.  Column 0 carries the paired integer sum (launch_batch binds it there).
+template <int NC>
+__global__ void __launch_bounds__(256) k_gb_consume_lean(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const __grid_constant__ GbBatch B) {
+    extern __shared__ __align__(16) uint64_t gb_stage[];
+    const int64_t npairs = B.n >> 1;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    uint64_t* const cells = T.entries + T.ws;              // {len | first, paired sum} per slot
+    int op[NC][2]; uint64_t* plane[NC][2]; int dt[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        dt[c] = B.cols[c].dtype;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int k = L.col_kbegin[c] + j;
+            const bool on = k < L.col_kbegin[c + 1] && k != L.pair_k;
+            op[c][j] = on ? L.wop[k] : -1;
+            plane[c][j] = on ? T.entries + gb_woff(0, 2 + L.wslot[k], T.ws, T.pw) : nullptr;
+        }
+    }
+    uint64_t* const cell0 = gb_stage + 2 * (int)threadIdx.x, * const cell1 = cell0 + 512;
+    int iter = 0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += gstride) {
+        if (((iter++) & 15) == 0 && *reinterpret_cast<volatile int*>(T.status)) break;
+        const ulonglong2 k2 = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(B.keys) + 2 * p);
+        ulonglong2 raw[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) raw[c] = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(B.cols[c].values) + 2 * p);
+        const uint64_t key0 = k2.x, key1 = k2.y;
+        const uint64_t s0 = table_hash(key0) >> T.shift, s1 = table_hash(key1) >> T.shift;
+        const uint64_t q0 = __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + s0)), q1 = __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + s1));
+        uint64_t* const e0 = key0 == GB_EMPTY ? gb_special(T, 1) : gb_resolve(T, key0, s0, q0, 0, 0);
+        uint64_t* const e1 = key1 == GB_EMPTY ? gb_special(T, 1) : gb_resolve(T, key1, s1, q1, 0, 0);
+        // bulk reduces first (see k_gb_consume); the staging cells of the previous iteration must have been read
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"((uint32_t)__cvta_generic_to_shared(cell0)), "l"(1ull), "l"(raw[0].x) : "memory");
+        asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"((uint32_t)__cvta_generic_to_shared(cell1)), "l"(1ull), "l"(raw[0].y) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (e0) bulk_add_u64x2(cells + 2 * (e0 - T.entries), cell0, 0, false);
+        if (e1) bulk_add_u64x2(cells + 2 * (e1 - T.entries), cell1, 0, false);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                if (op[c][j] < 0) continue;
+                if (e0) gb_apply(op[c][j], plane[c][j] + (e0 - T.entries), dt[c], raw[c].x, true);
+                if (e1) gb_apply(op[c][j], plane[c][j] + (e1 - T.entries), dt[c], raw[c].y, true);
+            }
+        }
+    }
+    // odd tail row: plain atomics
+    if ((B.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t row = B.n - 1;
+        const uint64_t key = reinterpret_cast<const uint64_t*>(B.keys)[row];
+        uint64_t* e = key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key);
+        if (e) {
+            atomicAdd(reinterpret_cast<unsigned*>(gb_wp(T, e, 1)), 1u);
+            for (int c = 0; c < L.n_cols; c++) {
+                const uint64_t rv = reinterpret_cast<const uint64_t*>(B.cols[c].values)[row];
+                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], gb_wp(T, e, 2 + L.wslot[k]), B.cols[c].dtype, rv, true);
+            }
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ void gb_merge_row(const GbLayout& L, const GbTableDev& T, const uint64_t* src, int meta, int64_t sws = 1, int64_t sslot = 0, int spw = 0);
@@ -1039,7 +1110,10 @@ void GroupByState::alloc_table(uint64_t new_cap) {
     T.es = soa ? 1 : L.stride; T.ws = soa ? (int64_t)(cap + 2) : 1; T.soa = soa; T.pass_bits = 0; T.pass_id = 0;
     // pair layout + bulk reduce (k_gb_consume<BULK>): only where the plain-RED kernels do not run on this table — the shared-memory plan
     // (few groups) and the heavy-hitter kernel keep word-major planes (their cold-path REDs on len and the paired sum would share a sector)
-    const int bulk = knob_int("BL_K5_BULK", 1);
+    // BL_K5_BULK: 0 never; 1 (default) where the lean kernel applies (measured 1.52-1.57 ms against 1.96 ms for the 3-RED kernel on C2;
+    // the GENERAL bulk kernel is issue-bound and loses: 2.26 ms, 4.25 vs 3.14 ms with 5 % nulls); 2 always (parity tests of the general kernel)
+    const int bulk_knob = knob_int("BL_K5_BULK", 1);
+    const int bulk = bulk_knob >= 2 ? 1 : (bulk_knob == 1 && lean_shape ? 1 : 0);
     bool smem_plan = false;     // same rule as launch_batch
     if (est_groups > 0 && knob_int("BL_K5_SMEM", 1)) { int64_t want = 16; while (2 * want < 3 * est_groups && want < (1 << 20)) want <<= 1; smem_plan = (size_t)(want + 2) * L.stride * 8 <= (size_t)72 * 1024; }
     T.pw = (soa && bulk > 0 && pair_word >= 2 && hot.rows == 0 && !smem_plan) ? pair_word : 0;
@@ -1168,7 +1242,18 @@ static void launch_consume_p(const GbLayout& L, const GbTableDev& T, const GbBat
 template <int KEY_ELEM, int KEY_CANON, bool KEY_NULLS>
 static void launch_consume(const GbLayout& L, const GbTableDev& T, const GbBatch& B, int grid) {
     const int pairs = knob_int("BL_K5_PAIRS", 1) == 2 ? 2 : 1;
-    if (T.pw && T.bulk_lanes > 0 && L.pair_k >= 0) launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 1, true>(L, T, B, grid);
+    if (T.pw && T.bulk_lanes > 0 && L.pair_k >= 0) {
+        // lean kernel for the common analytic shape (see k_gb_consume_lean)
+        bool lean = KEY_ELEM == 8 && KEY_CANON == 0 && !KEY_NULLS && T.bulk_lanes == 32 && !T.pass_bits && !T.hint && !L.need_first && L.need_len && L.n_cols >= 1 && L.n_cols <= 3 &&
+                    knob_int("BL_K5_LEAN", 1) != 0;
+        for (int c = 0; lean && c < L.n_cols; c++) lean = B.cols[c].elem == 8 && B.cols[c].validity == nullptr && L.col_kbegin[c + 1] - L.col_kbegin[c] <= 2;
+        if (lean) {
+            const size_t smem = (size_t)2 * 256 * 16;
+            if (L.n_cols == 1) PLB_LAUNCH("k5_groupby_agg", k_gb_consume_lean<1>, grid, 256, smem, L, T, B);
+            else if (L.n_cols == 2) PLB_LAUNCH("k5_groupby_agg", k_gb_consume_lean<2>, grid, 256, smem, L, T, B);
+            else PLB_LAUNCH("k5_groupby_agg", k_gb_consume_lean<3>, grid, 256, smem, L, T, B);
+        } else launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 1, true>(L, T, B, grid);
+    }
     else if (pairs == 2) launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 2, false>(L, T, B, grid);
     else launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 1, false>(L, T, B, grid);
 }
@@ -1220,7 +1305,11 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
     GbBatch B; memset(&B, 0, sizeof B);
     B.keys = key.v(); B.key_validity = key.vm(); B.n = key.len; B.row_base = (uint32_t)row_base; B.key_dtype = key.dtype;
     std::vector<const void*> col_ptr; std::vector<int> col_of_agg(plans.size(), -1);
-    for (size_t i = 0; i < plans.size(); i++) {
+    // pair layout: the column of the paired integer sum is bound first (column 0: the bulk-reduce kernel reads it with a static index)
+    std::vector<size_t> plan_order;
+    for (size_t i = 0; i < plans.size(); i++) if (T.pw && plans[i].main == T.pw - 2) plan_order.push_back(i);
+    for (size_t i = 0; i < plans.size(); i++) if (!(T.pw && plans[i].main == T.pw - 2)) plan_order.push_back(i);
+    for (size_t i : plan_order) {
         if (plans[i].kind == BL_AGG_LEN) continue;
         const DevCol* v = values[i];
         PLB_REQUIRE(v != nullptr && v->len == key.len, BL_ERR_INVALID, "group_by: value column length differs from key length");
@@ -1249,11 +1338,15 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
     }
     for (int c = Lb.n_cols; c <= GB_MAX_COLS; c++) Lb.col_kbegin[c] = k;
     Lb.pair_k = -1; Lb.pair_c = -1;
-    if (T.pw) for (int c = 0; c < Lb.n_cols; c++) for (int j = Lb.col_kbegin[c]; j < Lb.col_kbegin[c + 1]; j++) if (2 + Lb.wslot[j] == T.pw && Lb.wop[j] == W_ADD_INT) { Lb.pair_k = j; Lb.pair_c = c; }
+    if (T.pw) for (int c = 0; c < Lb.n_cols; c++) for (int j = Lb.col_kbegin[c]; j < Lb.col_kbegin[c + 1]; j++) if (c == 0 && 2 + Lb.wslot[j] == T.pw && Lb.wop[j] == W_ADD_INT) { Lb.pair_k = j; Lb.pair_c = c; }
     const int64_t n = key.len;
     if (n == 0) return;
-    const int bps = [] { const char* e = getenv("BL_K5_BPS"); int v = e ? atoi(e) : 8; return v > 0 ? v : 8; }();
+    // CTAs per SM of the grid-stride launch (more than are resident: 5-6): measured on C2 (profiles/r02_sweep_bulk_v4.jsonl), lean kernel
+    // 8 -> 1.573 ms, 16 -> 1.510, 32 -> 1.471, 48 -> 1.458; 3-RED kernel 8 -> 1.933, 16 -> 1.918, 24 -> 1.791 (shorter CTAs even out the tail)
+    const bool lean_table = T.pw != 0 && lean_shape;
+    const int bps = std::max(1, knob_int("BL_K5_BPS", lean_table ? 48 : 24));
     const int grid = grid_for((n / 2 + 1), 256, bps);
+    const int grid_hot = grid_for((n / 2 + 1), 256, std::max(1, knob_int("BL_K5_BPS", 8)));     // every warp merges its private rows at the end: keep the CTA count low
     const bool kn = key.validity != nullptr;
     const int elem = dtype_size(key.dtype);
     const int canon = key.dtype == BL_FLOAT64 ? 1 : (key.dtype == BL_FLOAT32 ? 2 : 0);
@@ -1295,7 +1388,7 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
     const bool use_hot = hot.rows > 0;
 #define GB_LAUNCH_ALL(E, C, KN)                                                      \
     do { for (int h = 0; h < (1 << pass_bits); h++) { Tp.pass_bits = pass_bits; Tp.pass_id = h;                                              \
-             if (use_hot) launch_hot<E, C, KN>(Lb, Tp, B, hot, grid); else launch_consume<E, C, KN>(Lb, Tp, B, grid); } } while (0)
+             if (use_hot) launch_hot<E, C, KN>(Lb, Tp, B, hot, grid_hot); else launch_consume<E, C, KN>(Lb, Tp, B, grid); } } while (0)
 #define GB_DISPATCH(E, C)                                                            \
     do { if (scap) { if (kn) launch_smem<E, C, true>(Lb, T, B, scap); else launch_smem<E, C, false>(Lb, T, B, scap); }                       \
          else if (kn) GB_LAUNCH_ALL(E, C, true); else GB_LAUNCH_ALL(E, C, false); } while (0)
@@ -1303,6 +1396,22 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
     else { if (canon == 2) GB_DISPATCH(4, 2); else GB_DISPATCH(4, 0); }
 #undef GB_DISPATCH
 #undef GB_LAUNCH_ALL
+}
+
+// does the batch have the shape k_gb_consume_lean takes?  (decides the table layout, so it is asked before alloc_table)
+void GroupByState::note_batch_shape(const DevCol& key, const std::vector<const DevCol*>& values) {
+    bool ok = pair_word >= 2 && !L.need_first && L.need_len && key.validity == nullptr && (key.dtype == BL_INT64 || key.dtype == BL_UINT64);
+    std::vector<const void*> cols; std::vector<int> words;
+    for (size_t i = 0; ok && i < plans.size(); i++) {
+        if (plans[i].kind == BL_AGG_LEN) continue;
+        const DevCol* v = i < values.size() ? values[i] : nullptr;
+        if (!v || dtype_size(v->dtype) != 8 || v->validity != nullptr) { ok = false; break; }
+        size_t c = 0; while (c < cols.size() && cols[c] != v->v()) c++;
+        if (c == cols.size()) { cols.push_back(v->v()); words.push_back(0); }
+        words[c] += plans[i].main >= 0 ? 1 : 0;
+    }
+    for (int w : words) ok = ok && w <= 2;
+    lean_shape = ok && !cols.empty() && cols.size() <= 3;
 }
 
 void GroupByState::grow(uint64_t new_cap) {
@@ -1340,7 +1449,7 @@ void GroupByState::consume_pipelined(const DevCol& key, const std::vector<const 
         const int64_t lo = (int64_t)ci * chunk_rows, len = std::min<int64_t>(chunk_rows, n - lo);
         PLB_CUDA(cudaStreamWaitEvent(c.stream, ready[ci], 0));
         DevCol ks = slice(key, lo, len);
-        if (ci == 0) alloc_table(choose_cap(ks, n));
+        if (ci == 0) { note_batch_shape(key, values); alloc_table(choose_cap(ks, n)); }
         std::vector<DevCol> vs(values.size()); std::vector<const DevCol*> vp(values.size(), nullptr);
         for (size_t i = 0; i < values.size(); i++) {
             if (!values[i]) continue;
@@ -1367,6 +1476,7 @@ void GroupByState::consume_all(const DevCol& key, const std::vector<const DevCol
     PLB_REQUIRE(key.dtype == key_dtype, BL_ERR_DTYPE, "group_by: key dtype differs from the plan");
     PLB_REQUIRE(key.len <= 0xFFFFFFFEll, BL_ERR_UNSUPPORTED, "group_by: more than 2^32-2 rows (IdxSize = u32)");
     uint64_t c = choose_cap(key, key.len);
+    note_batch_shape(key, values);
     if (consume_radix(key, values, c)) return;      // tables beyond L2: partition the rows instead (groupby_radix.cu)
     // optimistic: no host round trip here — finish() reads the status word together with the group count and, if the sampled
     // estimate was too small, redoes the batch into a table 8x larger (the inputs outlive the state in every caller)
@@ -1382,7 +1492,7 @@ void GroupByState::consume_all(const DevCol& key, const std::vector<const DevCol
 void GroupByState::consume(const DevCol& key, const std::vector<const DevCol*>& values, int64_t row_base) {
     PLB_REQUIRE(key.dtype == key_dtype, BL_ERR_DTYPE, "group_by: key dtype differs from the plan");
     PLB_REQUIRE(row_base + key.len <= 0xFFFFFFFEll, BL_ERR_UNSUPPORTED, "group_by: more than 2^32-2 rows (IdxSize = u32)");
-    if (!entries) alloc_table(choose_cap(key, key.len));
+    if (!entries) { note_batch_shape(key, values); alloc_table(choose_cap(key, key.len)); }
     else if (expected_groups <= 0) {
         // a later batch can bring more NEW keys than the spare capacity (sorted / time-clustered streams): sample every
         // batch and grow (a rehash keeps the accumulators) until groups so far + the batch's estimate fit at load <= 0.6

@@ -64,6 +64,7 @@ struct GroupByState {
     int64_t expected_groups;
     std::vector<AggPlan> plans;
     GbLayout L;
+    bool lean_shape = false;     // the first batch had the shape of k_gb_consume_lean (note_batch_shape)
     int pair_word = 0;           // table word (>= 2) of the first 64-bit integer sum when len is tracked too: candidates for the pair layout
     GbTableDev T{};
     DevPtr entries, status;
@@ -99,6 +100,7 @@ struct GroupByState {
 
    private:
     void alloc_table(uint64_t new_cap);
+    void note_batch_shape(const DevCol& key, const std::vector<const DevCol*>& values);
     uint64_t choose_cap(const DevCol& key, int64_t n_total);
     void build_hot_list(const void* candidates, int n_cand, bool null_hot, bool empty_hot, double sample_rows);
     void launch_batch(const DevCol& key, const std::vector<const DevCol*>& values, int64_t row_base);

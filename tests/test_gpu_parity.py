@@ -930,7 +930,7 @@ def test_group_by_deterministic_mode_is_bit_exact(plb):
 
 
 @pytest.mark.parametrize("knob,value", [("BL_K5_SOA", "0"), ("BL_K5_PAIRS", "2"), ("BL_K5_HINT", "1"), ("BL_K5_HINT", "3"), ("BL_K5_MULTIPASS", "0"), ("BL_K5_SMEM", "0"),
-                                        ("BL_K5_RADIX", "0"), ("BL_K5_LF", "30"), ("BL_K5_BULK", "0"), ("BL_K5_BULK_LANES", "12")])
+                                        ("BL_K5_RADIX", "0"), ("BL_K5_LF", "30"), ("BL_K5_BULK", "0"), ("BL_K5_BULK", "2"), ("BL_K5_LEAN", "0")])
 def test_group_by_knob_variants(plb, monkeypatch, knob, value):
     """Every documented BL_K5_* fallback (entry-major table, 4 rows per thread, L2 policy hints, single pass beyond L2, no
     CTA-private tables, ...) is read per call and has to give the reference's answer."""
@@ -952,10 +952,13 @@ def test_group_by_knob_variants(plb, monkeypatch, knob, value):
 
 
 @pytest.mark.parametrize("val_dtype,order", [("int64", False), ("int64", True), ("int32", False), ("uint64", True)])
-def test_group_by_bulk_reduce_pair_layout(plb, val_dtype, order):
-    """Pair layout + TMA bulk reduce (len and the first integer sum share a 16-byte table cell): the integer sum is NOT the first
+def test_group_by_bulk_reduce_pair_layout(plb, monkeypatch, val_dtype, order):
+    """General bulk kernel (BL_K5_BULK=2; by default only the lean kernel's shape takes the pair layout).
+    Pair layout + TMA bulk reduce (len and the first integer sum share a 16-byte table cell): the integer sum is NOT the first
     accumulator here (the displaced word moves to the sum's plane), values wrap, columns carry nulls, maintain_order tracks
     `first` in the high half of the cell's first word, and an odd row count exercises the scalar tail."""
+    monkeypatch.setenv("BL_K5_BULK", "2")
+    monkeypatch.setenv("BL_K5_BULK_LANES", "32" if order else "20")
     rng = np.random.default_rng(11)
     n, k = 400_001, 120_000
     key = (rng.integers(0, k, n) * 104729 - 5 * 10**8).astype(np.int64); key[::1009] = -2**63
@@ -973,6 +976,32 @@ def test_group_by_bulk_reduce_pair_layout(plb, val_dtype, order):
     for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
         assert v.dtype == ev.dtype, (kind, v.dtype, ev.dtype)
         assert_close(v, ev, m, em, f"pair layout {kind}")
+
+
+@pytest.mark.parametrize("shape", ["c2", "three_cols", "sum_last", "uint_key"])
+def test_group_by_lean_bulk_kernel(plb, shape):
+    """k_gb_consume_lean (default for 8-byte keys / value columns without nulls): len + integer sum as one 16-byte bulk reduce per row,
+    the other accumulators as REDs; i64::MIN keys (the table's EMPTY marker) take the special slot, wrapping sums, odd row count."""
+    rng = np.random.default_rng(21)
+    n, k = 500_001, 150_000
+    key = (rng.integers(0, k, n) * 104729 - 5 * 10**8).astype(np.int64); key[::1013] = -2**63
+    if shape == "uint_key":
+        key = key.view(np.uint64)
+    vi = rng.integers(-2**62, 2**62, n).astype(np.int64)
+    vf = rng.uniform(-50, 50, n).round(6)
+    vu = rng.integers(0, 2**63, n).astype(np.uint64)
+    aggs = {"c2": [("sum", vi, None), ("mean", vf, None), ("len", None, None)],
+            "three_cols": [("sum", vi, None), ("max", vi, None), ("mean", vf, None), ("min", vf, None), ("sum", vu, None), ("len", None, None)],
+            "sum_last": [("max", vf, None), ("mean", vf, None), ("count", vi, None), ("sum", vi, None)],
+            "uint_key": [("sum", vu, None), ("min", vu, None), ("mean", vi, None), ("len", None, None)]}[shape]
+    keys, kv, outs = GpuImpl(plb).group_by_agg(key, None, aggs, False)
+    ek, ekv, eouts, _ = oracle.group_by_agg(key, None, aggs, 8, False)
+    keys, kv, outs = sort_groups(keys, kv, outs)
+    ek, ekv, eouts = sort_groups(ek, ekv, eouts)
+    assert_close(keys, ek, kv, ekv, "keys")
+    for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
+        assert v.dtype == ev.dtype, (kind, v.dtype, ev.dtype)
+        assert_close(v, ev, m, em, f"lean {shape} {kind}")
 
 
 @pytest.mark.parametrize("knob,value", [("BL_JOIN_FUSED", "0"), ("BL_JOIN_TABLE", "compact"), ("BL_JOIN_DENSE", "0")])

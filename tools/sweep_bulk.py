@@ -17,7 +17,7 @@ STEPS = 5
 
 
 def run(label, env, key, vi, vf, dkey, dvi, dvf, nulls=None):
-    for k in ("BL_K5_BULK", "BL_K5_BULK_LANES", "BL_K5_BPS"):
+    for k in ("BL_K5_BULK", "BL_K5_BULK_LANES", "BL_K5_BPS", "BL_K5_HINT", "BL_K5_LEAN"):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env.items()})
 
@@ -53,18 +53,19 @@ def main():
     dkey, dvi, dvf = plb.to_device(key), plb.to_device(vi), plb.to_device(vf)
     a = (key, vi, vf, dkey, dvi, dvf)
     run("3 RED (word-major planes)", {"BL_K5_BULK": 0}, *a)
-    run("bulk reduce, all lanes", {"BL_K5_BULK": 1}, *a)
-    for lanes in (28, 24, 20, 16):
-        run(f"bulk reduce, {lanes} lanes", {"BL_K5_BULK": 1, "BL_K5_BULK_LANES": lanes}, *a)
-    for bps in (4, 6, 12, 16):
-        run(f"bulk reduce, all lanes, {bps} CTAs/SM", {"BL_K5_BULK": 1, "BL_K5_BPS": bps}, *a)
+    run("bulk reduce, lean kernel", {"BL_K5_BULK": 1}, *a)
+    run("bulk reduce, general kernel", {"BL_K5_BULK": 2, "BL_K5_LEAN": 0}, *a)
+    for bps in (10, 12, 16, 20, 24, 32, 48):
+        run(f"bulk reduce, lean kernel, {bps} CTAs/SM", {"BL_K5_BULK": 1, "BL_K5_BPS": bps}, *a)
+    for bps in (12, 16, 24):
+        run(f"3 RED, {bps} CTAs/SM", {"BL_K5_BULK": 0, "BL_K5_BPS": bps}, *a)
     # nullable value columns: null counters are extra REDs
     rng = np.random.default_rng(100)
     val_i, val_f = (plb.pack_bits(rng.random(ROWS) >= 0.05) for _ in range(2))
     nvi, nvf = plb.to_device(vi, val_i), plb.to_device(vf, val_f)
     an = (key, vi, vf, dkey, nvi, nvf)
     run("5% nulls, 3 RED", {"BL_K5_BULK": 0}, *an, nulls=val_i)
-    run("5% nulls, bulk reduce", {"BL_K5_BULK": 1}, *an, nulls=val_i)
+    run("5% nulls, default (3 RED: not the lean shape)", {"BL_K5_BULK": 1}, *an, nulls=val_i)
 
 
 if __name__ == "__main__":
