@@ -251,7 +251,9 @@ __global__ void __launch_bounds__(256) k_gb_consume(const __grid_constant__ GbLa
 // common analytic shape — 8-byte integer key without nulls, every value column 8 bytes wide without a validity bitmap, at most
 // two accumulators per column, single pass, pair layout — with everything that is uniform per launch hoisted out of the row
 // loop.  Column 0 carries the paired integer sum (launch_batch binds it there).
-template <int NC>
+// NULLS: the key and / or value columns may carry validity bitmaps (null keys -> the null group's slot, null values -> 0 for the
+// paired sum, skipped by the REDs, counted by W_NULLCNT words).
+template <int NC, bool NULLS>
 __global__ void __launch_bounds__(256) k_gb_consume_lean(const __grid_constant__ GbLayout L, const __grid_constant__ GbTableDev T, const __grid_constant__ GbBatch B) {
     extern __shared__ __align__(16) uint64_t gb_stage[];
     const int64_t npairs = B.n >> 1;
@@ -277,15 +279,25 @@ __global__ void __launch_bounds__(256) k_gb_consume_lean(const __grid_constant__
         ulonglong2 raw[NC];
 #pragma unroll
         for (int c = 0; c < NC; c++) raw[c] = ld_stream_u64x2(reinterpret_cast<const uint64_t*>(B.cols[c].values) + 2 * p);
+        // validity of the row pair (rows 2p, 2p+1 sit in one bitmap word): bit 0 / 1 of vbits[c]; key validity in kbits
+        unsigned vbits[NC], kbits = 3u;
+#pragma unroll
+        for (int c = 0; c < NC; c++) vbits[c] = 3u;
+        if (NULLS) {
+            const int sh = (int)((2 * p) & 31);
+            if (B.key_validity) kbits = (B.key_validity[(2 * p) >> 5] >> sh) & 3u;
+#pragma unroll
+            for (int c = 0; c < NC; c++) if (B.cols[c].validity) vbits[c] = (B.cols[c].validity[(2 * p) >> 5] >> sh) & 3u;
+        }
         const uint64_t key0 = k2.x, key1 = k2.y;
         const uint64_t s0 = table_hash(key0) >> T.shift, s1 = table_hash(key1) >> T.shift;
         const uint64_t q0 = __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + s0)), q1 = __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + s1));
-        uint64_t* const e0 = key0 == GB_EMPTY ? gb_special(T, 1) : gb_resolve(T, key0, s0, q0, 0, 0);
-        uint64_t* const e1 = key1 == GB_EMPTY ? gb_special(T, 1) : gb_resolve(T, key1, s1, q1, 0, 0);
+        uint64_t* const e0 = !(kbits & 1u) ? gb_special(T, 0) : (key0 == GB_EMPTY ? gb_special(T, 1) : gb_resolve(T, key0, s0, q0, 0, 0));
+        uint64_t* const e1 = !(kbits & 2u) ? gb_special(T, 0) : (key1 == GB_EMPTY ? gb_special(T, 1) : gb_resolve(T, key1, s1, q1, 0, 0));
         // bulk reduces first (see k_gb_consume); the staging cells of the previous iteration must have been read
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"((uint32_t)__cvta_generic_to_shared(cell0)), "l"(1ull), "l"(raw[0].x) : "memory");
-        asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"((uint32_t)__cvta_generic_to_shared(cell1)), "l"(1ull), "l"(raw[0].y) : "memory");
+        asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"((uint32_t)__cvta_generic_to_shared(cell0)), "l"(1ull), "l"((vbits[0] & 1u) ? raw[0].x : 0ull) : "memory");
+        asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"((uint32_t)__cvta_generic_to_shared(cell1)), "l"(1ull), "l"((vbits[0] & 2u) ? raw[0].y : 0ull) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (e0) bulk_add_u64x2(cells + 2 * (e0 - T.entries), cell0, 0, false);
         if (e1) bulk_add_u64x2(cells + 2 * (e1 - T.entries), cell1, 0, false);
@@ -295,8 +307,8 @@ __global__ void __launch_bounds__(256) k_gb_consume_lean(const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 if (op[c][j] < 0) continue;
-                if (e0) gb_apply(op[c][j], plane[c][j] + (e0 - T.entries), dt[c], raw[c].x, true);
-                if (e1) gb_apply(op[c][j], plane[c][j] + (e1 - T.entries), dt[c], raw[c].y, true);
+                if (e0) gb_apply(op[c][j], plane[c][j] + (e0 - T.entries), dt[c], raw[c].x, (vbits[c] & 1u) != 0);
+                if (e1) gb_apply(op[c][j], plane[c][j] + (e1 - T.entries), dt[c], raw[c].y, (vbits[c] & 2u) != 0);
             }
         }
     }
@@ -304,12 +316,14 @@ __global__ void __launch_bounds__(256) k_gb_consume_lean(const __grid_constant__
     if ((B.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const int64_t row = B.n - 1;
         const uint64_t key = reinterpret_cast<const uint64_t*>(B.keys)[row];
-        uint64_t* e = key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key);
+        const bool kvalid = B.key_validity == nullptr || bit_get(B.key_validity, row);
+        uint64_t* e = !kvalid ? gb_special(T, 0) : (key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key));
         if (e) {
             atomicAdd(reinterpret_cast<unsigned*>(gb_wp(T, e, 1)), 1u);
             for (int c = 0; c < L.n_cols; c++) {
                 const uint64_t rv = reinterpret_cast<const uint64_t*>(B.cols[c].values)[row];
-                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], gb_wp(T, e, 2 + L.wslot[k]), B.cols[c].dtype, rv, true);
+                const bool valid = B.cols[c].validity == nullptr || bit_get(B.cols[c].validity, row);
+                for (int k = L.col_kbegin[c]; k < L.col_kbegin[c + 1]; k++) gb_apply(L.wop[k], gb_wp(T, e, 2 + L.wslot[k]), B.cols[c].dtype, rv, valid);
             }
         }
     }
@@ -1244,14 +1258,16 @@ static void launch_consume(const GbLayout& L, const GbTableDev& T, const GbBatch
     const int pairs = knob_int("BL_K5_PAIRS", 1) == 2 ? 2 : 1;
     if (T.pw && T.bulk_lanes > 0 && L.pair_k >= 0) {
         // lean kernel for the common analytic shape (see k_gb_consume_lean)
-        bool lean = KEY_ELEM == 8 && KEY_CANON == 0 && !KEY_NULLS && T.bulk_lanes == 32 && !T.pass_bits && !T.hint && !L.need_first && L.need_len && L.n_cols >= 1 && L.n_cols <= 3 &&
+        bool lean = KEY_ELEM == 8 && KEY_CANON == 0 && T.bulk_lanes == 32 && !T.pass_bits && !T.hint && !L.need_first && L.need_len && L.n_cols >= 1 && L.n_cols <= 3 &&
                     knob_int("BL_K5_LEAN", 1) != 0;
-        for (int c = 0; lean && c < L.n_cols; c++) lean = B.cols[c].elem == 8 && B.cols[c].validity == nullptr && L.col_kbegin[c + 1] - L.col_kbegin[c] <= 2;
+        bool nulls = KEY_NULLS;
+        for (int c = 0; lean && c < L.n_cols; c++) { lean = B.cols[c].elem == 8 && L.col_kbegin[c + 1] - L.col_kbegin[c] <= 2; nulls = nulls || B.cols[c].validity != nullptr; }
         if (lean) {
             const size_t smem = (size_t)2 * 256 * 16;
-            if (L.n_cols == 1) PLB_LAUNCH("k5_groupby_agg", k_gb_consume_lean<1>, grid, 256, smem, L, T, B);
-            else if (L.n_cols == 2) PLB_LAUNCH("k5_groupby_agg", k_gb_consume_lean<2>, grid, 256, smem, L, T, B);
-            else PLB_LAUNCH("k5_groupby_agg", k_gb_consume_lean<3>, grid, 256, smem, L, T, B);
+#define GB_LEAN(NC) do { if (nulls) PLB_LAUNCH("k5_groupby_agg", (k_gb_consume_lean<NC, true>), grid, 256, smem, L, T, B); \
+                         else PLB_LAUNCH("k5_groupby_agg", (k_gb_consume_lean<NC, false>), grid, 256, smem, L, T, B); } while (0)
+            if (L.n_cols == 1) GB_LEAN(1); else if (L.n_cols == 2) GB_LEAN(2); else GB_LEAN(3);
+#undef GB_LEAN
         } else launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 1, true>(L, T, B, grid);
     }
     else if (pairs == 2) launch_consume_p<KEY_ELEM, KEY_CANON, KEY_NULLS, 2, false>(L, T, B, grid);
@@ -1400,15 +1416,15 @@ void GroupByState::launch_batch(const DevCol& key, const std::vector<const DevCo
 
 // does the batch have the shape k_gb_consume_lean takes?  (decides the table layout, so it is asked before alloc_table)
 void GroupByState::note_batch_shape(const DevCol& key, const std::vector<const DevCol*>& values) {
-    bool ok = pair_word >= 2 && !L.need_first && L.need_len && key.validity == nullptr && (key.dtype == BL_INT64 || key.dtype == BL_UINT64);
+    bool ok = pair_word >= 2 && !L.need_first && L.need_len && (key.dtype == BL_INT64 || key.dtype == BL_UINT64);
     std::vector<const void*> cols; std::vector<int> words;
     for (size_t i = 0; ok && i < plans.size(); i++) {
         if (plans[i].kind == BL_AGG_LEN) continue;
         const DevCol* v = i < values.size() ? values[i] : nullptr;
-        if (!v || dtype_size(v->dtype) != 8 || v->validity != nullptr) { ok = false; break; }
+        if (!v || dtype_size(v->dtype) != 8) { ok = false; break; }
         size_t c = 0; while (c < cols.size() && cols[c] != v->v()) c++;
         if (c == cols.size()) { cols.push_back(v->v()); words.push_back(0); }
-        words[c] += plans[i].main >= 0 ? 1 : 0;
+        words[c] += (plans[i].main >= 0 ? 1 : 0) + (plans[i].nullcnt >= 0 && v->validity != nullptr ? 1 : 0);
     }
     for (int w : words) ok = ok && w <= 2;
     lean_shape = ok && !cols.empty() && cols.size() <= 3;

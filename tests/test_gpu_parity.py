@@ -978,10 +978,11 @@ def test_group_by_bulk_reduce_pair_layout(plb, monkeypatch, val_dtype, order):
         assert_close(v, ev, m, em, f"pair layout {kind}")
 
 
-@pytest.mark.parametrize("shape", ["c2", "three_cols", "sum_last", "uint_key"])
+@pytest.mark.parametrize("shape", ["c2", "three_cols", "sum_last", "uint_key", "c2_nulls", "null_keys"])
 def test_group_by_lean_bulk_kernel(plb, shape):
-    """k_gb_consume_lean (default for 8-byte keys / value columns without nulls): len + integer sum as one 16-byte bulk reduce per row,
-    the other accumulators as REDs; i64::MIN keys (the table's EMPTY marker) take the special slot, wrapping sums, odd row count."""
+    """k_gb_consume_lean (default for 8-byte keys / value columns): len + integer sum as one 16-byte bulk reduce per row, the other
+    accumulators as REDs; i64::MIN keys (the table's EMPTY marker) take the special slot, wrapping sums, odd row count; with
+    validity bitmaps on the values (null -> 0 in the paired sum, null counters) and on the key (null group)."""
     rng = np.random.default_rng(21)
     n, k = 500_001, 150_000
     key = (rng.integers(0, k, n) * 104729 - 5 * 10**8).astype(np.int64); key[::1013] = -2**63
@@ -990,18 +991,73 @@ def test_group_by_lean_bulk_kernel(plb, shape):
     vi = rng.integers(-2**62, 2**62, n).astype(np.int64)
     vf = rng.uniform(-50, 50, n).round(6)
     vu = rng.integers(0, 2**63, n).astype(np.uint64)
+    nulls = shape in ("c2_nulls", "null_keys")
+    iv = (rng.random(n) > 0.05) if nulls else None
+    fv = (rng.random(n) > 0.3) if nulls else None
+    kvalid = (rng.random(n) > 0.001) if shape == "null_keys" else None
     aggs = {"c2": [("sum", vi, None), ("mean", vf, None), ("len", None, None)],
             "three_cols": [("sum", vi, None), ("max", vi, None), ("mean", vf, None), ("min", vf, None), ("sum", vu, None), ("len", None, None)],
             "sum_last": [("max", vf, None), ("mean", vf, None), ("count", vi, None), ("sum", vi, None)],
-            "uint_key": [("sum", vu, None), ("min", vu, None), ("mean", vi, None), ("len", None, None)]}[shape]
-    keys, kv, outs = GpuImpl(plb).group_by_agg(key, None, aggs, False)
-    ek, ekv, eouts, _ = oracle.group_by_agg(key, None, aggs, 8, False)
+            "uint_key": [("sum", vu, None), ("min", vu, None), ("mean", vi, None), ("len", None, None)],
+            "c2_nulls": [("sum", vi, iv), ("mean", vf, fv), ("len", None, None)],
+            "null_keys": [("sum", vi, iv), ("count", vi, iv), ("mean", vf, fv), ("len", None, None)]}[shape]
+    keys, kv, outs = GpuImpl(plb).group_by_agg(key, kvalid, aggs, False)
+    ek, ekv, eouts, _ = oracle.group_by_agg(key, kvalid, aggs, 8, False)
     keys, kv, outs = sort_groups(keys, kv, outs)
     ek, ekv, eouts = sort_groups(ek, ekv, eouts)
     assert_close(keys, ek, kv, ekv, "keys")
     for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
         assert v.dtype == ev.dtype, (kind, v.dtype, ev.dtype)
         assert_close(v, ev, m, em, f"lean {shape} {kind}")
+
+
+def test_group_by_pair_layout_readers(plb):
+    """Every reader of the pair table layout on one GPU: streaming consume with rehash (grow), hash-partitioned export + merge, and
+    the fused P2P export into a peer window (here: our own) + device-side merge — the N-GPU plan's kernels with world size 1."""
+    rng = np.random.default_rng(31)
+    n, k = 600_000, 90_000
+    key = (rng.permutation(n) % k).astype(np.int64) * 31 - 7
+    key[: n // 3] = np.sort(key[: n // 3])           # the first batch sees few distinct keys: later batches force a rehash
+    vi = rng.integers(-2**40, 2**40, n).astype(np.int64)
+    vf = rng.uniform(0, 100, n).round(6)
+    spec = [("sum", np.int64), ("mean", np.float64), ("len", None)]
+    nn = [False, False, False]
+    uk, inv = np.unique(key, return_inverse=True)
+    e_len = np.bincount(inv); e_sum = np.zeros(uk.size, np.int64); np.add.at(e_sum, inv, vi); e_mean = np.bincount(inv, weights=vf) / e_len
+
+    def check(res, sel=None, tag=""):
+        (kk, kv), outs = res
+        o = np.argsort(kk, kind="stable")
+        want = np.ones(uk.size, bool) if sel is None else sel
+        assert kv is None and np.array_equal(kk[o], uk[want]), tag + " keys"
+        assert np.array_equal(outs[0][0][o], e_sum[want]), tag + " sum"
+        assert np.allclose(outs[1][0][o], e_mean[want], rtol=1e-9), tag + " mean"
+        assert np.array_equal(outs[2][0][o].astype(np.int64), e_len[want]), tag + " len"
+
+    # streaming with growth
+    g = plb.GroupBy(np.int64, spec, nullable=nn)
+    for a, b in ((0, 50_000), (50_000, 200_000), (200_000, n)):
+        g.consume(key[a:b], [vi[a:b], vf[a:b], None], row_base=a)
+    check(g.finish(), tag="stream")
+    # export (2 partitions) + merge
+    s = plb.GroupBy(np.int64, spec, nullable=nn)
+    s.consume(key, [vi, vf, None])
+    ptr, rw, offs = s.export_partials(2)
+    part = oracle.hash_to_partition(oracle.dirty_hash(oracle.key_bits(uk)), 2)
+    for p_ in range(2):
+        f = plb.GroupBy(np.int64, spec, expected_groups=k + 1000, nullable=nn)
+        f.merge_partials(ptr + int(offs[p_]) * rw * 8, int(offs[p_ + 1] - offs[p_]))
+        check(f.finish(), part == p_, f"export partition {p_}")
+    plb.dev_free(ptr)
+    # fused P2P export into our own window + merge on the device
+    rows_per_src = k + 1024
+    win = plb.Window(1024 + rows_per_src * rw * 8)
+    s.export_partials_p2p_async([win.ptr], 0, rows_per_src, 1)
+    f = plb.GroupBy(np.int64, spec, expected_groups=k + 1000, nullable=nn)
+    f.merge_window_async(win.ptr, 1, rows_per_src, 1)
+    check(f.finish(), tag="p2p window")
+    del s, f, g
+    win.destroy()
 
 
 @pytest.mark.parametrize("knob,value", [("BL_JOIN_FUSED", "0"), ("BL_JOIN_TABLE", "compact"), ("BL_JOIN_DENSE", "0")])

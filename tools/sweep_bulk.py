@@ -53,11 +53,10 @@ def main():
     dkey, dvi, dvf = plb.to_device(key), plb.to_device(vi), plb.to_device(vf)
     a = (key, vi, vf, dkey, dvi, dvf)
     run("3 RED (word-major planes)", {"BL_K5_BULK": 0}, *a)
-    run("bulk reduce, lean kernel", {"BL_K5_BULK": 1}, *a)
-    run("bulk reduce, general kernel", {"BL_K5_BULK": 2, "BL_K5_LEAN": 0}, *a)
-    for bps in (10, 12, 16, 20, 24, 32, 48):
+    run("bulk reduce, lean kernel (default grid: 48 CTAs/SM)", {"BL_K5_BULK": 1}, *a)
+    for bps in (64, 96):
         run(f"bulk reduce, lean kernel, {bps} CTAs/SM", {"BL_K5_BULK": 1, "BL_K5_BPS": bps}, *a)
-    for bps in (12, 16, 24):
+    for bps in (32, 48):
         run(f"3 RED, {bps} CTAs/SM", {"BL_K5_BULK": 0, "BL_K5_BPS": bps}, *a)
     # nullable value columns: null counters are extra REDs
     rng = np.random.default_rng(100)
@@ -65,7 +64,7 @@ def main():
     nvi, nvf = plb.to_device(vi, val_i), plb.to_device(vf, val_f)
     an = (key, vi, vf, dkey, nvi, nvf)
     run("5% nulls, 3 RED", {"BL_K5_BULK": 0}, *an, nulls=val_i)
-    run("5% nulls, default (3 RED: not the lean shape)", {"BL_K5_BULK": 1}, *an, nulls=val_i)
+    run("5% nulls, lean bulk kernel", {"BL_K5_BULK": 1}, *an, nulls=val_i)
 
 
 if __name__ == "__main__":
