@@ -180,6 +180,36 @@ bl_status bl_groupby_agg_keys(const bl_column* keys, int32_t n_keys, const bl_ag
 bl_status bl_group_tuples(const bl_column* key_chunks, int32_t n_key_chunks, int32_t out_location,
                           bl_column* out_first, bl_column* out_offsets, bl_column* out_all);
 
+/* ---- string / binary keys: device-side dictionary encoding ------------------------ */
+/* Arrow LargeUtf8 / LargeBinary layout (polars-arrow/src/array/binary/mod.rs): value i = data[offsets[offset+i] ..
+ * offsets[offset+i+1]); validity bit (offset + i).  Polars hands strings out as view arrays (plugin.rs:165-166); the glue
+ * casts them with polars_arrow::compute::cast::utf8view_to_utf8 / binview_to_binary first. */
+typedef struct bl_string_column {
+    int32_t location;         /* BL_HOST | BL_DEVICE */
+    int32_t reserved;
+    int64_t length;           /* logical number of rows */
+    int64_t offset;           /* logical element offset into offsets and validity */
+    int64_t null_count;       /* -1 = unknown */
+    const int64_t* offsets;   /* offset + length + 1 entries */
+    const uint8_t* data;
+    const uint8_t* validity;  /* NULL = no nulls */
+    void* owner;              /* NULL = caller-owned; else release with bl_string_column_free */
+} bl_string_column;
+
+/* BinaryChunked::group_tuples (polars-core/src/frame/group_by/into_groups.rs:215-251) groups rows by their BYTES (hash of
+ * the bytes + equality, nulls = own group).  bl_string_encode materialises that relation as a UInt32 code column:
+ * out_codes[i] = index of the first row holding the same bytes as row i (null rows: null code).  The codes are an ordinary
+ * key for bl_groupby_agg / bl_hash_join / bl_group_tuples (for a join, encode the concatenation of both sides' chunks and
+ * split the codes), and the key values a group_by returns are the gather indices of the group keys (bl_string_gather).
+ * *n_distinct (optional) = number of distinct non-null values.  Exact: equal codes <=> equal bytes (verified on the device). */
+bl_status bl_string_encode(const bl_string_column* chunks, int32_t n_chunks, int32_t out_location, bl_column* out_codes, int64_t* n_distinct);
+/* out[i] = the string at row idx[i] of the (concatenated) chunks; a null index, BL_IDX_NULL or a null source row gives a
+ * null.  idx: BL_UINT32.  Out-of-range indices: BL_ERR_BOUNDS. */
+bl_status bl_string_gather(const bl_string_column* chunks, int32_t n_chunks, const bl_column* idx, int32_t out_location, bl_string_column* out);
+/* copy / move a string column between host and device (concatenates chunks) */
+bl_status bl_string_column_to(const bl_string_column* chunks, int32_t n_chunks, int32_t location, bl_string_column* out);
+void bl_string_column_free(bl_string_column* col);
+
 /* ---- K7/K8: hash join on one numeric key ----------------------------------------------- */
 /* (build_tables single_keys.rs:16-167, probe_inner single_keys_inner.rs:11-149,
  *  hash_join_tuples_left single_keys_left.rs:106-195) */

@@ -396,3 +396,21 @@ def hash_join_multi(left_keys, right_keys, left_valids=None, right_valids=None, 
     row_valid = None if nulls_equal else all_valid
     return hash_join(ids[:nl], ids[nl:], None if row_valid is None else row_valid[:nl], None if row_valid is None else row_valid[nl:],
                      how, nulls_equal, maintain_order, n_threads)
+
+
+def string_codes(values):
+    """BinaryChunked::group_tuples (polars-core/src/frame/group_by/into_groups.rs:215-251): rows are grouped by their BYTES
+    (to_bytes_hashes + equality; a null is its own group) and a group's `first` is the row of its first occurrence
+    (hashing.rs:26-63).  Returns (codes, valid, n_distinct): codes[i] = first row with the same bytes (IdxSize u32), valid[i] =
+    row i is non-null (None when there are no nulls), n_distinct = distinct non-null values.  Plain Python dict: test
+    infrastructure for small inputs, never the product path."""
+    first = {}
+    codes = np.zeros(len(values), np.uint32)
+    valid = np.ones(len(values), bool)
+    for i, v in enumerate(values):
+        if v is None:
+            valid[i] = False
+            continue
+        b = v.encode() if isinstance(v, str) else bytes(v)
+        codes[i] = first.setdefault(b, i)
+    return codes, (None if valid.all() else valid), len(first)

@@ -43,6 +43,11 @@ class BlColumn(C.Structure):
                 ("null_count", C.c_int64), ("values", C.c_void_p), ("validity", C.c_void_p), ("owner", C.c_void_p)]
 
 
+class BlStringColumn(C.Structure):
+    _fields_ = [("location", C.c_int32), ("reserved", C.c_int32), ("length", C.c_int64), ("offset", C.c_int64), ("null_count", C.c_int64),
+                ("offsets", C.c_void_p), ("data", C.c_void_p), ("validity", C.c_void_p), ("owner", C.c_void_p)]
+
+
 class BlAgg(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_chunks", C.c_int32), ("values", C.POINTER(BlColumn))]
 
@@ -318,6 +323,66 @@ def _finish(outs, location):
                 r.free()       # value arrays that view the buffer keep their OutColumn alive instead
         return np_res
     return res
+
+
+# ---------------------------------------------------------------------------------- string keys
+class StringColumn:
+    """A caller-owned host string / binary column in Arrow LargeUtf8 layout, built from a sequence of str / bytes / None
+    (or from ready-made `offsets` (int64, n + 1), `data` (uint8) and an optional bool `valid`).  `offset` / `length`
+    exercise Arrow slicing."""
+
+    def __init__(self, values=None, *, offsets=None, data=None, valid=None, offset: int = 0, length: int | None = None):
+        if values is not None:
+            enc = [None if v is None else (v.encode() if isinstance(v, str) else bytes(v)) for v in values]
+            lens = np.fromiter((0 if b is None else len(b) for b in enc), dtype=np.int64, count=len(enc))
+            offsets = np.zeros(len(enc) + 1, np.int64)
+            np.cumsum(lens, out=offsets[1:])
+            data = np.frombuffer(b"".join(b for b in enc if b is not None), dtype=np.uint8)
+            valid = None if all(b is not None for b in enc) else np.array([b is not None for b in enc], bool)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.data = np.ascontiguousarray(data, dtype=np.uint8) if data is not None and len(data) else np.zeros(1, np.uint8)
+        self.bits = None if valid is None else pack_bits(np.asarray(valid, bool))
+        self.offset = int(offset)
+        self.length = int(self.offsets.size - 1 - offset) if length is None else int(length)
+
+    def struct(self) -> BlStringColumn:
+        return BlStringColumn(HOST, 0, self.length, self.offset, 0 if self.bits is None else -1, self.offsets.ctypes.data, self.data.ctypes.data,
+                              None if self.bits is None else self.bits.ctypes.data, None)
+
+
+def _str_array(cols: Sequence[StringColumn]):
+    return (BlStringColumn * len(cols))(*[c.struct() for c in cols])
+
+
+def string_encode(col, location: int = HOST):
+    """bl_string_encode: -> ((codes, valid) | OutColumn, n_distinct).  codes[i] = first row holding the same bytes as row i."""
+    chunks = col if isinstance(col, list) else [col]
+    arr = _str_array(chunks)
+    out, nd = BlColumn(), C.c_int64()
+    _check(lib().bl_string_encode(arr, C.c_int32(len(chunks)), C.c_int32(location), C.byref(out), C.byref(nd)))
+    return _finish([out], location)[0], int(nd.value)
+
+
+def string_gather(col, idx) -> list:
+    """bl_string_gather with host output: -> list of bytes / None."""
+    chunks = col if isinstance(col, list) else [col]
+    arr = _str_array(chunks)
+    ic = _as_col(idx)
+    ist = ic.struct()
+    out = BlStringColumn()
+    _check(lib().bl_string_gather(arr, C.c_int32(len(chunks)), C.byref(ist), C.c_int32(HOST), C.byref(out)))
+    try:
+        n = int(out.length)
+        offs = np.ctypeslib.as_array(C.cast(out.offsets, C.POINTER(C.c_int64)), shape=(n + 1,)).copy()
+        total = int(offs[-1])
+        data = bytes(np.ctypeslib.as_array(C.cast(out.data, C.POINTER(C.c_uint8)), shape=(max(total, 1),))[:total])
+        valid = None
+        if out.validity:
+            valid = unpack_bits(np.ctypeslib.as_array(C.cast(out.validity, C.POINTER(C.c_uint8)), shape=((n + 7) // 8 or 1,)), n)
+        return [None if (valid is not None and not valid[i]) else data[offs[i]:offs[i + 1]] for i in range(n)]
+    finally:
+        lib().bl_string_column_free.restype = None
+        lib().bl_string_column_free(C.byref(out))
 
 
 # ---------------------------------------------------------------------------------- operators

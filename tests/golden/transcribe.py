@@ -2,8 +2,8 @@
 
 The reference cannot be built or imported in the authoring container (Rust nightly + ~400 crates,
 no cargo, no wheel — SURVEY.md §8(c)), so these known-answer tests are the literal inputs/outputs
-the reference's tests assert, each with its file:line.  String keys are dictionary-encoded to
-int64 codes in first-occurrence order (our path takes numeric keys).
+the reference's tests assert, each with its file:line.  In the numeric sections string keys are dictionary-encoded to
+int64 codes in first-occurrence order; `group_by_strings` keeps them as strings (bl_string_encode).
 `null` in a list = a null slot.
 
 Run `python tests/golden/transcribe.py` to regenerate tests/golden/reference_kats.json.
@@ -91,6 +91,34 @@ KATS = {
             "key": [0, 0, 0, 1], "key_dtype": "int64", "maintain_order": True,
             "aggs": [{"col": [1, 2, 3, 4], "dtype": dt, "kind": "mean", "expect": [2.0, 4.0]} for dt in ("uint32", "int32", "uint64", "float32", "float64")],
             "expect_key": [0, 1],
+        },
+    ],
+    "group_by_strings": [
+        {
+            "cite": "crates/polars-core/src/frame/group_by/mod.rs:948-1000 (test_group_by): string keys as they stand in the test",
+            "key": ["2020-08-21", "2020-08-21", "2020-08-22", "2020-08-23", "2020-08-22"], "maintain_order": True,
+            "expect_codes": [0, 0, 2, 3, 2], "expect_key": ["2020-08-21", "2020-08-22", "2020-08-23"],
+            "aggs": [{"col": [20, 10, 7, 9, 1], "dtype": "int32", "kind": "len", "expect": [2, 2, 1]},
+                     {"col": [20, 10, 7, 9, 1], "dtype": "int32", "kind": "mean", "expect": [15.0, 4.0, 9.0]},
+                     {"col": [20, 10, 7, 9, 1], "dtype": "int32", "kind": "sum", "expect": [30, 8, 9]}],
+        },
+        {
+            "cite": "py-polars/tests/unit/operations/test_group_by.py:32-52 (test_group_by): group_by('a', maintain_order=True).agg(sum('b'))",
+            "key": ["a", "b", "a", "b", "b", "c"], "maintain_order": True,
+            "expect_codes": [0, 1, 0, 1, 1, 5], "expect_key": ["a", "b", "c"],
+            "aggs": [{"col": [1, 2, 3, 4, 5, 6], "dtype": "int64", "kind": "sum", "expect": [4, 11, 6]}],
+        },
+        {
+            "cite": "py-polars/tests/unit/operations/test_group_by.py:54-70: group_by('b', maintain_order=True).agg(count('a')) == [('a', 2), ('b', 3)]",
+            "key": ["a", "a", "b", "b", "b"], "maintain_order": True,
+            "expect_codes": [0, 0, 2, 2, 2], "expect_key": ["a", "b"],
+            "aggs": [{"col": [1, 2, 3, 4, 5], "dtype": "int64", "kind": "count", "expect": [2, 3]}],
+        },
+        {
+            "cite": "crates/polars-core/src/frame/group_by/mod.rs:1157-1172 (test_group_by_null_handling)",
+            "key": ["a", "a", "a", "b", "b"], "maintain_order": True,
+            "expect_codes": [0, 0, 0, 3, 3], "expect_key": ["a", "b"],
+            "aggs": [{"col": [1, 2, N, N, 1], "dtype": "int32", "kind": "mean", "expect": [1.5, 1.0]}],
         },
     ],
     "group_by_multi": [

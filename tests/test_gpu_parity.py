@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
-from helpers import IDX_NULL, assert_close, pairs_sorted, run_group_by_kat, run_join_kat, sort_groups
+from helpers import IDX_NULL, assert_close, col, pairs_sorted, run_group_by_kat, run_join_kat, sort_groups
 
 pytestmark = pytest.mark.gpu
 
@@ -1137,3 +1137,79 @@ def test_pdsh_q1_from_the_reference_schema(plb):
         for o, ref in ((1, price[r].sum()), (2, dp[r].sum()), (3, ch[r].sum()), (4, qty[r].mean()), (5, price[r].mean()), (6, disc[r].mean())):
             assert abs(outs[o][0][g] - ref) <= 1e-9 * abs(ref), (o, k)
     assert [str(rf_dict[a]) + str(ls_dict[b]) for a, b in seen] == ["NO", "RF", "AF"]      # the groups of the sample, first-occurrence order
+
+
+# ------------------------------------------------------------------ string keys
+def test_string_keys_kats(plb, kats):
+    """The reference's string-key group_by tests end to end on the device: bl_string_encode -> bl_groupby_agg on the codes ->
+    bl_string_gather of the group keys."""
+    for case in kats["group_by_strings"]:
+        col_s = plb.StringColumn(case["key"])
+        (codes, cvalid), nd = plb.string_encode(col_s)
+        assert codes.dtype == np.uint32 and codes.tolist() == case["expect_codes"] and cvalid is None, case["cite"]
+        assert nd == len(case["expect_key"])
+        cols = [col(a["col"], a["dtype"]) for a in case["aggs"]]
+        aggs = [(a["kind"], c[0], c[1]) for a, c in zip(case["aggs"], cols)]
+        keys, kv, outs = GpuImpl(plb).group_by_agg(codes, None, aggs, True)
+        assert [b.decode() for b in plb.string_gather(col_s, keys)] == case["expect_key"], case["cite"]
+        for a, (v, m) in zip(case["aggs"], outs):
+            e, em = col(a["expect"], {"mean": "float64", "len": "uint32", "count": "uint32"}.get(a["kind"], a["dtype"]))
+            assert_close(v, e, m, em, what=f"{case['cite']} {a['kind']}")
+
+
+def _random_strings(rng, n, distinct, nulls):
+    pool = []
+    for i in range(distinct):
+        ln = int(rng.integers(0, 40)) if i % 50 else int(rng.integers(200, 3000))      # a few long values
+        pool.append(bytes(rng.integers(0, 256, ln, dtype=np.uint8)) if i % 3 else ("key-%d-" % i * (ln // 8 + 1))[:ln].encode())
+    pool[0] = b""                                                                       # the empty string is a value, not a null
+    vals = [pool[int(j)] for j in rng.integers(0, distinct, n)]
+    if nulls:
+        vals = [None if rng.random() < 0.07 else v for v in vals]
+    return vals
+
+
+@pytest.mark.parametrize("n,distinct,nulls", [(0, 1, False), (1, 1, True), (33, 5, True), (5_000, 4_000, True), (200_000, 30_000, False), (200_001, 7, True)])
+def test_string_encode_vs_oracle(plb, n, distinct, nulls):
+    rng = np.random.default_rng(n * 7 + distinct)
+    vals = _random_strings(rng, n, distinct, nulls)
+    ecodes, evalid, end = oracle.string_codes(vals)
+    (codes, cvalid), nd = plb.string_encode(plb.StringColumn(vals))
+    assert nd == end
+    assert_close(codes, ecodes, cvalid, evalid, "string codes")
+    if n >= 33:
+        # chunked + sliced input (Arrow offsets): chunk 0 = rows [0, a) of a column with 3 leading rows, chunk 1 = the rest
+        a = n // 3
+        lead = [b"zz", None, b"lead"]
+        c0 = plb.StringColumn(lead + vals[:a], offset=3, length=a)
+        c1 = plb.StringColumn(vals[a:] + [b"tail"], offset=0, length=n - a)
+        (codes2, cvalid2), nd2 = plb.string_encode([c0, c1])
+        assert nd2 == end
+        assert_close(codes2, ecodes, cvalid2, evalid, "string codes (chunked, sliced)")
+
+
+def test_string_group_by_and_gather(plb):
+    """group_by on a string key with nulls == the oracle's group_by on the oracle's codes; gather materialises the keys
+    (null group -> null key; BL_IDX_NULL / null index -> null; out-of-range index -> OutOfBoundsError)."""
+    rng = np.random.default_rng(77)
+    n = 120_001
+    vals = _random_strings(rng, n, 9_000, True)
+    vi = rng.integers(-10**6, 10**6, n).astype(np.int64)
+    vf = rng.uniform(0, 100, n).round(6)
+    aggs = [("sum", vi, None), ("mean", vf, None), ("len", None, None)]
+    scol = plb.StringColumn(vals)
+    (codes, cvalid), _ = plb.string_encode(scol)
+    keys, kv, outs = GpuImpl(plb).group_by_agg(codes, cvalid, aggs, True)
+    ecodes, evalid, _ = oracle.string_codes(vals)
+    ek, ekv, eouts, _ = oracle.group_by_agg(ecodes, evalid, aggs, 4, True)
+    assert_close(keys, ek, kv, ekv, "string group keys (codes)")
+    for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
+        assert_close(v, ev, m, em, "string group_by " + kind)
+    got = plb.string_gather(scol, (keys, kv))
+    exp = [None if (kv is not None and not kv[i]) else vals[int(keys[i])] for i in range(keys.size)]
+    assert got == exp
+    idx = np.array([0, plb.IDX_NULL, n - 1, 5, 5], np.uint32)
+    got = plb.string_gather(scol, (idx, np.array([True, True, True, False, True])))
+    assert got == [vals[0], None, vals[n - 1], None, vals[5]]
+    with pytest.raises(plb.OutOfBoundsError):
+        plb.string_gather(scol, np.array([n], np.uint32))

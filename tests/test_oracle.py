@@ -386,3 +386,38 @@ def test_first_last_var_std_vs_numpy():
         assert np.array_equal(vv, cnt > ddof)
         exp = np.array([np.var(x[r][valid[r]], ddof=ddof) if c > ddof else 0.0 for r, c in zip(rows, cnt)])
         assert np.allclose(var[vv], exp[vv], rtol=1e-9, atol=0) and np.allclose(std[vv], np.sqrt(exp[vv]), rtol=1e-9, atol=0)
+
+
+# ---------------------------------------------------------------- string keys
+def test_string_codes_kats(kats):
+    """The oracle's restatement of BinaryChunked::group_tuples against the reference's own string-key tests: the codes, the
+    distinct keys in first-occurrence order, and the aggregates the reference asserts (computed over the codes)."""
+    for case in kats["group_by_strings"]:
+        codes, valid, nd = oracle.string_codes(case["key"])
+        assert codes.tolist() == case["expect_codes"] and valid is None, case["cite"]
+        assert nd == len(case["expect_key"]), case["cite"]
+        run_group_by_kat(OracleImpl(2), dict(case, key=case["expect_codes"], key_dtype="uint32", expect_key=sorted(set(case["expect_codes"]))))
+        firsts = list(dict.fromkeys(case["expect_codes"]))
+        assert [case["key"][i] for i in firsts] == case["expect_key"], case["cite"]
+
+
+@pytest.mark.parametrize("n,distinct,nulls", [(0, 1, False), (1, 1, True), (1000, 37, True), (50_000, 20_000, False)])
+def test_string_codes_vs_arrow_dictionary(n, distinct, nulls):
+    rng = np.random.default_rng(n + distinct)
+    pool = [("k%d" % i) * int(rng.integers(0, 6)) + "x" * int(rng.integers(0, 3)) for i in range(distinct)]
+    vals = [pool[int(j)] for j in rng.integers(0, distinct, n)]
+    if nulls:
+        vals = [None if rng.random() < 0.1 else v for v in vals]
+    codes, valid, nd = oracle.string_codes(vals)
+    d = pa.array(vals, type=pa.large_string()).dictionary_encode()
+    idx = d.indices.to_numpy(zero_copy_only=False)
+    mask = np.array([v is not None for v in vals], bool)
+    assert nd == len(d.dictionary)
+    if n:
+        # arrow numbers the dictionary in first-occurrence order: value j first appears at the first row with index j
+        first_row = np.full(len(d.dictionary), -1, np.int64)
+        rows = np.flatnonzero(mask)
+        ids = idx[mask].astype(np.int64)
+        first_row[ids[::-1]] = rows[::-1]
+        assert np.array_equal(codes[mask], first_row[ids].astype(np.uint32))
+    assert (valid is None) == bool(mask.all())
