@@ -183,7 +183,7 @@ bl_status bl_group_tuples(const bl_column* key_chunks, int32_t n_key_chunks, int
 /* ---- string / binary keys: device-side dictionary encoding ------------------------ */
 /* Arrow LargeUtf8 / LargeBinary layout (polars-arrow/src/array/binary/mod.rs): value i = data[offsets[offset+i] ..
  * offsets[offset+i+1]); validity bit (offset + i).  Polars hands strings out as view arrays (plugin.rs:165-166); the glue
- * casts them with polars_arrow::compute::cast::utf8view_to_utf8 / binview_to_binary first. */
+ * casts them with polars_compute::cast::utf8view_to_utf8::<i64> (crates/polars-compute/src/cast/binview_to.rs:56) first. */
 typedef struct bl_string_column {
     int32_t location;         /* BL_HOST | BL_DEVICE */
     int32_t reserved;
@@ -206,6 +206,13 @@ bl_status bl_string_encode(const bl_string_column* chunks, int32_t n_chunks, int
 /* out[i] = the string at row idx[i] of the (concatenated) chunks; a null index, BL_IDX_NULL or a null source row gives a
  * null.  idx: BL_UINT32.  Out-of-range indices: BL_ERR_BOUNDS. */
 bl_status bl_string_gather(const bl_string_column* chunks, int32_t n_chunks, const bl_column* idx, int32_t out_location, bl_string_column* out);
+/* group_by / join on a string key in ONE call: encode -> bl_groupby_agg on the codes -> gather of the group keys
+ * (out_key: LargeUtf8, one value per group, null = the null group), resp. encode both sides together -> bl_hash_join on the
+ * codes (row-index tuples as bl_hash_join; with nulls_equal a null matches a null, single_keys_dispatch.rs:20-60). */
+bl_status bl_groupby_agg_strings(const bl_string_column* key_chunks, int32_t n_key_chunks, const bl_agg* aggs, int32_t n_aggs, int32_t maintain_order,
+                                 int32_t out_location, bl_string_column* out_key, bl_column* out_aggs);
+bl_status bl_hash_join_strings(const bl_string_column* left_chunks, int32_t n_left_chunks, const bl_string_column* right_chunks, int32_t n_right_chunks, int32_t how,
+                               int32_t nulls_equal, int32_t maintain_order, int32_t out_location, bl_column* out_left_idx, bl_column* out_right_idx);
 /* copy / move a string column between host and device (concatenates chunks) */
 bl_status bl_string_column_to(const bl_string_column* chunks, int32_t n_chunks, int32_t location, bl_string_column* out);
 void bl_string_column_free(bl_string_column* col);

@@ -363,14 +363,8 @@ def string_encode(col, location: int = HOST):
     return _finish([out], location)[0], int(nd.value)
 
 
-def string_gather(col, idx) -> list:
-    """bl_string_gather with host output: -> list of bytes / None."""
-    chunks = col if isinstance(col, list) else [col]
-    arr = _str_array(chunks)
-    ic = _as_col(idx)
-    ist = ic.struct()
-    out = BlStringColumn()
-    _check(lib().bl_string_gather(arr, C.c_int32(len(chunks)), C.byref(ist), C.c_int32(HOST), C.byref(out)))
+def _string_out_to_list(out: BlStringColumn) -> list:
+    """host BlStringColumn (library-owned) -> list of bytes / None; frees it."""
     try:
         n = int(out.length)
         offs = np.ctypeslib.as_array(C.cast(out.offsets, C.POINTER(C.c_int64)), shape=(n + 1,)).copy()
@@ -383,6 +377,52 @@ def string_gather(col, idx) -> list:
     finally:
         lib().bl_string_column_free.restype = None
         lib().bl_string_column_free(C.byref(out))
+
+
+def string_gather(col, idx) -> list:
+    """bl_string_gather with host output: -> list of bytes / None."""
+    chunks = col if isinstance(col, list) else [col]
+    arr = _str_array(chunks)
+    ic = _as_col(idx)
+    ist = ic.struct()
+    out = BlStringColumn()
+    _check(lib().bl_string_gather(arr, C.c_int32(len(chunks)), C.byref(ist), C.c_int32(HOST), C.byref(out)))
+    return _string_out_to_list(out)
+
+
+def group_by_agg_strings(key, aggs: Sequence, maintain_order: bool = False):
+    """bl_groupby_agg_strings (host outputs): key = StringColumn or list of chunks; aggs as in group_by_agg.
+    -> (group keys as a list of bytes / None, [agg outputs])."""
+    chunks = key if isinstance(key, list) else [key]
+    karr = _str_array(chunks)
+    keep, agg_structs, cache = [], [], {}
+    for kind, vals in aggs:
+        if kind == "len" or vals is None:
+            agg_structs.append(BlAgg(_agg_kind(kind), 0, None))
+            continue
+        ident = id(vals)
+        if ident not in cache:
+            cs = [_as_col(c) for c in (vals if isinstance(vals, list) else [vals])]
+            cache[ident] = (cs, _col_array(cs))
+        cs, arr = cache[ident]
+        keep.append((cs, arr))
+        agg_structs.append(BlAgg(_agg_kind(kind), len(cs), C.cast(arr, C.POINTER(BlColumn))))
+    aarr = (BlAgg * max(len(agg_structs), 1))(*agg_structs)
+    out_key, out_aggs = BlStringColumn(), (BlColumn * max(len(agg_structs), 1))()
+    _check(lib().bl_groupby_agg_strings(karr, C.c_int32(len(chunks)), aarr, C.c_int32(len(agg_structs)), C.c_int32(int(maintain_order)), C.c_int32(HOST),
+                                        C.byref(out_key), out_aggs))
+    return _string_out_to_list(out_key), _finish(list(out_aggs)[: len(agg_structs)], HOST)
+
+
+def hash_join_strings(left, right, how: str = "inner", nulls_equal: bool = False, maintain_order: str = "none", location: int = HOST):
+    """bl_hash_join_strings: row-index tuples of a join on a string key (both sides encoded together on the device)."""
+    lc = left if isinstance(left, list) else [left]
+    rc = right if isinstance(right, list) else [right]
+    la, ra = _str_array(lc), _str_array(rc)
+    ol, orr = BlColumn(), BlColumn()
+    _check(lib().bl_hash_join_strings(la, C.c_int32(len(lc)), ra, C.c_int32(len(rc)), C.c_int32(JOINS[how]), C.c_int32(int(nulls_equal)), C.c_int32(ORDERS[maintain_order]),
+                                      C.c_int32(location), C.byref(ol), C.byref(orr)))
+    return tuple(_finish([ol, orr], location))
 
 
 # ---------------------------------------------------------------------------------- operators

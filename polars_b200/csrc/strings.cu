@@ -291,6 +291,49 @@ bl_status bl_string_column_to(const bl_string_column* chunks, int32_t n_chunks, 
     BL_CATCH
 }
 
+// device view of a code column slice [pos, pos + len) as a caller-owned bl_column
+static bl_column codes_view(const DevCol& codes, int64_t pos, int64_t len) {
+    bl_column v; memset(&v, 0, sizeof v);
+    v.dtype = BL_UINT32; v.location = BL_DEVICE; v.length = len; v.offset = pos; v.null_count = codes.validity ? -1 : 0;
+    v.values = codes.v(); v.validity = codes.validity ? (const uint8_t*)codes.validity->p : nullptr;
+    return v;
+}
+
+bl_status bl_groupby_agg_strings(const bl_string_column* key_chunks, int32_t n_key_chunks, const bl_agg* aggs, int32_t n_aggs, int32_t maintain_order, int32_t out_location,
+                                 bl_string_column* out_key, bl_column* out_aggs) {
+    BL_TRY
+    PLB_REQUIRE(out_key != nullptr, BL_ERR_INVALID, "groupby_agg_strings: null output");
+    DevStr s = import_string(key_chunks, n_key_chunks);
+    DevCol codes = op_string_codes(s, nullptr);
+    const bl_column cv = codes_view(codes, 0, codes.len);
+    bl_column ok; memset(&ok, 0, sizeof ok);
+    const bl_status st = bl_groupby_agg(&cv, 1, aggs, n_aggs, maintain_order, out_location, &ok, out_aggs);      // the context lock is recursive
+    if (st != BL_OK) return st;
+    try {
+        DevCol ix = import_column(&ok, 1);
+        DevStr g = op_string_gather(s, ix);
+        export_string(g, out_location, out_key);
+    } catch (...) { bl_column_free(&ok); for (int i = 0; i < n_aggs; i++) bl_column_free(&out_aggs[i]); throw; }
+    bl_column_free(&ok);
+    BL_CATCH
+}
+
+bl_status bl_hash_join_strings(const bl_string_column* left_chunks, int32_t n_left_chunks, const bl_string_column* right_chunks, int32_t n_right_chunks, int32_t how,
+                               int32_t nulls_equal, int32_t maintain_order, int32_t out_location, bl_column* out_left_idx, bl_column* out_right_idx) {
+    BL_TRY
+    PLB_REQUIRE(left_chunks && right_chunks && n_left_chunks >= 1 && n_right_chunks >= 1, BL_ERR_INVALID, "hash_join_strings: null argument");
+    // both relations are encoded TOGETHER so that equal bytes get the same code on either side
+    std::vector<bl_string_column> all(left_chunks, left_chunks + n_left_chunks);
+    all.insert(all.end(), right_chunks, right_chunks + n_right_chunks);
+    int64_t nl = 0; for (int i = 0; i < n_left_chunks; i++) nl += left_chunks[i].length;
+    DevStr s = import_string(all.data(), (int)all.size());
+    DevCol codes = op_string_codes(s, nullptr);
+    const bl_column lv = codes_view(codes, 0, nl), rv = codes_view(codes, nl, codes.len - nl);
+    const bl_status st = bl_hash_join(&lv, 1, &rv, 1, how, nulls_equal, maintain_order, out_location, out_left_idx, out_right_idx);
+    if (st != BL_OK) return st;
+    BL_CATCH
+}
+
 void bl_string_column_free(bl_string_column* col) {
     if (!col || !col->owner) return;
     auto* own = reinterpret_cast<plb::StrOwner*>(col->owner);

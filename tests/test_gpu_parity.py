@@ -1213,3 +1213,34 @@ def test_string_group_by_and_gather(plb):
     assert got == [vals[0], None, vals[n - 1], None, vals[5]]
     with pytest.raises(plb.OutOfBoundsError):
         plb.string_gather(scol, np.array([n], np.uint32))
+
+
+def test_string_group_by_one_call_and_join(plb):
+    """bl_groupby_agg_strings == group_by on the oracle's codes with the keys gathered back; bl_hash_join_strings == the oracle's
+    join on codes computed over both sides together (exact tuple order), for every join kind, with null keys."""
+    rng = np.random.default_rng(78)
+    n = 60_000
+    vals = _random_strings(rng, n, 3_000, True)
+    vi = rng.integers(-1000, 1000, n).astype(np.int64)
+    vf = rng.uniform(0, 100, n).round(6)
+    aggs = [("sum", vi, None), ("mean", vf, None), ("len", None, None)]
+    gkeys, outs = plb.group_by_agg_strings(plb.StringColumn(vals), [("sum", plb.Column(vi)), ("mean", plb.Column(vf)), ("len", None)], True)
+    ecodes, evalid, _ = oracle.string_codes(vals)
+    ek, ekv, eouts, _ = oracle.group_by_agg(ecodes, evalid, aggs, 4, True)
+    assert gkeys == [None if (ekv is not None and not ekv[i]) else vals[int(ek[i])] for i in range(ek.size)]
+    for (kind, _, _), (v, m), (ev, em) in zip(aggs, outs, eouts):
+        assert_close(v, ev, m, em, "one-call string group_by " + kind)
+    # join
+    nl, nr = 40_000, 9_000
+    pool = _random_strings(rng, 6_000, 6_000, False)
+    left = [None if rng.random() < 0.03 else pool[int(j)] for j in rng.integers(0, 6_000, nl)]
+    right = [None if rng.random() < 0.03 else pool[int(j)] for j in rng.integers(0, 4_000, nr)]
+    codes, cvalid, _ = oracle.string_codes(left + right)
+    lk, rk = codes[:nl], codes[nl:]
+    lv = None if cvalid is None else cvalid[:nl]
+    rv = None if cvalid is None else cvalid[nl:]
+    for how in ("inner", "left", "semi", "anti", "full"):
+        for ne in (False, True):
+            (li, _), (ri, _) = plb.hash_join_strings(plb.StringColumn(left), plb.StringColumn(right), how, ne, "none")
+            eli, eri = oracle.hash_join(lk, rk, lv, rv, how, ne, "none", 4)
+            assert np.array_equal(li, eli) and np.array_equal(ri, eri), (how, ne)

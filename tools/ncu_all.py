@@ -35,6 +35,17 @@ plb.group_by_agg(dkey.view(), aggs(), False, location=D)      # K5r on C2 itself
 os.environ.pop("BL_K5_RADIX")
 del hkey
 
+# ---- string keys: device dictionary encoding (hash, first-row ids, verification) + gather of the distinct values
+ids = rng.integers(0, 200_000, 4_000_000)
+lens = 1 + (ids % 23).astype(np.int64)
+offs = np.zeros(ids.size + 1, np.int64); np.cumsum(lens, out=offs[1:])
+pos = np.arange(int(offs[-1]), dtype=np.int64) - np.repeat(offs[:-1], lens)
+sdata = ((np.repeat(ids, lens) * 31 + pos * 7) % 251).astype(np.uint8)
+scol = plb.StringColumn(offsets=offs, data=sdata)
+codes, _nd = plb.string_encode(scol, location=D)
+plb.string_gather(scol, np.unique(codes.to_numpy()[0])[:100_000].astype(np.uint32))
+del codes, scol, sdata, pos, offs, lens, ids
+
 # ---- multi-GPU export / merge kernels in one process: a window to ourselves (world size 1)
 g = plb.GroupBy(np.int64, [("sum", np.int64), ("mean", np.float64), ("len", None)], nullable=[False, False, False])
 g.consume(dkey.view(), [dvi.view(), dvf.view(), None])
