@@ -146,7 +146,8 @@ bl_status bl_gather(const bl_column* cols, int32_t n_cols, const bl_column* idx,
 enum { BL_AGG_SUM = 0, BL_AGG_MEAN = 1, BL_AGG_MIN = 2, BL_AGG_MAX = 3, BL_AGG_COUNT = 4, BL_AGG_LEN = 5,
        /* evaluated per group over the reference's GroupsIdx (row lists in row order), not by the fused atomics path: */
        BL_AGG_FIRST = 6, BL_AGG_LAST = 7,   /* value at the group's first / last row, nulls included (dispatch.rs:57-120) */
-       BL_AGG_VAR = 8, BL_AGG_STD = 9 };    /* Welford in row order, f64; null when count <= ddof (aggregations/mod.rs:1020-1178, take_agg/var.rs:11-41) */
+       BL_AGG_VAR = 8, BL_AGG_STD = 9,      /* Welford in row order, f64; null when count <= ddof (aggregations/mod.rs:1020-1178, take_agg/var.rs:11-41) */
+       BL_AGG_N_UNIQUE = 10 };              /* distinct values per group, a null counts as one (aggregations/dispatch.rs:285-345); UInt32; bl_groupby_agg only */
 /* delta degrees of freedom of VAR / STD travel in bits 16..23 of `kind` (Polars' default is 1) */
 #define BL_AGG_WITH_DDOF(kind, ddof) ((kind) | ((ddof) << 16))
 typedef struct bl_agg {

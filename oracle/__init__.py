@@ -414,3 +414,29 @@ def string_codes(values):
         b = v.encode() if isinstance(v, str) else bytes(v)
         codes[i] = first.setdefault(b, i)
     return codes, (None if valid.all() else valid), len(first)
+
+
+def group_n_unique(key, key_valid, values, valid, maintain_order=True):
+    """agg_n_unique (polars-core/src/frame/group_by/aggregations/dispatch.rs:285-345): per group, the number of distinct values
+    among the group's rows; a null is one value; floats compare by total equality (NaN == NaN, -0.0 == 0.0,
+    polars-utils/src/total_ord.rs:37-47).  Groups in first-occurrence order (null key = own group), as group_by_agg with
+    maintain_order.  Returns (first_row_of_group, counts u32).  Plain Python: test infrastructure for small inputs."""
+    key = np.asarray(key); values = np.asarray(values)
+    groups, firsts = {}, []
+    for i in range(key.size):
+        k = None if (key_valid is not None and not key_valid[i]) else (key[i].item() if key.dtype.kind != "f" else _canon_float(key[i]))
+        if valid is not None and not valid[i]:
+            v = None
+        else:
+            v = values[i].item() if values.dtype.kind != "f" else _canon_float(values[i])
+        if k not in groups:
+            groups[k] = set(); firsts.append(i)
+        groups[k].add(v)
+    return np.array(firsts, np.uint32), np.array([len(s) for s in groups.values()], np.uint32)
+
+
+def _canon_float(x):
+    x = float(x)
+    if x != x:
+        return "nan"
+    return 0.0 if x == 0.0 else x

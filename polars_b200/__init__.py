@@ -26,7 +26,7 @@ NP_OF = {v: k for k, v in DTYPES.items()}
 BOOL = 10
 OPS = {"add": 0, "sub": 1, "mul": 2, "floordiv": 3, "mod": 4, "truediv": 5}
 CMPS = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5}
-AGGS = {"sum": 0, "mean": 1, "min": 2, "max": 3, "count": 4, "len": 5, "first": 6, "last": 7, "var": 8 | (1 << 16), "std": 9 | (1 << 16)}
+AGGS = {"sum": 0, "mean": 1, "min": 2, "max": 3, "count": 4, "len": 5, "first": 6, "last": 7, "var": 8 | (1 << 16), "std": 9 | (1 << 16), "n_unique": 10}
 
 
 def _agg_kind(kind: str) -> int:

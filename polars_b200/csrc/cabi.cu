@@ -85,8 +85,12 @@ bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, cons
     };
     // Host inputs without nulls: chunked H2D on the copy stream overlapped with K5 on the compute stream.
     bool needs_groups_idx = ctx().deterministic;      // FIRST / LAST / VAR / STD fold per group over GroupsIdx (groupby_exact.cu)
-    for (int i = 0; i < n_aggs; i++) needs_groups_idx |= (aggs[i].kind & 0xFFFF) >= BL_AGG_FIRST;
-    bool pipelined = !needs_groups_idx && n_key_chunks == 1 && key_chunks[0].location == BL_HOST && (key_chunks[0].validity == nullptr || key_chunks[0].null_count == 0) &&
+    bool has_n_unique = false;
+    for (int i = 0; i < n_aggs; i++) {
+        if (aggs[i].kind == BL_AGG_N_UNIQUE) { has_n_unique = true; continue; }
+        needs_groups_idx |= (aggs[i].kind & 0xFFFF) >= BL_AGG_FIRST;
+    }
+    bool pipelined = !needs_groups_idx && !has_n_unique && n_key_chunks == 1 && key_chunks[0].location == BL_HOST && (key_chunks[0].validity == nullptr || key_chunks[0].null_count == 0) &&
                      key_chunks[0].length >= (int64_t)1 << 22 && dtype_size(key_chunks[0].dtype) >= 4 && key_chunks[0].dtype != BL_BOOL;
     for (int i = 0; i < n_aggs && pipelined; i++)
         if (aggs[i].kind != BL_AGG_LEN)
@@ -157,6 +161,21 @@ bl_status bl_groupby_agg(const bl_column* key_chunks, int32_t n_key_chunks, cons
         }
         vptr[i] = &vals[i];
         dts.push_back(vals[i].dtype);
+    }
+    // n_unique (agg_n_unique, aggregations/dispatch.rs:285-345: distinct values per group, a null counts as a value): a row is
+    // the FIRST occurrence of its (key, value) pair <=> its pair-group id equals its own index; the number of such rows per group
+    // is a COUNT over a flag column whose validity bitmap is that predicate.  Composed of K5 pieces: op_pack_keys (nulls and
+    // canonical floats folded into the packed value), op_group_first_ids, K2 compare against iota.
+    for (int i = 0; i < n_aggs; i++) {
+        if (aggs[i].kind != BL_AGG_N_UNIQUE) continue;
+        const int64_t n = key.len;
+        std::vector<DevCol> kv{key, vals[i]};
+        DevCol ids = op_group_first_ids(op_pack_keys(kv));
+        DevCol iota = make_col(BL_UINT32, n, false);
+        iota_u32(as<uint32_t>(iota.values), n, 0);
+        DevCol is_first = op_compare(BL_CMP_EQ, ids, iota, false);
+        DevCol flag; flag.dtype = BL_UINT32; flag.len = n; flag.values = ids.values; flag.validity = is_first.values; flag.null_count = -1;
+        vals[i] = flag; kinds[i] = BL_AGG_COUNT; dts[i] = BL_UINT32;
     }
     for (int i = 0; i < n_aggs; i++) nullable[i] = vptr[i] != nullptr && vptr[i]->validity != nullptr;
     DevCol ok; std::vector<DevCol> oa;

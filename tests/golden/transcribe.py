@@ -121,6 +121,13 @@ KATS = {
             "aggs": [{"col": [1, 2, N, N, 1], "dtype": "int32", "kind": "mean", "expect": [1.5, 1.0]}],
         },
     ],
+    "group_by_n_unique": [
+        {
+            "cite": "py-polars/tests/unit/operations/test_group_by.py:280-313 (test_group_by_shorthands, method n_unique): group_by('b', maintain_order=True).n_unique() == [('a', 2, 2), ('b', 3, 2)] — a null counts as a value",
+            "key": [0, 0, 1, 1, 1], "key_dtype": "int64",
+            "cols": [{"col": [1, 2, 3, 4, 5], "dtype": "int64", "expect": [2, 3]}, {"col": [N, 1, N, 1, N], "dtype": "int64", "expect": [2, 2]}],
+        },
+    ],
     "group_by_multi": [
         {
             "cite": "crates/polars-core/src/frame/group_by/mod.rs:1009-1047 (test_static_group_by_by_12_columns)",

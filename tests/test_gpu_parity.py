@@ -1244,3 +1244,33 @@ def test_string_group_by_one_call_and_join(plb):
             (li, _), (ri, _) = plb.hash_join_strings(plb.StringColumn(left), plb.StringColumn(right), how, ne, "none")
             eli, eri = oracle.hash_join(lk, rk, lv, rv, how, ne, "none", 4)
             assert np.array_equal(li, eli) and np.array_equal(ri, eri), (how, ne)
+
+
+@pytest.mark.parametrize("val_dtype,nulls", [("int64", False), ("int64", True), ("float64", True), ("int32", True), ("uint64", False)])
+def test_group_by_n_unique(plb, kats, val_dtype, nulls):
+    """BL_AGG_N_UNIQUE (agg_n_unique: a null counts as one value, NaN == NaN, -0.0 == 0.0) next to fused aggregations, against
+    the reference's KAT and the oracle's restatement; null keys form their own group."""
+    for case in kats["group_by_n_unique"]:
+        key, kvalid = col(case["key"], case["key_dtype"])
+        for c in case["cols"]:
+            v, valid = col(c["col"], c["dtype"])
+            _, _, outs = GpuImpl(plb).group_by_agg(key, kvalid, [("n_unique", v, valid)], True)
+            assert outs[0][0].dtype == np.uint32 and outs[0][0].tolist() == c["expect"] and outs[0][1] is None, case["cite"]
+    rng = np.random.default_rng(41)
+    n = 150_001
+    key = rng.integers(-500, 500, n).astype(np.int64)
+    kvalid = (rng.random(n) > 0.02) if nulls else None
+    if val_dtype == "float64":
+        v = rng.integers(-20, 20, n).astype(np.float64); v[rng.random(n) < 0.05] = np.nan; v[rng.random(n) < 0.05] = -0.0
+    else:
+        info = np.iinfo(val_dtype)
+        v = rng.integers(max(info.min, -30), 30, n).astype(val_dtype)
+    valid = (rng.random(n) > 0.1) if nulls else None
+    vi = rng.integers(-1000, 1000, n).astype(np.int64)
+    keys, kv, outs = GpuImpl(plb).group_by_agg(key, kvalid, [("sum", vi, None), ("n_unique", v, valid), ("len", None, None)], True)
+    firsts, counts = oracle.group_n_unique(key, kvalid, v, valid)
+    ek, ekv, eouts, _ = oracle.group_by_agg(key, kvalid, [("sum", vi, None), ("len", None, None)], 4, True)
+    assert_close(keys, ek, kv, ekv, "n_unique keys")
+    assert_close(outs[0][0], eouts[0][0], outs[0][1], eouts[0][1], "sum beside n_unique")
+    assert outs[1][0].dtype == np.uint32 and outs[1][1] is None and np.array_equal(outs[1][0], counts), "n_unique"
+    assert_close(outs[2][0], eouts[1][0], outs[2][1], eouts[1][1], "len beside n_unique")

@@ -5,7 +5,7 @@ import pyarrow as pa
 import pytest
 
 import oracle
-from helpers import IDX_NULL, OracleImpl, assert_close, pairs_sorted, run_group_by_kat, run_join_kat, sort_groups
+from helpers import IDX_NULL, OracleImpl, assert_close, col, pairs_sorted, run_group_by_kat, run_join_kat, sort_groups
 
 
 # ---------------------------------------------------------------- golden vectors
@@ -421,3 +421,23 @@ def test_string_codes_vs_arrow_dictionary(n, distinct, nulls):
         first_row[ids[::-1]] = rows[::-1]
         assert np.array_equal(codes[mask], first_row[ids].astype(np.uint32))
     assert (valid is None) == bool(mask.all())
+
+
+def test_n_unique_kat_and_pandas(kats):
+    import pandas as pd
+    for case in kats["group_by_n_unique"]:
+        key, kvalid = col(case["key"], case["key_dtype"])
+        for c in case["cols"]:
+            v, valid = col(c["col"], c["dtype"])
+            _, counts = oracle.group_n_unique(key, kvalid, v, valid)
+            assert counts.tolist() == c["expect"], case["cite"]
+    rng = np.random.default_rng(3)
+    n = 20_000
+    key = rng.integers(0, 300, n).astype(np.int64)
+    v = rng.integers(0, 40, n).astype(np.float64); v[rng.random(n) < 0.05] = np.nan
+    valid = rng.random(n) > 0.1
+    firsts, counts = oracle.group_n_unique(key, None, v, valid)
+    # pandas: NaN and None are both "NA" there, so map NaN to a sentinel value first and count NA (= null) as one value
+    s = pd.Series(np.where(np.isnan(v), -1.0, v)).where(valid)
+    exp = s.groupby(key, sort=False).nunique(dropna=False)
+    assert np.array_equal(key[firsts], exp.index.to_numpy()) and np.array_equal(counts, exp.to_numpy().astype(np.uint32))
