@@ -290,10 +290,19 @@ __global__ void __launch_bounds__(256) k_gb_consume_lean(const __grid_constant__
             for (int c = 0; c < NC; c++) if (B.cols[c].validity) vbits[c] = (B.cols[c].validity[(2 * p) >> 5] >> sh) & 3u;
         }
         const uint64_t key0 = k2.x, key1 = k2.y;
-        const uint64_t s0 = table_hash(key0) >> T.shift, s1 = table_hash(key1) >> T.shift;
-        const uint64_t q0 = __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + s0)), q1 = __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + s1));
-        uint64_t* const e0 = !(kbits & 1u) ? gb_special(T, 0) : (key0 == GB_EMPTY ? gb_special(T, 1) : gb_resolve(T, key0, s0, q0, 0, 0));
-        uint64_t* const e1 = !(kbits & 2u) ? gb_special(T, 0) : (key1 == GB_EMPTY ? gb_special(T, 1) : gb_resolve(T, key1, s1, q1, 0, 0));
+        const uint64_t h0 = table_hash(key0), h1 = table_hash(key1);
+        const uint64_t s0 = h0 >> T.shift, s1 = h1 >> T.shift;
+        const bool reg0 = (kbits & 1u) && key0 != GB_EMPTY, reg1 = (kbits & 2u) && key1 != GB_EMPTY;
+        // multi-pass mode (tables larger than L2): this launch only owns the slot sub-range `pass_id` (special groups: pass 0)
+        bool mine0 = true, mine1 = true;
+        if (T.pass_bits) {
+            mine0 = reg0 ? (int)(h0 >> (64 - T.pass_bits)) == T.pass_id : T.pass_id == 0;
+            mine1 = reg1 ? (int)(h1 >> (64 - T.pass_bits)) == T.pass_id : T.pass_id == 0;
+        }
+        const uint64_t q0 = (reg0 && mine0) ? __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + s0)) : 0ull;
+        const uint64_t q1 = (reg1 && mine1) ? __ldcg(reinterpret_cast<const unsigned long long*>(T.entries + s1)) : 0ull;
+        uint64_t* const e0 = !mine0 ? nullptr : (!(kbits & 1u) ? gb_special(T, 0) : (key0 == GB_EMPTY ? gb_special(T, 1) : gb_resolve(T, key0, s0, q0, 0, 0)));
+        uint64_t* const e1 = !mine1 ? nullptr : (!(kbits & 2u) ? gb_special(T, 0) : (key1 == GB_EMPTY ? gb_special(T, 1) : gb_resolve(T, key1, s1, q1, 0, 0)));
         // bulk reduces first (see k_gb_consume); the staging cells of the previous iteration must have been read
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"((uint32_t)__cvta_generic_to_shared(cell0)), "l"(1ull), "l"((vbits[0] & 1u) ? raw[0].x : 0ull) : "memory");
@@ -317,7 +326,9 @@ __global__ void __launch_bounds__(256) k_gb_consume_lean(const __grid_constant__
         const int64_t row = B.n - 1;
         const uint64_t key = reinterpret_cast<const uint64_t*>(B.keys)[row];
         const bool kvalid = B.key_validity == nullptr || bit_get(B.key_validity, row);
-        uint64_t* e = !kvalid ? gb_special(T, 0) : (key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key));
+        const bool regular = kvalid && key != GB_EMPTY;
+        const bool mine = !T.pass_bits || (regular ? (int)(table_hash(key) >> (64 - T.pass_bits)) == T.pass_id : T.pass_id == 0);
+        uint64_t* e = !mine ? nullptr : (!kvalid ? gb_special(T, 0) : (key == GB_EMPTY ? gb_special(T, 1) : gb_find_or_insert(T, key)));
         if (e) {
             atomicAdd(reinterpret_cast<unsigned*>(gb_wp(T, e, 1)), 1u);
             for (int c = 0; c < L.n_cols; c++) {
@@ -1258,7 +1269,7 @@ static void launch_consume(const GbLayout& L, const GbTableDev& T, const GbBatch
     const int pairs = knob_int("BL_K5_PAIRS", 1) == 2 ? 2 : 1;
     if (T.pw && T.bulk_lanes > 0 && L.pair_k >= 0) {
         // lean kernel for the common analytic shape (see k_gb_consume_lean)
-        bool lean = KEY_ELEM == 8 && KEY_CANON == 0 && T.bulk_lanes == 32 && !T.pass_bits && !T.hint && !L.need_first && L.need_len && L.n_cols >= 1 && L.n_cols <= 3 &&
+        bool lean = KEY_ELEM == 8 && KEY_CANON == 0 && T.bulk_lanes == 32 && !T.hint && !L.need_first && L.need_len && L.n_cols >= 1 && L.n_cols <= 3 &&
                     knob_int("BL_K5_LEAN", 1) != 0;
         bool nulls = KEY_NULLS;
         for (int c = 0; lean && c < L.n_cols; c++) { lean = B.cols[c].elem == 8 && L.col_kbegin[c + 1] - L.col_kbegin[c] <= 2; nulls = nulls || B.cols[c].validity != nullptr; }

@@ -48,6 +48,9 @@ void ensure_init(int device) {
     PLB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;
     PLB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    // L2 fetch granularity (cudaLimitMaxL2FetchGranularity, default 64 B): the random-access kernels (hashed join probe, gather
+    // from HBM) move ~100 B of DRAM per 8..32-byte access (ncu: 10.1 GB for 1e8 probes); BL_L2_FETCH=32 asks for sector-sized fetches
+    { const char* g = getenv("BL_L2_FETCH"); if (g && atoi(g) >= 16 && atoi(g) <= 128) PLB_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g))); }
     { const char* d = getenv("BL_DETERMINISTIC"); c->deterministic = d != nullptr && d[0] != '\0' && d[0] != '0'; }
     g_ctx = c;
 }
