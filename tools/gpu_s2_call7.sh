@@ -3,6 +3,7 @@
 # random-access kernels (hashed join probe, gather from HBM) — every process below runs with BL_L2_FETCH=32 except the pytest subset
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 mkdir -p gpurun_out
+echo "== smoke (prebuilt library)"; SMOKE_NO_REBUILD=1 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "group_by" -p no:cacheprovider > gpurun_out/pytest_groupby_s2b.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_groupby_s2b.log | cut -c1-250
 timeout 200 python tools/sweep_bulk.py > gpurun_out/r02_sweep_bulk_v6.jsonl 2> gpurun_out/sweep_bulk_v6.err; echo "sweep rc=$?"; cut -c1-230 gpurun_out/r02_sweep_bulk_v6.jsonl | tail -3
 export BL_L2_FETCH=32
