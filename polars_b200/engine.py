@@ -17,7 +17,7 @@ UDF bodies are written against the reference source only; the plan matcher (whic
 left to Polars) is tested with a mock NodeTraverser in tests/test_engine_matcher.py.  It is deliberately
 conservative: any node shape it does not recognise is left untouched (Polars executes it).
 Recognised:
-  * GroupBy(keys=[col, ...], aggs ⊆ {col.sum/mean/min/max/count, len}) over a DataFrameScan, optionally through
+  * GroupBy(keys=[col, ...], aggs ⊆ {col.sum/mean/min/max/count/first/last/var/std/n_unique, len}) over a DataFrameScan, optionally through
     one Filter(col <cmp> literal)                      -> bl_filter_cmp + bl_groupby_agg / bl_groupby_agg_keys
   * Join(inner|left|semi|anti, one key column per side) of two DataFrameScans -> bl_hash_join + bl_gather
 """
@@ -29,7 +29,8 @@ import numpy as np
 
 _NUMERIC = {"Int32": np.int32, "Int64": np.int64, "UInt32": np.uint32, "UInt64": np.uint64, "Float32": np.float32, "Float64": np.float64}
 _CMP = {"Eq": "eq", "NotEq": "ne", "Lt": "lt", "LtEq": "le", "Gt": "gt", "GtEq": "ge"}
-_AGG = {"sum": "sum", "mean": "mean", "min": "min", "max": "max", "count": "count"}
+_AGG = {"sum": "sum", "mean": "mean", "min": "min", "max": "max", "count": "count", "first": "first", "last": "last", "var": "var", "std": "std",
+        "n_unique": "n_unique"}
 
 
 class _Unsupported(Exception):
@@ -77,7 +78,12 @@ def _parse_agg(nt, expr_ir):
                 return "len", None, expr_ir.output_name          # include_nulls: every row of the group counts
             if opt not in (None, False):
                 raise _Unsupported("count options")
-        elif kind in ("sum", "mean") and opt is not None:
+        elif kind in ("var", "std"):
+            # options = ddof (visitor/expr_nodes.rs:1027-1040); the library carries it in the aggregation kind ("var:0", BL_AGG_WITH_DDOF)
+            if not isinstance(opt, int) or isinstance(opt, bool) or not 0 <= opt <= 255:
+                raise _Unsupported(f"{kind} ddof {opt!r}")
+            return f"{kind}:{opt}", col, expr_ir.output_name
+        elif kind in ("sum", "mean", "first", "last", "n_unique") and opt is not None:      # these carry no option
             raise _Unsupported(f"{kind} options")
         return kind, col, expr_ir.output_name
     raise _Unsupported(f"aggregation {name}")
@@ -124,6 +130,8 @@ def _plan_group_by(plb, nt, root_id, node):
     key_names = [_column_name(nt, k.node) for k in node.keys]       # several plain columns -> bl_groupby_agg_keys
     key_name = key_names[0]
     aggs = [_parse_agg(nt, a) for a in node.aggs]
+    if len(key_names) > 1 and any(kind == "n_unique" for kind, _, _ in aggs):
+        raise _Unsupported("n_unique with several key columns")       # BL_AGG_N_UNIQUE is a bl_groupby_agg (single key) aggregation
     nt.set_node(node.input)
     child = nt.view_current_node()
     flt = None

@@ -88,6 +88,27 @@ def test_count_with_include_nulls_is_len():
     assert engine._parse_agg(nt, expr_ir(2, "x")) == ("min", "x", "x")
 
 
+def test_var_std_ddof_first_last_n_unique():
+    """Agg.options of var / std is ddof (visitor/expr_nodes.rs:1027-1040) and travels in the library's aggregation kind; first / last /
+    n_unique carry no option; n_unique is a single-key aggregation of the library, so a two-key plan with it is left to Polars."""
+    nt = group_by_plan(agg_name="var", agg_options=1)
+    assert engine._parse_agg(nt, expr_ir(2, "x")) == ("var:1", "x", "x")
+    nt = group_by_plan(agg_name="std", agg_options=0)
+    assert engine._parse_agg(nt, expr_ir(2, "x")) == ("std:0", "x", "x")
+    for name in ("first", "last", "n_unique"):
+        nt = group_by_plan(agg_name=name)
+        assert engine._parse_agg(nt, expr_ir(2, "x")) == (name, "x", "x")
+        engine.execute_with_b200(nt)
+        assert callable(nt.udf)
+    for bad in (dict(agg_name="var", agg_options=None), dict(agg_name="std", agg_options=True), dict(agg_name="first", agg_options=1),
+                dict(agg_name="n_unique", n_keys=2)):
+        nt = group_by_plan(**bad)
+        engine.execute_with_b200(nt)
+        assert nt.udf is None, bad
+    import polars_b200 as plb
+    assert plb._agg_kind("var:0") == 8 and plb._agg_kind("std:2") == (9 | (2 << 16)) and plb._agg_kind("n_unique") == 10
+
+
 def join_plan(how="Inner", n_keys=1, nulls_equal=False, slc=None, suffix="_right", coalesce=True, order="none", options=None):
     exprs = {0: make("Column", name="k"), 1: make("Column", name="k"), 2: make("Column", name="k2")}
     nodes = {20: make("DataFrameScan", df=object(), projection=None, selection=None), 21: make("DataFrameScan", df=object(), projection=["k", "r"], selection=None)}
