@@ -93,6 +93,34 @@ KATS = {
             "expect_key": [0, 1],
         },
     ],
+    "group_by_ordered": [
+        {
+            "cite": "py-polars/tests/unit/operations/test_group_by.py:280-313 (test_group_by_shorthands: len, first, last, max, mean, min on group_by('b', maintain_order=True))",
+            "note": "b = a,a,b,b,b -> 0,0,1,1,1; column a = 1..5, column c = [None, 1, None, 1, None]",
+            "key": [0, 0, 1, 1, 1], "key_dtype": "int64", "maintain_order": True,
+            "aggs": [{"kind": "len", "expect": [2, 3]},
+                     {"col": [1, 2, 3, 4, 5], "dtype": "int64", "kind": "first", "expect": [1, 3]}, {"col": [N, 1, N, 1, N], "dtype": "int64", "kind": "first", "expect": [N, N]},
+                     {"col": [1, 2, 3, 4, 5], "dtype": "int64", "kind": "last", "expect": [2, 5]}, {"col": [N, 1, N, 1, N], "dtype": "int64", "kind": "last", "expect": [1, N]},
+                     {"col": [1, 2, 3, 4, 5], "dtype": "int64", "kind": "max", "expect": [2, 5]}, {"col": [N, 1, N, 1, N], "dtype": "int64", "kind": "max", "expect": [1, 1]},
+                     {"col": [1, 2, 3, 4, 5], "dtype": "int64", "kind": "mean", "expect": [1.5, 4.0]}],
+            "expect_key": [0, 1],
+        },
+        {
+            "cite": "py-polars/tests/unit/operations/test_group_by.py:280-313 (test_group_by_shorthands: mean, min of column c)",
+            "key": [0, 0, 1, 1, 1], "key_dtype": "int64", "maintain_order": True,
+            "aggs": [{"col": [N, 1, N, 1, N], "dtype": "int64", "kind": "mean", "expect": [1.0, 1.0]},
+                     {"col": [1, 2, 3, 4, 5], "dtype": "int64", "kind": "min", "expect": [1, 3]}, {"col": [N, 1, N, 1, N], "dtype": "int64", "kind": "min", "expect": [1, 1]}],
+            "expect_key": [0, 1],
+        },
+        {
+            "cite": "crates/polars-core/src/frame/group_by/mod.rs:1174-1196 (test_group_by_var): var(1) of [1, 2] == 0.5, std(1) == 1/sqrt(2)",
+            "note": "g = foo,foo,bar -> 0,0,1; the test asserts group 0 only; group 1 holds one value: count <= ddof gives null (take_agg/var.rs:11-41)",
+            "key": [0, 0, 1], "key_dtype": "int64", "maintain_order": True,
+            "aggs": [{"col": [1, 2, 3], "dtype": "int32", "kind": "var", "expect": [0.5, N]}, {"col": [1, 2, 3], "dtype": "int32", "kind": "std", "expect": [0.7071067811865476, N]},
+                     {"col": [1.0, 2.0, 3.0], "dtype": "float64", "kind": "var", "expect": [0.5, N]}],
+            "expect_key": [0, 1],
+        },
+    ],
     "group_by_strings": [
         {
             "cite": "crates/polars-core/src/frame/group_by/mod.rs:948-1000 (test_group_by): string keys as they stand in the test",

@@ -87,7 +87,7 @@ def _run_group_by_kat_one(impl, case):
     ek, ekv = col(case["expect_key"], case["key_dtype"])
     assert_close(keys, ek, kv, ekv, what=f"{case['cite']} keys")
     for a, (v, m) in zip(case["aggs"], outs):
-        exp_dt = {"mean": "float64", "len": "uint32", "count": "uint32"}.get(a["kind"], a["dtype"])
+        exp_dt = {"mean": "float64", "len": "uint32", "count": "uint32", "var": "float64", "std": "float64"}.get(a["kind"], a.get("dtype"))
         if a["kind"] == "mean" and a["dtype"] == "float32":
             exp_dt = "float32"
         e, em = col(a["expect"], exp_dt)

@@ -43,6 +43,11 @@ class GpuImpl:
 
 
 # ------------------------------------------------------------------ golden vectors
+def test_group_by_ordered_agg_kats(plb, kats):
+    for case in kats["group_by_ordered"]:
+        run_group_by_kat(GpuImpl(plb), case)
+
+
 def test_group_by_kats(plb, kats):
     for case in kats["group_by"]:
         run_group_by_kat(GpuImpl(plb), case)

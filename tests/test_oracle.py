@@ -25,6 +25,12 @@ def test_group_by_kats(kats, threads):
         run_group_by_kat(OracleImpl(threads), case)
 
 
+def test_group_by_ordered_agg_kats(kats):
+    """first / last / var / std (GroupsIdx-ordered aggregations) and the shorthand table of the reference's tests."""
+    for case in kats["group_by_ordered"]:
+        run_group_by_kat(OracleImpl(2), case)
+
+
 def test_join_kats(kats):
     for case in kats["join"]:
         impl = OracleImpl()
